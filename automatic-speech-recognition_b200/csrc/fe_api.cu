@@ -1,0 +1,552 @@
+// C-ABI implementation (see include/asr_frontend.h for the contract and the
+// reference call sites each entry point replaces).
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string.h>
+#include <string>
+#include <vector>
+#include <algorithm>
+
+#include "../../include/asr_frontend.h"
+#include "fe_kernels.cuh"
+
+using namespace fe;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+};
+
+struct HostPinned {
+    void* p = nullptr;
+    size_t cap = 0;
+};
+
+}  // namespace
+
+struct fe_handle {
+    int device = 0;
+    int num_sms = 0;
+    cudaStream_t stream = nullptr;
+    bool configured = false;
+    fe_config cfg{};
+    std::string err;
+
+    // device tables
+    DevBuf tw256, tw512, window, fb_start, fb_bin0, fb_w, dct;
+    int dct_stride = 0, full_spectrum = 0;
+    // resampler
+    std::vector<int> sp_up, sp_down, sp_tap_off;
+    DevBuf d_sp_up, d_sp_down, d_sp_tap_off, d_taps;
+
+    // per-run scratch (grow-only)
+    DevBuf d_utts, d_tile_prefix, d_tiles, d_atile_prefix, d_atiles, d_statics, d_pcm, d_out, d_scratch;
+    HostPinned h_stage;
+    std::vector<UttDesc> utts;
+    std::vector<long long> tile_prefix, atile_prefix;
+
+    int profiling = 0;
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    bool ev_valid = false, ev_k0 = false, ev_k2 = false;
+    int64_t launches = 0;
+    size_t k1_smem = 0;
+};
+
+namespace {
+
+int fail(fe_handle* h, int code, const std::string& msg) {
+    if (h) h->err = msg; else g_create_error = msg;
+    return code;
+}
+
+#define FE_CUDA(h, expr)                                                                     \
+    do {                                                                                     \
+        cudaError_t e__ = (expr);                                                            \
+        if (e__ != cudaSuccess)                                                              \
+            return fail(h, FE_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__)); \
+    } while (0)
+
+int ensure(fe_handle* h, DevBuf& b, size_t bytes) {
+    if (bytes <= b.cap) return FE_OK;
+    if (b.p) { FE_CUDA(h, cudaFree(b.p)); b.p = nullptr; b.cap = 0; }
+    size_t want = bytes + bytes / 8 + 256;
+    FE_CUDA(h, cudaMalloc(&b.p, want));
+    b.cap = want;
+    return FE_OK;
+}
+
+int ensure_pinned(fe_handle* h, HostPinned& b, size_t bytes) {
+    if (bytes <= b.cap) return FE_OK;
+    if (b.p) { FE_CUDA(h, cudaFreeHost(b.p)); b.p = nullptr; b.cap = 0; }
+    size_t want = bytes + bytes / 4 + 4096;
+    FE_CUDA(h, cudaMallocHost(&b.p, want));
+    b.cap = want;
+    return FE_OK;
+}
+
+int upload(fe_handle* h, DevBuf& b, const void* src, size_t bytes) {
+    int rc = ensure(h, b, bytes ? bytes : 16);
+    if (rc) return rc;
+    if (bytes) FE_CUDA(h, cudaMemcpy(b.p, src, bytes, cudaMemcpyHostToDevice));
+    return FE_OK;
+}
+
+void release(DevBuf& b) { if (b.p) cudaFree(b.p); b.p = nullptr; b.cap = 0; }
+
+bool is_device_ptr(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+inline long long round_up(long long x, long long m) { return (x + m - 1) / m * m; }
+
+// per-utterance host plan shared by fe_plan / fe_run
+struct Plan {
+    long long total_frames = 0, total_out = 0, total_tiles = 0, total_scratch = 0, total_atiles = 0;
+    long long pcm_span = 0;
+    bool any_speed = false;
+};
+
+int make_plan(fe_handle* h, const int64_t* pcm_offsets, const int64_t* pcm_lengths, int32_t n,
+              const int32_t* speed_idx, const float* gain, int64_t* out_offsets, int32_t* n_frames,
+              Plan& pl, bool fill_desc) {
+    const fe_config& c = h->cfg;
+    const int width = c.feat_dim * (c.cmvn ? 3 : 1);
+    const long long align = c.pcm_dtype == FE_PCM_INT16 ? 8 : 4;
+    if (fill_desc) { h->utts.resize(n); h->tile_prefix.resize(n + 1); h->atile_prefix.resize(n + 1); }
+    long long out_off = 0;
+    for (int i = 0; i < n; ++i) {
+        const long long len = pcm_lengths[i];
+        if (len < 0 || len > 0x7fffffffLL) return fail(h, FE_ERR_INVALID, "utterance length out of range");
+        int sidx = speed_idx ? speed_idx[i] : -1;
+        if (sidx >= (int)h->sp_up.size()) return fail(h, FE_ERR_INVALID, "speed_idx not configured");
+        if (sidx >= 0 && h->sp_up[sidx] == h->sp_down[sidx]) sidx = -1;
+        if (sidx >= 0 && c.pcm_dtype != FE_PCM_INT16)
+            return fail(h, FE_ERR_INVALID, "speed perturbation needs int16 PCM");
+        long long n_eff = sidx >= 0 ? fe_resampled_length(len, h->sp_up[sidx], h->sp_down[sidx]) : len;
+        long long L = fe_num_frames(n_eff, c.frame_len, c.hop);
+        if (L > 0x7fffffffLL / (width > 0 ? width : 1)) return fail(h, FE_ERR_INVALID, "utterance too long");
+        if (out_offsets) out_offsets[i] = out_off;
+        if (n_frames) n_frames[i] = (int32_t)L;
+        if (fill_desc) {
+            UttDesc& u = h->utts[i];
+            const long long off = pcm_offsets[i];
+            if (off < 0 || off % align) return fail(h, FE_ERR_INVALID, "pcm_offsets must be multiples of 16 bytes");
+            u.src_off = off;
+            u.n_src = (int)len;
+            u.n_samples = (int)n_eff;
+            u.n_frames = (int)L;
+            u.speed_idx = sidx;
+            u.gain = gain ? gain[i] : 1.f;
+            u.src_sel = sidx >= 0 ? 1 : 0;
+            u.pcm_off = sidx >= 0 ? pl.total_scratch : off;
+            u.out_off = out_off;
+            u.stat_off = c.cmvn ? pl.total_frames * c.feat_dim : out_off;
+            h->tile_prefix[i] = pl.total_tiles;
+            h->atile_prefix[i] = pl.total_atiles;
+            pl.pcm_span = std::max(pl.pcm_span, off + len);
+        }
+        if (sidx >= 0) {
+            pl.any_speed = true;
+            pl.total_scratch += round_up(n_eff, 8);
+            pl.total_atiles += (n_eff + kK0Outputs - 1) / kK0Outputs;
+        }
+        pl.total_frames += L;
+        pl.total_tiles += (L + kCtaFrames - 1) / kCtaFrames;
+        out_off += round_up(L * width, 4);
+    }
+    if (out_offsets) out_offsets[n] = out_off;
+    if (fill_desc) { h->tile_prefix[n] = pl.total_tiles; h->atile_prefix[n] = pl.total_atiles; }
+    pl.total_out = out_off;
+    return FE_OK;
+}
+
+template <typename K>
+int set_smem(fe_handle* h, K kernel, size_t bytes) {
+    FE_CUDA(h, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    return FE_OK;
+}
+
+int launch_k1(fe_handle* h, cudaStream_t st, const void* pcm, const short* scratch, const UttDesc* utts,
+              const int2* tiles, int n_tiles, const DevTables& dt, float* statics) {
+    const fe_config& c = h->cfg;
+    int grid = std::min<long long>(n_tiles, 2LL * h->num_sms);
+    if (grid <= 0) return FE_OK;
+    if (c.frame_len == 400 && c.hop == 160) {
+        if (c.pcm_dtype == FE_PCM_INT16)
+            k_frames_to_statics<400, 160, 0><<<grid, kCtaWarps * 32, h->k1_smem, st>>>(
+                pcm, scratch, utts, tiles, n_tiles, dt, statics, c.preemph);
+        else
+            k_frames_to_statics<400, 160, 1><<<grid, kCtaWarps * 32, h->k1_smem, st>>>(
+                pcm, scratch, utts, tiles, n_tiles, dt, statics, c.preemph);
+    } else {
+        return fail(h, FE_ERR_INVALID, "unsupported frame geometry");
+    }
+    h->launches++;
+    FE_CUDA(h, cudaGetLastError());
+    return FE_OK;
+}
+
+DevTables dev_tables(const fe_handle* h) {
+    const fe_config& c = h->cfg;
+    DevTables dt;
+    dt.tw256 = (const float2*)h->tw256.p;
+    dt.tw512 = (const float2*)h->tw512.p;
+    dt.window = c.window ? (const float*)h->window.p : nullptr;
+    dt.fb_start = (const int*)h->fb_start.p;
+    dt.fb_bin0 = (const int*)h->fb_bin0.p;
+    dt.fb_w = (const float*)h->fb_w.p;
+    dt.dct = (const float*)h->dct.p;
+    dt.nf = c.num_filters; dt.nnz = c.fb_nnz; dt.D = c.feat_dim; dt.dct_stride = h->dct_stride;
+    dt.full_spectrum = h->full_spectrum;
+    dt.is_mfcc = c.feat_type == FE_FEAT_MFCC;
+    dt.fbank_log = c.fbank_log; dt.dc_elim = c.dc_elimination;
+    return dt;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------
+extern "C" {
+
+int fe_abi_version(void) { return FE_ABI_VERSION; }
+
+int64_t fe_num_frames(int64_t n_samples, int32_t frame_len, int32_t hop) {
+    if (hop <= 0 || n_samples < frame_len) return 0;
+    return (n_samples - frame_len) / hop;      // floor for non-negative operands
+}
+
+int64_t fe_resampled_length(int64_t n_samples, int32_t up, int32_t down) {
+    if (up <= 0 || down <= 0) return n_samples;
+    return (n_samples * up + down - 1) / down;
+}
+
+const char* fe_last_error(fe_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int fe_create(int device, fe_handle** out) {
+    if (!out) return fail(nullptr, FE_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail(nullptr, FE_ERR_CUDA, std::string("no CUDA device (there is no CPU fallback): ") +
+                                              cudaGetErrorString(e));
+    if (device < 0 || device >= n) return fail(nullptr, FE_ERR_INVALID, "device index out of range");
+    FE_CUDA(nullptr, cudaSetDevice(device));
+    cudaDeviceProp prop;
+    FE_CUDA(nullptr, cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+        return fail(nullptr, FE_ERR_INVALID, "this library is built for sm_100a (Blackwell) only");
+    fe_handle* h = new fe_handle();
+    h->device = device;
+    h->num_sms = prop.multiProcessorCount;
+    FE_CUDA(nullptr, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    for (auto& ev : h->ev) FE_CUDA(nullptr, cudaEventCreate(&ev));
+    *out = h;
+    return FE_OK;
+}
+
+int fe_destroy(fe_handle* h) {
+    if (!h) return FE_OK;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    for (DevBuf* b : {&h->tw256, &h->tw512, &h->window, &h->fb_start, &h->fb_bin0, &h->fb_w, &h->dct,
+                      &h->d_sp_up, &h->d_sp_down, &h->d_sp_tap_off, &h->d_taps, &h->d_utts,
+                      &h->d_tile_prefix, &h->d_tiles, &h->d_atile_prefix, &h->d_atiles, &h->d_statics,
+                      &h->d_pcm, &h->d_out, &h->d_scratch})
+        release(*b);
+    if (h->h_stage.p) cudaFreeHost(h->h_stage.p);
+    for (auto& ev : h->ev) if (ev) cudaEventDestroy(ev);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return FE_OK;
+}
+
+int fe_configure(fe_handle* h, const fe_config* c) {
+    if (!h || !c) return FE_ERR_INVALID;
+    if (c->abi_version != FE_ABI_VERSION) return fail(h, FE_ERR_INVALID, "fe_config.abi_version mismatch");
+    if (c->nfft != kNfft) return fail(h, FE_ERR_INVALID, "only nfft = 512 is supported");
+    if (!(c->frame_len == 400 && c->hop == 160))
+        return fail(h, FE_ERR_INVALID, "unsupported frame geometry: kernels are built for 400/160 samples (25 ms / 10 ms at 16 kHz)");
+    if (c->num_filters < 1 || c->num_filters > kMaxFilters) return fail(h, FE_ERR_INVALID, "num_filters out of range [1,128]");
+    if (c->feat_dim < 1 || c->feat_dim > kMaxFilters) return fail(h, FE_ERR_INVALID, "feat_dim out of range [1,128]");
+    if (c->feat_type == FE_FEAT_MFCC && c->feat_dim > c->num_filters)
+        return fail(h, FE_ERR_INVALID, "mfcc: feat_dim must be <= num_filters");
+    if (c->feat_type == FE_FEAT_FBANK && c->feat_dim != c->num_filters)
+        return fail(h, FE_ERR_INVALID, "fbank: feat_dim must equal num_filters");
+    if (c->feat_type != FE_FEAT_MFCC && c->feat_type != FE_FEAT_FBANK) return fail(h, FE_ERR_INVALID, "bad feat_type");
+    if (!c->fb_row_start || !c->fb_first_bin || !c->fb_weights || !c->tw256 || !c->tw512)
+        return fail(h, FE_ERR_INVALID, "missing table pointer");
+    if (c->feat_type == FE_FEAT_MFCC && !c->dct) return fail(h, FE_ERR_INVALID, "mfcc needs the DCT table");
+    if (c->fb_row_start[c->num_filters] != c->fb_nnz) return fail(h, FE_ERR_INVALID, "filterbank CSR inconsistent");
+    FE_CUDA(h, cudaSetDevice(h->device));
+    FE_CUDA(h, cudaStreamSynchronize(h->stream));
+
+    int max_bin = 0;
+    for (int m = 0; m < c->num_filters; ++m) {
+        int w = c->fb_row_start[m + 1] - c->fb_row_start[m];
+        if (w < 0 || c->fb_first_bin[m] < 0 || c->fb_first_bin[m] + w > kBins)
+            return fail(h, FE_ERR_INVALID, "filterbank row outside the 257 FFT bins");
+        if (w > 0) max_bin = std::max(max_bin, c->fb_first_bin[m] + w - 1);
+    }
+    h->full_spectrum = max_bin > 128;
+
+    int rc;
+    if ((rc = upload(h, h->tw256, c->tw256, 256 * 2 * sizeof(float)))) return rc;
+    if ((rc = upload(h, h->tw512, c->tw512, kBins * 2 * sizeof(float)))) return rc;
+    if ((rc = upload(h, h->fb_start, c->fb_row_start, (c->num_filters + 1) * sizeof(int)))) return rc;
+    if ((rc = upload(h, h->fb_bin0, c->fb_first_bin, c->num_filters * sizeof(int)))) return rc;
+    {   // power rows hold |2X|^2: fold 1/(4*512) into the weights (exact, power of two)
+        std::vector<float> w(c->fb_nnz);
+        for (int i = 0; i < c->fb_nnz; ++i) w[i] = c->fb_weights[i] * (1.0f / 2048.0f);
+        if ((rc = upload(h, h->fb_w, w.data(), w.size() * sizeof(float)))) return rc;
+    }
+    h->dct_stride = 0;
+    if (c->feat_type == FE_FEAT_MFCC) {
+        const int nf4 = (c->num_filters + 3) & ~3;
+        h->dct_stride = nf4 + 4;                         // 16-byte rows, staggered banks
+        std::vector<float> d((size_t)c->feat_dim * h->dct_stride, 0.f);
+        for (int k = 0; k < c->feat_dim; ++k)
+            for (int m = 0; m < c->num_filters; ++m) d[(size_t)k * h->dct_stride + m] = c->dct[k * c->num_filters + m];
+        if ((rc = upload(h, h->dct, d.data(), d.size() * sizeof(float)))) return rc;
+    }
+    if (c->window) {
+        const int rows = (c->frame_len + 31) / 32;
+        std::vector<float> w((size_t)rows * 32, 0.f);
+        for (int n = 0; n < c->frame_len; ++n) w[(n / 32) * 32 + pcm_pos(n % 32)] = c->window[n];
+        if ((rc = upload(h, h->window, w.data(), w.size() * sizeof(float)))) return rc;
+    }
+    h->sp_up.clear(); h->sp_down.clear(); h->sp_tap_off.clear();
+    if (c->n_speeds > 0) {
+        if (!c->speed_up || !c->speed_down || !c->speed_taps) return fail(h, FE_ERR_INVALID, "missing resampler tables");
+        int off = 0;
+        for (int i = 0; i < c->n_speeds; ++i) {
+            if (c->speed_up[i] < 1 || c->speed_down[i] < 1 || c->speed_up[i] > 4096)
+                return fail(h, FE_ERR_INVALID, "bad speed ratio");
+            h->sp_up.push_back(c->speed_up[i]); h->sp_down.push_back(c->speed_down[i]); h->sp_tap_off.push_back(off);
+            off += c->speed_up[i] * 32;
+        }
+        if ((rc = upload(h, h->d_sp_up, h->sp_up.data(), h->sp_up.size() * sizeof(int)))) return rc;
+        if ((rc = upload(h, h->d_sp_down, h->sp_down.data(), h->sp_down.size() * sizeof(int)))) return rc;
+        if ((rc = upload(h, h->d_sp_tap_off, h->sp_tap_off.data(), h->sp_tap_off.size() * sizeof(int)))) return rc;
+        if ((rc = upload(h, h->d_taps, c->speed_taps, (size_t)off * sizeof(float)))) return rc;
+    }
+
+    h->cfg = *c;       // pointer members are only used as "present" flags from here on
+    K1Smem L = k1_smem_layout(c->num_filters, c->fb_nnz, c->feat_dim, h->dct_stride, c->window != nullptr,
+                              c->frame_len, c->hop, c->feat_type == FE_FEAT_MFCC);
+    h->k1_smem = L.total;
+    if (L.total > 227 * 1024) return fail(h, FE_ERR_INVALID, "configuration needs too much shared memory");
+    if ((rc = set_smem(h, k_frames_to_statics<400, 160, 0>, h->k1_smem))) return rc;
+    if ((rc = set_smem(h, k_frames_to_statics<400, 160, 1>, h->k1_smem))) return rc;
+    if ((rc = set_smem(h, k_cmvn_delta_pack, k2_smem_floats(c->feat_dim) * sizeof(float)))) return rc;
+    h->configured = true;
+    return FE_OK;
+}
+
+int fe_plan(fe_handle* h, const int64_t* pcm_lengths, int32_t n_utts, const int32_t* speed_idx,
+            int64_t* out_offsets, int32_t* n_frames) {
+    if (!h) return FE_ERR_INVALID;
+    if (!h->configured) return fail(h, FE_ERR_STATE, "fe_configure first");
+    if (n_utts < 0 || (n_utts > 0 && !pcm_lengths)) return fail(h, FE_ERR_INVALID, "bad arguments");
+    Plan pl;
+    return make_plan(h, nullptr, pcm_lengths, n_utts, speed_idx, nullptr, out_offsets, n_frames, pl, false);
+}
+
+int fe_run(fe_handle* h, const void* pcm, const int64_t* pcm_offsets, const int64_t* pcm_lengths,
+           int32_t n_utts, const int32_t* speed_idx, const float* gain,
+           float* out, int64_t out_capacity, int64_t* out_offsets, int32_t* n_frames, void* stream) {
+    if (!h) return FE_ERR_INVALID;
+    if (!h->configured) return fail(h, FE_ERR_STATE, "fe_configure first");
+    if (n_utts < 0) return fail(h, FE_ERR_INVALID, "n_utts < 0");
+    if (n_utts == 0) { if (out_offsets) out_offsets[0] = 0; return FE_OK; }
+    if (!pcm || !pcm_offsets || !pcm_lengths || !out) return fail(h, FE_ERR_INVALID, "NULL buffer");
+    const fe_config& c = h->cfg;
+    FE_CUDA(h, cudaSetDevice(h->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+
+    Plan pl;
+    int rc = make_plan(h, pcm_offsets, pcm_lengths, n_utts, speed_idx, gain, out_offsets, n_frames, pl, true);
+    if (rc) return rc;
+    if (pl.total_out > out_capacity) return fail(h, FE_ERR_CAPACITY, "out buffer too small for this batch");
+    if (pl.total_tiles > 0x7fffffffLL || pl.total_atiles > 0x7fffffffLL) return fail(h, FE_ERR_INVALID, "batch too large");
+
+    const size_t esz = c.pcm_dtype == FE_PCM_INT16 ? 2 : 4;
+    const bool pcm_on_dev = is_device_ptr(pcm), out_on_dev = is_device_ptr(out);
+
+    // descriptors -> pinned staging -> device (async on st)
+    const size_t b_utts = sizeof(UttDesc) * (size_t)n_utts, b_pref = sizeof(long long) * (size_t)(n_utts + 1);
+    if ((rc = ensure_pinned(h, h->h_stage, b_utts + 2 * b_pref))) return rc;
+    if ((rc = ensure(h, h->d_utts, b_utts))) return rc;
+    if ((rc = ensure(h, h->d_tile_prefix, b_pref))) return rc;
+    if ((rc = ensure(h, h->d_atile_prefix, b_pref))) return rc;
+    if ((rc = ensure(h, h->d_tiles, sizeof(int2) * (size_t)std::max<long long>(pl.total_tiles, 1)))) return rc;
+    if (c.cmvn && (rc = ensure(h, h->d_statics, sizeof(float) * (size_t)std::max<long long>(pl.total_frames * c.feat_dim, 1)))) return rc;
+    if (pl.any_speed) {
+        if ((rc = ensure(h, h->d_scratch, 2 * (size_t)pl.total_scratch))) return rc;
+        if ((rc = ensure(h, h->d_atiles, sizeof(int2) * (size_t)pl.total_atiles))) return rc;
+    }
+    const void* d_pcm = pcm;
+    float* d_out = out;
+    if (!pcm_on_dev) { if ((rc = ensure(h, h->d_pcm, esz * (size_t)pl.pcm_span))) return rc; d_pcm = h->d_pcm.p; }
+    if (!out_on_dev) { if ((rc = ensure(h, h->d_out, sizeof(float) * (size_t)std::max<long long>(pl.total_out, 1)))) return rc; d_out = (float*)h->d_out.p; }
+
+    // the previous run on this handle may still be reading the staging area
+    if (h->ev_valid) FE_CUDA(h, cudaEventSynchronize(h->ev[5]));
+    unsigned char* hs = (unsigned char*)h->h_stage.p;
+    memcpy(hs, h->utts.data(), b_utts);
+    memcpy(hs + b_utts, h->tile_prefix.data(), b_pref);
+    memcpy(hs + b_utts + b_pref, h->atile_prefix.data(), b_pref);
+    FE_CUDA(h, cudaMemcpyAsync(h->d_utts.p, hs, b_utts, cudaMemcpyHostToDevice, st));
+    FE_CUDA(h, cudaMemcpyAsync(h->d_tile_prefix.p, hs + b_utts, b_pref, cudaMemcpyHostToDevice, st));
+    if (pl.any_speed)
+        FE_CUDA(h, cudaMemcpyAsync(h->d_atile_prefix.p, hs + b_utts + b_pref, b_pref, cudaMemcpyHostToDevice, st));
+    if (!pcm_on_dev) FE_CUDA(h, cudaMemcpyAsync(h->d_pcm.p, pcm, esz * (size_t)pl.pcm_span, cudaMemcpyHostToDevice, st));
+
+    const bool prof = h->profiling != 0;
+    if (prof) FE_CUDA(h, cudaEventRecord(h->ev[0], st));
+    const int tb = 256, gb = (n_utts + tb - 1) / tb;
+    if (pl.total_tiles > 0) {
+        k_build_tiles<<<gb, tb, 0, st>>>((const UttDesc*)h->d_utts.p, (const long long*)h->d_tile_prefix.p, n_utts,
+                                         kCtaFrames, (int2*)h->d_tiles.p);
+        h->launches++;
+    }
+    h->ev_k0 = false;
+    if (pl.any_speed) {
+        // atiles: one entry per 1024 resampled samples; only perturbed utterances have atiles
+        // (n_frames is not the right count there, so a dedicated tiny builder pass)
+        std::vector<int2> at((size_t)pl.total_atiles);
+        for (int i = 0; i < n_utts; ++i) {
+            long long b = h->atile_prefix[i], e = h->atile_prefix[i + 1];
+            for (long long k = b; k < e; ++k) at[(size_t)k] = make_int2(i, (int)((k - b) * kK0Outputs));
+        }
+        FE_CUDA(h, cudaMemcpyAsync(h->d_atiles.p, at.data(), sizeof(int2) * at.size(), cudaMemcpyHostToDevice, st));
+        FE_CUDA(h, cudaStreamSynchronize(st));     // `at` is pageable and dies at scope end
+        if (prof) FE_CUDA(h, cudaEventRecord(h->ev[1], st));
+        int grid = (int)std::min<long long>(pl.total_atiles, 16LL * h->num_sms);
+        k_resample<<<grid, 256, 0, st>>>((const short*)d_pcm, (const UttDesc*)h->d_utts.p, (const int2*)h->d_atiles.p,
+                                         (int)pl.total_atiles, (const int*)h->d_sp_up.p, (const int*)h->d_sp_down.p,
+                                         (const int*)h->d_sp_tap_off.p, (const float*)h->d_taps.p,
+                                         (short*)h->d_scratch.p, 0);
+        h->launches++;
+        h->ev_k0 = true;
+    }
+    if (prof) FE_CUDA(h, cudaEventRecord(h->ev[2], st));
+    DevTables dt = dev_tables(h);
+    float* stat_base = c.cmvn ? (float*)h->d_statics.p : d_out;
+    if ((rc = launch_k1(h, st, d_pcm, (const short*)h->d_scratch.p, (const UttDesc*)h->d_utts.p,
+                        (const int2*)h->d_tiles.p, (int)pl.total_tiles, dt, stat_base))) return rc;
+    if (prof) FE_CUDA(h, cudaEventRecord(h->ev[3], st));
+    h->ev_k2 = false;
+    if (c.cmvn && pl.total_frames > 0) {
+        int grid = (int)std::min<long long>(n_utts, 8LL * h->num_sms);
+        k_cmvn_delta_pack<<<grid, kK2Threads, k2_smem_floats(c.feat_dim) * sizeof(float), st>>>(
+            (const UttDesc*)h->d_utts.p, n_utts, (const float*)h->d_statics.p, d_out, c.feat_dim, c.delta_mode);
+        h->launches++;
+        h->ev_k2 = true;
+    }
+    FE_CUDA(h, cudaGetLastError());
+    if (prof) FE_CUDA(h, cudaEventRecord(h->ev[4], st));
+    FE_CUDA(h, cudaEventRecord(h->ev[5], st));
+    h->ev_valid = true;
+    if (!out_on_dev) {
+        FE_CUDA(h, cudaMemcpyAsync(out, d_out, sizeof(float) * (size_t)pl.total_out, cudaMemcpyDeviceToHost, st));
+        FE_CUDA(h, cudaStreamSynchronize(st));
+    }
+    return FE_OK;
+}
+
+int fe_perturb(fe_handle* h, const int16_t* pcm, const int64_t* pcm_offsets, const int64_t* pcm_lengths,
+               int32_t n_utts, const int32_t* speed_idx, const float* gain, int16_t* dst,
+               int64_t dst_capacity, int64_t* dst_offsets, int64_t* dst_lengths, void* stream) {
+    if (!h) return FE_ERR_INVALID;
+    if (!h->configured) return fail(h, FE_ERR_STATE, "fe_configure first");
+    if (n_utts <= 0) { if (dst_offsets) dst_offsets[0] = 0; return n_utts == 0 ? FE_OK : FE_ERR_INVALID; }
+    if (!pcm || !pcm_offsets || !pcm_lengths || !dst || !dst_offsets || !dst_lengths)
+        return fail(h, FE_ERR_INVALID, "NULL buffer");
+    FE_CUDA(h, cudaSetDevice(h->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    std::vector<UttDesc> ut((size_t)n_utts);
+    std::vector<int2> at;
+    long long off = 0, span = 0;
+    for (int i = 0; i < n_utts; ++i) {
+        int sidx = speed_idx ? speed_idx[i] : -1;
+        if (sidx >= (int)h->sp_up.size()) return fail(h, FE_ERR_INVALID, "speed_idx not configured");
+        if (sidx >= 0 && h->sp_up[sidx] == h->sp_down[sidx]) sidx = -1;
+        long long len = pcm_lengths[i];
+        long long n_eff = sidx >= 0 ? fe_resampled_length(len, h->sp_up[sidx], h->sp_down[sidx]) : len;
+        UttDesc& u = ut[(size_t)i];
+        memset(&u, 0, sizeof(u));
+        u.src_off = pcm_offsets[i]; u.n_src = (int)len; u.n_samples = (int)n_eff; u.speed_idx = sidx;
+        u.gain = gain ? gain[i] : 1.f; u.out_off = off;
+        dst_offsets[i] = off; dst_lengths[i] = n_eff;
+        for (long long j = 0; j < n_eff; j += kK0Outputs) at.push_back(make_int2(i, (int)j));
+        off += round_up(n_eff, 8);
+        span = std::max(span, pcm_offsets[i] + len);
+    }
+    dst_offsets[n_utts] = off;
+    if (off > dst_capacity) return fail(h, FE_ERR_CAPACITY, "dst buffer too small");
+    if (at.empty()) return FE_OK;
+    const bool src_dev = is_device_ptr(pcm), dst_dev = is_device_ptr(dst);
+    int rc;
+    if ((rc = ensure(h, h->d_utts, sizeof(UttDesc) * ut.size()))) return rc;
+    if ((rc = ensure(h, h->d_atiles, sizeof(int2) * at.size()))) return rc;
+    const short* d_src = pcm; short* d_dst = dst;
+    if (!src_dev) { if ((rc = ensure(h, h->d_pcm, 2 * (size_t)span))) return rc; d_src = (const short*)h->d_pcm.p; }
+    if (!dst_dev) { if ((rc = ensure(h, h->d_scratch, 2 * (size_t)off))) return rc; d_dst = (short*)h->d_scratch.p; }
+    FE_CUDA(h, cudaMemcpyAsync(h->d_utts.p, ut.data(), sizeof(UttDesc) * ut.size(), cudaMemcpyHostToDevice, st));
+    FE_CUDA(h, cudaMemcpyAsync(h->d_atiles.p, at.data(), sizeof(int2) * at.size(), cudaMemcpyHostToDevice, st));
+    if (!src_dev) FE_CUDA(h, cudaMemcpyAsync(h->d_pcm.p, pcm, 2 * (size_t)span, cudaMemcpyHostToDevice, st));
+    FE_CUDA(h, cudaStreamSynchronize(st));
+    int grid = (int)std::min<long long>((long long)at.size(), 16LL * h->num_sms);
+    k_resample<<<grid, 256, 0, st>>>(d_src, (const UttDesc*)h->d_utts.p, (const int2*)h->d_atiles.p, (int)at.size(),
+                                     (const int*)h->d_sp_up.p, (const int*)h->d_sp_down.p,
+                                     (const int*)h->d_sp_tap_off.p, (const float*)h->d_taps.p, d_dst, 1);
+    h->launches++;
+    FE_CUDA(h, cudaGetLastError());
+    if (!dst_dev) {
+        FE_CUDA(h, cudaMemcpyAsync(dst, d_dst, 2 * (size_t)off, cudaMemcpyDeviceToHost, st));
+        FE_CUDA(h, cudaStreamSynchronize(st));
+    }
+    return FE_OK;
+}
+
+int fe_sync(fe_handle* h) {
+    if (!h) return FE_ERR_INVALID;
+    FE_CUDA(h, cudaSetDevice(h->device));
+    if (h->ev_valid) FE_CUDA(h, cudaEventSynchronize(h->ev[5]));
+    FE_CUDA(h, cudaStreamSynchronize(h->stream));
+    return FE_OK;
+}
+
+int fe_set_profiling(fe_handle* h, int on) { if (!h) return FE_ERR_INVALID; h->profiling = on; return FE_OK; }
+
+int fe_get_kernel_ms(fe_handle* h, float ms[4]) {
+    if (!h || !ms) return FE_ERR_INVALID;
+    ms[0] = ms[1] = ms[2] = ms[3] = 0.f;
+    if (!h->profiling || !h->ev_valid) return fail(h, FE_ERR_STATE, "no profiled run");
+    FE_CUDA(h, cudaEventSynchronize(h->ev[5]));
+    if (h->ev_k0) FE_CUDA(h, cudaEventElapsedTime(&ms[0], h->ev[1], h->ev[2]));
+    FE_CUDA(h, cudaEventElapsedTime(&ms[1], h->ev[2], h->ev[3]));
+    if (h->ev_k2) FE_CUDA(h, cudaEventElapsedTime(&ms[2], h->ev[3], h->ev[4]));
+    FE_CUDA(h, cudaEventElapsedTime(&ms[3], h->ev[0], h->ev[4]));
+    return FE_OK;
+}
+
+int64_t fe_launch_count(fe_handle* h) { return h ? h->launches : 0; }
+
+int64_t fe_device_bytes(fe_handle* h) {
+    if (!h) return 0;
+    size_t t = 0;
+    for (const DevBuf* b : {&h->d_utts, &h->d_tile_prefix, &h->d_tiles, &h->d_atile_prefix, &h->d_atiles,
+                            &h->d_statics, &h->d_pcm, &h->d_out, &h->d_scratch})
+        t += b->cap;
+    return (int64_t)t;
+}
+
+}  // extern "C"

@@ -1,0 +1,140 @@
+/* C-ABI of the B200 acoustic front-end (libasr_frontend.so).
+ *
+ * The reference has no FFI for this path; its de-facto boundary is one Python
+ * function plus the library calls it makes (all in /root/reference):
+ *
+ *   process_audios(audio_path, args)            preprocess.py:50-91
+ *     speechpy.feature.mfcc(...)                preprocess.py:72-76
+ *     speechpy.feature.mfe(...)                 preprocess.py:78-82
+ *     speechpy.processing.cmvn(feat, True)      preprocess.py:85
+ *     speechpy.feature.extract_derivative_feature(feat)   preprocess.py:86
+ *     feat.astype(np.float32)                   preprocess.py:88
+ *   SpeedAugmentation / VolumeAugmentation      utils/augmentation.py:6-31, 33-56
+ *
+ * These entry points are what a ctypes binding behind that function binds
+ * (INTEGRATION.md shows the stub).  Plain pointers and sizes only; every call
+ * returns 0 on success and a negative code on failure (never throws, never
+ * aborts); fe_last_error() gives the message.  A handle is NOT thread-safe: use
+ * one handle per (host thread, GPU).  There is no CPU fallback: without a CUDA
+ * device fe_create fails.
+ */
+#ifndef ASR_FRONTEND_H_
+#define ASR_FRONTEND_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FE_ABI_VERSION 1
+
+#define FE_OK 0
+#define FE_ERR_INVALID (-1)      /* bad argument / unsupported configuration */
+#define FE_ERR_CUDA (-2)         /* CUDA runtime error (message has the detail) */
+#define FE_ERR_CAPACITY (-3)     /* caller's output buffer is too small */
+#define FE_ERR_STATE (-4)        /* call order (e.g. run before configure) */
+
+#define FE_FEAT_MFCC 0           /* args.feat_type == 'mfcc'   preprocess.py:71 */
+#define FE_FEAT_FBANK 1          /* args.feat_type == 'fbank'  preprocess.py:77 */
+#define FE_DELTA_SPEECHPY 0      /* speechpy.processing.derivative_extraction as shipped */
+#define FE_DELTA_TIME_REGRESSION 1
+#define FE_PCM_INT16 0
+#define FE_PCM_FLOAT32 1
+
+typedef struct fe_handle fe_handle;
+
+/* Configuration + host-built constant tables (copied during fe_configure; the
+ * caller may free them afterwards).  Tables are computed in float64 on the host
+ * and rounded to float32 so host and device cannot disagree on a filter edge. */
+typedef struct fe_config {
+    int32_t abi_version;      /* FE_ABI_VERSION */
+    int32_t sample_rate;      /* informational (fs comes from the file, preprocess.py:69) */
+    int32_t frame_len;        /* samples; args.frame_length ms -> 400 at 16 kHz */
+    int32_t hop;              /* samples; args.frame_step ms   -> 160 at 16 kHz */
+    int32_t nfft;             /* 512 (speechpy default fft_length) */
+    int32_t num_filters;      /* 40 for mfcc; args.feat_dim for fbank */
+    int32_t feat_dim;         /* D: num_cepstral (mfcc) or num_filters (fbank) */
+    int32_t feat_type;        /* FE_FEAT_* */
+    int32_t cmvn;             /* args.cmvn: 1 -> CMVN + deltas, cube (L, D, 3); 0 -> (L, D) */
+    int32_t delta_mode;       /* FE_DELTA_* */
+    int32_t fbank_log;        /* 0 = linear mel energies (what mfe returns), 1 = log */
+    int32_t dc_elimination;   /* 1: c0 <- log(frame energy) (speechpy mfcc default) */
+    int32_t pcm_dtype;        /* FE_PCM_* */
+    float   preemph;          /* 0 = off (reference); else y[n] = x[n] - preemph * x[n-1], circular */
+    int32_t fb_nnz;
+    const int32_t* fb_row_start;   /* [num_filters + 1] CSR row starts */
+    const int32_t* fb_first_bin;   /* [num_filters] first FFT bin of each filter's run */
+    const float*   fb_weights;     /* [fb_nnz] triangle weights (unscaled) */
+    const float*   dct;            /* [feat_dim * num_filters] DCT-II ortho rows (mfcc only) */
+    const float*   window;         /* [frame_len] or NULL = rectangular (reference) */
+    const float*   tw256;          /* [16*16*2] W_256^(j k) as (cos, -sin) */
+    const float*   tw512;          /* [257*2]  (cos, sin)(2 pi k / 512) */
+    int32_t n_speeds;              /* resampler variants (speed perturbation), may be 0 */
+    const int32_t* speed_up;       /* [n_speeds] speed = down / up */
+    const int32_t* speed_down;     /* [n_speeds] */
+    const float*   speed_taps;     /* concatenated [up_i * 32] polyphase taps */
+} fe_config;
+
+/* Pure host helper: frame-count rule of speechpy.processing.stack_frames with
+ * zero_padding=False, floor((n - frame_len) / hop), clamped at 0.
+ * (tfrecord_data_loader.py:78-79 pins it: 522320 -> 3262, 559280 -> 3493.) */
+int64_t fe_num_frames(int64_t n_samples, int32_t frame_len, int32_t hop);
+
+/* ceil(n * up / down): utterance length after speed perturbation. */
+int64_t fe_resampled_length(int64_t n_samples, int32_t up, int32_t down);
+
+int fe_create(int device, fe_handle** out);
+int fe_destroy(fe_handle* h);
+int fe_configure(fe_handle* h, const fe_config* cfg);
+
+/* Host-only planning: per-utterance frame counts and output offsets (in floats,
+ * each utterance 16-byte aligned), so the caller can size `out`.
+ *   pcm_lengths[n]  samples per utterance
+ *   speed_idx[n]    index into the configured speeds, -1 = none; NULL = none
+ *   out_offsets[n+1], n_frames[n]  filled on return; out_offsets[n] = total floats */
+int fe_plan(fe_handle* h, const int64_t* pcm_lengths, int32_t n_utts, const int32_t* speed_idx,
+            int64_t* out_offsets, int32_t* n_frames);
+
+/* The hot path.  Replaces the loop body of process_audios (preprocess.py:67-89)
+ * for a whole batch of utterances.
+ *   pcm           packed PCM, host OR device pointer (detected); int16 or float32 per config
+ *   pcm_offsets[n] element offset of each utterance (multiple of 8 for int16, 4 for float32)
+ *   pcm_lengths[n] samples per utterance
+ *   speed_idx/gain per-utterance perturbation (NULL = none); gain g: clip(round(g * x))
+ *   out           host OR device pointer with room for out_capacity floats; utterance i
+ *                 is the C-contiguous (L_i, D, 3) float32 cube at out + out_offsets[i]
+ *                 ((L_i, D) when cmvn == 0)
+ *   out_offsets[n+1], n_frames[n]  filled on return (host arrays)
+ *   stream        cudaStream_t to run on, NULL = the handle's own stream
+ * Asynchronous for device `out` (fe_sync to wait); synchronous when `out` is host memory. */
+int fe_run(fe_handle* h, const void* pcm, const int64_t* pcm_offsets, const int64_t* pcm_lengths,
+           int32_t n_utts, const int32_t* speed_idx, const float* gain,
+           float* out, int64_t out_capacity, int64_t* out_offsets, int32_t* n_frames,
+           void* stream);
+
+/* Speed / volume perturbation only (utils/augmentation.py:6-56 without the
+ * file round-trip): int16 in -> int16 out, host or device pointers.
+ *   dst_offsets[n+1] filled on return (element offsets, multiples of 8). */
+int fe_perturb(fe_handle* h, const int16_t* pcm, const int64_t* pcm_offsets,
+               const int64_t* pcm_lengths, int32_t n_utts, const int32_t* speed_idx,
+               const float* gain, int16_t* dst, int64_t dst_capacity, int64_t* dst_offsets,
+               int64_t* dst_lengths, void* stream);
+
+int fe_sync(fe_handle* h);
+
+/* Measurement hooks.  With profiling on, each kernel of the last fe_run is
+ * bracketed by CUDA events on the launching stream.
+ *   ms[0] resample  ms[1] frames->statics  ms[2] cmvn+delta+pack  ms[3] whole device pass */
+int fe_set_profiling(fe_handle* h, int on);
+int fe_get_kernel_ms(fe_handle* h, float ms[4]);
+int64_t fe_launch_count(fe_handle* h);       /* kernels launched since fe_create */
+int64_t fe_device_bytes(fe_handle* h);       /* scratch currently held on the device */
+
+const char* fe_last_error(fe_handle* h);     /* h may be NULL: last fe_create error */
+int fe_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif  /* ASR_FRONTEND_H_ */
