@@ -1,0 +1,88 @@
+"""ctypes binding of libasr_frontend.so (declarations mirror include/asr_frontend.h).
+
+There is deliberately no fallback: if the shared library is missing or cannot be
+loaded the import of the product API fails with an explicit error."""
+import ctypes as C
+import os
+
+from . import build as _build
+
+FE_ABI_VERSION = 1
+FE_OK, FE_ERR_INVALID, FE_ERR_CUDA, FE_ERR_CAPACITY, FE_ERR_STATE = 0, -1, -2, -3, -4
+FE_FEAT_MFCC, FE_FEAT_FBANK = 0, 1
+FE_DELTA_SPEECHPY, FE_DELTA_TIME_REGRESSION = 0, 1
+FE_PCM_INT16, FE_PCM_FLOAT32 = 0, 1
+
+_i32p = C.POINTER(C.c_int32)
+_i64p = C.POINTER(C.c_int64)
+_f32p = C.POINTER(C.c_float)
+
+
+class FeConfig(C.Structure):
+    _fields_ = [
+        ("abi_version", C.c_int32), ("sample_rate", C.c_int32), ("frame_len", C.c_int32),
+        ("hop", C.c_int32), ("nfft", C.c_int32), ("num_filters", C.c_int32),
+        ("feat_dim", C.c_int32), ("feat_type", C.c_int32), ("cmvn", C.c_int32),
+        ("delta_mode", C.c_int32), ("fbank_log", C.c_int32), ("dc_elimination", C.c_int32),
+        ("pcm_dtype", C.c_int32), ("preemph", C.c_float), ("fb_nnz", C.c_int32),
+        ("fb_row_start", _i32p), ("fb_first_bin", _i32p), ("fb_weights", _f32p),
+        ("dct", _f32p), ("window", _f32p), ("tw256", _f32p), ("tw512", _f32p),
+        ("n_speeds", C.c_int32), ("speed_up", _i32p), ("speed_down", _i32p), ("speed_taps", _f32p),
+    ]
+
+
+# every symbol include/asr_frontend.h declares: name -> (restype, argtypes)
+SYMBOLS = {
+    "fe_abi_version": (C.c_int, []),
+    "fe_num_frames": (C.c_int64, [C.c_int64, C.c_int32, C.c_int32]),
+    "fe_resampled_length": (C.c_int64, [C.c_int64, C.c_int32, C.c_int32]),
+    "fe_create": (C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
+    "fe_destroy": (C.c_int, [C.c_void_p]),
+    "fe_configure": (C.c_int, [C.c_void_p, C.POINTER(FeConfig)]),
+    "fe_plan": (C.c_int, [C.c_void_p, _i64p, C.c_int32, _i32p, _i64p, _i32p]),
+    "fe_run": (C.c_int, [C.c_void_p, C.c_void_p, _i64p, _i64p, C.c_int32, _i32p, _f32p,
+                         C.c_void_p, C.c_int64, _i64p, _i32p, C.c_void_p]),
+    "fe_perturb": (C.c_int, [C.c_void_p, C.c_void_p, _i64p, _i64p, C.c_int32, _i32p, _f32p,
+                             C.c_void_p, C.c_int64, _i64p, _i64p, C.c_void_p]),
+    "fe_sync": (C.c_int, [C.c_void_p]),
+    "fe_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
+    "fe_get_kernel_ms": (C.c_int, [C.c_void_p, _f32p]),
+    "fe_launch_count": (C.c_int64, [C.c_void_p]),
+    "fe_device_bytes": (C.c_int64, [C.c_void_p]),
+    "fe_last_error": (C.c_char_p, [C.c_void_p]),
+}
+
+_lib = None
+
+
+class FrontendLibraryError(RuntimeError):
+    pass
+
+
+def library_path():
+    return _build.LIB_PATH
+
+
+def load():
+    """dlopen the in-tree CUDA library (build it with ``python -m <pkg>.build`` or
+    ``__graft_entry__.build()``).  No CPU path exists behind this call."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = library_path()
+    if not os.path.exists(path):
+        raise FrontendLibraryError(
+            "%s is missing: build the CUDA extension first (__graft_entry__.build()); "
+            "this package has no CPU fallback" % path)
+    try:
+        lib = C.CDLL(path)
+    except OSError as e:
+        raise FrontendLibraryError("cannot load %s: %s (no CPU fallback)" % (path, e))
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    if lib.fe_abi_version() != FE_ABI_VERSION:
+        raise FrontendLibraryError("ABI version mismatch: rebuild %s" % path)
+    _lib = lib
+    return lib

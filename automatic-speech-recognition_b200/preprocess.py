@@ -1,0 +1,107 @@
+"""Drop-in for the feature loop of the reference's preprocess.py.
+
+``process_audios(audio_path, args)`` keeps the reference signature and return value
+(/root/reference/preprocess.py:50-91): ``feats`` is a 1-D object ndarray whose element
+i is a C-contiguous float32 ``(L_i, feat_dim, 3)`` cube (``(L_i, feat_dim)`` when
+``args.cmvn`` is false) and ``featlen`` is a Python list of ints, in input order.
+``process_libri_feats`` reproduces the chunked on-disk format of
+preprocess.py:112-130 that create_tfrecord.py:32-40 and decode.py:82-83 read back."""
+import logging
+import os
+
+import joblib
+import numpy as np
+
+from . import audio_io
+from .frontend import Frontend, FrontendConfig
+
+# When a set holds more utterances than this the reference writes several pickles
+# (preprocess.py:17).
+_SAMPLE_THRESHOLD = 30000
+# host-side batching: PCM samples handed to the GPU per call (~1 audio-hour at 16 kHz)
+_BATCH_SAMPLES = 57_600_000
+
+_frontends = {}
+
+
+def _config_key(cfg: FrontendConfig, device):
+    return (device, cfg.sample_rate, cfg.frame_length, cfg.frame_step, cfg.feat_dim, cfg.feat_type,
+            cfg.cmvn, cfg.num_filters, cfg.delta_mode, cfg.bin_map, cfg.fbank_log, cfg.pcm_dtype,
+            cfg.preemph, cfg.dc_elimination, cfg.low_frequency, cfg.high_frequency, tuple(cfg.speeds),
+            None if cfg.window is None else cfg.window.tobytes())
+
+
+def get_frontend(cfg: FrontendConfig, device=0) -> Frontend:
+    """One cached handle per (configuration, device) for the calling process."""
+    key = _config_key(cfg, device)
+    fe = _frontends.get(key)
+    if fe is None:
+        fe = _frontends[key] = Frontend(cfg, device)
+    return fe
+
+
+def to_object_array(cubes):
+    """The reference's ``np.array(feats)`` (preprocess.py:91) relied on numpy < 1.24
+    making an object array out of ragged cubes; build it explicitly so equal-length
+    batches do not collapse into one dense 4-D array either."""
+    out = np.empty(len(cubes), dtype=object)
+    for i, c in enumerate(cubes):
+        out[i] = c
+    return out
+
+
+def process_pcm(pcm_list, args, fs=16000, device=0, speeds=None, gains=None, **switches):
+    """In-memory variant of process_audios: list of int16 (or float) arrays in."""
+    pcm_dtype = "int16" if all(np.asarray(p).dtype == np.int16 for p in pcm_list) else "float32"
+    cfg = FrontendConfig.from_args(args, sample_rate=fs, pcm_dtype=pcm_dtype, **switches)
+    fe = get_frontend(cfg, device)
+    for p in pcm_list:
+        if len(p) < cfg.frame_len:
+            # speechpy's stack_frames hits np.tile with a negative count here
+            raise ValueError("negative dimensions are not allowed")
+    cubes, featlen = [], []
+    start, acc = 0, 0
+    for i, p in enumerate(pcm_list):
+        acc += len(p)
+        if acc >= _BATCH_SAMPLES or i == len(pcm_list) - 1:
+            sl = slice(start, i + 1)
+            got = fe.extract(pcm_list[sl], None if speeds is None else speeds[sl],
+                             None if gains is None else gains[sl])
+            cubes.extend(got)
+            featlen.extend(len(g) for g in got)
+            start, acc = i + 1, 0
+    return to_object_array(cubes), featlen
+
+
+def process_audios(audio_path, args, device=0, **switches):
+    """Same signature and return value as the reference (preprocess.py:50-91)."""
+    pcm_list, fs_seen = [], None
+    for p in audio_path:
+        audio, fs = audio_io.read_audio(p)
+        if fs_seen is None:
+            fs_seen = fs
+        elif fs != fs_seen:
+            raise ValueError("mixed sample rates in one call: %d vs %d (%s)" % (fs_seen, fs, p))
+        pcm_list.append(audio)
+    if not pcm_list:
+        return to_object_array([]), []
+    return process_pcm(pcm_list, args, fs=fs_seen, device=device, **switches)
+
+
+def process_libri_feats(audio_path, cat, k, args, device=0, **switches):
+    """preprocess.py:112-130: chunk sets larger than 30 000 files into k pickles
+    ``{cat}-feats-{i}.pkl`` (else one ``{cat}-feats.pkl``) plus ``{cat}-featlen.npy``."""
+    os.makedirs(args.feat_dir, exist_ok=True)
+    if len(audio_path) > _SAMPLE_THRESHOLD:
+        featlen = []
+        n = len(audio_path) // k + 1
+        logging.info("Process %s audios...", cat)
+        for i in range(k):
+            feats, featlen_ = process_audios(audio_path[i * n:(i + 1) * n], args, device, **switches)
+            featlen += featlen_
+            joblib.dump(feats, args.feat_dir + "/{}-feats-{}.pkl".format(cat, i))
+    else:
+        feats, featlen = process_audios(audio_path, args, device, **switches)
+        joblib.dump(feats, args.feat_dir + "/{}-feats.pkl".format(cat))
+    np.save(args.feat_dir + "/{}-featlen.npy".format(cat), featlen)
+    return featlen
