@@ -9,6 +9,7 @@
 
 #include "../../include/asr_frontend.h"
 #include "fe_kernels.cuh"
+#include "fe_tables.h"
 
 using namespace fe;
 
@@ -37,8 +38,9 @@ struct fe_handle {
     std::string err;
 
     // device tables
-    DevBuf tw256, tw512, window, fb_start, fb_bin0, fb_w, dct;
-    int dct_stride = 0, full_spectrum = 0;
+    DevBuf tw256, tw512, window, mel_slot_off, mel_b0, mel_id, mel_w, dct;
+    int dct_stride = 0, full_spectrum = 0, mel_slots = 0, mel_entries = 0, nh = 0;
+    bool scratch_f32 = false;     // pre-emphasis materialises float PCM in the scratch buffer
     // resampler
     std::vector<int> sp_up, sp_down, sp_tap_off;
     DevBuf d_sp_up, d_sp_down, d_sp_tap_off, d_taps;
@@ -53,7 +55,7 @@ struct fe_handle {
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     bool ev_valid = false, ev_k0 = false, ev_k2 = false;
     int64_t launches = 0;
-    size_t k1_smem = 0;
+    size_t k1_smem[2] = {0, 0};      // [raw int16 input, float input]
 };
 
 namespace {
@@ -109,7 +111,7 @@ inline long long round_up(long long x, long long m) { return (x + m - 1) / m * m
 struct Plan {
     long long total_frames = 0, total_out = 0, total_tiles = 0, total_scratch = 0, total_atiles = 0;
     long long pcm_span = 0;
-    bool any_speed = false;
+    bool any_scratch = false;
 };
 
 int make_plan(fe_handle* h, const int64_t* pcm_offsets, const int64_t* pcm_lengths, int32_t n,
@@ -133,6 +135,13 @@ int make_plan(fe_handle* h, const int64_t* pcm_offsets, const int64_t* pcm_lengt
         if (L > 0x7fffffffLL / (width > 0 ? width : 1)) return fail(h, FE_ERR_INVALID, "utterance too long");
         if (out_offsets) out_offsets[i] = out_off;
         if (n_frames) n_frames[i] = (int32_t)L;
+        const float g = gain ? gain[i] : 1.f;
+        const bool preemph = c.preemph != 0.f;
+        if (preemph && (sidx >= 0 || g != 1.f))
+            return fail(h, FE_ERR_INVALID, "pre-emphasis cannot be combined with speed / gain perturbation");
+        if (g != 1.f && c.pcm_dtype != FE_PCM_INT16)
+            return fail(h, FE_ERR_INVALID, "gain perturbation needs int16 PCM");
+        const bool via_scratch = sidx >= 0 || g != 1.f || preemph;
         if (fill_desc) {
             UttDesc& u = h->utts[i];
             const long long off = pcm_offsets[i];
@@ -142,17 +151,17 @@ int make_plan(fe_handle* h, const int64_t* pcm_offsets, const int64_t* pcm_lengt
             u.n_samples = (int)n_eff;
             u.n_frames = (int)L;
             u.speed_idx = sidx;
-            u.gain = gain ? gain[i] : 1.f;
-            u.src_sel = sidx >= 0 ? 1 : 0;
-            u.pcm_off = sidx >= 0 ? pl.total_scratch : off;
+            u.gain = g;
+            u.src_sel = via_scratch ? 1 : 0;
+            u.pcm_off = via_scratch ? pl.total_scratch : off;
             u.out_off = out_off;
             u.stat_off = c.cmvn ? pl.total_frames * c.feat_dim : out_off;
             h->tile_prefix[i] = pl.total_tiles;
             h->atile_prefix[i] = pl.total_atiles;
             pl.pcm_span = std::max(pl.pcm_span, off + len);
         }
-        if (sidx >= 0) {
-            pl.any_speed = true;
+        if (via_scratch) {
+            pl.any_scratch = true;
             pl.total_scratch += round_up(n_eff, 8);
             pl.total_atiles += (n_eff + kK0Outputs - 1) / kK0Outputs;
         }
@@ -172,18 +181,18 @@ int set_smem(fe_handle* h, K kernel, size_t bytes) {
     return FE_OK;
 }
 
-int launch_k1(fe_handle* h, cudaStream_t st, const void* pcm, const short* scratch, const UttDesc* utts,
-              const int2* tiles, int n_tiles, const DevTables& dt, float* statics) {
+int launch_k1(fe_handle* h, cudaStream_t st, const void* pcm, const void* scratch, bool in_f32,
+              const TileDesc* tiles, int n_tiles, const DevTables& dt, float* statics) {
     const fe_config& c = h->cfg;
     int grid = std::min<long long>(n_tiles, 2LL * h->num_sms);
     if (grid <= 0) return FE_OK;
     if (c.frame_len == 400 && c.hop == 160) {
-        if (c.pcm_dtype == FE_PCM_INT16)
-            k_frames_to_statics<400, 160, 0><<<grid, kCtaWarps * 32, h->k1_smem, st>>>(
-                pcm, scratch, utts, tiles, n_tiles, dt, statics, c.preemph);
+        if (!in_f32)
+            k_frames_to_statics<400, 160, 0><<<grid, kCtaWarps * 32, h->k1_smem[0], st>>>(
+                pcm, scratch, tiles, n_tiles, dt, statics);
         else
-            k_frames_to_statics<400, 160, 1><<<grid, kCtaWarps * 32, h->k1_smem, st>>>(
-                pcm, scratch, utts, tiles, n_tiles, dt, statics, c.preemph);
+            k_frames_to_statics<400, 160, 1><<<grid, kCtaWarps * 32, h->k1_smem[1], st>>>(
+                pcm, scratch, tiles, n_tiles, dt, statics);
     } else {
         return fail(h, FE_ERR_INVALID, "unsupported frame geometry");
     }
@@ -192,20 +201,23 @@ int launch_k1(fe_handle* h, cudaStream_t st, const void* pcm, const short* scrat
     return FE_OK;
 }
 
-DevTables dev_tables(const fe_handle* h) {
+DevTables dev_tables(const fe_handle* h, bool in_f32) {
     const fe_config& c = h->cfg;
     DevTables dt;
-    dt.tw256 = (const float2*)h->tw256.p;
-    dt.tw512 = (const float2*)h->tw512.p;
-    dt.window = c.window ? (const float*)h->window.p : nullptr;
-    dt.fb_start = (const int*)h->fb_start.p;
-    dt.fb_bin0 = (const int*)h->fb_bin0.p;
-    dt.fb_w = (const float*)h->fb_w.p;
-    dt.dct = (const float*)h->dct.p;
-    dt.nf = c.num_filters; dt.nnz = c.fb_nnz; dt.D = c.feat_dim; dt.dct_stride = h->dct_stride;
+    dt.tw256 = (const float4*)h->tw256.p;
+    dt.tw512 = (const float4*)h->tw512.p;
+    dt.window = c.window ? (const float2*)h->window.p : nullptr;
+    dt.mel_slot_off = (const int*)h->mel_slot_off.p;
+    dt.mel_b0 = (const int*)h->mel_b0.p;
+    dt.mel_id = (const int*)h->mel_id.p;
+    dt.mel_w = (const float*)(in_f32 ? (const char*)h->mel_w.p + sizeof(float) * 8 * (size_t)h->mel_entries : (const char*)h->mel_w.p);
+    dt.dctf = (const float*)h->dct.p;
+    dt.mel_slots = h->mel_slots; dt.mel_entries = h->mel_entries;
+    dt.nf = c.num_filters; dt.D = c.feat_dim; dt.dct_stride = h->dct_stride; dt.nh = h->nh;
     dt.full_spectrum = h->full_spectrum;
     dt.is_mfcc = c.feat_type == FE_FEAT_MFCC;
     dt.fbank_log = c.fbank_log; dt.dc_elim = c.dc_elimination;
+    dt.pscale = in_f32 ? 1.0f : (1.0f / 1073741824.0f);      // raw int16 counts: (1/32768)^2
     return dt;
 }
 
@@ -255,7 +267,7 @@ int fe_destroy(fe_handle* h) {
     if (!h) return FE_OK;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
-    for (DevBuf* b : {&h->tw256, &h->tw512, &h->window, &h->fb_start, &h->fb_bin0, &h->fb_w, &h->dct,
+    for (DevBuf* b : {&h->tw256, &h->tw512, &h->window, &h->mel_slot_off, &h->mel_b0, &h->mel_id, &h->mel_w, &h->dct,
                       &h->d_sp_up, &h->d_sp_down, &h->d_sp_tap_off, &h->d_taps, &h->d_utts,
                       &h->d_tile_prefix, &h->d_tiles, &h->d_atile_prefix, &h->d_atiles, &h->d_statics,
                       &h->d_pcm, &h->d_out, &h->d_scratch})
@@ -297,30 +309,17 @@ int fe_configure(fe_handle* h, const fe_config* c) {
     h->full_spectrum = max_bin > 128;
 
     int rc;
-    if ((rc = upload(h, h->tw256, c->tw256, 256 * 2 * sizeof(float)))) return rc;
-    if ((rc = upload(h, h->tw512, c->tw512, kBins * 2 * sizeof(float)))) return rc;
-    if ((rc = upload(h, h->fb_start, c->fb_row_start, (c->num_filters + 1) * sizeof(int)))) return rc;
-    if ((rc = upload(h, h->fb_bin0, c->fb_first_bin, c->num_filters * sizeof(int)))) return rc;
-    {   // power rows hold |2X|^2: fold 1/(4*512) into the weights (exact, power of two)
-        std::vector<float> w(c->fb_nnz);
-        for (int i = 0; i < c->fb_nnz; ++i) w[i] = c->fb_weights[i] * (1.0f / 2048.0f);
-        if ((rc = upload(h, h->fb_w, w.data(), w.size() * sizeof(float)))) return rc;
-    }
-    h->dct_stride = 0;
-    if (c->feat_type == FE_FEAT_MFCC) {
-        const int nf4 = (c->num_filters + 3) & ~3;
-        h->dct_stride = nf4 + 4;                         // 16-byte rows, staggered banks
-        std::vector<float> d((size_t)c->feat_dim * h->dct_stride, 0.f);
-        for (int k = 0; k < c->feat_dim; ++k)
-            for (int m = 0; m < c->num_filters; ++m) d[(size_t)k * h->dct_stride + m] = c->dct[k * c->num_filters + m];
-        if ((rc = upload(h, h->dct, d.data(), d.size() * sizeof(float)))) return rc;
-    }
-    if (c->window) {
-        const int rows = (c->frame_len + 31) / 32;
-        std::vector<float> w((size_t)rows * 32, 0.f);
-        for (int n = 0; n < c->frame_len; ++n) w[(n / 32) * 32 + pcm_pos(n % 32)] = c->window[n];
-        if ((rc = upload(h, h->window, w.data(), w.size() * sizeof(float)))) return rc;
-    }
+    HostTables ht;
+    build_host_tables(*c, ht);
+    h->mel_slots = ht.mel_slots; h->mel_entries = ht.mel_entries; h->nh = ht.nh; h->dct_stride = ht.dct_stride;
+    if ((rc = upload(h, h->tw256, ht.tw256.data(), ht.tw256.size() * sizeof(float)))) return rc;
+    if ((rc = upload(h, h->tw512, ht.tw512.data(), ht.tw512.size() * sizeof(float)))) return rc;
+    if ((rc = upload(h, h->mel_slot_off, ht.mel_slot_off.data(), ht.mel_slot_off.size() * sizeof(int)))) return rc;
+    if ((rc = upload(h, h->mel_b0, ht.mel_b0.data(), ht.mel_b0.size() * sizeof(int)))) return rc;
+    if ((rc = upload(h, h->mel_id, ht.mel_id.data(), ht.mel_id.size() * sizeof(int)))) return rc;
+    if ((rc = upload(h, h->mel_w, ht.mel_w.data(), ht.mel_w.size() * sizeof(float)))) return rc;
+    if (c->feat_type == FE_FEAT_MFCC && (rc = upload(h, h->dct, ht.dctf.data(), ht.dctf.size() * sizeof(float)))) return rc;
+    if (c->window && (rc = upload(h, h->window, ht.window.data(), ht.window.size() * sizeof(float)))) return rc;
     h->sp_up.clear(); h->sp_down.clear(); h->sp_tap_off.clear();
     if (c->n_speeds > 0) {
         if (!c->speed_up || !c->speed_down || !c->speed_taps) return fail(h, FE_ERR_INVALID, "missing resampler tables");
@@ -338,12 +337,14 @@ int fe_configure(fe_handle* h, const fe_config* c) {
     }
 
     h->cfg = *c;       // pointer members are only used as "present" flags from here on
-    K1Smem L = k1_smem_layout(c->num_filters, c->fb_nnz, c->feat_dim, h->dct_stride, c->window != nullptr,
-                              c->frame_len, c->hop, c->feat_type == FE_FEAT_MFCC);
-    h->k1_smem = L.total;
-    if (L.total > 227 * 1024) return fail(h, FE_ERR_INVALID, "configuration needs too much shared memory");
-    if ((rc = set_smem(h, k_frames_to_statics<400, 160, 0>, h->k1_smem))) return rc;
-    if ((rc = set_smem(h, k_frames_to_statics<400, 160, 1>, h->k1_smem))) return rc;
+    for (int f32 = 0; f32 < 2; ++f32) {
+        K1Smem L = k1_smem_layout(h->mel_slots, h->mel_entries, c->feat_dim, h->dct_stride, c->window != nullptr,
+                                  c->frame_len, c->hop, c->feat_type == FE_FEAT_MFCC, f32);
+        h->k1_smem[f32] = L.total;
+        if (L.total > 227 * 1024) return fail(h, FE_ERR_INVALID, "configuration needs too much shared memory");
+    }
+    if ((rc = set_smem(h, k_frames_to_statics<400, 160, 0>, h->k1_smem[0]))) return rc;
+    if ((rc = set_smem(h, k_frames_to_statics<400, 160, 1>, h->k1_smem[1]))) return rc;
     if ((rc = set_smem(h, k_cmvn_delta_pack, k2_smem_floats(c->feat_dim) * sizeof(float)))) return rc;
     h->configured = true;
     return FE_OK;
@@ -385,10 +386,12 @@ int fe_run(fe_handle* h, const void* pcm, const int64_t* pcm_offsets, const int6
     if ((rc = ensure(h, h->d_utts, b_utts))) return rc;
     if ((rc = ensure(h, h->d_tile_prefix, b_pref))) return rc;
     if ((rc = ensure(h, h->d_atile_prefix, b_pref))) return rc;
-    if ((rc = ensure(h, h->d_tiles, sizeof(int2) * (size_t)std::max<long long>(pl.total_tiles, 1)))) return rc;
+    if ((rc = ensure(h, h->d_tiles, sizeof(TileDesc) * (size_t)std::max<long long>(pl.total_tiles, 1)))) return rc;
     if (c.cmvn && (rc = ensure(h, h->d_statics, sizeof(float) * (size_t)std::max<long long>(pl.total_frames * c.feat_dim, 1)))) return rc;
-    if (pl.any_speed) {
-        if ((rc = ensure(h, h->d_scratch, 2 * (size_t)pl.total_scratch))) return rc;
+    const bool preemph = c.preemph != 0.f;
+    const bool k1_f32 = preemph || c.pcm_dtype == FE_PCM_FLOAT32;      // what K1's stage A reads
+    if (pl.any_scratch) {
+        if ((rc = ensure(h, h->d_scratch, (preemph ? 4 : 2) * (size_t)pl.total_scratch + 64))) return rc;
         if ((rc = ensure(h, h->d_atiles, sizeof(int2) * (size_t)pl.total_atiles))) return rc;
     }
     const void* d_pcm = pcm;
@@ -404,8 +407,9 @@ int fe_run(fe_handle* h, const void* pcm, const int64_t* pcm_offsets, const int6
     memcpy(hs + b_utts + b_pref, h->atile_prefix.data(), b_pref);
     FE_CUDA(h, cudaMemcpyAsync(h->d_utts.p, hs, b_utts, cudaMemcpyHostToDevice, st));
     FE_CUDA(h, cudaMemcpyAsync(h->d_tile_prefix.p, hs + b_utts, b_pref, cudaMemcpyHostToDevice, st));
-    if (pl.any_speed)
+    if (pl.any_scratch)
         FE_CUDA(h, cudaMemcpyAsync(h->d_atile_prefix.p, hs + b_utts + b_pref, b_pref, cudaMemcpyHostToDevice, st));
+    if (((uintptr_t)d_pcm & 15) != 0) return fail(h, FE_ERR_INVALID, "pcm buffer must be 16-byte aligned");
     if (!pcm_on_dev) FE_CUDA(h, cudaMemcpyAsync(h->d_pcm.p, pcm, esz * (size_t)pl.pcm_span, cudaMemcpyHostToDevice, st));
 
     const bool prof = h->profiling != 0;
@@ -413,12 +417,12 @@ int fe_run(fe_handle* h, const void* pcm, const int64_t* pcm_offsets, const int6
     const int tb = 256, gb = (n_utts + tb - 1) / tb;
     if (pl.total_tiles > 0) {
         k_build_tiles<<<gb, tb, 0, st>>>((const UttDesc*)h->d_utts.p, (const long long*)h->d_tile_prefix.p, n_utts,
-                                         kCtaFrames, (int2*)h->d_tiles.p);
+                                         c.hop, c.feat_dim, (TileDesc*)h->d_tiles.p);
         h->launches++;
     }
     h->ev_k0 = false;
-    if (pl.any_speed) {
-        // atiles: one entry per 1024 resampled samples; only perturbed utterances have atiles
+    if (pl.any_scratch) {
+        // atiles: one entry per 1024 output samples; only utterances routed through scratch have atiles
         // (n_frames is not the right count there, so a dedicated tiny builder pass)
         std::vector<int2> at((size_t)pl.total_atiles);
         for (int i = 0; i < n_utts; ++i) {
@@ -429,18 +433,27 @@ int fe_run(fe_handle* h, const void* pcm, const int64_t* pcm_offsets, const int6
         FE_CUDA(h, cudaStreamSynchronize(st));     // `at` is pageable and dies at scope end
         if (prof) FE_CUDA(h, cudaEventRecord(h->ev[1], st));
         int grid = (int)std::min<long long>(pl.total_atiles, 16LL * h->num_sms);
-        k_resample<<<grid, 256, 0, st>>>((const short*)d_pcm, (const UttDesc*)h->d_utts.p, (const int2*)h->d_atiles.p,
-                                         (int)pl.total_atiles, (const int*)h->d_sp_up.p, (const int*)h->d_sp_down.p,
-                                         (const int*)h->d_sp_tap_off.p, (const float*)h->d_taps.p,
-                                         (short*)h->d_scratch.p, 0);
+        if (preemph) {
+            if (c.pcm_dtype == FE_PCM_INT16)
+                k_preemph<0><<<grid, 256, 0, st>>>(d_pcm, (const UttDesc*)h->d_utts.p, (const int2*)h->d_atiles.p,
+                                                   (int)pl.total_atiles, c.preemph, (float*)h->d_scratch.p);
+            else
+                k_preemph<1><<<grid, 256, 0, st>>>(d_pcm, (const UttDesc*)h->d_utts.p, (const int2*)h->d_atiles.p,
+                                                   (int)pl.total_atiles, c.preemph, (float*)h->d_scratch.p);
+        } else {
+            k_resample<<<grid, 256, 0, st>>>((const short*)d_pcm, (const UttDesc*)h->d_utts.p, (const int2*)h->d_atiles.p,
+                                             (int)pl.total_atiles, (const int*)h->d_sp_up.p, (const int*)h->d_sp_down.p,
+                                             (const int*)h->d_sp_tap_off.p, (const float*)h->d_taps.p,
+                                             (short*)h->d_scratch.p, 0);
+        }
         h->launches++;
         h->ev_k0 = true;
     }
     if (prof) FE_CUDA(h, cudaEventRecord(h->ev[2], st));
-    DevTables dt = dev_tables(h);
+    DevTables dt = dev_tables(h, k1_f32);
     float* stat_base = c.cmvn ? (float*)h->d_statics.p : d_out;
-    if ((rc = launch_k1(h, st, d_pcm, (const short*)h->d_scratch.p, (const UttDesc*)h->d_utts.p,
-                        (const int2*)h->d_tiles.p, (int)pl.total_tiles, dt, stat_base))) return rc;
+    if ((rc = launch_k1(h, st, d_pcm, h->d_scratch.p, k1_f32, (const TileDesc*)h->d_tiles.p,
+                        (int)pl.total_tiles, dt, stat_base))) return rc;
     if (prof) FE_CUDA(h, cudaEventRecord(h->ev[3], st));
     h->ev_k2 = false;
     if (c.cmvn && pl.total_frames > 0) {

@@ -7,13 +7,16 @@
 //   -> frame energy -> mel filterbank -> zero_handling -> log -> DCT-II(ortho)[:D]
 //   -> c0 <- log(energy).
 //
-// Geometry: one frame = 8 lanes, one warp = 4 consecutive frames of one utterance.
-// The 512-point real FFT is a 256-point complex FFT (z[m] = x[2m] + i x[2m+1])
-// split 16 x 16: stage A = two in-register FFT16 per lane over a (m = j + 16a,
-// j = t and t+8), twiddle W_256^(j k1), exchange through a swizzled shared
-// buffer, stage B = two in-register FFT16 per lane over j for rows k1 = {t, 16-t}
-// (lane 0: {8, 0}), so that Z[k] and Z[256-k] of the real-FFT post-pass sit in the
-// SAME lane and no second exchange is needed.
+// Geometry: one frame = 8 lanes (t = 0..7), one warp = 4 consecutive frames (fs = 0..3).
+// The 512-point real FFT is a 256-point complex FFT (z[m] = x[2m] + i x[2m+1]) split
+// 16 x 16.  Every lane runs TWO 16-point FFTs per stage, carried in the two halves of
+// packed f32x2 registers (Blackwell FADD2 / FMUL2 / FFMA2: one issue slot, two lanes
+// of FP32 work; negate / half-swap / broadcast operand modifiers are free):
+//   stage A  halves = complex points j = t and t+8 (m = j + 16 a, a = 0..15)
+//   exchange through a swizzled shared-memory region (scalar stores, 16-byte loads)
+//   stage B  halves = output rows k1 = rx and ry = 16 - rx, so Z[k] and Z[256-k] of
+//            the real-FFT split sit in the SAME lane (half-swapped operand) and no
+//            second exchange is needed.
 #pragma once
 #include <stdint.h>
 #include <math.h>
@@ -24,6 +27,7 @@
 #define FE_HD inline
 struct float2 { float x, y; };
 struct float4 { float x, y, z, w; };
+struct uint2 { unsigned x, y; };
 static inline float4 make_float4(float a, float b, float c, float d) { float4 v = {a, b, c, d}; return v; }
 static inline float2 make_float2(float a, float b) { float2 v = {a, b}; return v; }
 #endif
@@ -35,64 +39,82 @@ constexpr int kBins = 257;
 constexpr int kWarpFrames = 4;          // frames per warp pass
 constexpr int kCtaWarps = 8;
 constexpr int kCtaFrames = kWarpFrames * kCtaWarps;   // frames per tile-table entry
-constexpr int kERegion = 512;           // floats of exchange buffer per frame
+constexpr int kERegion = 512;           // floats of exchange buffer per frame (2 KB, 2 KB aligned)
 constexpr int kPStagger = 8;            // per-frame-slot float offset of the power row
-constexpr int kLogmelOff = 320;         // log-mel row offset inside the frame's region
+constexpr int kLogmelOff = 288;         // log-mel row inside the frame's region (after the power row)
+constexpr int kFoldS = 0, kFoldD = 64;  // folded DCT inputs (reuse the dead power row)
 constexpr int kMaxFilters = 128;
-constexpr int kTw256Stride = 17;        // float2 per row of the padded W_256 table
 constexpr float kEpsF64 = 2.220446049250313e-16f;   // np.finfo(float).eps, as float
 
 // ---------------------------------------------------------------------------
-// Shared-memory tables of one CTA (pointers into dynamic smem)
+// packed f32x2 arithmetic
+// ---------------------------------------------------------------------------
+#if defined(__CUDA_ARCH__)
+FE_HD float2 padd(float2 a, float2 b) { return __fadd2_rn(a, b); }
+FE_HD float2 psub(float2 a, float2 b) { return __fadd2_rn(a, make_float2(-b.x, -b.y)); }
+FE_HD float2 pmul(float2 a, float2 b) { return __fmul2_rn(a, b); }
+FE_HD float2 pfma(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+#else
+FE_HD float2 padd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+FE_HD float2 psub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+FE_HD float2 pmul(float2 a, float2 b) { return make_float2(a.x * b.x, a.y * b.y); }
+FE_HD float2 pfma(float2 a, float2 b, float2 c) { return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)); }
+#endif
+FE_HD float2 pbc(float s) { return make_float2(s, s); }
+FE_HD float2 pswap(float2 a) { return make_float2(a.y, a.x); }
+FE_HD float2 pneg(float2 a) { return make_float2(-a.x, -a.y); }
+FE_HD float2 pnfma(float2 a, float2 b, float2 c) { return pfma(pneg(a), b, c); }   // c - a*b
+
+// ---------------------------------------------------------------------------
+// Shared-memory tables of one CTA
 // ---------------------------------------------------------------------------
 struct SmemTables {
-    const float2* tw256;      // [16][kTw256Stride]  W_256^(j*k) = (cos, -sin)
-    const float2* tw512;      // [257]               (cos, sin)(2 pi k / 512)
-    const float*  window;     // [pcm layout of one frame, 13*32 floats] or nullptr
-    const int*    fb_start;   // [nf + 1]
-    const int*    fb_bin0;    // [nf]
-    const float*  fb_w;       // [nnz], pre-scaled by 1/2048
-    const float*  dct;        // [D][dct_stride]
-    int nf, D, dct_stride;
+    const float4* tw256;      // [16][16] k1-major, cfg = swap*8 + t: (wr(jx k1), wr(jy k1), wi(jx k1), wi(jy k1)), w = exp(-2 pi i j k1 / 256)
+    const float4* tw512;      // [8][16]  k2-major, cfg = Fe*8 + t: (cos kx, cos ky, sin kx, sin ky), k = r + 16 k2
+    const float2* window;     // [ROWS*16] (w[2m], w[2m+1]) per complex point m, or nullptr
+    // mel plan: S slots, slot s spans entries [slot_off[s], slot_off[s+1]) (even count);
+    // lane g of a frame owns filter mel_id[s*8+g] whose run starts at bin mel_b0[s*8+g]
+    const int*    mel_slot_off;   // [S + 1]
+    const int*    mel_b0;         // [S * 8]
+    const int*    mel_id;         // [S * 8]   (-1 = no filter)
+    const float*  mel_w;          // [entries * 8], pre-scaled by pscale / 2048
+    const float*  dctf;           // [D][dct_stride] folded DCT rows (n < ceil(nf/2)), zero padded
+    int mel_slots;
+    int nf, D, dct_stride, nh;    // nh = ceil(nf / 2)
     int full_spectrum;        // filterbank touches bins > 128
     int is_mfcc, fbank_log, dc_elim;
+    float pscale;             // 2^-30 when samples are raw int16 counts, 1 for float PCM
 };
 
-// position of sample r (0..31) inside a 32-float block of the staged PCM tile:
-// complex point j' = r/2 (re/im = r&1), u = j' & 7 (lane), h = j' >> 3 (which of
-// the lane's two FFT16) -> 4u + 2c + h, so one 16-byte load at 32a + 4t yields
-// (re_t, re_{t+8}, im_t, im_{t+8}) of row a.
-FE_HD int pcm_pos(int r) { int jp = r >> 1; return ((jp & 7) << 2) + ((r & 1) << 1) + (jp >> 3); }
-
 // ---------------------------------------------------------------------------
-// radix-4 butterfly and 16-point forward FFT on registers
+// radix-4 butterfly and 16-point forward FFT on packed registers
 // ---------------------------------------------------------------------------
-FE_HD void bfly4(float& r0, float& i0, float& r1, float& i1, float& r2, float& i2, float& r3, float& i3) {
-    float t0r = r0 + r2, t0i = i0 + i2;
-    float t1r = r0 - r2, t1i = i0 - i2;
-    float t2r = r1 + r3, t2i = i1 + i3;
-    float t3r = r1 - r3, t3i = i1 - i3;
-    r0 = t0r + t2r; i0 = t0i + t2i;
-    r2 = t0r - t2r; i2 = t0i - t2i;
-    r1 = t1r + t3i; i1 = t1i - t3r;     // t1 - i t3
-    r3 = t1r - t3i; i3 = t1i + t3r;     // t1 + i t3
+FE_HD void bfly4(float2& r0, float2& i0, float2& r1, float2& i1, float2& r2, float2& i2, float2& r3, float2& i3) {
+    float2 t0r = padd(r0, r2), t0i = padd(i0, i2);
+    float2 t1r = psub(r0, r2), t1i = psub(i0, i2);
+    float2 t2r = padd(r1, r3), t2i = padd(i1, i3);
+    float2 t3r = psub(r1, r3), t3i = psub(i1, i3);
+    r0 = padd(t0r, t2r); i0 = padd(t0i, t2i);
+    r2 = psub(t0r, t2r); i2 = psub(t0i, t2i);
+    r1 = padd(t1r, t3i); i1 = psub(t1i, t3r);     // t1 - i t3
+    r3 = psub(t1r, t3i); i3 = padd(t1i, t3r);     // t1 + i t3
 }
 
 // multiply (r, i) by exp(-2 pi i M / 16)
-template <int M> FE_HD void mul_w16(float& r, float& i) {
+template <int M> FE_HD void mul_w16(float2& r, float2& i) {
     constexpr float C1 = 0.92387953251128674f, S1 = 0.38268343236508977f, H = 0.70710678118654752f;
-    if (M == 1)      { float t = r * C1 + i * S1; i = i * C1 - r * S1; r = t; }
-    else if (M == 2) { float t = (r + i) * H;     i = (i - r) * H;     r = t; }
-    else if (M == 3) { float t = r * S1 + i * C1; i = i * S1 - r * C1; r = t; }
-    else if (M == 4) { float t = r; r = i; i = -t; }
-    else if (M == 6) { float t = (i - r) * H;     i = -(r + i) * H;    r = t; }
-    else if (M == 9) { float t = -r * C1 - i * S1; i = r * S1 - i * C1;  r = t; }
+    if (M == 1)      { float2 t = pfma(i, pbc(S1), pmul(r, pbc(C1))); i = pnfma(r, pbc(S1), pmul(i, pbc(C1))); r = t; }
+    else if (M == 2) { float2 t = pmul(padd(r, i), pbc(H)); i = pmul(psub(i, r), pbc(H)); r = t; }
+    else if (M == 3) { float2 t = pfma(i, pbc(C1), pmul(r, pbc(S1))); i = pnfma(r, pbc(C1), pmul(i, pbc(S1))); r = t; }
+    else if (M == 4) { float2 t = r; r = i; i = pneg(t); }
+    else if (M == 6) { float2 t = pmul(psub(i, r), pbc(H)); i = pmul(padd(r, i), pbc(-H)); r = t; }
+    else if (M == 9) { float2 t = pnfma(i, pbc(S1), pmul(r, pbc(-C1))); i = pfma(r, pbc(S1), pmul(i, pbc(-C1))); r = t; }
 }
 
 // In-place FFT16: input natural order x[n]; output X[k] lands at slot pos16(k).
 FE_HD constexpr int pos16(int k) { return (k >> 2) + ((k & 3) << 2); }
 
-FE_HD void fft16(float (&xr)[16], float (&xi)[16]) {
+FE_HD void fft16(float2 (&xr)[16], float2 (&xi)[16]) {
 #pragma unroll
     for (int n1 = 0; n1 < 4; ++n1)
         bfly4(xr[n1], xi[n1], xr[n1 + 4], xi[n1 + 4], xr[n1 + 8], xi[n1 + 8], xr[n1 + 12], xi[n1 + 12]);
@@ -106,140 +128,192 @@ FE_HD void fft16(float (&xr)[16], float (&xi)[16]) {
               xr[4 * k2 + 2], xi[4 * k2 + 2], xr[4 * k2 + 3], xi[4 * k2 + 3]);
 }
 
-// swizzled float offset of the 16-byte chunk holding (row k1, columns 2c, 2c+1)
-FE_HD int e_chunk(int k1, int c, int fs) { return (k1 << 5) + (((c ^ (k1 & 7) ^ ((fs & 1) << 2))) << 2); }
+// ---------------------------------------------------------------------------
+// Exchange region of one frame (512 floats, 2 KB aligned).  Element (row k1, column j,
+// plane re/im) lives at float index
+//     p*64 + plane*32 + 4*((j>>1) ^ p ^ X) + 2*(j&1) + (slot ^ F)
+// p = pair-row of k1 ({8,0} -> 0, {k,16-k} -> k), slot = which row of the pair,
+// X = 4*(fs&1) and F = (fs>>1 when p != 0) spread the four frames of a warp over the
+// banks.  All lane-dependent terms are XORs into the low 5 index bits, so an access is
+// "lane base XOR compile-time constant" plus an immediate offset.
+// ---------------------------------------------------------------------------
+FE_HD constexpr int e_prow(int k1) { return (k1 == 0 || k1 == 8) ? 0 : (k1 < 8 ? k1 : 16 - k1); }
+FE_HD constexpr int e_slot(int k1) { return (k1 == 0) ? 1 : (k1 == 8 ? 0 : (k1 < 8 ? 0 : 1)); }
+
+// XOR-addressable pointer into a 2 KB aligned shared region
+struct EPtr {
+#if defined(__CUDA_ARCH__)
+    uint32_t a;                              // shared-window byte address | lane bits
+    __device__ __forceinline__ EPtr x(int c) const { EPtr r; r.a = a ^ (uint32_t)(c << 2); return r; }
+#else
+    float* base; int l;
+    EPtr x(int c) const { EPtr r; r.base = base; r.l = l ^ c; return r; }
+#endif
+};
+
+#if defined(__CUDA_ARCH__)
+__device__ __forceinline__ void e_st(EPtr p, int off, float v) {
+    asm volatile("st.shared.f32 [%0], %1;" :: "r"(p.a + (uint32_t)(off << 2)), "f"(v) : "memory");
+}
+__device__ __forceinline__ float4 e_ld4(EPtr p, int off) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "r"(p.a + (uint32_t)(off << 2)) : "memory");
+    return v;
+}
+__device__ __forceinline__ EPtr e_make(const float* region, int lane_bits) {
+    EPtr p; p.a = (uint32_t)__cvta_generic_to_shared(region) | (uint32_t)(lane_bits << 2); return p;
+}
+#else
+inline void e_st(EPtr p, int off, float v) { p.base[p.l + off] = v; }
+inline float4 e_ld4(EPtr p, int off) { const float* q = p.base + p.l + off; return make_float4(q[0], q[1], q[2], q[3]); }
+inline EPtr e_make(float* region, int lane_bits) { EPtr p; p.base = region; p.l = lane_bits; return p; }
+#endif
 
 // ---------------------------------------------------------------------------
-// Phase 1 (stage A): load 13 rows of the frame, window, sum of squares, two FFT16,
-// twiddle, scatter into the frame's exchange region.
-//   pcm_f : staged PCM of this frame (tile base + fs*HOP), permuted layout
-//   e_f   : this frame's 512-float exchange region
-//   returns the lane's partial sum of squares (Parseval frame energy)
+// Phase 1 (stage A)
+//   raw_f : this frame's samples as staged by the bulk copy (int16 words or floats)
+//   e_f   : this frame's exchange region
+//   halves: .x = complex point jx = t + 8*swap, .y = jy = t + 8*(1-swap), swap = fs>>1
+//           (the swap makes the two 4-byte loads of a row bank-conflict free)
+//   returns the lane's partial sum of squares (Parseval frame energy, sample units)
 // ---------------------------------------------------------------------------
-template <int FRAME_LEN>
-FE_HD float stage_a(const float* pcm_f, float* e_f, const SmemTables& tb, int t, int fs) {
-    float r0[16], i0[16], r1[16], i1[16];
-    float ss = 0.f;
+template <int FRAME_LEN, int IN_F32>
+FE_HD float stage_a(const void* raw_f, float* e_f, const SmemTables& tb, int t, int fs) {
+    float2 re[16], im[16];
+    float2 ss = make_float2(0.f, 0.f);
     constexpr int ROWS = (FRAME_LEN + 31) / 32;
+    const int swap = fs >> 1;
+    const int jx = t + 8 * swap, jy = t + 8 * (1 - swap);
 #pragma unroll
     for (int a = 0; a < 16; ++a) {
         if (a < ROWS) {
-            float4 v = *reinterpret_cast<const float4*>(pcm_f + 32 * a + 4 * t);
+            float2 vr, vi;
+            if (IN_F32) {
+                const float2* pf = reinterpret_cast<const float2*>(raw_f);
+                float2 u = pf[16 * a + jx], v = pf[16 * a + jy];
+                vr = make_float2(u.x, v.x); vi = make_float2(u.y, v.y);
+            } else {
+                const uint32_t* pw = reinterpret_cast<const uint32_t*>(raw_f);
+                uint32_t u = pw[16 * a + jx], v = pw[16 * a + jy];
+                vr = make_float2((float)(short)(u & 0xffffu), (float)(short)(v & 0xffffu));
+                vi = make_float2((float)((int)u >> 16), (float)((int)v >> 16));
+            }
             if (tb.window) {
-                float4 w = *reinterpret_cast<const float4*>(tb.window + 32 * a + 4 * t);
-                v.x *= w.x; v.y *= w.y; v.z *= w.z; v.w *= w.w;
+                float2 w0 = tb.window[16 * a + jx], w1 = tb.window[16 * a + jy];
+                vr = pmul(vr, make_float2(w0.x, w1.x)); vi = pmul(vi, make_float2(w0.y, w1.y));
             }
-            // validity of sample n = 2 (j + 16 a) + c against FRAME_LEN (t-dependent only in the last row)
-            int n0 = 2 * (t + 16 * a), n1 = 2 * (t + 8 + 16 * a);
-            if (32 * a + 32 > FRAME_LEN) {
-                if (n0 >= FRAME_LEN) v.x = 0.f;
-                if (n0 + 1 >= FRAME_LEN) v.z = 0.f;
-                if (n1 >= FRAME_LEN) v.y = 0.f;
-                if (n1 + 1 >= FRAME_LEN) v.w = 0.f;
+            if (32 * a + 32 > FRAME_LEN) {      // zero padding inside the last row (sample n = 2 (j + 16 a) + c)
+                const int nx = 2 * (jx + 16 * a), ny = 2 * (jy + 16 * a);
+                if (nx >= FRAME_LEN) vr.x = 0.f;
+                if (nx + 1 >= FRAME_LEN) vi.x = 0.f;
+                if (ny >= FRAME_LEN) vr.y = 0.f;
+                if (ny + 1 >= FRAME_LEN) vi.y = 0.f;
             }
-            r0[a] = v.x; r1[a] = v.y; i0[a] = v.z; i1[a] = v.w;
-            ss = fmaf(v.x, v.x, ss); ss = fmaf(v.y, v.y, ss);
-            ss = fmaf(v.z, v.z, ss); ss = fmaf(v.w, v.w, ss);
+            re[a] = vr; im[a] = vi;
+            ss = pfma(vr, vr, ss); ss = pfma(vi, vi, ss);
         } else {
-            r0[a] = 0.f; r1[a] = 0.f; i0[a] = 0.f; i1[a] = 0.f;
+            re[a] = make_float2(0.f, 0.f); im[a] = make_float2(0.f, 0.f);
         }
     }
-    fft16(r0, i0);
-    fft16(r1, i1);
-    const float2* tw0 = tb.tw256 + t * kTw256Stride;
-    const float2* tw1 = tb.tw256 + (t + 8) * kTw256Stride;
-    const int c0 = t >> 1, c1 = (t + 8) >> 1, half = (t & 1) << 1;
+    fft16(re, im);
+    // twiddle W_256^(j k1) and scatter.  Lane part of the index (low 5 bits):
+    //   4*((t>>1) ^ X ^ 4*hb) + 2*(t&1) + F   with hb = j>>3 of the half being stored
+    const int X = (fs & 1) << 2, F = fs >> 1;
+    const int lb = (((t >> 1) ^ X) << 2) | ((t & 1) << 1);
+    const int hbx = swap << 4, hby = (1 - swap) << 4;           // chunk bit 2 = index bit 4
+    const EPtr x0 = e_make(e_f, lb ^ hbx), y0 = e_make(e_f, lb ^ hby);              // pair-row 0: no slot flip
+    const EPtr xF = e_make(e_f, (lb ^ hbx) | F), yF = e_make(e_f, (lb ^ hby) | F);
+    const int cfg = swap * 8 + t;
 #pragma unroll
     for (int k1 = 0; k1 < 16; ++k1) {
         const int s = pos16(k1);
-        float2 w0 = tw0[k1], w1 = tw1[k1];
-        float yr0 = r0[s] * w0.x - i0[s] * w0.y, yi0 = r0[s] * w0.y + i0[s] * w0.x;
-        float yr1 = r1[s] * w1.x - i1[s] * w1.y, yi1 = r1[s] * w1.y + i1[s] * w1.x;
-        *reinterpret_cast<float2*>(e_f + e_chunk(k1, c0, fs) + half) = make_float2(yr0, yi0);
-        *reinterpret_cast<float2*>(e_f + e_chunk(k1, c1, fs) + half) = make_float2(yr1, yi1);
+        float2 yr = re[s], yi = im[s];
+        if (k1 > 0) {
+            float4 w = tb.tw256[k1 * 16 + cfg];
+            float2 wr = make_float2(w.x, w.y), wi = make_float2(w.z, w.w);
+            float2 tr = pnfma(yi, wi, pmul(yr, wr));
+            yi = pfma(yr, wi, pmul(yi, wr));
+            yr = tr;
+        }
+        const int p = e_prow(k1), c = (p << 2) | e_slot(k1), off = p * 64;
+        const EPtr qx = (p == 0 ? x0 : xF).x(c), qy = (p == 0 ? y0 : yF).x(c);
+        e_st(qx, off, yr.x);
+        e_st(qy, off, yr.y);
+        e_st(qx, off + 32, yi.x);
+        e_st(qy, off + 32, yi.y);
     }
-    return ss;
+    return ss.x + ss.y;
 }
 
 // ---------------------------------------------------------------------------
-// Phase 2 (stage B): rows ra/rb of the exchange region -> two FFT16 over j.
-// Slot pos16(k2) of (ar, ai) holds Z[ra + 16 k2]; same for b.
+// Phase 2 (stage B): pair-row p = t of the exchange region -> packed FFT16 over j.
+// Halves: .x = row rx, .y = row ry; slot pos16(k2) holds Z[r + 16 k2].
 // ---------------------------------------------------------------------------
-struct LaneZ { float ar[16], ai[16], br[16], bi[16]; };
+struct LaneZ { float2 r[16], i[16]; };
 
-FE_HD int row_a(int t) { return t ? t : 8; }
-FE_HD int row_b(int t) { return t ? 16 - t : 0; }
+FE_HD int lane_flip(int t, int fs) { return t ? (fs >> 1) : 0; }
+FE_HD int row_x(int t, int fs) { return t == 0 ? 8 : (lane_flip(t, fs) ? 16 - t : t); }
+FE_HD int row_y(int t, int fs) { return t == 0 ? 0 : (lane_flip(t, fs) ? t : 16 - t); }
 
-FE_HD void stage_b(const float* e_f, LaneZ& z, int t, int fs) {
-    const int ra = row_a(t), rb = row_b(t);
+FE_HD void stage_b(float* e_f, LaneZ& z, int t, int fs) {
+    const int X = (fs & 1) << 2;
+    const EPtr b = e_make(e_f, t * 64 + ((t ^ X) << 2));
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
-        float4 va = *reinterpret_cast<const float4*>(e_f + e_chunk(ra, c, fs));
-        float4 vb = *reinterpret_cast<const float4*>(e_f + e_chunk(rb, c, fs));
-        z.ar[2 * c] = va.x; z.ai[2 * c] = va.y; z.ar[2 * c + 1] = va.z; z.ai[2 * c + 1] = va.w;
-        z.br[2 * c] = vb.x; z.bi[2 * c] = vb.y; z.br[2 * c + 1] = vb.z; z.bi[2 * c + 1] = vb.w;
+    for (int q = 0; q < 8; ++q) {
+        float4 vr = e_ld4(b.x(q << 2), 0);
+        float4 vi = e_ld4(b.x(q << 2), 32);
+        z.r[2 * q] = make_float2(vr.x, vr.y); z.r[2 * q + 1] = make_float2(vr.z, vr.w);
+        z.i[2 * q] = make_float2(vi.x, vi.y); z.i[2 * q + 1] = make_float2(vi.z, vi.w);
     }
-    fft16(z.ar, z.ai);
-    fft16(z.br, z.bi);
+    fft16(z.r, z.i);
 }
 
 // ---------------------------------------------------------------------------
-// Phase 3 (post-pass): real-FFT split, power (scaled by 4, i.e. |2X|^2; the
-// 1/2048 = 1/(4*512) lives in the filterbank weights), store the power row.
-//   p_f : power row of this frame (e_f + fs*kPStagger), indexed by bin
-//   returns |2 X[0]|^2 + |2 X[256]|^2 contribution pieces via x0/x256 (lane t==0)
+// Phase 3 (post-pass): real-FFT split, power |2X|^2 (the 1/2048 = 1/(4*512) lives in
+// the filterbank weights), scatter to the power row.
+//   lanes t >= 1: partner of half .x is half .y of slot 15-k2 and vice versa (free swap)
+//   lanes t == 0: rows 8 (.x) and 0 (.y) are self-paired
 // ---------------------------------------------------------------------------
-FE_HD void pair_power(float Ar, float Ai, float Pr, float Pi, float c, float s,
-                      float& plo, float& phi) {
-    // A = Z[k], partner Zp = Z[256-k]; B = conj(Zp)
-    float er = Ar + Pr, ei = Ai - Pi;         // 2E
-    float orr = Ar - Pr, oi = Ai + Pi;        // 2O
-    float tr = s * orr - c * oi;              // T = i w O, w = (c, -s)
-    float ti = c * orr + s * oi;
-    float xr = er - tr, xi = ei - ti;         // 2 X[k]
-    float yr = er + tr, yi = ei + ti;         // conj(2 X[256-k])
-    plo = xr * xr + xi * xi;
-    phi = yr * yr + yi * yi;
-}
-
-FE_HD void post_pass(const LaneZ& z, float* p_f, const SmemTables& tb, int t,
-                     float& x0, float& x256) {
+FE_HD void post_pass(const LaneZ& z, float* p_f, const SmemTables& tb, int t, int fs, float& x0, float& x256) {
     const bool t0 = (t == 0);
-    const int ra = row_a(t), rb = row_b(t);
-    // set 1: bins ra + 16 k2, partner Vb[15 - k2]; set 2: bins rb + 16 k2, partner Va[15 - k2]
+    const int rx = row_x(t, fs), ry = row_y(t, fs);
+    const int cfg = lane_flip(t, fs) * 8 + t;
 #pragma unroll
     for (int k2 = 0; k2 < 8; ++k2) {
-        const int sa = pos16(k2), sp = pos16(15 - k2);
-        // partner of set 1 = Vb[15-k2] = t0 ? Za[15-k2] : Zb[15-k2]      (upper half of Vb)
-        float p1r = t0 ? z.ar[sp] : z.br[sp];
-        float p1i = t0 ? z.ai[sp] : z.bi[sp];
-        // partner of set 2 = Va[15-k2] = t0 ? Zb[(16-k2)&15] : Za[15-k2] (upper half of Va)
-        const int sq = pos16((16 - k2) & 15);
-        float p2r = t0 ? z.br[sq] : z.ar[sp];
-        float p2i = t0 ? z.bi[sq] : z.ai[sp];
-        const int k_1 = ra + 16 * k2, k_2 = rb + 16 * k2;
-        float2 w1 = tb.tw512[k_1], w2 = tb.tw512[k_2];
-        float lo1, hi1, lo2, hi2;
-        pair_power(z.ar[sa], z.ai[sa], p1r, p1i, w1.x, w1.y, lo1, hi1);
-        pair_power(z.br[sa], z.bi[sa], p2r, p2i, w2.x, w2.y, lo2, hi2);
-        p_f[k_1] = lo1;
-        p_f[k_2] = lo2;
+        const int sa = pos16(k2), sp = pos16(15 - k2), sq = pos16((16 - k2) & 15);
+        float2 ar = z.r[sa], ai = z.i[sa];
+        // partner Z[256 - k]
+        float2 pr, pi;
+        pr.x = t0 ? z.r[sp].x : z.r[sp].y;   pr.y = t0 ? z.r[sq].y : z.r[sp].x;
+        pi.x = t0 ? z.i[sp].x : z.i[sp].y;   pi.y = t0 ? z.i[sq].y : z.i[sp].x;
+        float4 w = tb.tw512[k2 * 16 + cfg];
+        float2 c = make_float2(w.x, w.y), s = make_float2(w.z, w.w);
+        float2 er = padd(ar, pr), ei = psub(ai, pi);          // 2E  (B = conj(partner))
+        float2 orr = psub(ar, pr), oi = padd(ai, pi);         // 2O
+        float2 tr = pnfma(c, oi, pmul(s, orr));               // T = i w O, w = (c, -s)
+        float2 ti = pfma(s, oi, pmul(c, orr));
+        float2 xr = psub(er, tr), xi = psub(ei, ti);          // 2 X[k]
+        float2 plo = pfma(xi, xi, pmul(xr, xr));
+        p_f[rx + 16 * k2] = plo.x;
+        p_f[ry + 16 * k2] = plo.y;
         if (tb.full_spectrum) {
-            p_f[256 - k_1] = hi1;
-            p_f[256 - k_2] = hi2;      // k_2 == 0 (lane 0) writes bin 256
+            float2 yr = padd(er, tr), yi = padd(ei, ti);      // conj(2 X[256-k])
+            float2 phi = pfma(yi, yi, pmul(yr, yr));
+            p_f[256 - (rx + 16 * k2)] = phi.x;
+            p_f[256 - (ry + 16 * k2)] = phi.y;                // lane 0, k2 = 0 writes bin 256
         }
     }
-    // bin 128 = row 0, k2 = 8 (self-paired): 2 X[128] = 2 conj(Z[128]); lane 0 holds row 0 in b
-    float zr = z.br[pos16(8)], zi = z.bi[pos16(8)];
+    // bin 128 = row 0, k2 = 8 (self-paired): 2 X[128] = 2 conj(Z[128]); lane 0 holds row 0 in .y
+    float zr = z.r[pos16(8)].y, zi = z.i[pos16(8)].y;
     if (t0) p_f[128] = 4.f * (zr * zr + zi * zi);
-    // X[0] = Zr + Zi, X[256] = Zr - Zi of Z[0] (lane 0, row 0 slot 0)
-    x0 = z.br[0] + z.bi[0];
-    x256 = z.br[0] - z.bi[0];
+    x0 = z.r[0].y + z.i[0].y;         // X[0]   = Re Z[0] + Im Z[0]   (lane 0 only)
+    x256 = z.r[0].y - z.i[0].y;       // X[256] = Re Z[0] - Im Z[0]
 }
 
 // Parseval frame energy: sum_{k=0..256} |X_k|^2 / 512 = sum x^2 / 2 + (X0^2 + X256^2) / 1024
-FE_HD float frame_energy(float sumsq, float x0, float x256) {
-    float e = 0.5f * sumsq + (x0 * x0 + x256 * x256) * (1.0f / 1024.0f);
+FE_HD float frame_energy(float sumsq, float x0, float x256, float pscale) {
+    float e = (0.5f * sumsq + (x0 * x0 + x256 * x256) * (1.0f / 1024.0f)) * pscale;
     return e == 0.f ? kEpsF64 : e;
 }
 
@@ -251,88 +325,72 @@ FE_HD float fe_log(float x) {
 #endif
 }
 
-// ---------------------------------------------------------------------------
-// Phase 4: mel filterbank of one (frame, filter) task from the power row.
-// ---------------------------------------------------------------------------
-FE_HD float mel_task(const float* p_f, const SmemTables& tb, int m) {
-    const int s = tb.fb_start[m], e = tb.fb_start[m + 1];
-    const float* p = p_f + tb.fb_bin0[m];
-    float acc = 0.f;
-    for (int i = s; i < e; ++i) acc = fmaf(tb.fb_w[i], p[i - s], acc);
-    return acc == 0.f ? kEpsF64 : acc;
-}
-
-// ---------------------------------------------------------------------------
-// Phase 5: one cepstral coefficient from the log-mel row (rows padded with zeros
-// to a multiple of 4 floats).
-// ---------------------------------------------------------------------------
-FE_HD float dct_task(const float* logmel, const SmemTables& tb, int c) {
-    const float* d = tb.dct + c * tb.dct_stride;
-    float acc = 0.f;
-    const int n4 = (tb.nf + 3) >> 2;
-    for (int q = 0; q < n4; ++q) {
-        float4 a = *reinterpret_cast<const float4*>(d + 4 * q);
-        float4 b = *reinterpret_cast<const float4*>(logmel + 4 * q);
-        acc = fmaf(a.x, b.x, acc); acc = fmaf(a.y, b.y, acc);
-        acc = fmaf(a.z, b.z, acc); acc = fmaf(a.w, b.w, acc);
-    }
-    return acc;
-}
-
-// ---------------------------------------------------------------------------
-// Phase 0: stage one item (two sample pairs 16 apart) of the warp's PCM span.
-//   p      first sample of the warp's first frame;  n_samp  samples to stage (even)
-//   id     item index: block q = id >> 3, lane slot u = id & 7
-// ---------------------------------------------------------------------------
-FE_HD void stage_store(float* pcm_w, int id, float a0, float a1, float b0, float b1) {
-    *reinterpret_cast<float4*>(pcm_w + ((id >> 3) << 5) + ((id & 7) << 2)) = make_float4(a0, b0, a1, b1);
-}
-
-FE_HD void stage_item_i16(const short* p, int n_samp, int id, float* pcm_w) {
-    const int sA = ((id >> 3) << 5) + ((id & 7) << 1), sB = sA + 16;
-    float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
-    const float k = 1.0f / 32768.0f;
-#if defined(__CUDA_ARCH__)
-    if (sA < n_samp) { short2 v = __ldg(reinterpret_cast<const short2*>(p + sA)); a0 = (float)v.x * k; a1 = (float)v.y * k; }
-    if (sB < n_samp) { short2 v = __ldg(reinterpret_cast<const short2*>(p + sB)); b0 = (float)v.x * k; b1 = (float)v.y * k; }
-#else
-    if (sA < n_samp) { a0 = (float)p[sA] * k; a1 = (float)p[sA + 1] * k; }
-    if (sB < n_samp) { b0 = (float)p[sB] * k; b1 = (float)p[sB + 1] * k; }
-#endif
-    stage_store(pcm_w, id, a0, a1, b0, b1);
-}
-
-FE_HD void stage_item_f32(const float* p, int n_samp, int id, float* pcm_w) {
-    const int sA = ((id >> 3) << 5) + ((id & 7) << 1), sB = sA + 16;
-    float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
-    if (sA < n_samp) { a0 = p[sA]; a1 = p[sA + 1]; }
-    if (sB < n_samp) { b0 = p[sB]; b1 = p[sB + 1]; }
-    stage_store(pcm_w, id, a0, a1, b0, b1);
-}
-
 // rows inside the warp's exchange buffer e_w (kWarpFrames regions of kERegion floats)
 FE_HD float* power_row(float* e_w, int f) { return e_w + f * kERegion + f * kPStagger; }
-FE_HD float* logmel_row(float* e_w, int f) { return e_w + f * kERegion + kLogmelOff + f * kPStagger; }
+FE_HD float* logmel_row(float* e_w, int f) { return e_w + f * kERegion + kLogmelOff; }
 
-// Phase 4, one task: id -> (filter m = id >> 2, frame slot f = id & 3)
-FE_HD void mel_phase(float* e_w, const SmemTables& tb, int id, int nfw) {
-    const int m = id >> 2, f = id & 3;
-    if (f >= nfw) return;
-    float v = 0.f;
-    if (m < tb.nf) {
-        v = mel_task(power_row(e_w, f), tb, m);
+// ---------------------------------------------------------------------------
+// Phase 4: mel filterbank, lane g of frame fs walks its slot list (uniform trip counts).
+// ---------------------------------------------------------------------------
+FE_HD void mel_phase(float* e_w, const SmemTables& tb, int g, int fs) {
+    const float* p_f = power_row(e_w, fs);
+    float* row = logmel_row(e_w, fs);
+    for (int s = 0; s < tb.mel_slots; ++s) {
+        const int e0 = tb.mel_slot_off[s], e1 = tb.mel_slot_off[s + 1];
+        const int id = tb.mel_id[s * 8 + g];
+        const float* p = p_f + tb.mel_b0[s * 8 + g];
+        const float* w = tb.mel_w + e0 * 8 + g;
+        float acc0 = 0.f, acc1 = 0.f;
+        for (int e = 0; e < e1 - e0; e += 2) {
+            acc0 = fmaf(w[e * 8], p[e], acc0);
+            acc1 = fmaf(w[e * 8 + 8], p[e + 1], acc1);
+        }
+        float v = acc0 + acc1;
+        v = (v == 0.f) ? kEpsF64 : v;
         if (tb.is_mfcc || tb.fbank_log) v = fe_log(v);
+        if (id >= 0) row[id] = v;
     }
-    logmel_row(e_w, f)[m] = v;
 }
 
-// Phase 5, one task: id = f * D + c -> statics value of (frame slot f, coefficient c)
-FE_HD float emit_phase(float* e_w, const float* energies, const SmemTables& tb, int id) {
-    const int f = id / tb.D, c = id - f * tb.D;
-    const float* row = logmel_row(e_w, f);
-    if (!tb.is_mfcc) return row[c];
-    if (c == 0 && tb.dc_elim) return fe_log(energies[f]);
-    return dct_task(row, tb, c);
+// Phase 4b (mfcc): fold the log-mel row for the DCT: s[n] = x[n] + x[nf-1-n], d[n] = x[n] - x[nf-1-n]
+FE_HD void fold_phase(float* e_w, const SmemTables& tb, int g, int fs) {
+    const float* row = logmel_row(e_w, fs);
+    float* fs_ = e_w + fs * kERegion + kFoldS;
+    float* fd_ = e_w + fs * kERegion + kFoldD;
+    const int nh4 = (tb.nh + 3) & ~3;
+    for (int n = g; n < nh4; n += 8) {
+        float s = 0.f, d = 0.f;
+        if (n < tb.nh) {
+            const int m = tb.nf - 1 - n;
+            float a = row[n];
+            if (m == n) { s = a; d = 0.f; }
+            else { float b = row[m]; s = a + b; d = a - b; }
+        }
+        fs_[n] = s; fd_[n] = d;
+    }
+}
+
+// Phase 5 (mfcc): lane g computes coefficients c = g, g+8, ... (same parity as g -> one input array)
+FE_HD void dct_phase(float* e_w, const float* energies, const SmemTables& tb, int g, int fs, float* dst) {
+    const float* in = e_w + fs * kERegion + ((g & 1) ? kFoldD : kFoldS);
+    const int n4 = (tb.nh + 3) >> 2;
+    for (int c0 = g; c0 < tb.D; c0 += 16) {
+        const int c1 = c0 + 8;
+        const bool has1 = c1 < tb.D;
+        const float* d0 = tb.dctf + c0 * tb.dct_stride;
+        const float* d1 = tb.dctf + (has1 ? c1 : c0) * tb.dct_stride;
+        float a0 = 0.f, a1 = 0.f;
+        for (int q = 0; q < n4; ++q) {
+            float4 x = *reinterpret_cast<const float4*>(in + 4 * q);
+            float4 u = *reinterpret_cast<const float4*>(d0 + 4 * q);
+            float4 v = *reinterpret_cast<const float4*>(d1 + 4 * q);
+            a0 = fmaf(u.x, x.x, a0); a0 = fmaf(u.y, x.y, a0); a0 = fmaf(u.z, x.z, a0); a0 = fmaf(u.w, x.w, a0);
+            a1 = fmaf(v.x, x.x, a1); a1 = fmaf(v.y, x.y, a1); a1 = fmaf(v.z, x.z, a1); a1 = fmaf(v.w, x.w, a1);
+        }
+        if (c0 == 0 && tb.dc_elim) a0 = fe_log(energies[fs]);
+        dst[c0] = a0;
+        if (has1) dst[c1] = a1;
+    }
 }
 
 }  // namespace fe

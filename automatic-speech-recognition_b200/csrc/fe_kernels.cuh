@@ -1,8 +1,9 @@
 // sm_100a kernels of the acoustic front-end.
-//   K0  k_resample           speed perturbation (polyphase Kaiser-sinc) + requantise   utils/augmentation.py:6-31
+//   K0  k_resample           speed perturbation (polyphase Kaiser-sinc) + gain + requantise   utils/augmentation.py:6-56
+//   K0' k_preemph            optional pre-emphasis (speechpy.processing.preemphasis) to float scratch
 //   K1  k_frames_to_statics  framing -> rFFT512 -> power -> mel -> log -> DCT          preprocess.py:72-82
 //   K2  k_cmvn_delta_pack    per-utterance CMVN, delta, delta-delta, cube (L, D, 3)    preprocess.py:85-88
-//   k_build_tiles            (utterance, first frame) table for K1's persistent tile loop
+//   k_build_tiles            tile descriptors for K1's persistent tile loop
 #pragma once
 #include <cuda_runtime.h>
 #include "fe_core.cuh"
@@ -10,207 +11,235 @@
 namespace fe {
 
 struct UttDesc {
-    long long pcm_off;      // element offset of the samples K1 frames (source or K0 scratch)
+    long long pcm_off;      // element offset of the samples K1 frames (source or scratch)
     long long src_off;      // element offset in the caller's PCM buffer
     long long stat_off;     // float offset of frame 0's statics
     long long out_off;      // float offset of the utterance's output
     int n_samples;          // samples K1 frames (after speed perturbation)
     int n_src;              // samples in the caller's buffer
     int n_frames;
-    int src_sel;            // 0: caller's PCM, 1: K0 scratch (int16)
+    int src_sel;            // 0: caller's PCM, 1: scratch
     int speed_idx;          // -1 = none
     float gain;             // 1 = none
 };
 
+// one entry per kCtaFrames frames of one utterance (32 bytes, two 16-byte loads)
+struct __align__(16) TileDesc {
+    long long pcm_off;      // element offset of the tile's first sample
+    long long stat_off;     // float offset of the tile's first statics row
+    int n_frames;           // 1..kCtaFrames
+    int src_sel;
+    int utt;
+    int pad;
+};
+
 struct DevTables {
-    const float2* tw256;    // [256]
-    const float2* tw512;    // [257]
-    const float* window;    // [13*32] permuted frame layout, or nullptr
-    const int* fb_start; const int* fb_bin0; const float* fb_w;
-    const float* dct;       // [D][dct_stride]
-    int nf, nnz, D, dct_stride, full_spectrum, is_mfcc, fbank_log, dc_elim;
+    const float4* tw256;    // [16][16]
+    const float4* tw512;    // [8][16]
+    const float2* window;   // [ROWS*16] or nullptr
+    const int* mel_slot_off; const int* mel_b0; const int* mel_id; const float* mel_w;
+    const float* dctf;      // [D][dct_stride]
+    int mel_slots, mel_entries;
+    int nf, D, dct_stride, nh, full_spectrum, is_mfcc, fbank_log, dc_elim;
+    float pscale;
 };
 
 // ---------------------------------------------------------------------------
 __global__ void k_build_tiles(const UttDesc* __restrict__ utts, const long long* __restrict__ tile_prefix,
-                              int n_utts, int frames_per_tile, int2* __restrict__ tiles) {
+                              int n_utts, int hop, int D, TileDesc* __restrict__ tiles) {
     int u = blockIdx.x * blockDim.x + threadIdx.x;
     if (u >= n_utts) return;
+    const UttDesc d = utts[u];
     long long b = tile_prefix[u];
-    int nt = (utts[u].n_frames + frames_per_tile - 1) / frames_per_tile;
-    for (int i = 0; i < nt; ++i) tiles[b + i] = make_int2(u, i * frames_per_tile);
+    for (int f = 0; f < d.n_frames; f += kCtaFrames) {
+        TileDesc t;
+        t.pcm_off = d.pcm_off + (long long)f * hop;
+        t.stat_off = d.stat_off + (long long)f * D;
+        t.n_frames = min(kCtaFrames, d.n_frames - f);
+        t.src_sel = d.src_sel; t.utt = u; t.pad = 0;
+        tiles[b++] = t;
+    }
 }
 
 // ---------------------------------------------------------------------------
-// K1 shared-memory carve-up (bytes), shared by host (size) and device (pointers)
+// K1 shared-memory carve-up (bytes), shared by host (size) and device (pointers).
+// The exchange regions come first so that they are 2 KB aligned (the kernel rounds
+// the dynamic shared base up to 2 KB; the host adds 2 KB of slack).
 // ---------------------------------------------------------------------------
 struct K1Smem {
-    int off_tw256, off_tw512, off_window, off_fb_start, off_fb_bin0, off_fb_w, off_dct, off_warp;
-    int warp_pcm_floats, warp_bytes, total;
+    int off_e, off_raw, off_scr, off_tw256, off_tw512, off_window, off_slot, off_b0, off_id, off_melw, off_dct, off_bar;
+    int raw_bytes;          // one raw buffer of one warp
+    int total;
 };
 
 __host__ __device__ inline int align16(int x) { return (x + 15) & ~15; }
 
-__host__ __device__ inline K1Smem k1_smem_layout(int nf, int nnz, int D, int dct_stride, int has_window,
-                                                 int frame_len, int hop, int is_mfcc) {
+__host__ __device__ inline K1Smem k1_smem_layout(int mel_slots, int mel_entries, int D, int dct_stride, int has_window,
+                                                 int frame_len, int hop, int is_mfcc, int in_f32) {
     K1Smem s;
+    const int rows = (frame_len + 31) / 32;
     int o = 0;
-    s.off_tw256 = o;    o = align16(o + 16 * kTw256Stride * 8);
-    s.off_tw512 = o;    o = align16(o + kBins * 8);
-    s.off_window = o;   o = align16(o + (has_window ? ((frame_len + 31) / 32) * 32 * 4 : 0));
-    s.off_fb_start = o; o = align16(o + (nf + 1) * 4);
-    s.off_fb_bin0 = o;  o = align16(o + nf * 4);
-    s.off_fb_w = o;     o = align16(o + nnz * 4);
-    s.off_dct = o;      o = align16(o + (is_mfcc ? D * dct_stride * 4 : 0));
-    s.off_warp = o;
-    s.warp_pcm_floats = (kWarpFrames - 1) * hop + ((frame_len + 31) / 32) * 32;
-    s.warp_bytes = align16(s.warp_pcm_floats * 4) + kWarpFrames * kERegion * 4 + 64 * 4;
-    s.total = o + kCtaWarps * s.warp_bytes;
+    s.off_e = o;      o += kCtaWarps * kWarpFrames * kERegion * 4;
+    s.raw_bytes = align16(((kWarpFrames - 1) * hop + rows * 32) * (in_f32 ? 4 : 2));
+    s.off_raw = o;    o += kCtaWarps * 2 * s.raw_bytes;
+    s.off_scr = o;    o += kCtaWarps * 64 * 4;
+    s.off_tw256 = o;  o += 16 * 16 * 16;
+    s.off_tw512 = o;  o += 8 * 16 * 16;
+    s.off_window = o; o = align16(o + (has_window ? rows * 16 * 8 : 0));
+    s.off_slot = o;   o = align16(o + (mel_slots + 1) * 4);
+    s.off_b0 = o;     o = align16(o + mel_slots * 8 * 4);
+    s.off_id = o;     o = align16(o + mel_slots * 8 * 4);
+    s.off_melw = o;   o = align16(o + mel_entries * 8 * 4);
+    s.off_dct = o;    o = align16(o + (is_mfcc ? D * dct_stride * 4 : 0));
+    s.off_bar = o;    o += kCtaWarps * 2 * 8;
+    s.total = o + 2048;     // slack for the 2 KB round-up
     return s;
 }
 
-// one staged sample of utterance `u`: gain + requantise (int16 path) and scale to [-1, 1)
-template <int PCM_F32>
-__device__ __forceinline__ float fetch_sample(const void* __restrict__ src, long long idx, float gain) {
-    if (PCM_F32) {
-        float v = __ldg(reinterpret_cast<const float*>(src) + idx);
-        if (gain != 1.f) v = fminf(fmaxf(v * gain, -1.f), 32767.f / 32768.f);
-        return v;
-    } else {
-        float v = (float)__ldg(reinterpret_cast<const short*>(src) + idx);
-        if (gain != 1.f) v = fminf(fmaxf(rintf(v * gain), -32768.f), 32767.f);
-        return v * (1.0f / 32768.0f);
-    }
+// ---------------------------------------------------------------------------
+// mbarrier / bulk-copy (TMA 1-D) helpers
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra WAIT_DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t}"
+        :: "r"(bar), "r"(parity) : "memory");
 }
 
-template <int FRAME_LEN, int HOP, int PCM_F32>
+template <int FRAME_LEN, int HOP, int IN_F32>
 __global__ void __launch_bounds__(kCtaWarps * 32, 2)
-k_frames_to_statics(const void* __restrict__ pcm, const short* __restrict__ scratch,
-                    const UttDesc* __restrict__ utts, const int2* __restrict__ tiles, int n_tiles,
-                    DevTables dt, float* __restrict__ statics, float preemph) {
-    static_assert(HOP % 32 == 0, "staged layout needs frame starts on 32-float blocks");
-    static_assert(FRAME_LEN % 2 == 0 && FRAME_LEN <= kNfft, "frame must fit the 512-point FFT");
-    extern __shared__ __align__(16) unsigned char smem[];
-    const K1Smem L = k1_smem_layout(dt.nf, dt.nnz, dt.D, dt.dct_stride, dt.window != nullptr,
-                                    FRAME_LEN, HOP, dt.is_mfcc);
-    float2* s_tw256 = reinterpret_cast<float2*>(smem + L.off_tw256);
-    float2* s_tw512 = reinterpret_cast<float2*>(smem + L.off_tw512);
-    float* s_window = reinterpret_cast<float*>(smem + L.off_window);
-    int* s_fb_start = reinterpret_cast<int*>(smem + L.off_fb_start);
-    int* s_fb_bin0 = reinterpret_cast<int*>(smem + L.off_fb_bin0);
-    float* s_fb_w = reinterpret_cast<float*>(smem + L.off_fb_w);
+k_frames_to_statics(const void* __restrict__ pcm, const void* __restrict__ scratch,
+                    const TileDesc* __restrict__ tiles, int n_tiles,
+                    DevTables dt, float* __restrict__ statics) {
+    static_assert(HOP % 8 == 0 && FRAME_LEN % 8 == 0 && FRAME_LEN <= kNfft, "bulk copies need 16-byte granules");
+    extern __shared__ unsigned char smem_dyn[];
+    unsigned char* smem = smem_dyn + ((2048u - (smem_u32(smem_dyn) & 2047u)) & 2047u);
+    const K1Smem L = k1_smem_layout(dt.mel_slots, dt.mel_entries, dt.D, dt.dct_stride, dt.window != nullptr,
+                                    FRAME_LEN, HOP, dt.is_mfcc, IN_F32);
+    float4* s_tw256 = reinterpret_cast<float4*>(smem + L.off_tw256);
+    float4* s_tw512 = reinterpret_cast<float4*>(smem + L.off_tw512);
+    float2* s_window = reinterpret_cast<float2*>(smem + L.off_window);
+    int* s_slot = reinterpret_cast<int*>(smem + L.off_slot);
+    int* s_b0 = reinterpret_cast<int*>(smem + L.off_b0);
+    int* s_id = reinterpret_cast<int*>(smem + L.off_id);
+    float* s_melw = reinterpret_cast<float*>(smem + L.off_melw);
     float* s_dct = reinterpret_cast<float*>(smem + L.off_dct);
 
     const int tid = threadIdx.x;
-    for (int i = tid; i < 256; i += blockDim.x) s_tw256[(i >> 4) * kTw256Stride + (i & 15)] = dt.tw256[i];
-    for (int i = tid; i < kBins; i += blockDim.x) s_tw512[i] = dt.tw512[i];
-    if (dt.window) for (int i = tid; i < ((FRAME_LEN + 31) / 32) * 32; i += blockDim.x) s_window[i] = dt.window[i];
-    for (int i = tid; i <= dt.nf; i += blockDim.x) s_fb_start[i] = dt.fb_start[i];
-    for (int i = tid; i < dt.nf; i += blockDim.x) s_fb_bin0[i] = dt.fb_bin0[i];
-    for (int i = tid; i < dt.nnz; i += blockDim.x) s_fb_w[i] = dt.fb_w[i];
-    if (dt.is_mfcc) for (int i = tid; i < dt.D * dt.dct_stride; i += blockDim.x) s_dct[i] = dt.dct[i];
+    const int warp = tid >> 5, lane = tid & 31;
+    constexpr int ROWS = (FRAME_LEN + 31) / 32;
+    for (int i = tid; i < 256; i += blockDim.x) s_tw256[i] = dt.tw256[i];
+    for (int i = tid; i < 128; i += blockDim.x) s_tw512[i] = dt.tw512[i];
+    if (dt.window) for (int i = tid; i < ROWS * 16; i += blockDim.x) s_window[i] = dt.window[i];
+    for (int i = tid; i <= dt.mel_slots; i += blockDim.x) s_slot[i] = dt.mel_slot_off[i];
+    for (int i = tid; i < dt.mel_slots * 8; i += blockDim.x) { s_b0[i] = dt.mel_b0[i]; s_id[i] = dt.mel_id[i]; }
+    for (int i = tid; i < dt.mel_entries * 8; i += blockDim.x) s_melw[i] = dt.mel_w[i];
+    if (dt.is_mfcc) for (int i = tid; i < dt.D * dt.dct_stride; i += blockDim.x) s_dct[i] = dt.dctf[i];
+
+    const uint32_t bar0 = smem_u32(smem + L.off_bar + warp * 16);     // two mbarriers per warp
+    if (lane == 0) { mbar_init(bar0, 1); mbar_init(bar0 + 8, 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
 
     SmemTables tb;
     tb.tw256 = s_tw256; tb.tw512 = s_tw512; tb.window = dt.window ? s_window : nullptr;
-    tb.fb_start = s_fb_start; tb.fb_bin0 = s_fb_bin0; tb.fb_w = s_fb_w; tb.dct = s_dct;
-    tb.nf = dt.nf; tb.D = dt.D; tb.dct_stride = dt.dct_stride; tb.full_spectrum = dt.full_spectrum;
-    tb.is_mfcc = dt.is_mfcc; tb.fbank_log = dt.fbank_log; tb.dc_elim = dt.dc_elim;
+    tb.mel_slot_off = s_slot; tb.mel_b0 = s_b0; tb.mel_id = s_id; tb.mel_w = s_melw; tb.dctf = s_dct;
+    tb.mel_slots = dt.mel_slots; tb.nf = dt.nf; tb.D = dt.D; tb.dct_stride = dt.dct_stride; tb.nh = dt.nh;
+    tb.full_spectrum = dt.full_spectrum; tb.is_mfcc = dt.is_mfcc; tb.fbank_log = dt.fbank_log;
+    tb.dc_elim = dt.dc_elim; tb.pscale = dt.pscale;
 
-    const int warp = tid >> 5, lane = tid & 31;
     const int fs = lane >> 3, t = lane & 7;
-    unsigned char* wbase = smem + L.off_warp + warp * L.warp_bytes;
-    float* pcm_w = reinterpret_cast<float*>(wbase);
-    float* e_w = reinterpret_cast<float*>(wbase + align16(L.warp_pcm_floats * 4));
-    float* scr_w = e_w + kWarpFrames * kERegion;      // [0..31] sum-of-squares partials, [32..35] energies
+    float* e_w = reinterpret_cast<float*>(smem + L.off_e) + warp * kWarpFrames * kERegion;
+    unsigned char* raw_w = smem + L.off_raw + warp * 2 * L.raw_bytes;
+    float* scr_w = reinterpret_cast<float*>(smem + L.off_scr) + warp * 64;   // [0..31] sum-of-squares, [32..35] energies
     const int D = dt.D;
-    const int nf4 = (dt.nf + 3) & ~3;
+    constexpr int ESZ = IN_F32 ? 4 : 2;
 
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int2 te = tiles[tile];
-        const UttDesc u = utts[te.x];
-        const int f0 = te.y + warp * kWarpFrames;
-        const int nfw = min(kWarpFrames, u.n_frames - f0);
-        if (nfw <= 0) continue;                                   // warp-uniform
+    // issue the bulk copy of this warp's slice of tile `td` into raw buffer `buf`
+    auto prefetch = [&](const TileDesc& td, int buf) {
+        const int nfw = min(kWarpFrames, td.n_frames - warp * kWarpFrames);
+        if (nfw > 0 && lane == 0) {
+            const unsigned char* base = reinterpret_cast<const unsigned char*>(td.src_sel ? scratch : pcm);
+            const unsigned char* src = base + (td.pcm_off + (long long)warp * kWarpFrames * HOP) * ESZ;
+            const uint32_t bytes = (uint32_t)(((nfw - 1) * HOP + FRAME_LEN) * ESZ);
+            mbar_expect_tx(bar0 + 8 * buf, bytes);
+            bulk_g2s(smem_u32(raw_w + buf * L.raw_bytes), src, bytes, bar0 + 8 * buf);
+        }
+    };
 
-        // ---- phase 0: stage PCM of frames [f0, f0+nfw) as float, permuted 32-blocks ----
-        {
-            const long long s0 = (long long)f0 * HOP;
-            const int n_samp = (nfw - 1) * HOP + FRAME_LEN;
-            const int items = ((n_samp + 31) >> 5) << 3;
-            const void* src = u.src_sel ? (const void*)(scratch + u.pcm_off)
-                                        : (PCM_F32 ? (const void*)(reinterpret_cast<const float*>(pcm) + u.pcm_off)
-                                                   : (const void*)(reinterpret_cast<const short*>(pcm) + u.pcm_off));
-            const bool f32 = PCM_F32 && !u.src_sel;
-            const bool plain = (u.gain == 1.f) && (preemph == 0.f);
-            for (int id = lane; id < items; id += 32) {
-                const int sA = ((id >> 3) << 5) + ((id & 7) << 1), sB = sA + 16;
-                if (plain) {
-                    if (f32) stage_item_f32(reinterpret_cast<const float*>(src) + s0, n_samp, id, pcm_w);
-                    else     stage_item_i16(reinterpret_cast<const short*>(src) + s0, n_samp, id, pcm_w);
-                } else {
-                    // gain / pre-emphasis path: sample by sample (pre-emphasis is circular over the utterance)
-                    float v[4]; const int sidx[4] = {sA, sA + 1, sB, sB + 1};
+    int tile = blockIdx.x;
+    TileDesc cur;
+    if (tile < n_tiles) { cur = tiles[tile]; prefetch(cur, 0); }
+    uint32_t phase = 0;      // bit b = parity to wait for on barrier b
+    int buf = 0;
+    for (; tile < n_tiles; tile += gridDim.x) {
+        const int nxt = tile + gridDim.x;
+        TileDesc next;
+        if (nxt < n_tiles) next = tiles[nxt];
+        const int nfw = min(kWarpFrames, cur.n_frames - warp * kWarpFrames);
+        if (nfw > 0) {
+            mbar_wait(bar0 + 8 * buf, (phase >> buf) & 1u);
+            phase ^= 1u << buf;
+        }
+        // the other buffer was last read in the previous iteration's stage A (a __syncwarp ago)
+        if (nxt < n_tiles) prefetch(next, buf ^ 1);
+        if (nfw > 0) {
+            const bool active = fs < nfw;
+            float* e_f = e_w + fs * kERegion;
+            const unsigned char* raw_f = raw_w + buf * L.raw_bytes + fs * HOP * ESZ;
+
+            // ---- phase 1: stage A ----
+            if (active) scr_w[lane] = stage_a<FRAME_LEN, IN_F32>(raw_f, e_f, tb, t, fs);
+            __syncwarp();
+            // ---- phase 2: stage B ----
+            LaneZ z;
+            if (active) stage_b(e_f, z, t, fs);
+            __syncwarp();
+            // ---- phase 3: post-pass, power row, frame energy ----
+            if (active) {
+                float x0, x256;
+                post_pass(z, power_row(e_w, fs), tb, t, fs, x0, x256);
+                if (t == 0) {
+                    float s = 0.f;
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        v[e] = 0.f;
-                        if (sidx[e] < n_samp) {
-                            long long n = s0 + sidx[e];
-                            float x = f32 ? fetch_sample<1>(src, n, u.gain) : fetch_sample<0>(src, n, u.gain);
-                            if (preemph != 0.f) {
-                                long long pn = n > 0 ? n - 1 : (long long)u.n_samples - 1;
-                                float xp = f32 ? fetch_sample<1>(src, pn, u.gain) : fetch_sample<0>(src, pn, u.gain);
-                                x = x - preemph * xp;
-                            }
-                            v[e] = x;
-                        }
-                    }
-                    stage_store(pcm_w, id, v[0], v[1], v[2], v[3]);
+                    for (int i = 0; i < 8; ++i) s += scr_w[fs * 8 + i];
+                    scr_w[32 + fs] = frame_energy(s, x0, x256, tb.pscale);
                 }
             }
-        }
-        __syncwarp();
-
-        const bool active = fs < nfw;
-        float* e_f = e_w + fs * kERegion;
-        float* p_f = e_f + fs * kPStagger;
-
-        // ---- phase 1: stage A ----
-        if (active) {
-            float ss = stage_a<FRAME_LEN>(pcm_w + fs * HOP, e_f, tb, t, fs);
-            scr_w[lane] = ss;
-        }
-        __syncwarp();
-
-        // ---- phase 2: stage B ----
-        LaneZ z;
-        if (active) stage_b(e_f, z, t, fs);
-        __syncwarp();
-
-        // ---- phase 3: post-pass, power row, frame energy ----
-        if (active) {
-            float x0, x256;
-            post_pass(z, p_f, tb, t, x0, x256);
-            if (t == 0) {
-                float s = 0.f;
-#pragma unroll
-                for (int i = 0; i < 8; ++i) s += scr_w[fs * 8 + i];
-                scr_w[32 + fs] = frame_energy(s, x0, x256);
+            __syncwarp();
+            // ---- phase 4: mel filterbank (+ log) ----
+            if (active) mel_phase(e_w, tb, t, fs);
+            __syncwarp();
+            float* dst = statics + cur.stat_off + (long long)(warp * kWarpFrames) * D;
+            if (tb.is_mfcc) {
+                if (active) fold_phase(e_w, tb, t, fs);
+                __syncwarp();
+                if (active) dct_phase(e_w, scr_w + 32, tb, t, fs, dst + fs * D);
+            } else {
+                for (int f = 0; f < nfw; ++f) {
+                    const float* row = logmel_row(e_w, f);
+                    for (int m = lane; m < D; m += 32) dst[f * D + m] = row[m];
+                }
             }
+            __syncwarp();
         }
-        __syncwarp();
-
-        // ---- phase 4: mel filterbank (+ log) into the per-frame row ----
-        for (int id = lane; id < kWarpFrames * nf4; id += 32) mel_phase(e_w, tb, id, nfw);
-        __syncwarp();
-
-        // ---- phase 5: DCT (mfcc) or copy (fbank) -> statics[(f0 + f) * D + c] ----
-        {
-            float* dst = statics + u.stat_off + (long long)f0 * D;
-            const int ntask = nfw * D;
-            for (int id = lane; id < ntask; id += 32) dst[id] = emit_phase(e_w, scr_w + 32, tb, id);
-        }
-        __syncwarp();
+        cur = next;
+        buf ^= 1;
     }
 }
 
@@ -338,7 +367,8 @@ k_cmvn_delta_pack(const UttDesc* __restrict__ utts, int n_utts, const float* __r
 
 // ---------------------------------------------------------------------------
 // K0: speed perturbation.  y[j] = sum_t taps[(j*down) % up][t] * x[floor(j*down/up) - 15 + t],
-// x = 0 off the ends, int16 in -> round-half-even, saturate -> int16 out.
+// x = 0 off the ends, int16 in -> (* gain) -> round-half-even, saturate -> int16 out.
+// speed_idx < 0: gain only.
 // ---------------------------------------------------------------------------
 constexpr int kK0Outputs = 1024;
 
@@ -377,6 +407,30 @@ k_resample(const short* __restrict__ pcm, const UttDesc* __restrict__ utts,
             }
             if (u.gain != 1.f) acc *= u.gain;
             y[j] = (short)fminf(fmaxf(rintf(acc), -32768.f), 32767.f);
+        }
+    }
+}
+
+// K0': pre-emphasis y[n] = x[n] - a x[n-1], circular over the utterance (np.roll), to float scratch
+template <int PCM_F32>
+__global__ void __launch_bounds__(256)
+k_preemph(const void* __restrict__ pcm, const UttDesc* __restrict__ utts, const int2* __restrict__ atiles,
+          int n_atiles, float coef, float* __restrict__ dst) {
+    for (int tile = blockIdx.x; tile < n_atiles; tile += gridDim.x) {
+        const int2 te = atiles[tile];
+        const UttDesc u = utts[te.x];
+        const int j1 = min(te.y + kK0Outputs, u.n_samples);
+        for (int j = te.y + threadIdx.x; j < j1; j += blockDim.x) {
+            const int jp = j > 0 ? j - 1 : u.n_samples - 1;
+            float a, b;
+            if (PCM_F32) {
+                const float* x = reinterpret_cast<const float*>(pcm) + u.src_off;
+                a = x[j]; b = x[jp];
+            } else {
+                const short* x = reinterpret_cast<const short*>(pcm) + u.src_off;
+                a = (float)x[j] * (1.0f / 32768.0f); b = (float)x[jp] * (1.0f / 32768.0f);
+            }
+            dst[u.pcm_off + j] = a - coef * b;
         }
     }
 }

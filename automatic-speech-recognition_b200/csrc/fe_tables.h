@@ -1,0 +1,98 @@
+// Host-side re-layout of the configuration tables into the shapes the K1 phases read
+// (shared by the library's fe_configure and by tests/host_sim, so the CPU replay of the
+// kernel dataflow sees byte-identical tables).
+#pragma once
+#include <algorithm>
+#include <vector>
+#include "../../include/asr_frontend.h"
+#include "fe_core.cuh"
+
+namespace fe {
+
+struct HostTables {
+    std::vector<float> tw256;       // [16][16][4]  k1-major, cfg = swap*8 + t
+    std::vector<float> tw512;       // [8][16][4]   k2-major, cfg = flip*8 + t
+    std::vector<float> window;      // [rows*32]    (w[2m], w[2m+1]) per complex point
+    std::vector<int> mel_slot_off, mel_b0, mel_id;
+    std::vector<float> mel_w;       // [2][entries*8]: int16-count scale, then float scale
+    std::vector<float> dctf;        // [D][dct_stride]
+    int mel_slots = 0, mel_entries = 0, nh = 0, dct_stride = 0;
+};
+
+inline void build_host_tables(const fe_config& c, HostTables& t) {
+    // stage-A twiddles: (wr(jx k1), wr(jy k1), wi(jx k1), wi(jy k1)), jx = t + 8 swap, jy = t + 8 (1 - swap)
+    t.tw256.assign(16 * 16 * 4, 0.f);
+    for (int k1 = 0; k1 < 16; ++k1)
+        for (int cfg = 0; cfg < 16; ++cfg) {
+            const int swap = cfg >> 3, tt = cfg & 7;
+            const int jx = tt + 8 * swap, jy = tt + 8 * (1 - swap);
+            float* o = &t.tw256[(k1 * 16 + cfg) * 4];
+            o[0] = c.tw256[(jx * 16 + k1) * 2];     o[1] = c.tw256[(jy * 16 + k1) * 2];
+            o[2] = c.tw256[(jx * 16 + k1) * 2 + 1]; o[3] = c.tw256[(jy * 16 + k1) * 2 + 1];
+        }
+    // post-pass twiddles: (cos kx, cos ky, sin kx, sin ky), k = row + 16 k2
+    t.tw512.assign(8 * 16 * 4, 0.f);
+    for (int k2 = 0; k2 < 8; ++k2)
+        for (int cfg = 0; cfg < 16; ++cfg) {
+            const int tt = cfg & 7, fs = (cfg >> 3) << 1;
+            const int kx = row_x(tt, fs) + 16 * k2, ky = row_y(tt, fs) + 16 * k2;
+            float* o = &t.tw512[(k2 * 16 + cfg) * 4];
+            o[0] = c.tw512[kx * 2];     o[1] = c.tw512[ky * 2];
+            o[2] = c.tw512[kx * 2 + 1]; o[3] = c.tw512[ky * 2 + 1];
+        }
+    // mel plan: filters sorted by run length, 8 per slot (one per lane of a frame); every slot
+    // is padded to the longest run in it (even count) so trip counts are lane-uniform
+    const int nf = c.num_filters;
+    std::vector<int> order(nf);
+    for (int m = 0; m < nf; ++m) order[m] = m;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+        return c.fb_row_start[a + 1] - c.fb_row_start[a] < c.fb_row_start[b + 1] - c.fb_row_start[b]; });
+    const int S = (nf + 7) / 8;
+    t.mel_slot_off.assign(S + 1, 0); t.mel_b0.assign(S * 8, 0); t.mel_id.assign(S * 8, -1);
+    for (int s = 0; s < S; ++s) {
+        int e = 0;
+        for (int g = 0; g < 8 && s * 8 + g < nf; ++g) {
+            const int m = order[s * 8 + g];
+            e = std::max(e, c.fb_row_start[m + 1] - c.fb_row_start[m]);
+        }
+        e = std::max(2, (e + 1) & ~1);
+        t.mel_slot_off[s + 1] = t.mel_slot_off[s] + e;
+    }
+    const int entries = t.mel_slot_off[S];
+    t.mel_w.assign((size_t)entries * 8 * 2, 0.f);
+    for (int s = 0; s < S; ++s) {
+        const int e = t.mel_slot_off[s + 1] - t.mel_slot_off[s];
+        for (int g = 0; g < 8 && s * 8 + g < nf; ++g) {
+            const int m = order[s * 8 + g];
+            const int n = c.fb_row_start[m + 1] - c.fb_row_start[m];
+            int bin0 = n > 0 ? c.fb_first_bin[m] : 0, shift = 0;
+            if (bin0 + e > kBins) { shift = bin0 + e - kBins; bin0 -= shift; }   // keep padded reads inside the row
+            t.mel_id[s * 8 + g] = m; t.mel_b0[s * 8 + g] = bin0;
+            for (int i = 0; i < n; ++i) {
+                const float v = c.fb_weights[c.fb_row_start[m] + i] * (1.0f / 2048.0f);   // rows hold |2X|^2
+                const size_t at = ((size_t)(t.mel_slot_off[s] + shift + i)) * 8 + g;
+                t.mel_w[at] = v * (1.0f / 1073741824.0f);
+                t.mel_w[(size_t)entries * 8 + at] = v;
+            }
+        }
+    }
+    t.mel_slots = S; t.mel_entries = entries;
+    // folded DCT: y_c = sum_{n < nh} C[c][n] * (x[n] + (-1)^c x[nf-1-n])
+    t.nh = (nf + 1) / 2;
+    t.dct_stride = 0;
+    t.dctf.clear();
+    if (c.feat_type == FE_FEAT_MFCC) {
+        t.dct_stride = ((t.nh + 3) & ~3) + 4;            // 16-byte rows, staggered banks
+        t.dctf.assign((size_t)c.feat_dim * t.dct_stride, 0.f);
+        for (int k = 0; k < c.feat_dim; ++k)
+            for (int m = 0; m < t.nh; ++m) t.dctf[(size_t)k * t.dct_stride + m] = c.dct[k * nf + m];
+    }
+    t.window.clear();
+    if (c.window) {
+        const int rows = (c.frame_len + 31) / 32;
+        t.window.assign((size_t)rows * 32, 0.f);
+        for (int n = 0; n < c.frame_len; ++n) t.window[n] = c.window[n];
+    }
+}
+
+}  // namespace fe

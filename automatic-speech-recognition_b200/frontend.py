@@ -79,6 +79,71 @@ class FrontendConfig:
         return self.feat_dim * (3 if self.cmvn else 1)
 
 
+def make_fe_config(c: "FrontendConfig"):
+    """FrontendConfig -> (ctypes fe_config, keep-alive dict of the numpy tables it points
+    to, {speed: index}).  Pure host code (no CUDA): also used by the CPU replay of the
+    kernel dataflow in tests/host_sim."""
+    if c.feat_type not in ("mfcc", "fbank"):
+        raise ValueError("feat_type must be 'mfcc' or 'fbank'")
+    if c.fft_length != tables.NFFT:
+        raise ValueError("only fft_length=512 is supported")
+    nf = c.n_filters
+    fb = tables.mel_filterbank_dense(nf, c.sample_rate, c.low_frequency, c.high_frequency, c.bin_map)
+    row_start, first_bin, w = tables.filterbank_csr(fb)
+    keep = {
+        "row_start": np.ascontiguousarray(row_start, dtype=np.int32),
+        "first_bin": np.ascontiguousarray(first_bin, dtype=np.int32),
+        "w": np.ascontiguousarray(w, dtype=np.float32),
+        "tw256": np.ascontiguousarray(tables.twiddles_256().reshape(-1), dtype=np.float32),
+        "tw512": np.ascontiguousarray(tables.twiddles_512().reshape(-1), dtype=np.float32),
+    }
+    cfg = _lib.FeConfig()
+    cfg.abi_version = _lib.FE_ABI_VERSION
+    cfg.sample_rate = int(c.sample_rate)
+    cfg.frame_len, cfg.hop, cfg.nfft = c.frame_len, c.hop, c.fft_length
+    cfg.num_filters, cfg.feat_dim = nf, int(c.feat_dim)
+    cfg.feat_type = _lib.FE_FEAT_MFCC if c.feat_type == "mfcc" else _lib.FE_FEAT_FBANK
+    cfg.cmvn = int(bool(c.cmvn))
+    cfg.delta_mode = {"speechpy_as_shipped": _lib.FE_DELTA_SPEECHPY,
+                      "time_regression": _lib.FE_DELTA_TIME_REGRESSION}[c.delta_mode]
+    cfg.fbank_log = int(bool(c.fbank_log))
+    cfg.dc_elimination = int(bool(c.dc_elimination))
+    cfg.pcm_dtype = {"int16": _lib.FE_PCM_INT16, "float32": _lib.FE_PCM_FLOAT32}[c.pcm_dtype]
+    cfg.preemph = float(c.preemph or 0.0)
+    cfg.fb_nnz = int(keep["w"].size)
+    cfg.fb_row_start = _ptr(keep["row_start"], C.c_int32)
+    cfg.fb_first_bin = _ptr(keep["first_bin"], C.c_int32)
+    cfg.fb_weights = _ptr(keep["w"], C.c_float)
+    if c.feat_type == "mfcc":
+        keep["dct"] = np.ascontiguousarray(tables.dct_ortho(nf, c.feat_dim).reshape(-1), dtype=np.float32)
+        cfg.dct = _ptr(keep["dct"], C.c_float)
+    if c.window is not None:
+        win = np.ascontiguousarray(c.window, dtype=np.float32)
+        if win.shape != (c.frame_len,):
+            raise ValueError("window must have frame_len entries")
+        keep["window"] = win
+        cfg.window = _ptr(win, C.c_float)
+    cfg.tw256 = _ptr(keep["tw256"], C.c_float)
+    cfg.tw512 = _ptr(keep["tw512"], C.c_float)
+    speeds = [s for s in c.speeds if abs(s - 1.0) > 1e-12]
+    speed_index = {}
+    if speeds:
+        ups, downs, taps = [], [], []
+        for i, s in enumerate(speeds):
+            up, down = tables.speed_ratio(s)
+            ups.append(up); downs.append(down)
+            taps.append(tables.resampler_taps(s).astype(np.float32).reshape(-1))
+            speed_index[round(float(s), 6)] = i
+        keep["sp_up"] = np.asarray(ups, dtype=np.int32)
+        keep["sp_down"] = np.asarray(downs, dtype=np.int32)
+        keep["sp_taps"] = np.ascontiguousarray(np.concatenate(taps), dtype=np.float32)
+        cfg.n_speeds = len(speeds)
+        cfg.speed_up = _ptr(keep["sp_up"], C.c_int32)
+        cfg.speed_down = _ptr(keep["sp_down"], C.c_int32)
+        cfg.speed_taps = _ptr(keep["sp_taps"], C.c_float)
+    return cfg, keep, speed_index
+
+
 def num_frames(n_samples, frame_len=400, hop=160):
     """floor((N - frame_len) / hop), clamped at 0 (speechpy stack_frames, zero_padding=False)."""
     return int(_lib.load().fe_num_frames(int(n_samples), int(frame_len), int(hop)))
@@ -112,7 +177,6 @@ class Frontend:
         if rc != 0:
             msg = self._lib.fe_last_error(None)
             raise RuntimeError("fe_create(device=%d) failed (%d): %s" % (device, rc, msg.decode() if msg else ""))
-        self._speed_index = {}
         self._configure()
 
     # -- lifecycle ---------------------------------------------------------
@@ -140,65 +204,7 @@ class Frontend:
 
     # -- configuration -----------------------------------------------------
     def _configure(self):
-        c = self.config
-        if c.feat_type not in ("mfcc", "fbank"):
-            raise ValueError("feat_type must be 'mfcc' or 'fbank'")
-        if c.fft_length != tables.NFFT:
-            raise ValueError("only fft_length=512 is supported")
-        nf = c.n_filters
-        fb = tables.mel_filterbank_dense(nf, c.sample_rate, c.low_frequency, c.high_frequency, c.bin_map)
-        row_start, first_bin, w = tables.filterbank_csr(fb)
-        self._keep = keep = {
-            "row_start": np.ascontiguousarray(row_start, dtype=np.int32),
-            "first_bin": np.ascontiguousarray(first_bin, dtype=np.int32),
-            "w": np.ascontiguousarray(w, dtype=np.float32),
-            "tw256": np.ascontiguousarray(tables.twiddles_256().reshape(-1), dtype=np.float32),
-            "tw512": np.ascontiguousarray(tables.twiddles_512().reshape(-1), dtype=np.float32),
-        }
-        cfg = _lib.FeConfig()
-        cfg.abi_version = _lib.FE_ABI_VERSION
-        cfg.sample_rate = int(c.sample_rate)
-        cfg.frame_len, cfg.hop, cfg.nfft = c.frame_len, c.hop, c.fft_length
-        cfg.num_filters, cfg.feat_dim = nf, int(c.feat_dim)
-        cfg.feat_type = _lib.FE_FEAT_MFCC if c.feat_type == "mfcc" else _lib.FE_FEAT_FBANK
-        cfg.cmvn = int(bool(c.cmvn))
-        cfg.delta_mode = {"speechpy_as_shipped": _lib.FE_DELTA_SPEECHPY,
-                          "time_regression": _lib.FE_DELTA_TIME_REGRESSION}[c.delta_mode]
-        cfg.fbank_log = int(bool(c.fbank_log))
-        cfg.dc_elimination = int(bool(c.dc_elimination))
-        cfg.pcm_dtype = {"int16": _lib.FE_PCM_INT16, "float32": _lib.FE_PCM_FLOAT32}[c.pcm_dtype]
-        cfg.preemph = float(c.preemph or 0.0)
-        cfg.fb_nnz = int(keep["w"].size)
-        cfg.fb_row_start = _ptr(keep["row_start"], C.c_int32)
-        cfg.fb_first_bin = _ptr(keep["first_bin"], C.c_int32)
-        cfg.fb_weights = _ptr(keep["w"], C.c_float)
-        if c.feat_type == "mfcc":
-            keep["dct"] = np.ascontiguousarray(tables.dct_ortho(nf, c.feat_dim).reshape(-1), dtype=np.float32)
-            cfg.dct = _ptr(keep["dct"], C.c_float)
-        if c.window is not None:
-            win = np.ascontiguousarray(c.window, dtype=np.float32)
-            if win.shape != (c.frame_len,):
-                raise ValueError("window must have frame_len entries")
-            keep["window"] = win
-            cfg.window = _ptr(win, C.c_float)
-        cfg.tw256 = _ptr(keep["tw256"], C.c_float)
-        cfg.tw512 = _ptr(keep["tw512"], C.c_float)
-        speeds = [s for s in c.speeds if abs(s - 1.0) > 1e-12]
-        self._speed_index = {}
-        if speeds:
-            ups, downs, taps = [], [], []
-            for i, s in enumerate(speeds):
-                up, down = tables.speed_ratio(s)
-                ups.append(up); downs.append(down)
-                taps.append(tables.resampler_taps(s).astype(np.float32).reshape(-1))
-                self._speed_index[round(float(s), 6)] = i
-            keep["sp_up"] = np.asarray(ups, dtype=np.int32)
-            keep["sp_down"] = np.asarray(downs, dtype=np.int32)
-            keep["sp_taps"] = np.ascontiguousarray(np.concatenate(taps), dtype=np.float32)
-            cfg.n_speeds = len(speeds)
-            cfg.speed_up = _ptr(keep["sp_up"], C.c_int32)
-            cfg.speed_down = _ptr(keep["sp_down"], C.c_int32)
-            cfg.speed_taps = _ptr(keep["sp_taps"], C.c_float)
+        cfg, self._keep, self._speed_index = make_fe_config(self.config)
         self._check(self._lib.fe_configure(self._h, C.byref(cfg)), "fe_configure")
 
     # -- helpers -----------------------------------------------------------
