@@ -37,12 +37,12 @@ namespace fe {
 constexpr int kNfft = 512;
 constexpr int kBins = 257;
 constexpr int kWarpFrames = 4;          // frames per warp pass
-constexpr int kCtaWarps = 8;
+constexpr int kCtaWarps = 6;
 constexpr int kCtaFrames = kWarpFrames * kCtaWarps;   // frames per tile-table entry
 constexpr int kERegion = 512;           // floats of exchange buffer per frame (2 KB, 2 KB aligned)
 constexpr int kPStagger = 8;            // per-frame-slot float offset of the power row
 constexpr int kLogmelOff = 288;         // log-mel row inside the frame's region (after the power row)
-constexpr int kFoldS = 0, kFoldD = 64;  // folded DCT inputs (reuse the dead power row)
+constexpr int kFoldS = 0, kFoldD = 96;  // folded DCT inputs (reuse the dead power row)
 constexpr int kMaxFilters = 128;
 constexpr float kEpsF64 = 2.220446049250313e-16f;   // np.finfo(float).eps, as float
 
@@ -72,7 +72,8 @@ struct SmemTables {
     const float4* tw256;      // [16][16] k1-major, cfg = swap*8 + t: (wr(jx k1), wr(jy k1), wi(jx k1), wi(jy k1)), w = exp(-2 pi i j k1 / 256)
     const float4* tw512;      // [8][16]  k2-major, cfg = Fe*8 + t: (cos kx, cos ky, sin kx, sin ky), k = r + 16 k2
     const float2* window;     // [ROWS*16] (w[2m], w[2m+1]) per complex point m, or nullptr
-    // mel plan: S slots, slot s spans entries [slot_off[s], slot_off[s+1]) (even count);
+    // mel plan: S slots, slot s spans entries [slot_off[s], slot_off[s+1]) (multiple of 4; weights
+    // stored as float4 groups [entry/4][lane g]);
     // lane g of a frame owns filter mel_id[s*8+g] whose run starts at bin mel_b0[s*8+g]
     const int*    mel_slot_off;   // [S + 1]
     const int*    mel_b0;         // [S * 8]
@@ -327,7 +328,8 @@ FE_HD float fe_log(float x) {
 
 // rows inside the warp's exchange buffer e_w (kWarpFrames regions of kERegion floats)
 FE_HD float* power_row(float* e_w, int f) { return e_w + f * kERegion + f * kPStagger; }
-FE_HD float* logmel_row(float* e_w, int f) { return e_w + f * kERegion + kLogmelOff; }
+FE_HD float* logmel_row(float* e_w, int f) { return e_w + f * kERegion + kLogmelOff + f * kPStagger; }
+FE_HD float* fold_row(float* e_w, int f, int odd) { return e_w + f * kERegion + (odd ? kFoldD : kFoldS) + f * kPStagger; }
 
 // ---------------------------------------------------------------------------
 // Phase 4: mel filterbank, lane g of frame fs walks its slot list (uniform trip counts).
@@ -336,14 +338,17 @@ FE_HD void mel_phase(float* e_w, const SmemTables& tb, int g, int fs) {
     const float* p_f = power_row(e_w, fs);
     float* row = logmel_row(e_w, fs);
     for (int s = 0; s < tb.mel_slots; ++s) {
-        const int e0 = tb.mel_slot_off[s], e1 = tb.mel_slot_off[s + 1];
+        const int e0 = tb.mel_slot_off[s], n4 = (tb.mel_slot_off[s + 1] - e0) >> 2;
         const int id = tb.mel_id[s * 8 + g];
         const float* p = p_f + tb.mel_b0[s * 8 + g];
-        const float* w = tb.mel_w + e0 * 8 + g;
+        const float4* w = reinterpret_cast<const float4*>(tb.mel_w) + (e0 >> 2) * 8 + g;
         float acc0 = 0.f, acc1 = 0.f;
-        for (int e = 0; e < e1 - e0; e += 2) {
-            acc0 = fmaf(w[e * 8], p[e], acc0);
-            acc1 = fmaf(w[e * 8 + 8], p[e + 1], acc1);
+        for (int q = 0; q < n4; ++q) {
+            const float4 ww = w[q * 8];
+            acc0 = fmaf(ww.x, p[4 * q], acc0);
+            acc1 = fmaf(ww.y, p[4 * q + 1], acc1);
+            acc0 = fmaf(ww.z, p[4 * q + 2], acc0);
+            acc1 = fmaf(ww.w, p[4 * q + 3], acc1);
         }
         float v = acc0 + acc1;
         v = (v == 0.f) ? kEpsF64 : v;
@@ -355,8 +360,8 @@ FE_HD void mel_phase(float* e_w, const SmemTables& tb, int g, int fs) {
 // Phase 4b (mfcc): fold the log-mel row for the DCT: s[n] = x[n] + x[nf-1-n], d[n] = x[n] - x[nf-1-n]
 FE_HD void fold_phase(float* e_w, const SmemTables& tb, int g, int fs) {
     const float* row = logmel_row(e_w, fs);
-    float* fs_ = e_w + fs * kERegion + kFoldS;
-    float* fd_ = e_w + fs * kERegion + kFoldD;
+    float* fs_ = fold_row(e_w, fs, 0);
+    float* fd_ = fold_row(e_w, fs, 1);
     const int nh4 = (tb.nh + 3) & ~3;
     for (int n = g; n < nh4; n += 8) {
         float s = 0.f, d = 0.f;
@@ -372,7 +377,7 @@ FE_HD void fold_phase(float* e_w, const SmemTables& tb, int g, int fs) {
 
 // Phase 5 (mfcc): lane g computes coefficients c = g, g+8, ... (same parity as g -> one input array)
 FE_HD void dct_phase(float* e_w, const float* energies, const SmemTables& tb, int g, int fs, float* dst) {
-    const float* in = e_w + fs * kERegion + ((g & 1) ? kFoldD : kFoldS);
+    const float* in = fold_row(e_w, fs, g & 1);
     const int n4 = (tb.nh + 3) >> 2;
     for (int c0 = g; c0 < tb.D; c0 += 16) {
         const int c1 = c0 + 8;

@@ -183,21 +183,25 @@ k_frames_to_statics(const void* __restrict__ pcm, const void* __restrict__ scrat
     };
 
     int tile = blockIdx.x;
-    TileDesc cur;
+    const int stride = gridDim.x;
+    TileDesc cur, next;
+    cur.n_frames = 0; next.n_frames = 0;
     if (tile < n_tiles) { cur = tiles[tile]; prefetch(cur, 0); }
+    if (tile + stride < n_tiles) next = tiles[tile + stride];
     uint32_t phase = 0;      // bit b = parity to wait for on barrier b
     int buf = 0;
-    for (; tile < n_tiles; tile += gridDim.x) {
-        const int nxt = tile + gridDim.x;
-        TileDesc next;
-        if (nxt < n_tiles) next = tiles[nxt];
+    for (; tile < n_tiles; tile += stride) {
+        // descriptor two tiles ahead: in flight during this whole iteration
+        TileDesc nn;
+        nn.n_frames = 0;
+        if (tile + 2 * stride < n_tiles) nn = tiles[tile + 2 * stride];
         const int nfw = min(kWarpFrames, cur.n_frames - warp * kWarpFrames);
         if (nfw > 0) {
             mbar_wait(bar0 + 8 * buf, (phase >> buf) & 1u);
             phase ^= 1u << buf;
         }
-        // the other buffer was last read in the previous iteration's stage A (a __syncwarp ago)
-        if (nxt < n_tiles) prefetch(next, buf ^ 1);
+        // the other buffer was last read in the previous iteration's stage A (several __syncwarp ago)
+        if (tile + stride < n_tiles) prefetch(next, buf ^ 1);
         if (nfw > 0) {
             const bool active = fs < nfw;
             float* e_f = e_w + fs * kERegion;
@@ -239,6 +243,7 @@ k_frames_to_statics(const void* __restrict__ pcm, const void* __restrict__ scrat
             __syncwarp();
         }
         cur = next;
+        next = nn;
         buf ^= 1;
     }
 }
@@ -284,7 +289,17 @@ k_cmvn_delta_pack(const UttDesc* __restrict__ utts, int n_utts, const float* __r
         float* o = out + utts[ui].out_off;
 
         float s = 0.f;
-        if (act) for (int tt = r; tt < L; tt += R) s += x[(long long)tt * D + c];
+        if (act) {      // four independent row streams per thread keep loads in flight
+            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+            const float* xc = x + c;
+            int tt = r;
+            for (; tt + 3 * R < L; tt += 4 * R) {
+                s0 += xc[(long long)tt * D]; s1 += xc[(long long)(tt + R) * D];
+                s2 += xc[(long long)(tt + 2 * R) * D]; s3 += xc[(long long)(tt + 3 * R) * D];
+            }
+            for (; tt < L; tt += R) s0 += xc[(long long)tt * D];
+            s = (s0 + s1) + (s2 + s3);
+        }
         red[tid] = s;
         __syncthreads();
         if (tid < D) {
@@ -295,7 +310,18 @@ k_cmvn_delta_pack(const UttDesc* __restrict__ utts, int n_utts, const float* __r
         __syncthreads();
         const float mu = act ? mean[c] : 0.f;
         float q = 0.f;
-        if (act) for (int tt = r; tt < L; tt += R) { float d = x[(long long)tt * D + c] - mu; q = fmaf(d, d, q); }
+        if (act) {
+            float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
+            const float* xc = x + c;
+            int tt = r;
+            for (; tt + 3 * R < L; tt += 4 * R) {
+                float d0 = xc[(long long)tt * D] - mu, d1 = xc[(long long)(tt + R) * D] - mu;
+                float d2 = xc[(long long)(tt + 2 * R) * D] - mu, d3 = xc[(long long)(tt + 3 * R) * D] - mu;
+                q0 = fmaf(d0, d0, q0); q1 = fmaf(d1, d1, q1); q2 = fmaf(d2, d2, q2); q3 = fmaf(d3, d3, q3);
+            }
+            for (; tt < L; tt += R) { float d = xc[(long long)tt * D] - mu; q0 = fmaf(d, d, q0); }
+            q = (q0 + q1) + (q2 + q3);
+        }
         red[tid] = q;
         __syncthreads();
         if (tid < D) {

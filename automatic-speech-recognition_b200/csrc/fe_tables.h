@@ -41,7 +41,7 @@ inline void build_host_tables(const fe_config& c, HostTables& t) {
             o[2] = c.tw512[kx * 2 + 1]; o[3] = c.tw512[ky * 2 + 1];
         }
     // mel plan: filters sorted by run length, 8 per slot (one per lane of a frame); every slot
-    // is padded to the longest run in it (even count) so trip counts are lane-uniform
+    // is padded to the longest run in it (multiple of 4) so trip counts are lane-uniform
     const int nf = c.num_filters;
     std::vector<int> order(nf);
     for (int m = 0; m < nf; ++m) order[m] = m;
@@ -55,7 +55,7 @@ inline void build_host_tables(const fe_config& c, HostTables& t) {
             const int m = order[s * 8 + g];
             e = std::max(e, c.fb_row_start[m + 1] - c.fb_row_start[m]);
         }
-        e = std::max(2, (e + 1) & ~1);
+        e = std::max(4, (e + 3) & ~3);
         t.mel_slot_off[s + 1] = t.mel_slot_off[s] + e;
     }
     const int entries = t.mel_slot_off[S];
@@ -70,7 +70,8 @@ inline void build_host_tables(const fe_config& c, HostTables& t) {
             t.mel_id[s * 8 + g] = m; t.mel_b0[s * 8 + g] = bin0;
             for (int i = 0; i < n; ++i) {
                 const float v = c.fb_weights[c.fb_row_start[m] + i] * (1.0f / 2048.0f);   // rows hold |2X|^2
-                const size_t at = ((size_t)(t.mel_slot_off[s] + shift + i)) * 8 + g;
+                const int ee = t.mel_slot_off[s] + shift + i;       // float4 groups: [entry/4][lane][entry%4]
+                const size_t at = ((size_t)(ee >> 2) * 8 + g) * 4 + (ee & 3);
                 t.mel_w[at] = v * (1.0f / 1073741824.0f);
                 t.mel_w[(size_t)entries * 8 + at] = v;
             }
