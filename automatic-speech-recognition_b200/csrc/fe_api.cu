@@ -38,7 +38,8 @@ struct fe_handle {
     std::string err;
 
     // device tables
-    DevBuf tw256, tw512, window, mel_slot_off, mel_b0, mel_id, mel_w, dct;
+    DevBuf tw256, tw512, window, mel_b0, mel_id, mel_w, dct;
+    int mel_n4[16] = {0}, mel_e4[16] = {0};
     int dct_stride = 0, full_spectrum = 0, mel_slots = 0, mel_entries = 0, nh = 0;
     bool scratch_f32 = false;     // pre-emphasis materialises float PCM in the scratch buffer
     // resampler
@@ -187,12 +188,17 @@ int launch_k1(fe_handle* h, cudaStream_t st, const void* pcm, const void* scratc
     int grid = std::min<long long>(n_tiles, 2LL * h->num_sms);
     if (grid <= 0) return FE_OK;
     if (c.frame_len == 400 && c.hop == 160) {
+        K1Params P;
+        P.dt = dt;
+        P.L = k1_smem_layout(h->mel_slots, h->mel_entries, c.feat_dim, h->dct_stride, c.window != nullptr,
+                             c.frame_len, c.hop, c.feat_type == FE_FEAT_MFCC, in_f32);
+        memcpy(P.mel_n4, h->mel_n4, sizeof(P.mel_n4)); memcpy(P.mel_e4, h->mel_e4, sizeof(P.mel_e4));
         if (!in_f32)
             k_frames_to_statics<400, 160, 0><<<grid, kCtaWarps * 32, h->k1_smem[0], st>>>(
-                pcm, scratch, tiles, n_tiles, dt, statics);
+                pcm, scratch, tiles, n_tiles, P, statics);
         else
             k_frames_to_statics<400, 160, 1><<<grid, kCtaWarps * 32, h->k1_smem[1], st>>>(
-                pcm, scratch, tiles, n_tiles, dt, statics);
+                pcm, scratch, tiles, n_tiles, P, statics);
     } else {
         return fail(h, FE_ERR_INVALID, "unsupported frame geometry");
     }
@@ -207,7 +213,6 @@ DevTables dev_tables(const fe_handle* h, bool in_f32) {
     dt.tw256 = (const float4*)h->tw256.p;
     dt.tw512 = (const float4*)h->tw512.p;
     dt.window = c.window ? (const float2*)h->window.p : nullptr;
-    dt.mel_slot_off = (const int*)h->mel_slot_off.p;
     dt.mel_b0 = (const int*)h->mel_b0.p;
     dt.mel_id = (const int*)h->mel_id.p;
     dt.mel_w = (const float*)(in_f32 ? (const char*)h->mel_w.p + sizeof(float) * 8 * (size_t)h->mel_entries : (const char*)h->mel_w.p);
@@ -267,7 +272,7 @@ int fe_destroy(fe_handle* h) {
     if (!h) return FE_OK;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
-    for (DevBuf* b : {&h->tw256, &h->tw512, &h->window, &h->mel_slot_off, &h->mel_b0, &h->mel_id, &h->mel_w, &h->dct,
+    for (DevBuf* b : {&h->tw256, &h->tw512, &h->window, &h->mel_b0, &h->mel_id, &h->mel_w, &h->dct,
                       &h->d_sp_up, &h->d_sp_down, &h->d_sp_tap_off, &h->d_taps, &h->d_utts,
                       &h->d_tile_prefix, &h->d_tiles, &h->d_atile_prefix, &h->d_atiles, &h->d_statics,
                       &h->d_pcm, &h->d_out, &h->d_scratch})
@@ -314,7 +319,8 @@ int fe_configure(fe_handle* h, const fe_config* c) {
     h->mel_slots = ht.mel_slots; h->mel_entries = ht.mel_entries; h->nh = ht.nh; h->dct_stride = ht.dct_stride;
     if ((rc = upload(h, h->tw256, ht.tw256.data(), ht.tw256.size() * sizeof(float)))) return rc;
     if ((rc = upload(h, h->tw512, ht.tw512.data(), ht.tw512.size() * sizeof(float)))) return rc;
-    if ((rc = upload(h, h->mel_slot_off, ht.mel_slot_off.data(), ht.mel_slot_off.size() * sizeof(int)))) return rc;
+    if (ht.mel_slots > kMaxMelSlots) return fail(h, FE_ERR_INVALID, "too many mel slots");
+    memcpy(h->mel_n4, ht.mel_n4, sizeof(h->mel_n4)); memcpy(h->mel_e4, ht.mel_e4, sizeof(h->mel_e4));
     if ((rc = upload(h, h->mel_b0, ht.mel_b0.data(), ht.mel_b0.size() * sizeof(int)))) return rc;
     if ((rc = upload(h, h->mel_id, ht.mel_id.data(), ht.mel_id.size() * sizeof(int)))) return rc;
     if ((rc = upload(h, h->mel_w, ht.mel_w.data(), ht.mel_w.size() * sizeof(float)))) return rc;

@@ -72,10 +72,12 @@ struct SmemTables {
     const float4* tw256;      // [16][16] k1-major, cfg = swap*8 + t: (wr(jx k1), wr(jy k1), wi(jx k1), wi(jy k1)), w = exp(-2 pi i j k1 / 256)
     const float4* tw512;      // [8][16]  k2-major, cfg = Fe*8 + t: (cos kx, cos ky, sin kx, sin ky), k = r + 16 k2
     const float2* window;     // [ROWS*16] (w[2m], w[2m+1]) per complex point m, or nullptr
-    // mel plan: S slots, slot s spans entries [slot_off[s], slot_off[s+1]) (multiple of 4; weights
-    // stored as float4 groups [entry/4][lane g]);
-    // lane g of a frame owns filter mel_id[s*8+g] whose run starts at bin mel_b0[s*8+g]
-    const int*    mel_slot_off;   // [S + 1]
+    // mel plan: S slots; slot s has mel_n4[s] float4 weight groups starting at group mel_e4[s]
+    // (weights stored [group][lane g][4]); lane g of a frame owns filter mel_id[s*8+g] whose
+    // (padded) run starts at bin mel_b0[s*8+g].  mel_n4 / mel_e4 live in the constant bank on
+    // the device so the trip counts are warp-uniform by construction.
+    const int*    mel_n4;         // [S]
+    const int*    mel_e4;         // [S]
     const int*    mel_b0;         // [S * 8]
     const int*    mel_id;         // [S * 8]   (-1 = no filter)
     const float*  mel_w;          // [entries * 8], pre-scaled by pscale / 2048
@@ -318,9 +320,13 @@ FE_HD float frame_energy(float sumsq, float x0, float x256, float pscale) {
     return e == 0.f ? kEpsF64 : e;
 }
 
+// natural log of a normal positive float (inputs are >= 2.2e-16 after zero handling, so the
+// denormal pre-scaling of __logf is dead weight): lg2.approx * ln 2
 FE_HD float fe_log(float x) {
 #if defined(__CUDA_ARCH__)
-    return __logf(x);
+    float r;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r * 0.693147180559945309f;
 #else
     return logf(x);
 #endif
@@ -337,11 +343,12 @@ FE_HD float* fold_row(float* e_w, int f, int odd) { return e_w + f * kERegion + 
 FE_HD void mel_phase(float* e_w, const SmemTables& tb, int g, int fs) {
     const float* p_f = power_row(e_w, fs);
     float* row = logmel_row(e_w, fs);
+    const bool want_log = tb.is_mfcc || tb.fbank_log;
     for (int s = 0; s < tb.mel_slots; ++s) {
-        const int e0 = tb.mel_slot_off[s], n4 = (tb.mel_slot_off[s + 1] - e0) >> 2;
+        const int n4 = tb.mel_n4[s];
         const int id = tb.mel_id[s * 8 + g];
         const float* p = p_f + tb.mel_b0[s * 8 + g];
-        const float4* w = reinterpret_cast<const float4*>(tb.mel_w) + (e0 >> 2) * 8 + g;
+        const float4* w = reinterpret_cast<const float4*>(tb.mel_w) + tb.mel_e4[s] * 8 + g;
         float acc0 = 0.f, acc1 = 0.f;
         for (int q = 0; q < n4; ++q) {
             const float4 ww = w[q * 8];
@@ -352,7 +359,7 @@ FE_HD void mel_phase(float* e_w, const SmemTables& tb, int g, int fs) {
         }
         float v = acc0 + acc1;
         v = (v == 0.f) ? kEpsF64 : v;
-        if (tb.is_mfcc || tb.fbank_log) v = fe_log(v);
+        if (want_log) v = fe_log(v);
         if (id >= 0) row[id] = v;
     }
 }

@@ -37,12 +37,14 @@ struct DevTables {
     const float4* tw256;    // [16][16]
     const float4* tw512;    // [8][16]
     const float2* window;   // [ROWS*16] or nullptr
-    const int* mel_slot_off; const int* mel_b0; const int* mel_id; const float* mel_w;
+    const int* mel_b0; const int* mel_id; const float* mel_w;
     const float* dctf;      // [D][dct_stride]
     int mel_slots, mel_entries;
     int nf, D, dct_stride, nh, full_spectrum, is_mfcc, fbank_log, dc_elim;
     float pscale;
 };
+
+constexpr int kMaxMelSlots = 16;     // ceil(kMaxFilters / 8)
 
 // ---------------------------------------------------------------------------
 __global__ void k_build_tiles(const UttDesc* __restrict__ utts, const long long* __restrict__ tile_prefix,
@@ -67,7 +69,7 @@ __global__ void k_build_tiles(const UttDesc* __restrict__ utts, const long long*
 // the dynamic shared base up to 2 KB; the host adds 2 KB of slack).
 // ---------------------------------------------------------------------------
 struct K1Smem {
-    int off_e, off_raw, off_scr, off_tw256, off_tw512, off_window, off_slot, off_b0, off_id, off_melw, off_dct, off_bar;
+    int off_e, off_raw, off_scr, off_tw256, off_tw512, off_window, off_b0, off_id, off_melw, off_dct, off_bar;
     int raw_bytes;          // one raw buffer of one warp
     int total;
 };
@@ -86,7 +88,6 @@ __host__ __device__ inline K1Smem k1_smem_layout(int mel_slots, int mel_entries,
     s.off_tw256 = o;  o += 16 * 16 * 16;
     s.off_tw512 = o;  o += 8 * 16 * 16;
     s.off_window = o; o = align16(o + (has_window ? rows * 16 * 8 : 0));
-    s.off_slot = o;   o = align16(o + (mel_slots + 1) * 4);
     s.off_b0 = o;     o = align16(o + mel_slots * 8 * 4);
     s.off_id = o;     o = align16(o + mel_slots * 8 * 4);
     s.off_melw = o;   o = align16(o + mel_entries * 8 * 4);
@@ -121,36 +122,54 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         :: "r"(bar), "r"(parity) : "memory");
 }
 
+// everything K1 needs besides the data pointers; lives in the constant bank (uniform loads,
+// uniform loop bounds, nothing to rematerialise per tile)
+struct K1Params {
+    DevTables dt;
+    K1Smem L;
+    int mel_n4[kMaxMelSlots];       // float4 weight groups per mel slot
+    int mel_e4[kMaxMelSlots];       // first float4 group of each slot
+};
+
+#define FE_OPAQUE(v) asm volatile("" : "+r"(v))
+
 template <int FRAME_LEN, int HOP, int IN_F32>
 __global__ void __launch_bounds__(kCtaWarps * 32, 2)
 k_frames_to_statics(const void* __restrict__ pcm, const void* __restrict__ scratch,
                     const TileDesc* __restrict__ tiles, int n_tiles,
-                    DevTables dt, float* __restrict__ statics) {
+                    const __grid_constant__ K1Params P, float* __restrict__ statics) {
     static_assert(HOP % 8 == 0 && FRAME_LEN % 8 == 0 && FRAME_LEN <= kNfft, "bulk copies need 16-byte granules");
     extern __shared__ unsigned char smem_dyn[];
+    const DevTables& dt = P.dt;
+    const K1Smem& L = P.L;
     unsigned char* smem = smem_dyn + ((2048u - (smem_u32(smem_dyn) & 2047u)) & 2047u);
-    const K1Smem L = k1_smem_layout(dt.mel_slots, dt.mel_entries, dt.D, dt.dct_stride, dt.window != nullptr,
-                                    FRAME_LEN, HOP, dt.is_mfcc, IN_F32);
     float4* s_tw256 = reinterpret_cast<float4*>(smem + L.off_tw256);
     float4* s_tw512 = reinterpret_cast<float4*>(smem + L.off_tw512);
     float2* s_window = reinterpret_cast<float2*>(smem + L.off_window);
-    int* s_slot = reinterpret_cast<int*>(smem + L.off_slot);
     int* s_b0 = reinterpret_cast<int*>(smem + L.off_b0);
     int* s_id = reinterpret_cast<int*>(smem + L.off_id);
     float* s_melw = reinterpret_cast<float*>(smem + L.off_melw);
     float* s_dct = reinterpret_cast<float*>(smem + L.off_dct);
 
     const int tid = threadIdx.x;
-    const int warp = tid >> 5, lane = tid & 31;
     constexpr int ROWS = (FRAME_LEN + 31) / 32;
     for (int i = tid; i < 256; i += blockDim.x) s_tw256[i] = dt.tw256[i];
     for (int i = tid; i < 128; i += blockDim.x) s_tw512[i] = dt.tw512[i];
     if (dt.window) for (int i = tid; i < ROWS * 16; i += blockDim.x) s_window[i] = dt.window[i];
-    for (int i = tid; i <= dt.mel_slots; i += blockDim.x) s_slot[i] = dt.mel_slot_off[i];
     for (int i = tid; i < dt.mel_slots * 8; i += blockDim.x) { s_b0[i] = dt.mel_b0[i]; s_id[i] = dt.mel_id[i]; }
     for (int i = tid; i < dt.mel_entries * 8; i += blockDim.x) s_melw[i] = dt.mel_w[i];
     if (dt.is_mfcc) for (int i = tid; i < dt.D * dt.dct_stride; i += blockDim.x) s_dct[i] = dt.dctf[i];
 
+    // per-thread constants, pinned in registers (FE_OPAQUE stops the compiler from
+    // re-deriving them from threadIdx inside the tile loop)
+    int lane = tid & 31, warp = tid >> 5;
+    FE_OPAQUE(lane); FE_OPAQUE(warp);
+    const int fs = lane >> 3, t = lane & 7;
+    constexpr int ESZ = IN_F32 ? 4 : 2;
+    uint32_t o_e = (uint32_t)(smem - smem_dyn) + L.off_e + warp * (kWarpFrames * kERegion * 4);   // warp's exchange buffer
+    uint32_t o_raw = (uint32_t)(smem - smem_dyn) + L.off_raw + warp * 2 * L.raw_bytes;
+    uint32_t o_scr = (uint32_t)(smem - smem_dyn) + L.off_scr + warp * 256;
+    FE_OPAQUE(o_e); FE_OPAQUE(o_raw); FE_OPAQUE(o_scr);
     const uint32_t bar0 = smem_u32(smem + L.off_bar + warp * 16);     // two mbarriers per warp
     if (lane == 0) { mbar_init(bar0, 1); mbar_init(bar0 + 8, 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -158,17 +177,11 @@ k_frames_to_statics(const void* __restrict__ pcm, const void* __restrict__ scrat
 
     SmemTables tb;
     tb.tw256 = s_tw256; tb.tw512 = s_tw512; tb.window = dt.window ? s_window : nullptr;
-    tb.mel_slot_off = s_slot; tb.mel_b0 = s_b0; tb.mel_id = s_id; tb.mel_w = s_melw; tb.dctf = s_dct;
+    tb.mel_n4 = P.mel_n4; tb.mel_e4 = P.mel_e4; tb.mel_b0 = s_b0; tb.mel_id = s_id; tb.mel_w = s_melw; tb.dctf = s_dct;
     tb.mel_slots = dt.mel_slots; tb.nf = dt.nf; tb.D = dt.D; tb.dct_stride = dt.dct_stride; tb.nh = dt.nh;
     tb.full_spectrum = dt.full_spectrum; tb.is_mfcc = dt.is_mfcc; tb.fbank_log = dt.fbank_log;
     tb.dc_elim = dt.dc_elim; tb.pscale = dt.pscale;
-
-    const int fs = lane >> 3, t = lane & 7;
-    float* e_w = reinterpret_cast<float*>(smem + L.off_e) + warp * kWarpFrames * kERegion;
-    unsigned char* raw_w = smem + L.off_raw + warp * 2 * L.raw_bytes;
-    float* scr_w = reinterpret_cast<float*>(smem + L.off_scr) + warp * 64;   // [0..31] sum-of-squares, [32..35] energies
     const int D = dt.D;
-    constexpr int ESZ = IN_F32 ? 4 : 2;
 
     // issue the bulk copy of this warp's slice of tile `td` into raw buffer `buf`
     auto prefetch = [&](const TileDesc& td, int buf) {
@@ -178,7 +191,7 @@ k_frames_to_statics(const void* __restrict__ pcm, const void* __restrict__ scrat
             const unsigned char* src = base + (td.pcm_off + (long long)warp * kWarpFrames * HOP) * ESZ;
             const uint32_t bytes = (uint32_t)(((nfw - 1) * HOP + FRAME_LEN) * ESZ);
             mbar_expect_tx(bar0 + 8 * buf, bytes);
-            bulk_g2s(smem_u32(raw_w + buf * L.raw_bytes), src, bytes, bar0 + 8 * buf);
+            bulk_g2s(smem_u32(smem_dyn + o_raw + buf * L.raw_bytes), src, bytes, bar0 + 8 * buf);
         }
     };
 
@@ -204,8 +217,10 @@ k_frames_to_statics(const void* __restrict__ pcm, const void* __restrict__ scrat
         if (tile + stride < n_tiles) prefetch(next, buf ^ 1);
         if (nfw > 0) {
             const bool active = fs < nfw;
+            float* e_w = reinterpret_cast<float*>(smem_dyn + o_e);
+            float* scr_w = reinterpret_cast<float*>(smem_dyn + o_scr);       // [0..31] sum-of-squares, [32..35] energies
             float* e_f = e_w + fs * kERegion;
-            const unsigned char* raw_f = raw_w + buf * L.raw_bytes + fs * HOP * ESZ;
+            const unsigned char* raw_f = smem_dyn + o_raw + buf * L.raw_bytes + fs * HOP * ESZ;
 
             // ---- phase 1: stage A ----
             if (active) scr_w[lane] = stage_a<FRAME_LEN, IN_F32>(raw_f, e_f, tb, t, fs);

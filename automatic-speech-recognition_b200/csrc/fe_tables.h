@@ -17,6 +17,7 @@ struct HostTables {
     std::vector<float> mel_w;       // [2][entries*8]: int16-count scale, then float scale
     std::vector<float> dctf;        // [D][dct_stride]
     int mel_slots = 0, mel_entries = 0, nh = 0, dct_stride = 0;
+    int mel_n4[16] = {0}, mel_e4[16] = {0};
 };
 
 inline void build_host_tables(const fe_config& c, HostTables& t) {
@@ -78,6 +79,7 @@ inline void build_host_tables(const fe_config& c, HostTables& t) {
         }
     }
     t.mel_slots = S; t.mel_entries = entries;
+    for (int s = 0; s < S && s < 16; ++s) { t.mel_e4[s] = t.mel_slot_off[s] >> 2; t.mel_n4[s] = (t.mel_slot_off[s + 1] - t.mel_slot_off[s]) >> 2; }
     // folded DCT: y_c = sum_{n < nh} C[c][n] * (x[n] + (-1)^c x[nf-1-n])
     t.nh = (nf + 1) / 2;
     t.dct_stride = 0;

@@ -17,7 +17,7 @@ void fill_tables(const fe_config& c, const HostTables& ht, bool in_f32, SmemTabl
     tb.tw256 = reinterpret_cast<const float4*>(ht.tw256.data());
     tb.tw512 = reinterpret_cast<const float4*>(ht.tw512.data());
     tb.window = c.window ? reinterpret_cast<const float2*>(ht.window.data()) : nullptr;
-    tb.mel_slot_off = ht.mel_slot_off.data(); tb.mel_b0 = ht.mel_b0.data(); tb.mel_id = ht.mel_id.data();
+    tb.mel_n4 = ht.mel_n4; tb.mel_e4 = ht.mel_e4; tb.mel_b0 = ht.mel_b0.data(); tb.mel_id = ht.mel_id.data();
     tb.mel_w = ht.mel_w.data() + (in_f32 ? (size_t)ht.mel_entries * 8 : 0);
     tb.dctf = ht.dctf.data();
     tb.mel_slots = ht.mel_slots; tb.nf = c.num_filters; tb.D = c.feat_dim; tb.dct_stride = ht.dct_stride; tb.nh = ht.nh;
