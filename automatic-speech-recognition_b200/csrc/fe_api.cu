@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <string.h>
+#include <stdlib.h>
 #include <string>
 #include <vector>
 #include <algorithm>
@@ -38,7 +39,7 @@ struct fe_handle {
     std::string err;
 
     // device tables
-    DevBuf tw256, tw512, window, mel_b0, mel_id, mel_w, dct;
+    DevBuf tw256, tw512, window, mel_bi, mel_w, dct;
     int mel_n4[16] = {0}, mel_e4[16] = {0};
     int dct_stride = 0, full_spectrum = 0, mel_slots = 0, mel_entries = 0, nh = 0;
     bool scratch_f32 = false;     // pre-emphasis materialises float PCM in the scratch buffer
@@ -57,6 +58,7 @@ struct fe_handle {
     bool ev_valid = false, ev_k0 = false, ev_k2 = false;
     int64_t launches = 0;
     size_t k1_smem[2] = {0, 0};      // [raw int16 input, float input]
+    int k1_warps = 8;                // warps per K1 CTA (8 -> 128 regs/thread, 6 -> 168); FE_K1_WARPS overrides
 };
 
 namespace {
@@ -167,7 +169,7 @@ int make_plan(fe_handle* h, const int64_t* pcm_offsets, const int64_t* pcm_lengt
             pl.total_atiles += (n_eff + kK0Outputs - 1) / kK0Outputs;
         }
         pl.total_frames += L;
-        pl.total_tiles += (L + kCtaFrames - 1) / kCtaFrames;
+        pl.total_tiles += (L + h->k1_warps * kWarpFrames - 1) / (h->k1_warps * kWarpFrames);
         out_off += round_up(L * width, 4);
     }
     if (out_offsets) out_offsets[n] = out_off;
@@ -191,14 +193,23 @@ int launch_k1(fe_handle* h, cudaStream_t st, const void* pcm, const void* scratc
         K1Params P;
         P.dt = dt;
         P.L = k1_smem_layout(h->mel_slots, h->mel_entries, c.feat_dim, h->dct_stride, c.window != nullptr,
-                             c.frame_len, c.hop, c.feat_type == FE_FEAT_MFCC, in_f32);
+                             c.frame_len, c.hop, c.feat_type == FE_FEAT_MFCC, in_f32, h->k1_warps);
         memcpy(P.mel_n4, h->mel_n4, sizeof(P.mel_n4)); memcpy(P.mel_e4, h->mel_e4, sizeof(P.mel_e4));
-        if (!in_f32)
-            k_frames_to_statics<400, 160, 0><<<grid, kCtaWarps * 32, h->k1_smem[0], st>>>(
-                pcm, scratch, tiles, n_tiles, P, statics);
-        else
-            k_frames_to_statics<400, 160, 1><<<grid, kCtaWarps * 32, h->k1_smem[1], st>>>(
-                pcm, scratch, tiles, n_tiles, P, statics);
+        const bool win = c.window != nullptr;
+#define FE_LAUNCH_K1(F32, WIN)                                                                             \
+        do {                                                                                               \
+            if (h->k1_warps == 8)                                                                          \
+                k_frames_to_statics<400, 160, F32, WIN, 8><<<grid, 256, h->k1_smem[F32], st>>>(            \
+                    pcm, scratch, tiles, n_tiles, P, statics);                                             \
+            else                                                                                           \
+                k_frames_to_statics<400, 160, F32, WIN, 6><<<grid, 192, h->k1_smem[F32], st>>>(            \
+                    pcm, scratch, tiles, n_tiles, P, statics);                                             \
+        } while (0)
+        if (!in_f32 && !win) FE_LAUNCH_K1(0, 0);
+        else if (!in_f32) FE_LAUNCH_K1(0, 1);
+        else if (!win) FE_LAUNCH_K1(1, 0);
+        else FE_LAUNCH_K1(1, 1);
+#undef FE_LAUNCH_K1
     } else {
         return fail(h, FE_ERR_INVALID, "unsupported frame geometry");
     }
@@ -213,8 +224,7 @@ DevTables dev_tables(const fe_handle* h, bool in_f32) {
     dt.tw256 = (const float4*)h->tw256.p;
     dt.tw512 = (const float4*)h->tw512.p;
     dt.window = c.window ? (const float2*)h->window.p : nullptr;
-    dt.mel_b0 = (const int*)h->mel_b0.p;
-    dt.mel_id = (const int*)h->mel_id.p;
+    dt.mel_bi = (const int*)h->mel_bi.p;
     dt.mel_w = (const float*)(in_f32 ? (const char*)h->mel_w.p + sizeof(float) * 8 * (size_t)h->mel_entries : (const char*)h->mel_w.p);
     dt.dctf = (const float*)h->dct.p;
     dt.mel_slots = h->mel_slots; dt.mel_entries = h->mel_entries;
@@ -272,7 +282,7 @@ int fe_destroy(fe_handle* h) {
     if (!h) return FE_OK;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
-    for (DevBuf* b : {&h->tw256, &h->tw512, &h->window, &h->mel_b0, &h->mel_id, &h->mel_w, &h->dct,
+    for (DevBuf* b : {&h->tw256, &h->tw512, &h->window, &h->mel_bi, &h->mel_w, &h->dct,
                       &h->d_sp_up, &h->d_sp_down, &h->d_sp_tap_off, &h->d_taps, &h->d_utts,
                       &h->d_tile_prefix, &h->d_tiles, &h->d_atile_prefix, &h->d_atiles, &h->d_statics,
                       &h->d_pcm, &h->d_out, &h->d_scratch})
@@ -321,8 +331,7 @@ int fe_configure(fe_handle* h, const fe_config* c) {
     if ((rc = upload(h, h->tw512, ht.tw512.data(), ht.tw512.size() * sizeof(float)))) return rc;
     if (ht.mel_slots > kMaxMelSlots) return fail(h, FE_ERR_INVALID, "too many mel slots");
     memcpy(h->mel_n4, ht.mel_n4, sizeof(h->mel_n4)); memcpy(h->mel_e4, ht.mel_e4, sizeof(h->mel_e4));
-    if ((rc = upload(h, h->mel_b0, ht.mel_b0.data(), ht.mel_b0.size() * sizeof(int)))) return rc;
-    if ((rc = upload(h, h->mel_id, ht.mel_id.data(), ht.mel_id.size() * sizeof(int)))) return rc;
+    if ((rc = upload(h, h->mel_bi, ht.mel_bi.data(), ht.mel_bi.size() * sizeof(int)))) return rc;
     if ((rc = upload(h, h->mel_w, ht.mel_w.data(), ht.mel_w.size() * sizeof(float)))) return rc;
     if (c->feat_type == FE_FEAT_MFCC && (rc = upload(h, h->dct, ht.dctf.data(), ht.dctf.size() * sizeof(float)))) return rc;
     if (c->window && (rc = upload(h, h->window, ht.window.data(), ht.window.size() * sizeof(float)))) return rc;
@@ -343,14 +352,21 @@ int fe_configure(fe_handle* h, const fe_config* c) {
     }
 
     h->cfg = *c;       // pointer members are only used as "present" flags from here on
+    if (const char* e = getenv("FE_K1_WARPS")) h->k1_warps = atoi(e) == 6 ? 6 : 8;
     for (int f32 = 0; f32 < 2; ++f32) {
         K1Smem L = k1_smem_layout(h->mel_slots, h->mel_entries, c->feat_dim, h->dct_stride, c->window != nullptr,
-                                  c->frame_len, c->hop, c->feat_type == FE_FEAT_MFCC, f32);
+                                  c->frame_len, c->hop, c->feat_type == FE_FEAT_MFCC, f32, h->k1_warps);
         h->k1_smem[f32] = L.total;
         if (L.total > 227 * 1024) return fail(h, FE_ERR_INVALID, "configuration needs too much shared memory");
     }
-    if ((rc = set_smem(h, k_frames_to_statics<400, 160, 0>, h->k1_smem[0]))) return rc;
-    if ((rc = set_smem(h, k_frames_to_statics<400, 160, 1>, h->k1_smem[1]))) return rc;
+    if ((rc = set_smem(h, k_frames_to_statics<400, 160, 0, 0, 6>, h->k1_smem[0]))) return rc;
+    if ((rc = set_smem(h, k_frames_to_statics<400, 160, 0, 1, 6>, h->k1_smem[0]))) return rc;
+    if ((rc = set_smem(h, k_frames_to_statics<400, 160, 1, 0, 6>, h->k1_smem[1]))) return rc;
+    if ((rc = set_smem(h, k_frames_to_statics<400, 160, 1, 1, 6>, h->k1_smem[1]))) return rc;
+    if ((rc = set_smem(h, k_frames_to_statics<400, 160, 0, 0, 8>, h->k1_smem[0]))) return rc;
+    if ((rc = set_smem(h, k_frames_to_statics<400, 160, 0, 1, 8>, h->k1_smem[0]))) return rc;
+    if ((rc = set_smem(h, k_frames_to_statics<400, 160, 1, 0, 8>, h->k1_smem[1]))) return rc;
+    if ((rc = set_smem(h, k_frames_to_statics<400, 160, 1, 1, 8>, h->k1_smem[1]))) return rc;
     if ((rc = set_smem(h, k_cmvn_delta_pack, k2_smem_floats(c->feat_dim) * sizeof(float)))) return rc;
     h->configured = true;
     return FE_OK;
@@ -423,7 +439,7 @@ int fe_run(fe_handle* h, const void* pcm, const int64_t* pcm_offsets, const int6
     const int tb = 256, gb = (n_utts + tb - 1) / tb;
     if (pl.total_tiles > 0) {
         k_build_tiles<<<gb, tb, 0, st>>>((const UttDesc*)h->d_utts.p, (const long long*)h->d_tile_prefix.p, n_utts,
-                                         c.hop, c.feat_dim, (TileDesc*)h->d_tiles.p);
+                                         c.hop, c.feat_dim, h->k1_warps * kWarpFrames, (TileDesc*)h->d_tiles.p);
         h->launches++;
     }
     h->ev_k0 = false;

@@ -37,8 +37,6 @@ namespace fe {
 constexpr int kNfft = 512;
 constexpr int kBins = 257;
 constexpr int kWarpFrames = 4;          // frames per warp pass
-constexpr int kCtaWarps = 6;
-constexpr int kCtaFrames = kWarpFrames * kCtaWarps;   // frames per tile-table entry
 constexpr int kERegion = 512;           // floats of exchange buffer per frame (2 KB, 2 KB aligned)
 constexpr int kPStagger = 8;            // per-frame-slot float offset of the power row
 constexpr int kLogmelOff = 288;         // log-mel row inside the frame's region (after the power row)
@@ -72,14 +70,13 @@ struct SmemTables {
     const float4* tw256;      // [16][16] k1-major, cfg = swap*8 + t: (wr(jx k1), wr(jy k1), wi(jx k1), wi(jy k1)), w = exp(-2 pi i j k1 / 256)
     const float4* tw512;      // [8][16]  k2-major, cfg = Fe*8 + t: (cos kx, cos ky, sin kx, sin ky), k = r + 16 k2
     const float2* window;     // [ROWS*16] (w[2m], w[2m+1]) per complex point m, or nullptr
-    // mel plan: S slots; slot s has mel_n4[s] float4 weight groups starting at group mel_e4[s]
-    // (weights stored [group][lane g][4]); lane g of a frame owns filter mel_id[s*8+g] whose
-    // (padded) run starts at bin mel_b0[s*8+g].  mel_n4 / mel_e4 live in the constant bank on
-    // the device so the trip counts are warp-uniform by construction.
+    // mel plan: S slots; slot s has mel_n4[s] float4 weight groups (weights stored
+    // [group][lane g][4], groups of all slots back to back); lane g of a frame owns filter
+    // id = mel_bi[s*8+g] >> 16 (0xffff = none) whose (padded) run starts at bin
+    // mel_bi[s*8+g] & 0xffff.  mel_n4 lives in the constant bank on the device so the trip
+    // counts are warp-uniform by construction.
     const int*    mel_n4;         // [S]
-    const int*    mel_e4;         // [S]
-    const int*    mel_b0;         // [S * 8]
-    const int*    mel_id;         // [S * 8]   (-1 = no filter)
+    const int*    mel_bi;         // [S * 8]
     const float*  mel_w;          // [entries * 8], pre-scaled by pscale / 2048
     const float*  dctf;           // [D][dct_stride] folded DCT rows (n < ceil(nf/2)), zero padded
     int mel_slots;
@@ -181,7 +178,7 @@ inline EPtr e_make(float* region, int lane_bits) { EPtr p; p.base = region; p.l 
 //           (the swap makes the two 4-byte loads of a row bank-conflict free)
 //   returns the lane's partial sum of squares (Parseval frame energy, sample units)
 // ---------------------------------------------------------------------------
-template <int FRAME_LEN, int IN_F32>
+template <int FRAME_LEN, int IN_F32, int HAS_WINDOW>
 FE_HD float stage_a(const void* raw_f, float* e_f, const SmemTables& tb, int t, int fs) {
     float2 re[16], im[16];
     float2 ss = make_float2(0.f, 0.f);
@@ -202,7 +199,7 @@ FE_HD float stage_a(const void* raw_f, float* e_f, const SmemTables& tb, int t, 
                 vr = make_float2((float)(short)(u & 0xffffu), (float)(short)(v & 0xffffu));
                 vi = make_float2((float)((int)u >> 16), (float)((int)v >> 16));
             }
-            if (tb.window) {
+            if (HAS_WINDOW) {
                 float2 w0 = tb.window[16 * a + jx], w1 = tb.window[16 * a + jy];
                 vr = pmul(vr, make_float2(w0.x, w1.x)); vi = pmul(vi, make_float2(w0.y, w1.y));
             }
@@ -344,11 +341,12 @@ FE_HD void mel_phase(float* e_w, const SmemTables& tb, int g, int fs) {
     const float* p_f = power_row(e_w, fs);
     float* row = logmel_row(e_w, fs);
     const bool want_log = tb.is_mfcc || tb.fbank_log;
+    const float4* w = reinterpret_cast<const float4*>(tb.mel_w) + g;
+    const int* bi = tb.mel_bi + g;
     for (int s = 0; s < tb.mel_slots; ++s) {
         const int n4 = tb.mel_n4[s];
-        const int id = tb.mel_id[s * 8 + g];
-        const float* p = p_f + tb.mel_b0[s * 8 + g];
-        const float4* w = reinterpret_cast<const float4*>(tb.mel_w) + tb.mel_e4[s] * 8 + g;
+        const int d = bi[s * 8];
+        const float* p = p_f + (d & 0xffff);
         float acc0 = 0.f, acc1 = 0.f;
         for (int q = 0; q < n4; ++q) {
             const float4 ww = w[q * 8];
@@ -357,10 +355,12 @@ FE_HD void mel_phase(float* e_w, const SmemTables& tb, int g, int fs) {
             acc0 = fmaf(ww.z, p[4 * q + 2], acc0);
             acc1 = fmaf(ww.w, p[4 * q + 3], acc1);
         }
+        w += n4 * 8;
         float v = acc0 + acc1;
         v = (v == 0.f) ? kEpsF64 : v;
         if (want_log) v = fe_log(v);
-        if (id >= 0) row[id] = v;
+        const int id = d >> 16;
+        if (id != 0xffff) row[id] = v;
     }
 }
 
@@ -383,7 +383,7 @@ FE_HD void fold_phase(float* e_w, const SmemTables& tb, int g, int fs) {
 }
 
 // Phase 5 (mfcc): lane g computes coefficients c = g, g+8, ... (same parity as g -> one input array)
-FE_HD void dct_phase(float* e_w, const float* energies, const SmemTables& tb, int g, int fs, float* dst) {
+FE_HD void dct_phase(float* e_w, const float* energies, const SmemTables& tb, int g, int fs, float* dst, bool store) {
     const float* in = fold_row(e_w, fs, g & 1);
     const int n4 = (tb.nh + 3) >> 2;
     for (int c0 = g; c0 < tb.D; c0 += 16) {
@@ -400,8 +400,37 @@ FE_HD void dct_phase(float* e_w, const float* energies, const SmemTables& tb, in
             a1 = fmaf(v.x, x.x, a1); a1 = fmaf(v.y, x.y, a1); a1 = fmaf(v.z, x.z, a1); a1 = fmaf(v.w, x.w, a1);
         }
         if (c0 == 0 && tb.dc_elim) a0 = fe_log(energies[fs]);
-        dst[c0] = a0;
-        if (has1) dst[c1] = a1;
+        if (store) dst[c0] = a0;
+        if (store && has1) dst[c1] = a1;
+    }
+}
+
+// Phase 5 variant for nf % 8 == 0 (the reference's 40 filters): the fold
+// x[n] +- x[nf-1-n] is done on the fly from the log-mel row (16-byte loads from both ends),
+// so no separate fold phase and no extra synchronisation.
+FE_HD void dct_phase_fused(float* e_w, const float* energies, const SmemTables& tb, int g, int fs, float* dst, bool store) {
+    const float* row = logmel_row(e_w, fs);
+    const float sgn = (g & 1) ? -1.f : 1.f;          // parity of every coefficient this lane owns
+    const int n4 = tb.nh >> 2;
+    for (int c0 = g; c0 < tb.D; c0 += 16) {
+        const int c1 = c0 + 8;
+        const bool has1 = c1 < tb.D;
+        const float* d0 = tb.dctf + c0 * tb.dct_stride;
+        const float* d1 = tb.dctf + (has1 ? c1 : c0) * tb.dct_stride;
+        float a0 = 0.f, a1 = 0.f;
+        for (int q = 0; q < n4; ++q) {
+            float4 lo = *reinterpret_cast<const float4*>(row + 4 * q);
+            float4 hi = *reinterpret_cast<const float4*>(row + tb.nf - 4 - 4 * q);
+            float4 u = *reinterpret_cast<const float4*>(d0 + 4 * q);
+            float4 v = *reinterpret_cast<const float4*>(d1 + 4 * q);
+            const float x0 = fmaf(sgn, hi.w, lo.x), x1 = fmaf(sgn, hi.z, lo.y);
+            const float x2 = fmaf(sgn, hi.y, lo.z), x3 = fmaf(sgn, hi.x, lo.w);
+            a0 = fmaf(u.x, x0, a0); a0 = fmaf(u.y, x1, a0); a0 = fmaf(u.z, x2, a0); a0 = fmaf(u.w, x3, a0);
+            a1 = fmaf(v.x, x0, a1); a1 = fmaf(v.y, x1, a1); a1 = fmaf(v.z, x2, a1); a1 = fmaf(v.w, x3, a1);
+        }
+        if (c0 == 0 && tb.dc_elim) a0 = fe_log(energies[fs]);
+        if (store) dst[c0] = a0;
+        if (store && has1) dst[c1] = a1;
     }
 }
 

@@ -23,11 +23,11 @@ struct UttDesc {
     float gain;             // 1 = none
 };
 
-// one entry per kCtaFrames frames of one utterance (32 bytes, two 16-byte loads)
+// one entry per tile (warps-per-CTA x 4 frames) of one utterance (32 bytes, two 16-byte loads)
 struct __align__(16) TileDesc {
     long long pcm_off;      // element offset of the tile's first sample
     long long stat_off;     // float offset of the tile's first statics row
-    int n_frames;           // 1..kCtaFrames
+    int n_frames;           // 1..tile_frames
     int src_sel;
     int utt;
     int pad;
@@ -37,7 +37,7 @@ struct DevTables {
     const float4* tw256;    // [16][16]
     const float4* tw512;    // [8][16]
     const float2* window;   // [ROWS*16] or nullptr
-    const int* mel_b0; const int* mel_id; const float* mel_w;
+    const int* mel_bi; const float* mel_w;
     const float* dctf;      // [D][dct_stride]
     int mel_slots, mel_entries;
     int nf, D, dct_stride, nh, full_spectrum, is_mfcc, fbank_log, dc_elim;
@@ -48,16 +48,16 @@ constexpr int kMaxMelSlots = 16;     // ceil(kMaxFilters / 8)
 
 // ---------------------------------------------------------------------------
 __global__ void k_build_tiles(const UttDesc* __restrict__ utts, const long long* __restrict__ tile_prefix,
-                              int n_utts, int hop, int D, TileDesc* __restrict__ tiles) {
+                              int n_utts, int hop, int D, int tile_frames, TileDesc* __restrict__ tiles) {
     int u = blockIdx.x * blockDim.x + threadIdx.x;
     if (u >= n_utts) return;
     const UttDesc d = utts[u];
     long long b = tile_prefix[u];
-    for (int f = 0; f < d.n_frames; f += kCtaFrames) {
+    for (int f = 0; f < d.n_frames; f += tile_frames) {
         TileDesc t;
         t.pcm_off = d.pcm_off + (long long)f * hop;
         t.stat_off = d.stat_off + (long long)f * D;
-        t.n_frames = min(kCtaFrames, d.n_frames - f);
+        t.n_frames = min(tile_frames, d.n_frames - f);
         t.src_sel = d.src_sel; t.utt = u; t.pad = 0;
         tiles[b++] = t;
     }
@@ -69,7 +69,7 @@ __global__ void k_build_tiles(const UttDesc* __restrict__ utts, const long long*
 // the dynamic shared base up to 2 KB; the host adds 2 KB of slack).
 // ---------------------------------------------------------------------------
 struct K1Smem {
-    int off_e, off_raw, off_scr, off_tw256, off_tw512, off_window, off_b0, off_id, off_melw, off_dct, off_bar;
+    int off_e, off_raw, off_scr, off_tw256, off_tw512, off_window, off_bi, off_melw, off_dct, off_bar;
     int raw_bytes;          // one raw buffer of one warp
     int total;
 };
@@ -77,22 +77,21 @@ struct K1Smem {
 __host__ __device__ inline int align16(int x) { return (x + 15) & ~15; }
 
 __host__ __device__ inline K1Smem k1_smem_layout(int mel_slots, int mel_entries, int D, int dct_stride, int has_window,
-                                                 int frame_len, int hop, int is_mfcc, int in_f32) {
+                                                 int frame_len, int hop, int is_mfcc, int in_f32, int warps) {
     K1Smem s;
     const int rows = (frame_len + 31) / 32;
     int o = 0;
-    s.off_e = o;      o += kCtaWarps * kWarpFrames * kERegion * 4;
+    s.off_e = o;      o += warps * kWarpFrames * kERegion * 4;
     s.raw_bytes = align16(((kWarpFrames - 1) * hop + rows * 32) * (in_f32 ? 4 : 2));
-    s.off_raw = o;    o += kCtaWarps * 2 * s.raw_bytes;
-    s.off_scr = o;    o += kCtaWarps * 64 * 4;
+    s.off_raw = o;    o += warps * 2 * s.raw_bytes;
+    s.off_scr = o;    o += warps * 64 * 4;
     s.off_tw256 = o;  o += 16 * 16 * 16;
     s.off_tw512 = o;  o += 8 * 16 * 16;
     s.off_window = o; o = align16(o + (has_window ? rows * 16 * 8 : 0));
-    s.off_b0 = o;     o = align16(o + mel_slots * 8 * 4);
-    s.off_id = o;     o = align16(o + mel_slots * 8 * 4);
+    s.off_bi = o;     o = align16(o + mel_slots * 8 * 4);
     s.off_melw = o;   o = align16(o + mel_entries * 8 * 4);
     s.off_dct = o;    o = align16(o + (is_mfcc ? D * dct_stride * 4 : 0));
-    s.off_bar = o;    o += kCtaWarps * 2 * 8;
+    s.off_bar = o;    o += warps * 2 * 8;
     s.total = o + 2048;     // slack for the 2 KB round-up
     return s;
 }
@@ -133,8 +132,8 @@ struct K1Params {
 
 #define FE_OPAQUE(v) asm volatile("" : "+r"(v))
 
-template <int FRAME_LEN, int HOP, int IN_F32>
-__global__ void __launch_bounds__(kCtaWarps * 32, 2)
+template <int FRAME_LEN, int HOP, int IN_F32, int HAS_WINDOW, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 2)
 k_frames_to_statics(const void* __restrict__ pcm, const void* __restrict__ scratch,
                     const TileDesc* __restrict__ tiles, int n_tiles,
                     const __grid_constant__ K1Params P, float* __restrict__ statics) {
@@ -146,8 +145,7 @@ k_frames_to_statics(const void* __restrict__ pcm, const void* __restrict__ scrat
     float4* s_tw256 = reinterpret_cast<float4*>(smem + L.off_tw256);
     float4* s_tw512 = reinterpret_cast<float4*>(smem + L.off_tw512);
     float2* s_window = reinterpret_cast<float2*>(smem + L.off_window);
-    int* s_b0 = reinterpret_cast<int*>(smem + L.off_b0);
-    int* s_id = reinterpret_cast<int*>(smem + L.off_id);
+    int* s_bi = reinterpret_cast<int*>(smem + L.off_bi);
     float* s_melw = reinterpret_cast<float*>(smem + L.off_melw);
     float* s_dct = reinterpret_cast<float*>(smem + L.off_dct);
 
@@ -156,7 +154,7 @@ k_frames_to_statics(const void* __restrict__ pcm, const void* __restrict__ scrat
     for (int i = tid; i < 256; i += blockDim.x) s_tw256[i] = dt.tw256[i];
     for (int i = tid; i < 128; i += blockDim.x) s_tw512[i] = dt.tw512[i];
     if (dt.window) for (int i = tid; i < ROWS * 16; i += blockDim.x) s_window[i] = dt.window[i];
-    for (int i = tid; i < dt.mel_slots * 8; i += blockDim.x) { s_b0[i] = dt.mel_b0[i]; s_id[i] = dt.mel_id[i]; }
+    for (int i = tid; i < dt.mel_slots * 8; i += blockDim.x) s_bi[i] = dt.mel_bi[i];
     for (int i = tid; i < dt.mel_entries * 8; i += blockDim.x) s_melw[i] = dt.mel_w[i];
     if (dt.is_mfcc) for (int i = tid; i < dt.D * dt.dct_stride; i += blockDim.x) s_dct[i] = dt.dctf[i];
 
@@ -177,7 +175,7 @@ k_frames_to_statics(const void* __restrict__ pcm, const void* __restrict__ scrat
 
     SmemTables tb;
     tb.tw256 = s_tw256; tb.tw512 = s_tw512; tb.window = dt.window ? s_window : nullptr;
-    tb.mel_n4 = P.mel_n4; tb.mel_e4 = P.mel_e4; tb.mel_b0 = s_b0; tb.mel_id = s_id; tb.mel_w = s_melw; tb.dctf = s_dct;
+    tb.mel_n4 = P.mel_n4; tb.mel_bi = s_bi; tb.mel_w = s_melw; tb.dctf = s_dct;
     tb.mel_slots = dt.mel_slots; tb.nf = dt.nf; tb.D = dt.D; tb.dct_stride = dt.dct_stride; tb.nh = dt.nh;
     tb.full_spectrum = dt.full_spectrum; tb.is_mfcc = dt.is_mfcc; tb.fbank_log = dt.fbank_log;
     tb.dc_elim = dt.dc_elim; tb.pscale = dt.pscale;
@@ -222,15 +220,18 @@ k_frames_to_statics(const void* __restrict__ pcm, const void* __restrict__ scrat
             float* e_f = e_w + fs * kERegion;
             const unsigned char* raw_f = smem_dyn + o_raw + buf * L.raw_bytes + fs * HOP * ESZ;
 
+            // Lanes of frame slots beyond nfw (last, partial tile of an utterance) run the same
+            // code on stale shared memory and only their global stores are masked: no divergence,
+            // no reconvergence bookkeeping inside the phases.
             // ---- phase 1: stage A ----
-            if (active) scr_w[lane] = stage_a<FRAME_LEN, IN_F32>(raw_f, e_f, tb, t, fs);
+            scr_w[lane] = stage_a<FRAME_LEN, IN_F32, HAS_WINDOW>(raw_f, e_f, tb, t, fs);
             __syncwarp();
             // ---- phase 2: stage B ----
             LaneZ z;
-            if (active) stage_b(e_f, z, t, fs);
+            stage_b(e_f, z, t, fs);
             __syncwarp();
             // ---- phase 3: post-pass, power row, frame energy ----
-            if (active) {
+            {
                 float x0, x256;
                 post_pass(z, power_row(e_w, fs), tb, t, fs, x0, x256);
                 if (t == 0) {
@@ -242,13 +243,17 @@ k_frames_to_statics(const void* __restrict__ pcm, const void* __restrict__ scrat
             }
             __syncwarp();
             // ---- phase 4: mel filterbank (+ log) ----
-            if (active) mel_phase(e_w, tb, t, fs);
+            mel_phase(e_w, tb, t, fs);
             __syncwarp();
             float* dst = statics + cur.stat_off + (long long)(warp * kWarpFrames) * D;
             if (tb.is_mfcc) {
-                if (active) fold_phase(e_w, tb, t, fs);
-                __syncwarp();
-                if (active) dct_phase(e_w, scr_w + 32, tb, t, fs, dst + fs * D);
+                if ((tb.nf & 7) == 0) {
+                    dct_phase_fused(e_w, scr_w + 32, tb, t, fs, dst + fs * D, active);
+                } else {
+                    fold_phase(e_w, tb, t, fs);
+                    __syncwarp();
+                    dct_phase(e_w, scr_w + 32, tb, t, fs, dst + fs * D, active);
+                }
             } else {
                 for (int f = 0; f < nfw; ++f) {
                     const float* row = logmel_row(e_w, f);

@@ -13,7 +13,7 @@ struct HostTables {
     std::vector<float> tw256;       // [16][16][4]  k1-major, cfg = swap*8 + t
     std::vector<float> tw512;       // [8][16][4]   k2-major, cfg = flip*8 + t
     std::vector<float> window;      // [rows*32]    (w[2m], w[2m+1]) per complex point
-    std::vector<int> mel_slot_off, mel_b0, mel_id;
+    std::vector<int> mel_slot_off, mel_b0, mel_id, mel_bi;    // mel_bi = id << 16 | first bin
     std::vector<float> mel_w;       // [2][entries*8]: int16-count scale, then float scale
     std::vector<float> dctf;        // [D][dct_stride]
     int mel_slots = 0, mel_entries = 0, nh = 0, dct_stride = 0;
@@ -80,6 +80,8 @@ inline void build_host_tables(const fe_config& c, HostTables& t) {
     }
     t.mel_slots = S; t.mel_entries = entries;
     for (int s = 0; s < S && s < 16; ++s) { t.mel_e4[s] = t.mel_slot_off[s] >> 2; t.mel_n4[s] = (t.mel_slot_off[s + 1] - t.mel_slot_off[s]) >> 2; }
+    t.mel_bi.assign(S * 8, 0);
+    for (int i = 0; i < S * 8; ++i) t.mel_bi[i] = ((t.mel_id[i] < 0 ? 0xffff : t.mel_id[i]) << 16) | t.mel_b0[i];
     // folded DCT: y_c = sum_{n < nh} C[c][n] * (x[n] + (-1)^c x[nf-1-n])
     t.nh = (nf + 1) / 2;
     t.dct_stride = 0;

@@ -17,7 +17,7 @@ void fill_tables(const fe_config& c, const HostTables& ht, bool in_f32, SmemTabl
     tb.tw256 = reinterpret_cast<const float4*>(ht.tw256.data());
     tb.tw512 = reinterpret_cast<const float4*>(ht.tw512.data());
     tb.window = c.window ? reinterpret_cast<const float2*>(ht.window.data()) : nullptr;
-    tb.mel_n4 = ht.mel_n4; tb.mel_e4 = ht.mel_e4; tb.mel_b0 = ht.mel_b0.data(); tb.mel_id = ht.mel_id.data();
+    tb.mel_n4 = ht.mel_n4; tb.mel_bi = ht.mel_bi.data();
     tb.mel_w = ht.mel_w.data() + (in_f32 ? (size_t)ht.mel_entries * 8 : 0);
     tb.dctf = ht.dctf.data();
     tb.mel_slots = ht.mel_slots; tb.nf = c.num_filters; tb.D = c.feat_dim; tb.dct_stride = ht.dct_stride; tb.nh = ht.nh;
@@ -50,7 +50,8 @@ int run(const fe_config& c, const void* pcm, int n_samples, float* statics) {
         memcpy(raw, static_cast<const unsigned char*>(pcm) + (size_t)f0 * HOP * ESZ, (size_t)((nfw - 1) * HOP + FL) * ESZ);
         for (int lane = 0; lane < 32; ++lane) {
             int fs = lane >> 3, t = lane & 7;
-            if (fs < nfw) scr_w[lane] = stage_a<FL, IN_F32>(raw + fs * HOP * ESZ, e_w + fs * kERegion, tb, t, fs);
+            if (fs < nfw) scr_w[lane] = c.window ? stage_a<FL, IN_F32, 1>(raw + fs * HOP * ESZ, e_w + fs * kERegion, tb, t, fs)
+                                                 : stage_a<FL, IN_F32, 0>(raw + fs * HOP * ESZ, e_w + fs * kERegion, tb, t, fs);
         }
         for (int lane = 0; lane < 32; ++lane) {
             int fs = lane >> 3, t = lane & 7;
@@ -69,10 +70,13 @@ int run(const fe_config& c, const void* pcm, int n_samples, float* statics) {
         }
         for (int lane = 0; lane < 32; ++lane) if ((lane >> 3) < nfw) mel_phase(e_w, tb, lane & 7, lane >> 3);
         float* dst = statics + (long long)f0 * D;
-        if (tb.is_mfcc) {
+        if (tb.is_mfcc && (tb.nf & 7) == 0) {
+            for (int lane = 0; lane < 32; ++lane)
+                if ((lane >> 3) < nfw) dct_phase_fused(e_w, scr_w + 32, tb, lane & 7, lane >> 3, dst + (lane >> 3) * D, true);
+        } else if (tb.is_mfcc) {
             for (int lane = 0; lane < 32; ++lane) if ((lane >> 3) < nfw) fold_phase(e_w, tb, lane & 7, lane >> 3);
             for (int lane = 0; lane < 32; ++lane)
-                if ((lane >> 3) < nfw) dct_phase(e_w, scr_w + 32, tb, lane & 7, lane >> 3, dst + (lane >> 3) * D);
+                if ((lane >> 3) < nfw) dct_phase(e_w, scr_w + 32, tb, lane & 7, lane >> 3, dst + (lane >> 3) * D, true);
         } else {
             for (int f = 0; f < nfw; ++f) for (int m = 0; m < D; ++m) dst[f * D + m] = logmel_row(e_w, f)[m];
         }
