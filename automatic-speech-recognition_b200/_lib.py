@@ -12,6 +12,7 @@ FE_OK, FE_ERR_INVALID, FE_ERR_CUDA, FE_ERR_CAPACITY, FE_ERR_STATE = 0, -1, -2, -
 FE_FEAT_MFCC, FE_FEAT_FBANK = 0, 1
 FE_DELTA_SPEECHPY, FE_DELTA_TIME_REGRESSION = 0, 1
 FE_PCM_INT16, FE_PCM_FLOAT32 = 0, 1
+FE_POST_MEAN, FE_POST_VAR, FE_POST_DELTAS = 1, 2, 4
 
 _i32p = C.POINTER(C.c_int32)
 _i64p = C.POINTER(C.c_int64)
@@ -44,8 +45,11 @@ SYMBOLS = {
                          C.c_void_p, C.c_int64, _i64p, _i32p, C.c_void_p]),
     "fe_perturb": (C.c_int, [C.c_void_p, C.c_void_p, _i64p, _i64p, C.c_int32, _i32p, _f32p,
                              C.c_void_p, C.c_int64, _i64p, _i64p, C.c_void_p]),
+    "fe_postprocess": (C.c_int, [C.c_void_p, C.c_void_p, _i64p, _i32p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                 C.c_void_p, C.c_int64, _i64p, C.c_void_p]),
     "fe_sync": (C.c_int, [C.c_void_p]),
     "fe_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
+    "fe_measure_fp32_peak": (C.c_int, [C.c_void_p, _f32p]),
     "fe_get_kernel_ms": (C.c_int, [C.c_void_p, _f32p]),
     "fe_launch_count": (C.c_int64, [C.c_void_p]),
     "fe_device_bytes": (C.c_int64, [C.c_void_p]),

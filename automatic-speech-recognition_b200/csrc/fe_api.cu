@@ -54,8 +54,12 @@ struct fe_handle {
     std::vector<long long> tile_prefix, atile_prefix;
 
     int profiling = 0;
-    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    bool ev_valid = false, ev_k0 = false, ev_k2 = false;
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // ev[5]: end of the last run
+    bool ev_valid = false;
+    // profiled runs since fe_set_profiling(1): one event set per run (no sync inside the timed region)
+    struct ProfSet { cudaEvent_t e[5]; bool k0, k2; };
+    std::vector<ProfSet> prof;
+    size_t prof_used = 0;
     int64_t launches = 0;
     size_t k1_smem[2] = {0, 0};      // [raw int16 input, float input]
     int k1_warps = 8;                // warps per K1 CTA (8 -> 128 regs/thread, 6 -> 168); FE_K1_WARPS overrides
@@ -198,12 +202,17 @@ int launch_k1(fe_handle* h, cudaStream_t st, const void* pcm, const void* scratc
         const bool win = c.window != nullptr;
 #define FE_LAUNCH_K1(F32, WIN)                                                                             \
         do {                                                                                               \
-            if (h->k1_warps == 8)                                                                          \
+            if (h->k1_warps == 8) {                                                                        \
+                cudaFuncSetAttribute(k_frames_to_statics<400, 160, F32, WIN, 8>,                           \
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->k1_smem[F32]);   \
                 k_frames_to_statics<400, 160, F32, WIN, 8><<<grid, 256, h->k1_smem[F32], st>>>(            \
                     pcm, scratch, tiles, n_tiles, P, statics);                                             \
-            else                                                                                           \
+            } else {                                                                                       \
+                cudaFuncSetAttribute(k_frames_to_statics<400, 160, F32, WIN, 6>,                           \
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->k1_smem[F32]);   \
                 k_frames_to_statics<400, 160, F32, WIN, 6><<<grid, 192, h->k1_smem[F32], st>>>(            \
                     pcm, scratch, tiles, n_tiles, P, statics);                                             \
+            }                                                                                              \
         } while (0)
         if (!in_f32 && !win) FE_LAUNCH_K1(0, 0);
         else if (!in_f32) FE_LAUNCH_K1(0, 1);
@@ -289,6 +298,7 @@ int fe_destroy(fe_handle* h) {
         release(*b);
     if (h->h_stage.p) cudaFreeHost(h->h_stage.p);
     for (auto& ev : h->ev) if (ev) cudaEventDestroy(ev);
+    for (auto& p : h->prof) for (auto& e : p.e) if (e) cudaEventDestroy(e);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return FE_OK;
@@ -359,15 +369,6 @@ int fe_configure(fe_handle* h, const fe_config* c) {
         h->k1_smem[f32] = L.total;
         if (L.total > 227 * 1024) return fail(h, FE_ERR_INVALID, "configuration needs too much shared memory");
     }
-    if ((rc = set_smem(h, k_frames_to_statics<400, 160, 0, 0, 6>, h->k1_smem[0]))) return rc;
-    if ((rc = set_smem(h, k_frames_to_statics<400, 160, 0, 1, 6>, h->k1_smem[0]))) return rc;
-    if ((rc = set_smem(h, k_frames_to_statics<400, 160, 1, 0, 6>, h->k1_smem[1]))) return rc;
-    if ((rc = set_smem(h, k_frames_to_statics<400, 160, 1, 1, 6>, h->k1_smem[1]))) return rc;
-    if ((rc = set_smem(h, k_frames_to_statics<400, 160, 0, 0, 8>, h->k1_smem[0]))) return rc;
-    if ((rc = set_smem(h, k_frames_to_statics<400, 160, 0, 1, 8>, h->k1_smem[0]))) return rc;
-    if ((rc = set_smem(h, k_frames_to_statics<400, 160, 1, 0, 8>, h->k1_smem[1]))) return rc;
-    if ((rc = set_smem(h, k_frames_to_statics<400, 160, 1, 1, 8>, h->k1_smem[1]))) return rc;
-    if ((rc = set_smem(h, k_cmvn_delta_pack, k2_smem_floats(c->feat_dim) * sizeof(float)))) return rc;
     h->configured = true;
     return FE_OK;
 }
@@ -434,15 +435,24 @@ int fe_run(fe_handle* h, const void* pcm, const int64_t* pcm_offsets, const int6
     if (((uintptr_t)d_pcm & 15) != 0) return fail(h, FE_ERR_INVALID, "pcm buffer must be 16-byte aligned");
     if (!pcm_on_dev) FE_CUDA(h, cudaMemcpyAsync(h->d_pcm.p, pcm, esz * (size_t)pl.pcm_span, cudaMemcpyHostToDevice, st));
 
-    const bool prof = h->profiling != 0;
-    if (prof) FE_CUDA(h, cudaEventRecord(h->ev[0], st));
+    const bool prof = h->profiling != 0 && h->prof_used < 4096;
+    fe_handle::ProfSet* ps = nullptr;
+    if (prof) {
+        if (h->prof_used == h->prof.size()) {
+            fe_handle::ProfSet n{};
+            for (auto& e : n.e) FE_CUDA(h, cudaEventCreate(&e));
+            h->prof.push_back(n);
+        }
+        ps = &h->prof[h->prof_used++];
+        ps->k0 = ps->k2 = false;
+        FE_CUDA(h, cudaEventRecord(ps->e[0], st));
+    }
     const int tb = 256, gb = (n_utts + tb - 1) / tb;
     if (pl.total_tiles > 0) {
         k_build_tiles<<<gb, tb, 0, st>>>((const UttDesc*)h->d_utts.p, (const long long*)h->d_tile_prefix.p, n_utts,
                                          c.hop, c.feat_dim, h->k1_warps * kWarpFrames, (TileDesc*)h->d_tiles.p);
         h->launches++;
     }
-    h->ev_k0 = false;
     if (pl.any_scratch) {
         // atiles: one entry per 1024 output samples; only utterances routed through scratch have atiles
         // (n_frames is not the right count there, so a dedicated tiny builder pass)
@@ -453,7 +463,7 @@ int fe_run(fe_handle* h, const void* pcm, const int64_t* pcm_offsets, const int6
         }
         FE_CUDA(h, cudaMemcpyAsync(h->d_atiles.p, at.data(), sizeof(int2) * at.size(), cudaMemcpyHostToDevice, st));
         FE_CUDA(h, cudaStreamSynchronize(st));     // `at` is pageable and dies at scope end
-        if (prof) FE_CUDA(h, cudaEventRecord(h->ev[1], st));
+        if (prof) FE_CUDA(h, cudaEventRecord(ps->e[1], st));
         int grid = (int)std::min<long long>(pl.total_atiles, 16LL * h->num_sms);
         if (preemph) {
             if (c.pcm_dtype == FE_PCM_INT16)
@@ -469,24 +479,25 @@ int fe_run(fe_handle* h, const void* pcm, const int64_t* pcm_offsets, const int6
                                              (short*)h->d_scratch.p, 0);
         }
         h->launches++;
-        h->ev_k0 = true;
+        if (prof) ps->k0 = true;
     }
-    if (prof) FE_CUDA(h, cudaEventRecord(h->ev[2], st));
+    if (prof) FE_CUDA(h, cudaEventRecord(ps->e[2], st));
     DevTables dt = dev_tables(h, k1_f32);
     float* stat_base = c.cmvn ? (float*)h->d_statics.p : d_out;
     if ((rc = launch_k1(h, st, d_pcm, h->d_scratch.p, k1_f32, (const TileDesc*)h->d_tiles.p,
                         (int)pl.total_tiles, dt, stat_base))) return rc;
-    if (prof) FE_CUDA(h, cudaEventRecord(h->ev[3], st));
-    h->ev_k2 = false;
+    if (prof) FE_CUDA(h, cudaEventRecord(ps->e[3], st));
     if (c.cmvn && pl.total_frames > 0) {
         int grid = (int)std::min<long long>(n_utts, 8LL * h->num_sms);
+        FE_CUDA(h, cudaFuncSetAttribute(k_cmvn_delta_pack, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)(k2_smem_floats(c.feat_dim) * sizeof(float))));
         k_cmvn_delta_pack<<<grid, kK2Threads, k2_smem_floats(c.feat_dim) * sizeof(float), st>>>(
-            (const UttDesc*)h->d_utts.p, n_utts, (const float*)h->d_statics.p, d_out, c.feat_dim, c.delta_mode);
+            (const UttDesc*)h->d_utts.p, n_utts, (const float*)h->d_statics.p, d_out, c.feat_dim, c.delta_mode, 7);
         h->launches++;
-        h->ev_k2 = true;
+        if (prof) ps->k2 = true;
     }
     FE_CUDA(h, cudaGetLastError());
-    if (prof) FE_CUDA(h, cudaEventRecord(h->ev[4], st));
+    if (prof) FE_CUDA(h, cudaEventRecord(ps->e[4], st));
     FE_CUDA(h, cudaEventRecord(h->ev[5], st));
     h->ev_valid = true;
     if (!out_on_dev) {
@@ -551,6 +562,52 @@ int fe_perturb(fe_handle* h, const int16_t* pcm, const int64_t* pcm_offsets, con
     return FE_OK;
 }
 
+int fe_postprocess(fe_handle* h, const float* feats, const int64_t* feat_offsets, const int32_t* n_frames,
+                   int32_t n_utts, int32_t D, int32_t mode, int32_t delta_mode, float* out, int64_t out_capacity,
+                   int64_t* out_offsets, void* stream) {
+    if (!h) return FE_ERR_INVALID;
+    if (n_utts < 0 || D < 1 || D > kK2Threads) return fail(h, FE_ERR_INVALID, "bad n_utts / D");
+    if (n_utts == 0) { if (out_offsets) out_offsets[0] = 0; return FE_OK; }
+    if (!feats || !feat_offsets || !n_frames || !out || !out_offsets) return fail(h, FE_ERR_INVALID, "NULL buffer");
+    FE_CUDA(h, cudaSetDevice(h->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    const int W = (mode & 4) ? 3 : 1;
+    std::vector<UttDesc> ut((size_t)n_utts);
+    long long off = 0, span = 0;
+    for (int i = 0; i < n_utts; ++i) {
+        UttDesc& u = ut[(size_t)i];
+        memset(&u, 0, sizeof(u));
+        if (feat_offsets[i] < 0 || n_frames[i] < 0) return fail(h, FE_ERR_INVALID, "negative offset / length");
+        u.stat_off = feat_offsets[i]; u.out_off = off; u.n_frames = n_frames[i];
+        out_offsets[i] = off;
+        off += round_up((long long)n_frames[i] * D * W, 4);
+        span = std::max<long long>(span, feat_offsets[i] + (long long)n_frames[i] * D);
+    }
+    out_offsets[n_utts] = off;
+    if (off > out_capacity) return fail(h, FE_ERR_CAPACITY, "out buffer too small");
+    const bool in_dev = is_device_ptr(feats), out_dev = is_device_ptr(out);
+    int rc;
+    if ((rc = ensure(h, h->d_utts, sizeof(UttDesc) * ut.size()))) return rc;
+    const float* d_in = feats; float* d_out = out;
+    if (!in_dev) { if ((rc = ensure(h, h->d_statics, sizeof(float) * (size_t)std::max<long long>(span, 1)))) return rc; d_in = (const float*)h->d_statics.p; }
+    if (!out_dev) { if ((rc = ensure(h, h->d_out, sizeof(float) * (size_t)std::max<long long>(off, 1)))) return rc; d_out = (float*)h->d_out.p; }
+    FE_CUDA(h, cudaMemcpyAsync(h->d_utts.p, ut.data(), sizeof(UttDesc) * ut.size(), cudaMemcpyHostToDevice, st));
+    if (!in_dev) FE_CUDA(h, cudaMemcpyAsync(h->d_statics.p, feats, sizeof(float) * (size_t)span, cudaMemcpyHostToDevice, st));
+    FE_CUDA(h, cudaStreamSynchronize(st));
+    FE_CUDA(h, cudaFuncSetAttribute(k_cmvn_delta_pack, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)(k2_smem_floats(D) * sizeof(float))));
+    int grid = (int)std::min<long long>(n_utts, 8LL * h->num_sms);
+    k_cmvn_delta_pack<<<grid, kK2Threads, k2_smem_floats(D) * sizeof(float), st>>>(
+        (const UttDesc*)h->d_utts.p, n_utts, d_in, d_out, D, delta_mode, mode);
+    h->launches++;
+    FE_CUDA(h, cudaGetLastError());
+    if (!out_dev) {
+        FE_CUDA(h, cudaMemcpyAsync(out, d_out, sizeof(float) * (size_t)off, cudaMemcpyDeviceToHost, st));
+    }
+    FE_CUDA(h, cudaStreamSynchronize(st));
+    return FE_OK;
+}
+
 int fe_sync(fe_handle* h) {
     if (!h) return FE_ERR_INVALID;
     FE_CUDA(h, cudaSetDevice(h->device));
@@ -559,17 +616,54 @@ int fe_sync(fe_handle* h) {
     return FE_OK;
 }
 
-int fe_set_profiling(fe_handle* h, int on) { if (!h) return FE_ERR_INVALID; h->profiling = on; return FE_OK; }
+int fe_measure_fp32_peak(fe_handle* h, float* tflops) {
+    if (!h || !tflops) return FE_ERR_INVALID;
+    FE_CUDA(h, cudaSetDevice(h->device));
+    const int grid = h->num_sms * 8, block = 256, iters = 20000;
+    int rc;
+    if ((rc = ensure(h, h->d_out, sizeof(float) * (size_t)grid * block))) return rc;
+    cudaEvent_t e0, e1;
+    FE_CUDA(h, cudaEventCreate(&e0)); FE_CUDA(h, cudaEventCreate(&e1));
+    float best = 0.f;
+    k_fp32_peak<<<grid, block, 0, h->stream>>>((float*)h->d_out.p, 200);
+    for (int rep = 0; rep < 3; ++rep) {
+        FE_CUDA(h, cudaEventRecord(e0, h->stream));
+        k_fp32_peak<<<grid, block, 0, h->stream>>>((float*)h->d_out.p, iters);
+        FE_CUDA(h, cudaEventRecord(e1, h->stream));
+        FE_CUDA(h, cudaEventSynchronize(e1));
+        float ms = 0.f;
+        FE_CUDA(h, cudaEventElapsedTime(&ms, e0, e1));
+        const double flops = (double)grid * block * iters * 8.0 * 2.0 * 2.0;     // 8 FFMA2 = 16 FMA = 32 FLOP
+        best = std::max(best, (float)(flops / (ms * 1e-3) / 1e12));
+    }
+    h->launches += 4;
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    *tflops = best;
+    return FE_OK;
+}
+
+int fe_set_profiling(fe_handle* h, int on) {
+    if (!h) return FE_ERR_INVALID;
+    h->profiling = on;
+    h->prof_used = 0;            // a new measurement window
+    return FE_OK;
+}
 
 int fe_get_kernel_ms(fe_handle* h, float ms[4]) {
     if (!h || !ms) return FE_ERR_INVALID;
     ms[0] = ms[1] = ms[2] = ms[3] = 0.f;
-    if (!h->profiling || !h->ev_valid) return fail(h, FE_ERR_STATE, "no profiled run");
-    FE_CUDA(h, cudaEventSynchronize(h->ev[5]));
-    if (h->ev_k0) FE_CUDA(h, cudaEventElapsedTime(&ms[0], h->ev[1], h->ev[2]));
-    FE_CUDA(h, cudaEventElapsedTime(&ms[1], h->ev[2], h->ev[3]));
-    if (h->ev_k2) FE_CUDA(h, cudaEventElapsedTime(&ms[2], h->ev[3], h->ev[4]));
-    FE_CUDA(h, cudaEventElapsedTime(&ms[3], h->ev[0], h->ev[4]));
+    if (h->prof_used == 0) return fail(h, FE_ERR_STATE, "no profiled run");
+    FE_CUDA(h, cudaEventSynchronize(h->prof[h->prof_used - 1].e[4]));
+    double acc[4] = {0, 0, 0, 0};
+    for (size_t i = 0; i < h->prof_used; ++i) {
+        const fe_handle::ProfSet& p = h->prof[i];
+        float v = 0.f;
+        if (p.k0) { FE_CUDA(h, cudaEventElapsedTime(&v, p.e[1], p.e[2])); acc[0] += v; }
+        FE_CUDA(h, cudaEventElapsedTime(&v, p.e[2], p.e[3])); acc[1] += v;
+        if (p.k2) { FE_CUDA(h, cudaEventElapsedTime(&v, p.e[3], p.e[4])); acc[2] += v; }
+        FE_CUDA(h, cudaEventElapsedTime(&v, p.e[0], p.e[4])); acc[3] += v;
+    }
+    for (int k = 0; k < 4; ++k) ms[k] = (float)(acc[k] / (double)h->prof_used);   // mean over the window
     return FE_OK;
 }
 

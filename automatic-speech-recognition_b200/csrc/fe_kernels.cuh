@@ -287,7 +287,11 @@ __host__ __device__ inline int k2_smem_floats(int D) {
 
 __global__ void __launch_bounds__(kK2Threads)
 k_cmvn_delta_pack(const UttDesc* __restrict__ utts, int n_utts, const float* __restrict__ statics,
-                  float* __restrict__ out, int D, int delta_mode) {
+                  float* __restrict__ out, int D, int delta_mode, int flags) {
+    // flags: bit0 subtract the mean, bit1 divide by (std + 2^-30), bit2 append delta / delta-delta
+    // (cube (L, D, 3)); without bit2 the output is the (L, D) matrix.  The front-end uses 7.
+    const bool f_mean = flags & 1, f_var = flags & 2, f_delta = flags & 4;
+    const int W = f_delta ? 3 : 1;
     extern __shared__ __align__(16) float sm2[];
     const int RB = k2_rows_per_chunk(D);
     float* red = sm2;
@@ -309,7 +313,7 @@ k_cmvn_delta_pack(const UttDesc* __restrict__ utts, int n_utts, const float* __r
         float* o = out + utts[ui].out_off;
 
         float s = 0.f;
-        if (act) {      // four independent row streams per thread keep loads in flight
+        if (act && f_mean) {      // four independent row streams per thread keep loads in flight
             float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
             const float* xc = x + c;
             int tt = r;
@@ -328,9 +332,9 @@ k_cmvn_delta_pack(const UttDesc* __restrict__ utts, int n_utts, const float* __r
             mean[tid] = m / (float)L;
         }
         __syncthreads();
-        const float mu = act ? mean[c] : 0.f;
+        const float mu = (act && f_mean) ? mean[c] : 0.f;
         float q = 0.f;
-        if (act) {
+        if (act && f_var) {
             float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
             const float* xc = x + c;
             int tt = r;
@@ -350,7 +354,7 @@ k_cmvn_delta_pack(const UttDesc* __restrict__ utts, int n_utts, const float* __r
             inv[tid] = 1.0f / (sqrtf(v / (float)L) + 9.313225746154785e-10f);   // 2^-30
         }
         __syncthreads();
-        const float iv = act ? inv[c] : 0.f;
+        const float iv = (act && f_var) ? inv[c] : 1.f;
 
         for (int t0 = 0; t0 < L; t0 += RB) {
             const int nrow = min(RB, L - t0);
@@ -364,8 +368,9 @@ k_cmvn_delta_pack(const UttDesc* __restrict__ utts, int n_utts, const float* __r
                 __syncthreads();
                 if (act) for (int row = r; row < nrow; row += R) {
                     float dd = (d1[row * D + cp1] + 2.f * d1[row * D + cp2]) / 10.f;
-                    float* q3 = cube + (row * D + c) * 3;
-                    q3[0] = vt[row * D + c]; q3[1] = d1[row * D + c]; q3[2] = dd;
+                    float* q3 = cube + (row * D + c) * W;
+                    q3[0] = vt[row * D + c];
+                    if (f_delta) { q3[1] = d1[row * D + c]; q3[2] = dd; }
                 }
             } else {
                 // textbook regression along time, edge replication; vt row i <-> frame clamp(t0-4+i),
@@ -394,14 +399,15 @@ k_cmvn_delta_pack(const UttDesc* __restrict__ utts, int n_utts, const float* __r
                         int ap = min(tt + k, L - 1) - (t0 - 2), am = max(tt - k, 0) - (t0 - 2);
                         acc += (float)k * (d1[ap * D + c] - d1[am * D + c]);
                     }
-                    float* q3 = cube + (row * D + c) * 3;
-                    q3[0] = vt[(row + 4) * D + c]; q3[1] = d1[(row + 2) * D + c]; q3[2] = acc / 10.f;
+                    float* q3 = cube + (row * D + c) * W;
+                    q3[0] = vt[(row + 4) * D + c];
+                    if (f_delta) { q3[1] = d1[(row + 2) * D + c]; q3[2] = acc / 10.f; }
                 }
             }
             __syncthreads();
             // coalesced copy of nrow * 3D floats; chunk start is 16-byte aligned (RB % 4 == 0)
-            const int total = nrow * 3 * D;
-            float* dst = o + (long long)t0 * 3 * D;
+            const int total = nrow * W * D;
+            float* dst = o + (long long)t0 * W * D;
             const int n4 = total >> 2;
             for (int i = tid; i < n4; i += kK2Threads)
                 reinterpret_cast<float4*>(dst)[i] = reinterpret_cast<const float4*>(cube)[i];
@@ -479,6 +485,22 @@ k_preemph(const void* __restrict__ pcm, const UttDesc* __restrict__ utts, const 
             dst[u.pcm_off + j] = a - coef * b;
         }
     }
+}
+
+// FP32 roofline denominator measured on the spot: independent packed FFMA2 chains, no memory.
+__global__ void __launch_bounds__(256) k_fp32_peak(float* __restrict__ out, int iters) {
+    float2 x[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) x[i] = make_float2(threadIdx.x * 1e-3f + i, threadIdx.x * 2e-3f - i);
+    const float2 a = make_float2(1.0001f, 0.9999f), b = make_float2(0.5f, 0.25f);
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) x[i] = __ffma2_rn(x[i], a, b);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += x[i].x + x[i].y;
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
 }  // namespace fe

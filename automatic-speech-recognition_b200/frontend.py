@@ -319,6 +319,39 @@ class Frontend:
             "fe_perturb")
         return [dst[int(d_off[i]):int(d_off[i]) + int(d_len[i])].copy() for i in range(n)]
 
+    def postprocess(self, mats, mean=True, var=True, deltas=True, delta_mode=None):
+        """CMVN and/or delta cube for a list of (L, D) float matrices (host in, host out):
+        speechpy.processing.cmvn / speechpy.feature.extract_derivative_feature as batch calls."""
+        if len(mats) == 0:
+            return []
+        D = int(mats[0].shape[1])
+        mats = [np.ascontiguousarray(m, dtype=np.float32) for m in mats]
+        if any(m.ndim != 2 or m.shape[1] != D for m in mats):
+            raise ValueError("all matrices must be (L, %d)" % D)
+        n = len(mats)
+        nfr = np.asarray([m.shape[0] for m in mats], dtype=np.int32)
+        sizes = (nfr.astype(np.int64) * D + 3) // 4 * 4
+        off = np.zeros(n, dtype=np.int64)
+        if n > 1:
+            np.cumsum(sizes[:-1], out=off[1:])
+        packed = np.zeros(max(int(sizes.sum()), 4), dtype=np.float32)
+        for m, o in zip(mats, off):
+            packed[o:o + m.size] = m.reshape(-1)
+        W = 3 if deltas else 1
+        out = np.empty(max(int(((nfr.astype(np.int64) * D * W + 3) // 4 * 4).sum()), 4), dtype=np.float32)
+        out_off = np.zeros(n + 1, dtype=np.int64)
+        mode = (_lib.FE_POST_MEAN if mean else 0) | (_lib.FE_POST_VAR if var else 0) | (_lib.FE_POST_DELTAS if deltas else 0)
+        dm = self.config.delta_mode if delta_mode is None else delta_mode
+        dm = {"speechpy_as_shipped": _lib.FE_DELTA_SPEECHPY, "time_regression": _lib.FE_DELTA_TIME_REGRESSION}[dm]
+        self._check(self._lib.fe_postprocess(
+            self._h, C.c_void_p(packed.ctypes.data), _ptr(off, C.c_int64), _ptr(nfr, C.c_int32), n, D, mode, dm,
+            C.c_void_p(out.ctypes.data), out.size, _ptr(out_off, C.c_int64), None), "fe_postprocess")
+        res = []
+        for i in range(n):
+            a = out[int(out_off[i]):int(out_off[i]) + int(nfr[i]) * D * W]
+            res.append(a.reshape((int(nfr[i]), D, 3) if deltas else (int(nfr[i]), D)))
+        return res
+
     # -- measurement hooks ---------------------------------------------------
     def sync(self):
         self._check(self._lib.fe_sync(self._h), "fe_sync")
@@ -330,6 +363,12 @@ class Frontend:
         ms = (C.c_float * 4)()
         self._check(self._lib.fe_get_kernel_ms(self._h, ms), "fe_get_kernel_ms")
         return {"resample": ms[0], "frames_to_statics": ms[1], "cmvn_delta_pack": ms[2], "device_pass": ms[3]}
+
+    def measure_fp32_peak(self):
+        """TFLOP/s sustained by packed FFMA2 chains on this GPU (roofline denominator)."""
+        v = C.c_float()
+        self._check(self._lib.fe_measure_fp32_peak(self._h, C.byref(v)), "fe_measure_fp32_peak")
+        return float(v.value)
 
     def launch_count(self):
         return int(self._lib.fe_launch_count(self._h))

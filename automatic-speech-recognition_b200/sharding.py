@@ -58,10 +58,12 @@ def merge_shards(parts, shard_results, n_total):
     return out
 
 
-def process_pcm_sharded(pcm_list, args, fs=16000, gather_to=0, **switches):
+def process_pcm_sharded(pcm_list, args, fs=16000, gather_to=0, extract_fn=None, **switches):
     """Every rank calls this with the SAME ``pcm_list``; each extracts its LPT shard on
     its own GPU (LOCAL_RANK) and rank ``gather_to`` gets the re-assembled
-    (feats, featlen); other ranks get (None, None).  Falls back to a single shard when
+    (feats, featlen); other ranks get (None, None).  ``extract_fn`` (same signature as
+    process_pcm) is the per-shard feature call; tests inject a stand-in to exercise the
+    partition / gather logic without a GPU.  Falls back to a single shard when
     torch.distributed is not initialised."""
     import os
     from .preprocess import process_pcm, to_object_array
@@ -79,7 +81,8 @@ def process_pcm_sharded(pcm_list, args, fs=16000, gather_to=0, **switches):
     parts = lpt_partition(frame_counts(lengths, frame_len, hop) + 1, world) if world > 1 else \
         [np.arange(len(pcm_list), dtype=np.int64)]
     mine = [pcm_list[int(i)] for i in parts[rank]]
-    feats, _ = process_pcm(mine, args, fs=fs, device=device, **switches) if mine else (to_object_array([]), [])
+    extract = extract_fn or process_pcm
+    feats, _ = extract(mine, args, fs=fs, device=device, **switches) if mine else (to_object_array([]), [])
     if world == 1:
         return feats, [len(f) for f in feats]
     gathered = [None] * world if rank == gather_to else None

@@ -1,0 +1,369 @@
+#!/usr/bin/env python
+"""Headline benchmark: audio-hours/second of MFCC-39 + per-utterance CMVN on N B200s.
+
+    python bench.py --gpus N --steps K --warmup W            (N > 1: launched under torchrun)
+    python bench.py --impl reference ...                     (the reference's CPU path, host cores)
+
+A step = one pass of the hot path (tile build, frames->statics, cmvn+delta+pack) over this
+rank's shard of BASELINE.json configs[4]: the synthetic 1000-hour LibriSpeech-length corpus,
+sharded 8 ways (125 audio-hours per GPU, weak scaling: N = 8 is the whole corpus).  `value`
+times the device-resident pass with CUDA events; `e2e` times the same call from pinned host
+PCM to pinned host features (H2D + D2H inside).  One JSON line on stdout (rank 0)."""
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+import types
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+PKG = "automatic-speech-recognition_b200"
+
+METRIC = "audio-hours/sec MFCC-39+CMVN"
+UNIT = "audio-h/s"
+FS = 16000
+FLOP_PER_FRAME_K1 = 14284        # rFFT 11520 + power/energy 1284 + mel 400 + log 41 + DCT 1040 (- rounding)
+FLOP_PER_FRAME_ALL = 14440       # + CMVN 78 + deltas 78
+BYTES_PER_FRAME_ALL = 476        # 320 B int16 in + 156 B cube out
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--hours-per-gpu", type=float, default=125.0)
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--cpu-sample-hours", type=float, default=None, help="audio-hours the CPU baseline times")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def shard_lengths(hours, seed):
+    """LibriSpeech-like utterance lengths: clip(N(12.3, 3.8^2), 2, 35) s."""
+    synth = importlib.import_module(PKG + ".synth")
+    rng = np.random.default_rng(seed)
+    n = int(hours * 3600.0 / 12.3) + 1
+    lens = synth.durations(n, 2, 35, rng, "librispeech")
+    cut = int(np.searchsorted(np.cumsum(lens), hours * 3600.0 * FS)) + 1
+    return lens[:cut]
+
+
+def ref_args():
+    return types.SimpleNamespace(frame_step=10, frame_length=25, feat_dim=13, feat_type="mfcc", cmvn=True)
+
+
+# ----------------------------------------------------------------------------------------
+# CPU reference path (oracle port of preprocess.py:50-91 over speechpy), all host cores
+# ----------------------------------------------------------------------------------------
+def _cpu_worker(chunk):
+    from oracle import speechpy_ref as ref
+    a = ref_args()
+    t = 0
+    try:                                    # one BLAS thread per worker process: the pool owns the cores
+        from threadpoolctl import threadpool_limits
+        ctx = threadpool_limits(1)
+    except Exception:
+        import contextlib
+        ctx = contextlib.nullcontext()
+    with ctx:
+        for p in chunk:
+            f = ref.features_one(p, FS, a.frame_length, a.frame_step, a.feat_dim, a.feat_type, a.cmvn)
+            t += len(f)
+    return t
+
+
+def cpu_pass(pcm_list, pool, cores):
+    chunks = [pcm_list[i::cores] for i in range(cores)]
+    t0 = time.perf_counter()
+    frames = sum(pool.map(_cpu_worker, chunks))
+    return time.perf_counter() - t0, frames
+
+
+def cpu_baseline(pcm_list, reps=1):
+    import multiprocessing as mp
+    cores = os.cpu_count() or 1
+    hours = sum(len(p) for p in pcm_list) / FS / 3600.0
+    with mp.get_context("fork").Pool(cores) as pool:
+        cpu_pass(pcm_list[:cores], pool, cores)                      # warm the workers
+        best = min(cpu_pass(pcm_list, pool, cores)[0] for _ in range(reps))
+    return hours / best, cores, hours, best
+
+
+def cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
+def host_sample(hours, seed):
+    synth = importlib.import_module(PKG + ".synth")
+    lens = shard_lengths(hours, seed)
+    return synth.noise_corpus_fast(lens, seed + 1)
+
+
+def run_reference(a):
+    """--impl reference: the reference's CPU path on this box's host cores, same metric/config."""
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    cores = os.cpu_count() or 1
+    hours = a.cpu_sample_hours or min(0.35 * cores, 6.0)             # ~10-20 s of CPU work per step
+    pcm = host_sample(hours, 5678)
+    hours = sum(len(p) for p in pcm) / FS / 3600.0
+    times = []
+    with mp.get_context("fork").Pool(cores) as pool:
+        for i in range(a.warmup + a.steps):
+            dt, _ = cpu_pass(pcm, pool, cores)
+            if i >= a.warmup:
+                times.append(dt)
+    ms = 1e3 * sum(times) / len(times)
+    value = hours / (ms * 1e-3)
+    sample = "%.2f audio-h (%d utterances) of the same LibriSpeech-length distribution per step" % (hours, len(pcm))
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "configs[4] 1000-hour LibriSpeech-length corpus, MFCC-39 (13+d+dd) + per-utterance CMVN; "
+                               "bounded sample per step", "sample": sample, "cpu": cpu_model()},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                         "note": "oracle = numpy restatement of preprocess.py:50-91 over speechpy (speechpy itself not "
+                                 "installable here); multiprocessing over all host cores; decode excluded"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+# ----------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.idx = gpu_index
+        self.stop_flag = threading.Event()
+        self.samples = []
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in out.strip().split(",")]
+                if len(f) >= 8:
+                    self.samples.append(f)
+            except Exception:
+                pass
+            self.stop_flag.wait(0.1)
+
+    def summary(self):
+        sm = [float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit()]
+        mx = [float(s[2]) for s in self.samples if s[2].replace(".", "").isdigit()]
+        reasons = set()
+        for s in self.samples:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(self.samples)}
+
+
+def main():
+    a = parse()
+    if a.impl == "reference":
+        return run_reference(a)
+
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    if world != a.gpus and world > 1:
+        raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (a.gpus, world))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    pkg = importlib.import_module(PKG)
+    importlib.import_module(PKG + ".build").build_library()
+
+    # ---- this rank's shard, generated on the device (seeded) ----
+    lens = shard_lengths(a.hours_per_gpu, 5678 + rank)
+    pad = (lens + 7) // 8 * 8
+    off = np.concatenate(([0], np.cumsum(pad)))[:-1].astype(np.int64)
+    total = int(pad.sum())
+    hours = float(lens.sum()) / FS / 3600.0
+    g = torch.Generator(device="cuda")
+    g.manual_seed(91 + rank)
+    d_pcm = torch.empty(total, dtype=torch.int16, device="cuda")
+    CH = 1 << 27
+    for s in range(0, total, CH):
+        e = min(total, s + CH)
+        d_pcm[s:e] = (torch.randn(e - s, device="cuda", generator=g) * 3000.0).clamp_(-32768, 32767).to(torch.int16)
+    cfg = pkg.FrontendConfig()                      # mfcc, D=13, cmvn, as-shipped deltas: MFCC-39 cube
+    fe = pkg.Frontend(cfg, device=local)
+    out_off, nfr = fe.plan(lens)
+    frames = int(nfr.sum())
+    d_out = torch.empty(int(out_off[-1]), dtype=torch.float32, device="cuda")
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def step():
+        fe.run_packed(d_pcm, off, lens, out=d_out, stream=stream)
+
+    fp32_peak = fe.measure_fp32_peak()
+    for _ in range(max(a.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+
+    # ---- timed region: device-resident ----
+    fe.set_profiling(True)
+    sampler = ClockSampler(local)
+    sampler.start()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    l0 = fe.launch_count()
+    k1_ms, k2_ms = [], []
+    ev[0].record()
+    for _ in range(a.steps):
+        step()
+    ev[1].record()
+    torch.cuda.synchronize()
+    launches = fe.launch_count() - l0
+    km = fe.kernel_ms()                               # mean over the timed steps, events on the launching stream
+    k1_ms.append(km["frames_to_statics"]); k2_ms.append(km["cmvn_delta_pack"])
+    if world > 1:
+        dist.barrier()
+    sampler.stop_flag.set()
+    sampler.join(timeout=3)
+    ms_total = ev[0].elapsed_time(ev[1])
+    t = torch.tensor([ms_total, hours, float(frames)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        ms_total, hours_all, frames_all = float(tmax[0]), float(tsum[1]), float(tsum[2])
+    else:
+        hours_all, frames_all = hours, float(frames)
+    ms_per_step = ms_total / a.steps
+    value = hours_all / (ms_per_step * 1e-3)
+    fe.set_profiling(False)
+
+    # ---- end to end: pinned host PCM -> features in pinned host memory, through the public API ----
+    e2e = None
+    try:
+        h_pcm_t = torch.empty(total, dtype=torch.int16).pin_memory()
+        h_pcm_t.copy_(d_pcm)
+        h_out_t = torch.empty(int(out_off[-1]), dtype=torch.float32).pin_memory()
+        h_pcm, h_out = h_pcm_t.numpy(), h_out_t.numpy()
+        fe.run_packed(h_pcm, off, lens, out=h_out)                      # warm (device staging buffers)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(a.e2e_steps):
+            fe.run_packed(h_pcm, off, lens, out=h_out)                  # synchronous for host outputs
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / a.e2e_steps
+        td = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(td, op=dist.ReduceOp.MAX)
+        e2e = {"value": hours_all / float(td[0]), "unit": UNIT, "h2d_bytes_per_step": int(total * 2),
+               "d2h_bytes_per_step": int(out_off[-1]) * 4, "ms_per_step": float(td[0]) * 1e3,
+               "api": "Frontend.run_packed(host ndarray) -> fe_run (C-ABI), pinned host buffers"}
+        chk = float(np.abs(h_out[:int(out_off[64])] - d_out[:int(out_off[64])].cpu().numpy()).max())
+    except Exception as ex:                                             # e.g. not enough pinnable host memory
+        e2e = {"value": None, "unit": UNIT, "error": str(ex)[:200]}
+        chk = None
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier(); dist.destroy_process_group()
+        return
+
+    # ---- checker (not timed): first utterances against the oracle ----
+    parity = None
+    try:
+        from oracle import speechpy_ref as ref
+        cubes = fe.split(d_out[:int(out_off[4])], out_off[:5], nfr[:4])
+        errs = []
+        for i, c in enumerate(cubes):
+            p = d_pcm[int(off[i]):int(off[i]) + int(lens[i])].cpu().numpy()
+            errs.append(float(np.abs(c - ref.features_one(p)).max()))
+        parity = {"utterances": len(errs), "max_abs_err_vs_oracle": max(errs), "host_vs_device_max_abs": chk}
+    except Exception as ex:
+        parity = {"error": str(ex)[:200]}
+
+    # ---- CPU baseline on this box's host cores, bounded sample of the same shard ----
+    cpu = None
+    if world == 1 and not a.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        want_h = a.cpu_sample_hours or min(0.35 * cores, 6.0)
+        n_s = int(np.searchsorted(np.cumsum(lens), want_h * 3600 * FS)) + 1
+        sample = [d_pcm[int(off[i]):int(off[i]) + int(lens[i])].cpu().numpy() for i in range(min(n_s, len(lens)))]
+        v, cores, h_s, secs = cpu_baseline(sample)
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": "first %d utterances (%.2f audio-h) of the rank-0 shard, %.1f s on %d processes" % (len(sample), h_s, secs, cores),
+               "cpu": cpu_model()}
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    k1 = float(np.mean(k1_ms)) * 1e-3
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "k1_traffic.json")))
+        traffic = float(tj["dram_bytes_per_frame"]) * frames
+    except Exception:
+        pass
+    ach = frames * FLOP_PER_FRAME_K1 / k1 / 1e12
+    roofline = {
+        "kernel": "k_frames_to_statics", "bound": "fp32", "achieved": ach, "peak": fp32_peak, "unit": "TFLOP/s",
+        "frac": ach / fp32_peak, "traffic": traffic,
+        "peak_source": "measured live: packed FFMA2 chains (fe_measure_fp32_peak); nominal 148 SM x 128 lanes x 2 x 1.965 GHz = 74.5",
+        "frac_of_nominal": ach / 74.5,
+        "algorithmic_flop_per_frame": FLOP_PER_FRAME_K1, "frames_per_launch": frames, "launch_ms": k1 * 1e3,
+        "hbm": {"achieved_gbs": frames * (320 + 52) / k1 / 1e9, "peak_gbs": hbm_peak,
+                "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650 (B200_PROFILING.md)",
+                "algorithmic_bytes_per_frame": 372},
+        "whole_pass": {"flop_per_frame": FLOP_PER_FRAME_ALL, "bytes_per_frame": BYTES_PER_FRAME_ALL,
+                       "achieved_tflops": frames_all * FLOP_PER_FRAME_ALL / (ms_per_step * 1e-3) / 1e12 / world,
+                       "achieved_gbs": frames_all * BYTES_PER_FRAME_ALL / (ms_per_step * 1e-3) / 1e9 / world},
+        "cmvn_delta_pack_ms": float(np.mean(k2_ms)),
+    }
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "BASELINE configs[4]: 1000-hour LibriSpeech-length corpus, MFCC-39 (13+d+dd) + per-utterance "
+                               "CMVN, sharded 8 ways -> %.0f audio-h per GPU (weak scaling; N=8 is the whole corpus)" % a.hours_per_gpu,
+                   "audio_hours_per_gpu": hours, "utterances_per_gpu": int(len(lens)), "frames_per_gpu": frames,
+                   "pcm": "int16 16 kHz, seeded on-device Gaussian noise (broadband), clip(N(12.3,3.8^2),2,35) s",
+                   "l2": "inputs (%.1f GB/GPU) far larger than the 126 MB L2; no flush needed" % (total * 2 / 1e9),
+                   "sharding": "utterances, no collective (per-utterance CMVN)"},
+        "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+        "clocks": sampler.summary(), "parity_check": parity,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.barrier(); dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

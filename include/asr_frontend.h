@@ -121,12 +121,30 @@ int fe_perturb(fe_handle* h, const int16_t* pcm, const int64_t* pcm_offsets,
                const float* gain, int16_t* dst, int64_t dst_capacity, int64_t* dst_offsets,
                int64_t* dst_lengths, void* stream);
 
+/* speechpy.processing.cmvn(vec, variance_normalization) and
+ * speechpy.feature.extract_derivative_feature(feature) on their own (preprocess.py:85-86),
+ * for a batch of (L_i, D) float32 matrices, host or device pointers.  Needs no fe_configure.
+ *   feat_offsets[n] float offsets of each matrix, n_frames[n] rows
+ *   mode  bit0 subtract the per-column mean, bit1 divide by (std + 2^-30), bit2 append delta and
+ *         delta-delta -> (L, D, 3); without bit2 the result stays (L, D)
+ *   out_offsets[n+1] filled on return (floats, 16-byte aligned).  Synchronous. */
+#define FE_POST_MEAN 1
+#define FE_POST_VAR 2
+#define FE_POST_DELTAS 4
+int fe_postprocess(fe_handle* h, const float* feats, const int64_t* feat_offsets, const int32_t* n_frames,
+                   int32_t n_utts, int32_t feat_dim, int32_t mode, int32_t delta_mode,
+                   float* out, int64_t out_capacity, int64_t* out_offsets, void* stream);
+
 int fe_sync(fe_handle* h);
 
-/* Measurement hooks.  With profiling on, each kernel of the last fe_run is
- * bracketed by CUDA events on the launching stream.
+/* Measurement hooks.  With profiling on, every kernel of every fe_run is bracketed by CUDA
+ * events on the launching stream (no synchronisation); fe_get_kernel_ms returns the MEAN over the
+ * runs since fe_set_profiling(h, 1) was last called.
  *   ms[0] resample  ms[1] frames->statics  ms[2] cmvn+delta+pack  ms[3] whole device pass */
 int fe_set_profiling(fe_handle* h, int on);
+/* FP32 CUDA-core peak of this GPU as sustained by independent packed FFMA2 chains (TFLOP/s); the
+ * measured denominator of the kernels' FP32 roofline. */
+int fe_measure_fp32_peak(fe_handle* h, float* tflops);
 int fe_get_kernel_ms(fe_handle* h, float ms[4]);
 int64_t fe_launch_count(fe_handle* h);       /* kernels launched since fe_create */
 int64_t fe_device_bytes(fe_handle* h);       /* scratch currently held on the device */

@@ -1,0 +1,54 @@
+"""The C-ABI shared library loads here (no GPU) and exports exactly what include/asr_frontend.h declares."""
+import ctypes
+import importlib
+import os
+import re
+
+import pytest
+
+from conftest import ROOT, PKG, _has_gpu
+
+
+def header_symbols():
+    txt = open(os.path.join(ROOT, "include", "asr_frontend.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(fe_[a-z_0-9]+)\s*\(", txt)))
+
+
+def test_library_exports_every_declared_symbol(pkg):
+    _lib = importlib.import_module(PKG + "._lib")
+    lib = ctypes.CDLL(pkg.library_path())
+    names = header_symbols()
+    assert len(names) >= 14
+    for n in names:
+        assert hasattr(lib, n), "missing export %s" % n
+    assert sorted(_lib.SYMBOLS) == names, "ctypes table and header disagree"
+    assert _lib.load().fe_abi_version() == _lib.FE_ABI_VERSION
+
+
+def test_pure_host_entry_points(pkg, golden):
+    lib = importlib.import_module(PKG + "._lib").load()
+    for n, L in zip(golden["frame_count_n"], golden["frame_count_L"]):
+        assert lib.fe_num_frames(int(n), 400, 160) == int(L)
+    assert lib.fe_num_frames(399, 400, 160) == 0
+    assert lib.fe_resampled_length(16000, 10, 9) == 17778 and lib.fe_resampled_length(16000, 10, 11) == 14546
+    assert pkg.num_frames(559280) == 3493
+
+
+def test_config_struct_matches_header(pkg):
+    _lib = importlib.import_module(PKG + "._lib")
+    txt = open(os.path.join(ROOT, "include", "asr_frontend.h")).read()
+    body = txt[txt.index("typedef struct fe_config {"):txt.index("} fe_config;")]
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    fields = re.findall(r"\b(?:int32_t|float|const\s+\w+\s*\*)\s*(\w+)\s*;", body)
+    assert fields == [f[0] for f in _lib.FeConfig._fields_]
+
+
+@pytest.mark.skipif(_has_gpu(), reason="checks the no-GPU failure mode")
+def test_no_cpu_fallback(pkg):
+    with pytest.raises(RuntimeError, match="no CUDA device"):
+        pkg.Frontend()
+    from conftest import make_args
+    import numpy as np
+    with pytest.raises(RuntimeError):
+        pkg.process_pcm([np.zeros(1000, np.int16)], make_args())

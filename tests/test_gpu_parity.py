@@ -1,0 +1,212 @@
+"""GPU parity: the CUDA path, called through the reference-shaped API / the C-ABI, against the CPU
+oracle on the same seeded inputs (sizes the oracle finishes in seconds), against the committed golden
+vectors, and -- at BASELINE.json's full sizes -- through size-independent properties.
+
+Tolerance (BASELINE.json north_star): frame counts bit-exact; features max-abs <= 1e-3 OR rel <= 1e-4."""
+import numpy as np
+import pytest
+
+from conftest import assert_close, make_args
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def corpus1(pkg):
+    """config 1 in small: U(2,15) s, mfcc-13, cmvn."""
+    return pkg.synth.corpus(40, 2.0, 15.0, seed=1234)
+
+
+def _check_batch(pkg, ref, pcm, args, what, **sw):
+    feats, featlen = pkg.process_pcm(pcm, args, **sw)
+    want, want_len = ref.process_audios(pcm, args, **sw)
+    assert featlen == want_len, what                       # bit-exact frame counts
+    assert feats.dtype == object and feats.shape == (len(pcm),)
+    worst = 0.0
+    for a, b in zip(feats, want):
+        assert a.dtype == np.float32 and a.flags.c_contiguous
+        worst = max(worst, assert_close(a, b, what=what))
+    return worst
+
+
+def test_config1_mfcc39_cmvn(pkg, ref, corpus1, args):
+    _check_batch(pkg, ref, corpus1, args, "config1 mfcc-39")
+
+
+def test_config2_fbank80_librispeech_lengths(pkg, ref):
+    rng = np.random.default_rng(2345)
+    lens = pkg.synth.durations(10, 2, 35, rng, "librispeech").tolist() + [35 * 16000, 2 * 16000]
+    pcm = [pkg.synth.utterance(n, rng) for n in lens]
+    _check_batch(pkg, ref, pcm, make_args(feat_type="fbank", feat_dim=80), "config2 fbank-80 (linear, as mfe)")
+    _check_batch(pkg, ref, pcm[:4], make_args(feat_type="fbank", feat_dim=80), "config2 fbank-80 log", fbank_log=True)
+
+
+def test_config3_speed_perturbation(pkg, ref, sox, corpus1):
+    pcm = corpus1[:9]
+    speeds = [0.9, 1.0, 1.1] * 3
+    fe = pkg.Frontend(pkg.FrontendConfig())
+    got_pcm = fe.perturb(pcm, speeds=speeds)
+    want_pcm = [sox.speed_perturb(p, s) for p, s in zip(pcm, speeds)]
+    for a, b in zip(got_pcm, want_pcm):
+        assert len(a) == len(b)                                       # output length bit-exact
+        d = np.abs(a.astype(np.int32) - b.astype(np.int32))
+        assert d.max() <= 1 and (d > 0).mean() < 0.02                 # fp32 vs fp64 rounding at .5 boundaries
+    got = fe.extract(pcm, speeds=speeds)                              # resample fused in front of framing
+    for a, p in zip(got, want_pcm):
+        assert_close(a, ref.features_one(p), what="speed-perturbed mfcc")
+    fe.close()
+
+
+def test_volume_perturbation(pkg, ref, sox, corpus1):
+    gains = [0.8, 1.5, 1.23, 1.0, 3.0]
+    fe = pkg.Frontend(pkg.FrontendConfig())
+    got_pcm = fe.perturb(corpus1[:5], gains=gains)
+    for a, p, g in zip(got_pcm, corpus1, gains):
+        assert np.array_equal(a, sox.volume_perturb(p, g))            # integer work: bit-exact
+    got = fe.extract(corpus1[:5], gains=gains)
+    for a, p, g in zip(got, corpus1, gains):
+        assert_close(a, ref.features_one(sox.volume_perturb(p, g)), what="gain")
+    fe.close()
+
+
+@pytest.mark.parametrize("sw", [dict(delta_mode="time_regression"), dict(bin_map="nfft_plus_one"),
+                                dict(preemph=0.98), dict(window=np.hamming(400))])
+def test_switches(pkg, ref, corpus1, args, sw):
+    _check_batch(pkg, ref, corpus1[:8], args, "switch %s" % list(sw), **sw)
+
+
+def test_cmvn_false_and_feat_dims(pkg, ref, corpus1):
+    _check_batch(pkg, ref, corpus1[:6], make_args(cmvn=False), "mfcc no cmvn")
+    _check_batch(pkg, ref, corpus1[:6], make_args(feat_dim=39), "run.sh default feat_dim=39")   # run.sh:41-50
+    _check_batch(pkg, ref, corpus1[:6], make_args(feat_type="fbank", feat_dim=40), "fbank-40")
+    _check_batch(pkg, ref, corpus1[:6], make_args(feat_type="fbank", feat_dim=23, cmvn=False), "fbank-23 (odd)")
+
+
+def test_float_pcm_input(pkg, ref, corpus1, args):
+    pcm = [ref.pcm_to_float(p).astype(np.float32) for p in corpus1[:5]]
+    feats, featlen = pkg.process_pcm(pcm, args)
+    for a, p in zip(feats, corpus1):
+        assert_close(a, ref.features_one(p), what="float32 pcm")
+
+
+def test_golden_vectors_on_gpu(pkg, golden):
+    pcm = [golden["pcm_%d" % i] for i in range(3)]
+    for key, a, sw in (("mfcc13", make_args(), {}), ("mfcc13_nocmvn", make_args(cmvn=False), {}),
+                       ("mfcc13_timereg", make_args(), dict(delta_mode="time_regression")),
+                       ("fbank80", make_args(feat_type="fbank", feat_dim=80), {}),
+                       ("fbank40_log", make_args(feat_type="fbank", feat_dim=40), dict(fbank_log=True))):
+        feats, _ = pkg.process_pcm(pcm, a, **sw)
+        for i, f in enumerate(feats):
+            assert_close(f, golden["%s_%d" % (key, i)], what="golden %s[%d]" % (key, i))
+    fe = pkg.Frontend(pkg.FrontendConfig())
+    y = fe.perturb([pcm[0]], speeds=[0.9])[0]
+    assert np.abs(y.astype(int) - golden["speed09_pcm_0"].astype(int)).max() <= 1
+    assert np.array_equal(fe.perturb([pcm[0]], gains=[1.23])[0], golden["gain123_pcm_0"])
+    fe.close()
+
+
+def test_edge_cases(pkg, ref, args):
+    rng = np.random.default_rng(7)
+    mk = lambda n: (rng.normal(size=n) * 3000).astype(np.int16)
+    pcm = [mk(470), mk(560), mk(559), mk(720), mk(400), mk(16000), np.zeros(4000, np.int16),
+           mk(400 + 160 * 32), mk(400 + 160 * 33), mk(400 + 160 * 31 + 159)]
+    feats, featlen = pkg.process_pcm(pcm, args)
+    assert featlen == [0, 1, 0, 2, 0, 97, 22, 32, 33, 31]
+    assert feats[0].shape == (0, 13, 3) and feats[4].shape == (0, 13, 3)
+    assert np.all(feats[1][:, :, 0] == 0)                              # one frame: (x - mean) / (0 + eps) = 0
+    for a, p in zip(feats, pcm):
+        assert_close(a, ref.features_one(p), what="edge")
+        assert np.isfinite(a).all()
+    with pytest.raises(ValueError):                                    # N < 400: the reference raises too
+        pkg.process_pcm([mk(399)], args)
+    f0, l0 = pkg.process_pcm([], args)
+    assert len(f0) == 0 and l0 == []
+
+
+def test_maximum_length_matches_reference_comment(pkg, ref, args):
+    # tfrecord_data_loader.py:79: longest test-clean utterance (559 280 samples) has 3493 frames
+    rng = np.random.default_rng(8)
+    p = pkg.synth.utterance(559280, rng)
+    feats, featlen = pkg.process_pcm([p], args)
+    assert featlen == [3493] and feats[0].shape == (3493, 13, 3)
+    assert_close(feats[0], ref.features_one(p), what="35 s utterance")
+
+
+def test_bitwise_determinism_and_batch_independence(pkg, corpus1, args):
+    a, _ = pkg.process_pcm(corpus1, args)
+    b, _ = pkg.process_pcm(corpus1, args)
+    assert all(np.array_equal(x, y) for x, y in zip(a, b))
+    alone, _ = pkg.process_pcm([corpus1[7]], args)
+    assert np.array_equal(alone[0], a[7])                              # no cross-utterance state
+    rev, _ = pkg.process_pcm(corpus1[::-1], args)
+    assert all(np.array_equal(x, y) for x, y in zip(rev[::-1], a))
+
+
+def test_sharded_equals_unsharded_bitwise(pkg, corpus1, args):
+    full, _ = pkg.process_pcm(corpus1, args)
+    lens = [len(p) for p in corpus1]
+    for world in (2, 8):
+        parts = pkg.sharding.lpt_partition(pkg.sharding.frame_counts(lens) + 1, world)
+        res = [list(pkg.process_pcm([corpus1[int(i)] for i in idx], args)[0]) for idx in parts]
+        merged = pkg.sharding.merge_shards(parts, res, len(corpus1))
+        assert all(np.array_equal(x, y) for x, y in zip(merged, full))
+
+
+def test_full_size_properties_config1(pkg, ref):
+    """BASELINE config 1 at full size (1000 utterances, 2.36 audio-hours): size-independent checks."""
+    rng = np.random.default_rng(1234)
+    lens = pkg.synth.durations(1000, 2, 15, rng)
+    pcm = pkg.synth.noise_corpus_fast(lens, seed=4)
+    feats, featlen = pkg.process_pcm(pcm, make_args())
+    assert featlen == [int((n - 400) // 160) for n in lens]
+    tot = 0
+    for f in feats[::7]:
+        st = f[:, :, 0].astype(np.float64)
+        assert np.abs(st.mean(0)).max() < 2e-4 and np.abs(st.std(0) - 1).max() < 2e-4      # per-utterance CMVN
+        d1 = (st[:, np.minimum(np.arange(13) + 1, 12)] + 2 * st[:, np.minimum(np.arange(13) + 2, 12)]) / 10
+        assert np.abs(f[:, :, 1] - d1).max() < 1e-5                                          # delta identity
+        tot += len(f)
+    assert tot > 0
+    for i in (0, 499, 999):                                                                 # spot parity
+        assert_close(feats[i], ref.features_one(pcm[i]), what="config1 full spot")
+    # linearity of the power path: 2x amplitude -> mfcc c1.. unchanged, c0 (log energy) + log 4 (before CMVN)
+    x = pcm[3]
+    a, _ = pkg.process_pcm([x // 2 * 2], make_args(cmvn=False))
+    b, _ = pkg.process_pcm([x // 2], make_args(cmvn=False))
+    assert np.abs((a[0][:, 0] - b[0][:, 0]) - np.log(4.0)).max() < 1e-4
+    assert np.abs(a[0][:, 1:] - b[0][:, 1:]).max() < 1e-3
+
+
+def test_speechpy_shims(pkg, ref, corpus1):
+    sp = pkg.speechpy_shim
+    x = ref.pcm_to_float(corpus1[0])
+    m = sp.mfcc(x, 16000, frame_length=0.025, frame_stride=0.010, num_cepstral=13)
+    want = ref.mfcc(x, 16000, 0.025, 0.010, 13)
+    assert m.dtype == np.float64 and np.abs(m - want).max() < 1e-4
+    f, e = sp.mfe(x, 16000, frame_length=0.025, frame_stride=0.010, num_filters=40)
+    wf, we = ref.mfe(x, 16000, 0.025, 0.010, 40)
+    assert np.max(np.abs(f - wf) / np.abs(wf)) < 1e-4 and np.max(np.abs(e - we) / we) < 1e-4
+    c = sp.cmvn(want, True)
+    assert_close(c, ref.cmvn(want, True), what="cmvn shim")
+    assert_close(sp.cmvn(want, False), ref.cmvn(want, False), what="cmvn shim (mean only)")
+    cube = sp.extract_derivative_feature(ref.cmvn(want, True))
+    assert_close(cube, ref.extract_derivative_feature(ref.cmvn(want, True)), what="delta shim")
+    with pytest.raises(RuntimeError, match="frame geometry"):
+        sp.mfcc(x, 16000)                                              # speechpy default 20 ms frames: unsupported
+
+
+def test_process_audios_files_and_pickles(pkg, ref, tmp_path, corpus1, args):
+    paths = []
+    for i, p in enumerate(corpus1[:4]):
+        path = str(tmp_path / ("utt%d.wav" % i))
+        pkg.audio_io.write_audio(path, p, 16000)
+        paths.append(path)
+    feats, featlen = pkg.process_audios(paths, args)                   # the reference signature
+    for a, p in zip(feats, corpus1):
+        assert_close(a, ref.features_one(p), what="process_audios")
+    import joblib
+    args.feat_dir = str(tmp_path / "feats")
+    pkg.process_libri_feats(paths, "dev", 1, args)
+    back = joblib.load(args.feat_dir + "/dev-feats.pkl")
+    assert all(np.array_equal(a, b) for a, b in zip(back, feats))
+    assert np.load(args.feat_dir + "/dev-featlen.npy").tolist() == featlen
