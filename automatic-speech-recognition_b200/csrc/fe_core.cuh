@@ -67,8 +67,11 @@ FE_HD float2 pnfma(float2 a, float2 b, float2 c) { return pfma(pneg(a), b, c); }
 // Shared-memory tables of one CTA
 // ---------------------------------------------------------------------------
 struct SmemTables {
-    const float4* tw256;      // [16][16] k1-major, cfg = swap*8 + t: (wr(jx k1), wr(jy k1), wi(jx k1), wi(jy k1)), w = exp(-2 pi i j k1 / 256)
-    const float4* tw512;      // [8][16]  k2-major, cfg = Fe*8 + t: (cos kx, cos ky, sin kx, sin ky), k = r + 16 k2
+    // twiddles are generated from a few per-lane bases (shared-memory wavefronts are the scarce
+    // resource of this kernel, packed FP32 issue slots are not):
+    const float4* tw256;      // [6][16] cfg = swap*8 + t: (wr(jx m), wr(jy m), wi(jx m), wi(jy m)) for m = 1,2,3,4,8,12;
+                              //         W_256^(j k1) = W^(j 4a) * W^(j b), k1 = 4a + b
+    const float4* tw512;      // [16]    cfg = Fe*8 + t: (cos rx, cos ry, sin rx, sin ry) * 2pi/512; bins r + 16 k2 by rotation
     const float2* window;     // [ROWS*16] (w[2m], w[2m+1]) per complex point m, or nullptr
     // mel plan: S slots; slot s has mel_n4[s] float4 weight groups (weights stored
     // [group][lane g][4], groups of all slots back to back); lane g of a frame owns filter
@@ -225,13 +228,27 @@ FE_HD float stage_a(const void* raw_f, float* e_f, const SmemTables& tb, int t, 
     const EPtr x0 = e_make(e_f, lb ^ hbx), y0 = e_make(e_f, lb ^ hby);              // pair-row 0: no slot flip
     const EPtr xF = e_make(e_f, (lb ^ hbx) | F), yF = e_make(e_f, (lb ^ hby) | F);
     const int cfg = swap * 8 + t;
+    // bases W^(j b) (b = 1..3) and W^(4 j a) (a = 1..3), packed over the two halves
+    float2 br[4], bi_[4], ar[4], ai[4];
+#pragma unroll
+    for (int m = 1; m < 4; ++m) {
+        float4 wb = tb.tw256[(m - 1) * 16 + cfg], wa = tb.tw256[(m + 2) * 16 + cfg];
+        br[m] = make_float2(wb.x, wb.y); bi_[m] = make_float2(wb.z, wb.w);
+        ar[m] = make_float2(wa.x, wa.y); ai[m] = make_float2(wa.z, wa.w);
+    }
 #pragma unroll
     for (int k1 = 0; k1 < 16; ++k1) {
         const int s = pos16(k1);
+        const int a4 = k1 >> 2, b4 = k1 & 3;
         float2 yr = re[s], yi = im[s];
         if (k1 > 0) {
-            float4 w = tb.tw256[k1 * 16 + cfg];
-            float2 wr = make_float2(w.x, w.y), wi = make_float2(w.z, w.w);
+            float2 wr, wi;
+            if (a4 == 0) { wr = br[b4]; wi = bi_[b4]; }
+            else if (b4 == 0) { wr = ar[a4]; wi = ai[a4]; }
+            else {
+                wr = pnfma(ai[a4], bi_[b4], pmul(ar[a4], br[b4]));
+                wi = pfma(ar[a4], bi_[b4], pmul(ai[a4], br[b4]));
+            }
             float2 tr = pnfma(yi, wi, pmul(yr, wr));
             yi = pfma(yr, wi, pmul(yi, wr));
             yr = tr;
@@ -279,6 +296,13 @@ FE_HD void post_pass(const LaneZ& z, float* p_f, const SmemTables& tb, int t, in
     const bool t0 = (t == 0);
     const int rx = row_x(t, fs), ry = row_y(t, fs);
     const int cfg = lane_flip(t, fs) * 8 + t;
+    const float4 wb = tb.tw512[cfg];
+    const float2 c0 = make_float2(wb.x, wb.y), s0 = make_float2(wb.z, wb.w);     // angle of bins rx, ry
+    // cos / sin of pi k2 / 16 (bins advance by 16 -> angle by 2 pi 16 / 512)
+    constexpr float RC[8] = {1.f, 0.98078528040323043f, 0.92387953251128674f, 0.83146961230254524f,
+                             0.70710678118654752f, 0.55557023301960218f, 0.38268343236508977f, 0.19509032201612825f};
+    constexpr float RS[8] = {0.f, 0.19509032201612825f, 0.38268343236508977f, 0.55557023301960218f,
+                             0.70710678118654752f, 0.83146961230254524f, 0.92387953251128674f, 0.98078528040323043f};
 #pragma unroll
     for (int k2 = 0; k2 < 8; ++k2) {
         const int sa = pos16(k2), sp = pos16(15 - k2), sq = pos16((16 - k2) & 15);
@@ -287,8 +311,11 @@ FE_HD void post_pass(const LaneZ& z, float* p_f, const SmemTables& tb, int t, in
         float2 pr, pi;
         pr.x = t0 ? z.r[sp].x : z.r[sp].y;   pr.y = t0 ? z.r[sq].y : z.r[sp].x;
         pi.x = t0 ? z.i[sp].x : z.i[sp].y;   pi.y = t0 ? z.i[sq].y : z.i[sp].x;
-        float4 w = tb.tw512[k2 * 16 + cfg];
-        float2 c = make_float2(w.x, w.y), s = make_float2(w.z, w.w);
+        float2 c = c0, s = s0;
+        if (k2 > 0) {
+            c = pnfma(s0, pbc(RS[k2]), pmul(c0, pbc(RC[k2])));
+            s = pfma(c0, pbc(RS[k2]), pmul(s0, pbc(RC[k2])));
+        }
         float2 er = padd(ar, pr), ei = psub(ai, pi);          // 2E  (B = conj(partner))
         float2 orr = psub(ar, pr), oi = padd(ai, pi);         // 2O
         float2 tr = pnfma(c, oi, pmul(s, orr));               // T = i w O, w = (c, -s)
@@ -337,6 +364,25 @@ FE_HD float* fold_row(float* e_w, int f, int odd) { return e_w + f * kERegion + 
 // ---------------------------------------------------------------------------
 // Phase 4: mel filterbank, lane g of frame fs walks its slot list (uniform trip counts).
 // ---------------------------------------------------------------------------
+// one slot with a compile-time number of weight groups: all loads first, then the FMAs
+template <int N4>
+FE_HD float mel_slot(const float4* w, const float* p) {
+    float4 ww[N4], pv[N4];
+#pragma unroll
+    for (int q = 0; q < N4; ++q) ww[q] = w[q * 8];
+#pragma unroll
+    for (int q = 0; q < N4; ++q) pv[q] = *reinterpret_cast<const float4*>(p + 4 * q);   // runs start 16-byte aligned
+    float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll
+    for (int q = 0; q < N4; ++q) {
+        acc0 = fmaf(ww[q].x, pv[q].x, acc0);
+        acc1 = fmaf(ww[q].y, pv[q].y, acc1);
+        acc0 = fmaf(ww[q].z, pv[q].z, acc0);
+        acc1 = fmaf(ww[q].w, pv[q].w, acc1);
+    }
+    return acc0 + acc1;
+}
+
 FE_HD void mel_phase(float* e_w, const SmemTables& tb, int g, int fs) {
     const float* p_f = power_row(e_w, fs);
     float* row = logmel_row(e_w, fs);
@@ -344,19 +390,27 @@ FE_HD void mel_phase(float* e_w, const SmemTables& tb, int g, int fs) {
     const float4* w = reinterpret_cast<const float4*>(tb.mel_w) + g;
     const int* bi = tb.mel_bi + g;
     for (int s = 0; s < tb.mel_slots; ++s) {
-        const int n4 = tb.mel_n4[s];
+        const int n4 = tb.mel_n4[s];                 // warp-uniform (constant bank)
         const int d = bi[s * 8];
         const float* p = p_f + (d & 0xffff);
-        float acc0 = 0.f, acc1 = 0.f;
-        for (int q = 0; q < n4; ++q) {
-            const float4 ww = w[q * 8];
-            acc0 = fmaf(ww.x, p[4 * q], acc0);
-            acc1 = fmaf(ww.y, p[4 * q + 1], acc1);
-            acc0 = fmaf(ww.z, p[4 * q + 2], acc0);
-            acc1 = fmaf(ww.w, p[4 * q + 3], acc1);
+        float v;
+        if (n4 == 1) v = mel_slot<1>(w, p);
+        else if (n4 == 2) v = mel_slot<2>(w, p);
+        else if (n4 == 3) v = mel_slot<3>(w, p);
+        else if (n4 == 4) v = mel_slot<4>(w, p);
+        else {
+            float acc0 = 0.f, acc1 = 0.f;
+            for (int q = 0; q < n4; ++q) {
+                const float4 ww = w[q * 8];
+                const float4 pv = *reinterpret_cast<const float4*>(p + 4 * q);
+                acc0 = fmaf(ww.x, pv.x, acc0);
+                acc1 = fmaf(ww.y, pv.y, acc1);
+                acc0 = fmaf(ww.z, pv.z, acc0);
+                acc1 = fmaf(ww.w, pv.w, acc1);
+            }
+            v = acc0 + acc1;
         }
         w += n4 * 8;
-        float v = acc0 + acc1;
         v = (v == 0.f) ? kEpsF64 : v;
         if (want_log) v = fe_log(v);
         const int id = d >> 16;
@@ -408,6 +462,23 @@ FE_HD void dct_phase(float* e_w, const float* energies, const SmemTables& tb, in
 // Phase 5 variant for nf % 8 == 0 (the reference's 40 filters): the fold
 // x[n] +- x[nf-1-n] is done on the fly from the log-mel row (16-byte loads from both ends),
 // so no separate fold phase and no extra synchronisation.
+template <int N4>
+FE_HD void dct_pair(const float* row, int nf, const float* d0, const float* d1, float sgn, int n4, float& a0, float& a1) {
+    a0 = 0.f; a1 = 0.f;
+    const int n = N4 > 0 ? N4 : n4;
+#pragma unroll
+    for (int q = 0; q < n; ++q) {
+        float4 lo = *reinterpret_cast<const float4*>(row + 4 * q);
+        float4 hi = *reinterpret_cast<const float4*>(row + nf - 4 - 4 * q);
+        float4 u = *reinterpret_cast<const float4*>(d0 + 4 * q);
+        float4 v = *reinterpret_cast<const float4*>(d1 + 4 * q);
+        const float x0 = fmaf(sgn, hi.w, lo.x), x1 = fmaf(sgn, hi.z, lo.y);
+        const float x2 = fmaf(sgn, hi.y, lo.z), x3 = fmaf(sgn, hi.x, lo.w);
+        a0 = fmaf(u.x, x0, a0); a0 = fmaf(u.y, x1, a0); a0 = fmaf(u.z, x2, a0); a0 = fmaf(u.w, x3, a0);
+        a1 = fmaf(v.x, x0, a1); a1 = fmaf(v.y, x1, a1); a1 = fmaf(v.z, x2, a1); a1 = fmaf(v.w, x3, a1);
+    }
+}
+
 FE_HD void dct_phase_fused(float* e_w, const float* energies, const SmemTables& tb, int g, int fs, float* dst, bool store) {
     const float* row = logmel_row(e_w, fs);
     const float sgn = (g & 1) ? -1.f : 1.f;          // parity of every coefficient this lane owns
@@ -417,17 +488,9 @@ FE_HD void dct_phase_fused(float* e_w, const float* energies, const SmemTables& 
         const bool has1 = c1 < tb.D;
         const float* d0 = tb.dctf + c0 * tb.dct_stride;
         const float* d1 = tb.dctf + (has1 ? c1 : c0) * tb.dct_stride;
-        float a0 = 0.f, a1 = 0.f;
-        for (int q = 0; q < n4; ++q) {
-            float4 lo = *reinterpret_cast<const float4*>(row + 4 * q);
-            float4 hi = *reinterpret_cast<const float4*>(row + tb.nf - 4 - 4 * q);
-            float4 u = *reinterpret_cast<const float4*>(d0 + 4 * q);
-            float4 v = *reinterpret_cast<const float4*>(d1 + 4 * q);
-            const float x0 = fmaf(sgn, hi.w, lo.x), x1 = fmaf(sgn, hi.z, lo.y);
-            const float x2 = fmaf(sgn, hi.y, lo.z), x3 = fmaf(sgn, hi.x, lo.w);
-            a0 = fmaf(u.x, x0, a0); a0 = fmaf(u.y, x1, a0); a0 = fmaf(u.z, x2, a0); a0 = fmaf(u.w, x3, a0);
-            a1 = fmaf(v.x, x0, a1); a1 = fmaf(v.y, x1, a1); a1 = fmaf(v.z, x2, a1); a1 = fmaf(v.w, x3, a1);
-        }
+        float a0, a1;
+        if (n4 == 5) dct_pair<5>(row, tb.nf, d0, d1, sgn, n4, a0, a1);       // 40 filters (the reference)
+        else dct_pair<0>(row, tb.nf, d0, d1, sgn, n4, a0, a1);
         if (c0 == 0 && tb.dc_elim) a0 = fe_log(energies[fs]);
         if (store) dst[c0] = a0;
         if (store && has1) dst[c1] = a1;

@@ -34,8 +34,8 @@ struct __align__(16) TileDesc {
 };
 
 struct DevTables {
-    const float4* tw256;    // [16][16]
-    const float4* tw512;    // [8][16]
+    const float4* tw256;    // [6][16]
+    const float4* tw512;    // [16]
     const float2* window;   // [ROWS*16] or nullptr
     const int* mel_bi; const float* mel_w;
     const float* dctf;      // [D][dct_stride]
@@ -85,8 +85,8 @@ __host__ __device__ inline K1Smem k1_smem_layout(int mel_slots, int mel_entries,
     s.raw_bytes = align16(((kWarpFrames - 1) * hop + rows * 32) * (in_f32 ? 4 : 2));
     s.off_raw = o;    o += warps * 2 * s.raw_bytes;
     s.off_scr = o;    o += warps * 64 * 4;
-    s.off_tw256 = o;  o += 16 * 16 * 16;
-    s.off_tw512 = o;  o += 8 * 16 * 16;
+    s.off_tw256 = o;  o += 6 * 16 * 16;
+    s.off_tw512 = o;  o += 16 * 16;
     s.off_window = o; o = align16(o + (has_window ? rows * 16 * 8 : 0));
     s.off_bi = o;     o = align16(o + mel_slots * 8 * 4);
     s.off_melw = o;   o = align16(o + mel_entries * 8 * 4);
@@ -151,8 +151,8 @@ k_frames_to_statics(const void* __restrict__ pcm, const void* __restrict__ scrat
 
     const int tid = threadIdx.x;
     constexpr int ROWS = (FRAME_LEN + 31) / 32;
-    for (int i = tid; i < 256; i += blockDim.x) s_tw256[i] = dt.tw256[i];
-    for (int i = tid; i < 128; i += blockDim.x) s_tw512[i] = dt.tw512[i];
+    for (int i = tid; i < 96; i += blockDim.x) s_tw256[i] = dt.tw256[i];
+    for (int i = tid; i < 16; i += blockDim.x) s_tw512[i] = dt.tw512[i];
     if (dt.window) for (int i = tid; i < ROWS * 16; i += blockDim.x) s_window[i] = dt.window[i];
     for (int i = tid; i < dt.mel_slots * 8; i += blockDim.x) s_bi[i] = dt.mel_bi[i];
     for (int i = tid; i < dt.mel_entries * 8; i += blockDim.x) s_melw[i] = dt.mel_w[i];
@@ -312,16 +312,19 @@ k_cmvn_delta_pack(const UttDesc* __restrict__ utts, int n_utts, const float* __r
         const float* x = statics + utts[ui].stat_off;
         float* o = out + utts[ui].out_off;
 
+        // mean = x[0] + mean(x - x[0]): the shift keeps a constant column (digital silence) exactly
+        // constant, so its deviations are exactly 0 instead of one rounding error normalised to +-1
+        const float shift = (act && f_mean) ? x[c] : 0.f;
         float s = 0.f;
         if (act && f_mean) {      // four independent row streams per thread keep loads in flight
             float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
             const float* xc = x + c;
             int tt = r;
             for (; tt + 3 * R < L; tt += 4 * R) {
-                s0 += xc[(long long)tt * D]; s1 += xc[(long long)(tt + R) * D];
-                s2 += xc[(long long)(tt + 2 * R) * D]; s3 += xc[(long long)(tt + 3 * R) * D];
+                s0 += xc[(long long)tt * D] - shift; s1 += xc[(long long)(tt + R) * D] - shift;
+                s2 += xc[(long long)(tt + 2 * R) * D] - shift; s3 += xc[(long long)(tt + 3 * R) * D] - shift;
             }
-            for (; tt < L; tt += R) s0 += xc[(long long)tt * D];
+            for (; tt < L; tt += R) s0 += xc[(long long)tt * D] - shift;
             s = (s0 + s1) + (s2 + s3);
         }
         red[tid] = s;
@@ -329,7 +332,7 @@ k_cmvn_delta_pack(const UttDesc* __restrict__ utts, int n_utts, const float* __r
         if (tid < D) {
             float m = 0.f;
             for (int rr = 0; rr < R; ++rr) m += red[rr * D + tid];
-            mean[tid] = m / (float)L;
+            mean[tid] = x[tid] + m / (float)L;
         }
         __syncthreads();
         const float mu = (act && f_mean) ? mean[c] : 0.f;
