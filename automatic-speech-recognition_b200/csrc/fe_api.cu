@@ -48,7 +48,7 @@ struct fe_handle {
     DevBuf d_sp_up, d_sp_down, d_sp_tap_off, d_taps;
 
     // per-run scratch (grow-only)
-    DevBuf d_utts, d_tile_prefix, d_tiles, d_atile_prefix, d_atiles, d_statics, d_pcm, d_out, d_scratch;
+    DevBuf d_utts, d_tile_prefix, d_tiles, d_atile_prefix, d_atiles, d_statics, d_stats, d_pcm, d_out, d_scratch;
     HostPinned h_stage;
     std::vector<UttDesc> utts;
     std::vector<long long> tile_prefix, atile_prefix;
@@ -227,6 +227,46 @@ int launch_k1(fe_handle* h, cudaStream_t st, const void* pcm, const void* scratc
     return FE_OK;
 }
 
+// K2a + K2b: per-utterance statistics, then the tile-parallel normalise / delta / pack pass
+int launch_k2(fe_handle* h, cudaStream_t st, const UttDesc* utts, int n_utts, const TileDesc* tiles, long long n_tiles,
+              const float* statics, float* out, int D, int tile_frames, int delta_mode, int flags) {
+    int rc;
+    if ((rc = ensure(h, h->d_stats, sizeof(float) * 2 * (size_t)D * (size_t)n_utts))) return rc;
+    if (flags & 3) {
+        const int grid = (int)std::min<long long>(n_utts, 32LL * h->num_sms);
+        k_utt_stats<<<grid, kStatThreads, (kStatThreads + std::min(D, kStatThreads)) * sizeof(float), st>>>(
+            utts, n_utts, statics, (float*)h->d_stats.p, D, flags);
+        h->launches++;
+    } else {
+        // no normalisation: mean 0, scale 1
+        std::vector<float> id((size_t)2 * D);
+        for (int i = 0; i < D; ++i) { id[i] = 0.f; id[D + i] = 1.f; }
+        for (int u = 0; u < n_utts; ++u)
+            FE_CUDA(h, cudaMemcpyAsync((float*)h->d_stats.p + (size_t)u * 2 * D, id.data(), sizeof(float) * 2 * D,
+                                       cudaMemcpyHostToDevice, st));
+        FE_CUDA(h, cudaStreamSynchronize(st));
+    }
+    if (n_tiles > 0) {
+        const size_t smem = k2_smem_floats(D, tile_frames) * sizeof(float);
+        const int grid = (int)std::min<long long>(n_tiles, 12LL * h->num_sms);
+#define FE_LAUNCH_PACK(DT)                                                                                          \
+        do {                                                                                                        \
+            FE_CUDA(h, cudaFuncSetAttribute(k_norm_delta_pack<DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            k_norm_delta_pack<DT><<<grid, kPackThreads, smem, st>>>(tiles, (int)n_tiles, statics,                   \
+                (const float*)h->d_stats.p, out, D, tile_frames, delta_mode, flags);                                \
+        } while (0)
+        if (D == 13) FE_LAUNCH_PACK(13);
+        else if (D == 39) FE_LAUNCH_PACK(39);
+        else if (D == 40) FE_LAUNCH_PACK(40);
+        else if (D == 80) FE_LAUNCH_PACK(80);
+        else FE_LAUNCH_PACK(0);
+#undef FE_LAUNCH_PACK
+        h->launches++;
+    }
+    FE_CUDA(h, cudaGetLastError());
+    return FE_OK;
+}
+
 DevTables dev_tables(const fe_handle* h, bool in_f32) {
     const fe_config& c = h->cfg;
     DevTables dt;
@@ -293,7 +333,7 @@ int fe_destroy(fe_handle* h) {
     cudaStreamSynchronize(h->stream);
     for (DevBuf* b : {&h->tw256, &h->tw512, &h->window, &h->mel_bi, &h->mel_w, &h->dct,
                       &h->d_sp_up, &h->d_sp_down, &h->d_sp_tap_off, &h->d_taps, &h->d_utts,
-                      &h->d_tile_prefix, &h->d_tiles, &h->d_atile_prefix, &h->d_atiles, &h->d_statics,
+                      &h->d_tile_prefix, &h->d_tiles, &h->d_atile_prefix, &h->d_atiles, &h->d_statics, &h->d_stats,
                       &h->d_pcm, &h->d_out, &h->d_scratch})
         release(*b);
     if (h->h_stage.p) cudaFreeHost(h->h_stage.p);
@@ -488,12 +528,9 @@ int fe_run(fe_handle* h, const void* pcm, const int64_t* pcm_offsets, const int6
                         (int)pl.total_tiles, dt, stat_base))) return rc;
     if (prof) FE_CUDA(h, cudaEventRecord(ps->e[3], st));
     if (c.cmvn && pl.total_frames > 0) {
-        int grid = (int)std::min<long long>(n_utts, 8LL * h->num_sms);
-        FE_CUDA(h, cudaFuncSetAttribute(k_cmvn_delta_pack, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)(k2_smem_floats(c.feat_dim) * sizeof(float))));
-        k_cmvn_delta_pack<<<grid, kK2Threads, k2_smem_floats(c.feat_dim) * sizeof(float), st>>>(
-            (const UttDesc*)h->d_utts.p, n_utts, (const float*)h->d_statics.p, d_out, c.feat_dim, c.delta_mode, 7);
-        h->launches++;
+        if ((rc = launch_k2(h, st, (const UttDesc*)h->d_utts.p, n_utts, (const TileDesc*)h->d_tiles.p, pl.total_tiles,
+                            (const float*)h->d_statics.p, d_out, c.feat_dim, h->k1_warps * kWarpFrames,
+                            c.delta_mode, 7))) return rc;
         if (prof) ps->k2 = true;
     }
     FE_CUDA(h, cudaGetLastError());
@@ -566,7 +603,7 @@ int fe_postprocess(fe_handle* h, const float* feats, const int64_t* feat_offsets
                    int32_t n_utts, int32_t D, int32_t mode, int32_t delta_mode, float* out, int64_t out_capacity,
                    int64_t* out_offsets, void* stream) {
     if (!h) return FE_ERR_INVALID;
-    if (n_utts < 0 || D < 1 || D > kK2Threads) return fail(h, FE_ERR_INVALID, "bad n_utts / D");
+    if (n_utts < 0 || D < 1 || D > 1024) return fail(h, FE_ERR_INVALID, "bad n_utts / D");
     if (n_utts == 0) { if (out_offsets) out_offsets[0] = 0; return FE_OK; }
     if (!feats || !feat_offsets || !n_frames || !out || !out_offsets) return fail(h, FE_ERR_INVALID, "NULL buffer");
     FE_CUDA(h, cudaSetDevice(h->device));
@@ -587,20 +624,28 @@ int fe_postprocess(fe_handle* h, const float* feats, const int64_t* feat_offsets
     if (off > out_capacity) return fail(h, FE_ERR_CAPACITY, "out buffer too small");
     const bool in_dev = is_device_ptr(feats), out_dev = is_device_ptr(out);
     int rc;
+    const int tile_frames = 32;
+    std::vector<long long> tpref((size_t)n_utts + 1, 0);
+    for (int i = 0; i < n_utts; ++i) tpref[(size_t)i + 1] = tpref[(size_t)i] + (n_frames[i] + tile_frames - 1) / tile_frames;
+    const long long n_tiles = tpref[(size_t)n_utts];
+    if (n_tiles > 0x7fffffffLL) return fail(h, FE_ERR_INVALID, "batch too large");
     if ((rc = ensure(h, h->d_utts, sizeof(UttDesc) * ut.size()))) return rc;
+    if ((rc = ensure(h, h->d_tile_prefix, sizeof(long long) * tpref.size()))) return rc;
+    if ((rc = ensure(h, h->d_tiles, sizeof(TileDesc) * (size_t)std::max<long long>(n_tiles, 1)))) return rc;
     const float* d_in = feats; float* d_out = out;
     if (!in_dev) { if ((rc = ensure(h, h->d_statics, sizeof(float) * (size_t)std::max<long long>(span, 1)))) return rc; d_in = (const float*)h->d_statics.p; }
     if (!out_dev) { if ((rc = ensure(h, h->d_out, sizeof(float) * (size_t)std::max<long long>(off, 1)))) return rc; d_out = (float*)h->d_out.p; }
     FE_CUDA(h, cudaMemcpyAsync(h->d_utts.p, ut.data(), sizeof(UttDesc) * ut.size(), cudaMemcpyHostToDevice, st));
+    FE_CUDA(h, cudaMemcpyAsync(h->d_tile_prefix.p, tpref.data(), sizeof(long long) * tpref.size(), cudaMemcpyHostToDevice, st));
     if (!in_dev) FE_CUDA(h, cudaMemcpyAsync(h->d_statics.p, feats, sizeof(float) * (size_t)span, cudaMemcpyHostToDevice, st));
     FE_CUDA(h, cudaStreamSynchronize(st));
-    FE_CUDA(h, cudaFuncSetAttribute(k_cmvn_delta_pack, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)(k2_smem_floats(D) * sizeof(float))));
-    int grid = (int)std::min<long long>(n_utts, 8LL * h->num_sms);
-    k_cmvn_delta_pack<<<grid, kK2Threads, k2_smem_floats(D) * sizeof(float), st>>>(
-        (const UttDesc*)h->d_utts.p, n_utts, d_in, d_out, D, delta_mode, mode);
-    h->launches++;
-    FE_CUDA(h, cudaGetLastError());
+    if (n_tiles > 0) {
+        k_build_tiles<<<(n_utts + 255) / 256, 256, 0, st>>>((const UttDesc*)h->d_utts.p, (const long long*)h->d_tile_prefix.p,
+                                                            n_utts, 160, D, tile_frames, (TileDesc*)h->d_tiles.p);
+        h->launches++;
+    }
+    if ((rc = launch_k2(h, st, (const UttDesc*)h->d_utts.p, n_utts, (const TileDesc*)h->d_tiles.p, n_tiles, d_in, d_out,
+                        D, tile_frames, delta_mode, mode))) return rc;
     if (!out_dev) {
         FE_CUDA(h, cudaMemcpyAsync(out, d_out, sizeof(float) * (size_t)off, cudaMemcpyDeviceToHost, st));
     }

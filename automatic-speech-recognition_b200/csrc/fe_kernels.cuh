@@ -2,7 +2,8 @@
 //   K0  k_resample           speed perturbation (polyphase Kaiser-sinc) + gain + requantise   utils/augmentation.py:6-56
 //   K0' k_preemph            optional pre-emphasis (speechpy.processing.preemphasis) to float scratch
 //   K1  k_frames_to_statics  framing -> rFFT512 -> power -> mel -> log -> DCT          preprocess.py:72-82
-//   K2  k_cmvn_delta_pack    per-utterance CMVN, delta, delta-delta, cube (L, D, 3)    preprocess.py:85-88
+//   K2a k_utt_stats          per-utterance mean / std of the statics (CMVN)            preprocess.py:85
+//   K2b k_norm_delta_pack    normalise, delta, delta-delta, cube (L, D, 3)             preprocess.py:86-88
 //   k_build_tiles            tile descriptors for K1's persistent tile loop
 #pragma once
 #include <cuda_runtime.h>
@@ -23,13 +24,16 @@ struct UttDesc {
     float gain;             // 1 = none
 };
 
-// one entry per tile (warps-per-CTA x 4 frames) of one utterance (32 bytes, two 16-byte loads)
+// one entry per tile (warps-per-CTA x 4 frames) of one utterance (48 bytes, three 16-byte loads)
 struct __align__(16) TileDesc {
     long long pcm_off;      // element offset of the tile's first sample
     long long stat_off;     // float offset of the tile's first statics row
+    long long out_off;      // float offset of the utterance's output (frame 0)
     int n_frames;           // 1..tile_frames
     int src_sel;
     int utt;
+    int first_frame;        // of this tile inside the utterance
+    int utt_frames;
     int pad;
 };
 
@@ -58,6 +62,7 @@ __global__ void k_build_tiles(const UttDesc* __restrict__ utts, const long long*
         t.pcm_off = d.pcm_off + (long long)f * hop;
         t.stat_off = d.stat_off + (long long)f * D;
         t.n_frames = min(tile_frames, d.n_frames - f);
+        t.out_off = d.out_off; t.first_frame = f; t.utt_frames = d.n_frames;
         t.src_sel = d.src_sel; t.utt = u; t.pad = 0;
         tiles[b++] = t;
     }
@@ -269,154 +274,193 @@ k_frames_to_statics(const void* __restrict__ pcm, const void* __restrict__ scrat
 }
 
 // ---------------------------------------------------------------------------
-// K2: per-utterance CMVN (two-pass mean / population std, eps = 2^-30), deltas,
-// cube pack.  One CTA per utterance (grid-stride).
+// K2a k_utt_stats: per-utterance mean and 1 / (population std + 2^-30) of every statics column
+// (speechpy.processing.cmvn, preprocess.py:85).  One 128-thread CTA per utterance (grid-stride),
+// two passes, fixed-order block reductions (deterministic).  mean = x[0] + mean(x - x[0]): the
+// shift keeps a constant column (digital silence) exactly constant.
+// flags: bit0 subtract the mean, bit1 divide by the std (stats[u] = {mean[D], inv[D]}).
 // ---------------------------------------------------------------------------
-constexpr int kK2Threads = 256;
+constexpr int kStatThreads = 128;
 
-__host__ __device__ inline int k2_rows_per_chunk(int D) {
-    int rb = 8192 / (3 * D);
-    if (rb > 64) rb = 64;
-    rb &= ~3;
-    return rb < 4 ? 4 : rb;
-}
-__host__ __device__ inline int k2_smem_floats(int D) {
-    int rb = k2_rows_per_chunk(D);
-    return kK2Threads + 2 * D + (rb + 8) * D + (rb + 4) * D + rb * 3 * D + 8;
-}
-
-__global__ void __launch_bounds__(kK2Threads)
-k_cmvn_delta_pack(const UttDesc* __restrict__ utts, int n_utts, const float* __restrict__ statics,
-                  float* __restrict__ out, int D, int delta_mode, int flags) {
-    // flags: bit0 subtract the mean, bit1 divide by (std + 2^-30), bit2 append delta / delta-delta
-    // (cube (L, D, 3)); without bit2 the output is the (L, D) matrix.  The front-end uses 7.
-    const bool f_mean = flags & 1, f_var = flags & 2, f_delta = flags & 4;
-    const int W = f_delta ? 3 : 1;
-    extern __shared__ __align__(16) float sm2[];
-    const int RB = k2_rows_per_chunk(D);
-    float* red = sm2;
-    float* mean = red + kK2Threads;
-    float* inv = mean + D;
-    float* cube = inv + D + ((4 - ((kK2Threads + 2 * D) & 3)) & 3);   // 16-byte aligned
-    float* vt = cube + RB * 3 * D;
-    float* d1 = vt + (RB + 8) * D;
+__global__ void __launch_bounds__(kStatThreads)
+k_utt_stats(const UttDesc* __restrict__ utts, int n_utts, const float* __restrict__ statics,
+            float* __restrict__ stats, int D, int flags) {
+    extern __shared__ float sm_s[];           // red[kStatThreads] | mean[D]
+    float* red = sm_s;
+    float* mean = sm_s + kStatThreads;
+    const bool f_mean = flags & 1, f_var = flags & 2;
     const int tid = threadIdx.x;
-    const int R = kK2Threads / D;
-    const int c = tid % D, r = tid / D;
-    const bool act = r < R;
-    const int cp1 = min(c + 1, D - 1), cp2 = min(c + 2, D - 1);
-
+    const int G = D <= kStatThreads ? kStatThreads / D : 1;      // row groups
     for (int ui = blockIdx.x; ui < n_utts; ui += gridDim.x) {
         const int L = utts[ui].n_frames;
+        float* st = stats + (long long)ui * 2 * D;
         if (L <= 0) continue;
         const float* x = statics + utts[ui].stat_off;
-        float* o = out + utts[ui].out_off;
-
-        // mean = x[0] + mean(x - x[0]): the shift keeps a constant column (digital silence) exactly
-        // constant, so its deviations are exactly 0 instead of one rounding error normalised to +-1
-        const float shift = (act && f_mean) ? x[c] : 0.f;
-        float s = 0.f;
-        if (act && f_mean) {      // four independent row streams per thread keep loads in flight
-            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-            const float* xc = x + c;
-            int tt = r;
-            for (; tt + 3 * R < L; tt += 4 * R) {
-                s0 += xc[(long long)tt * D] - shift; s1 += xc[(long long)(tt + R) * D] - shift;
-                s2 += xc[(long long)(tt + 2 * R) * D] - shift; s3 += xc[(long long)(tt + 3 * R) * D] - shift;
-            }
-            for (; tt < L; tt += R) s0 += xc[(long long)tt * D] - shift;
-            s = (s0 + s1) + (s2 + s3);
-        }
-        red[tid] = s;
-        __syncthreads();
-        if (tid < D) {
-            float m = 0.f;
-            for (int rr = 0; rr < R; ++rr) m += red[rr * D + tid];
-            mean[tid] = x[tid] + m / (float)L;
-        }
-        __syncthreads();
-        const float mu = (act && f_mean) ? mean[c] : 0.f;
-        float q = 0.f;
-        if (act && f_var) {
-            float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
-            const float* xc = x + c;
-            int tt = r;
-            for (; tt + 3 * R < L; tt += 4 * R) {
-                float d0 = xc[(long long)tt * D] - mu, d1 = xc[(long long)(tt + R) * D] - mu;
-                float d2 = xc[(long long)(tt + 2 * R) * D] - mu, d3 = xc[(long long)(tt + 3 * R) * D] - mu;
-                q0 = fmaf(d0, d0, q0); q1 = fmaf(d1, d1, q1); q2 = fmaf(d2, d2, q2); q3 = fmaf(d3, d3, q3);
-            }
-            for (; tt < L; tt += R) { float d = xc[(long long)tt * D] - mu; q0 = fmaf(d, d, q0); }
-            q = (q0 + q1) + (q2 + q3);
-        }
-        red[tid] = q;
-        __syncthreads();
-        if (tid < D) {
-            float v = 0.f;
-            for (int rr = 0; rr < R; ++rr) v += red[rr * D + tid];
-            inv[tid] = 1.0f / (sqrtf(v / (float)L) + 9.313225746154785e-10f);   // 2^-30
-        }
-        __syncthreads();
-        const float iv = (act && f_var) ? inv[c] : 1.f;
-
-        for (int t0 = 0; t0 < L; t0 += RB) {
-            const int nrow = min(RB, L - t0);
-            if (delta_mode == 0) {
-                // speechpy as shipped: deltas slide along the coefficient axis of the same frame
-                if (act) for (int row = r; row < nrow; row += R)
-                    vt[row * D + c] = (x[(long long)(t0 + row) * D + c] - mu) * iv;
-                __syncthreads();
-                if (act) for (int row = r; row < nrow; row += R)
-                    d1[row * D + c] = (vt[row * D + cp1] + 2.f * vt[row * D + cp2]) / 10.f;
-                __syncthreads();
-                if (act) for (int row = r; row < nrow; row += R) {
-                    float dd = (d1[row * D + cp1] + 2.f * d1[row * D + cp2]) / 10.f;
-                    float* q3 = cube + (row * D + c) * W;
-                    q3[0] = vt[row * D + c];
-                    if (f_delta) { q3[1] = d1[row * D + c]; q3[2] = dd; }
-                }
-            } else {
-                // textbook regression along time, edge replication; vt row i <-> frame clamp(t0-4+i),
-                // d1 row i <-> frame clamp(t0-2+i)
-                if (act) for (int i = r; i < nrow + 8; i += R) {
-                    int a = min(max(t0 - 4 + i, 0), L - 1);
-                    vt[i * D + c] = (x[(long long)a * D + c] - mu) * iv;
-                }
-                __syncthreads();
-                if (act) for (int i = r; i < nrow + 4; i += R) {
-                    int sfr = min(max(t0 - 2 + i, 0), L - 1);
-                    float acc = 0.f;
+        for (int cb = 0; cb < D; cb += kStatThreads) {           // column blocks (D > 128 only loops)
+            const int c = cb + tid % (D < kStatThreads ? D : kStatThreads);
+            const int r = D < kStatThreads ? tid / D : 0;
+            const bool act = r < G && c < D;
+            const float shift = (act && f_mean) ? x[c] : 0.f;
+            float s = 0.f;
+            if (act && f_mean) {
+                float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};      // eight row streams in flight per thread
+                const float* xc = x + c;
+                int t = r;
+                for (; t + 7 * G < L; t += 8 * G) {
+                    float v[8];
 #pragma unroll
-                    for (int k = 1; k <= 2; ++k) {
-                        int ap = min(sfr + k, L - 1) - (t0 - 4), am = max(sfr - k, 0) - (t0 - 4);
-                        acc += (float)k * (vt[ap * D + c] - vt[am * D + c]);
-                    }
-                    d1[i * D + c] = acc / 10.f;
-                }
-                __syncthreads();
-                if (act) for (int row = r; row < nrow; row += R) {
-                    int tt = t0 + row;
-                    float acc = 0.f;
+                    for (int k = 0; k < 8; ++k) v[k] = xc[(long long)(t + k * G) * D];
 #pragma unroll
-                    for (int k = 1; k <= 2; ++k) {
-                        int ap = min(tt + k, L - 1) - (t0 - 2), am = max(tt - k, 0) - (t0 - 2);
-                        acc += (float)k * (d1[ap * D + c] - d1[am * D + c]);
-                    }
-                    float* q3 = cube + (row * D + c) * W;
-                    q3[0] = vt[(row + 4) * D + c];
-                    if (f_delta) { q3[1] = d1[(row + 2) * D + c]; q3[2] = acc / 10.f; }
+                    for (int k = 0; k < 8; ++k) a[k] += v[k] - shift;
                 }
+                for (; t < L; t += G) a[0] += xc[(long long)t * D] - shift;
+                s = ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
+            }
+            red[tid] = s;
+            __syncthreads();
+            if (tid < D - cb && tid < kStatThreads) {
+                float m = 0.f;
+                if (f_mean) {
+                    const int w = D < kStatThreads ? D : kStatThreads;
+                    for (int rr = 0; rr < G; ++rr) m += red[rr * w + tid];
+                    m = x[cb + tid] + m / (float)L;
+                }
+                mean[tid] = m;
+                st[cb + tid] = m;
             }
             __syncthreads();
-            // coalesced copy of nrow * 3D floats; chunk start is 16-byte aligned (RB % 4 == 0)
-            const int total = nrow * W * D;
-            float* dst = o + (long long)t0 * W * D;
-            const int n4 = total >> 2;
-            for (int i = tid; i < n4; i += kK2Threads)
-                reinterpret_cast<float4*>(dst)[i] = reinterpret_cast<const float4*>(cube)[i];
-            for (int i = (n4 << 2) + tid; i < total; i += kK2Threads) dst[i] = cube[i];
+            const float mu = act ? mean[c - cb] : 0.f;
+            float q = 0.f;
+            if (act && f_var) {
+                float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                const float* xc = x + c;
+                int t = r;
+                for (; t + 7 * G < L; t += 8 * G) {
+                    float v[8];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) v[k] = xc[(long long)(t + k * G) * D] - mu;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) a[k] = fmaf(v[k], v[k], a[k]);
+                }
+                for (; t < L; t += G) { float d = xc[(long long)t * D] - mu; a[0] = fmaf(d, d, a[0]); }
+                q = ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
+            }
+            __syncthreads();
+            red[tid] = q;
+            __syncthreads();
+            if (tid < D - cb && tid < kStatThreads) {
+                float iv = 1.f;
+                if (f_var) {
+                    float v = 0.f;
+                    const int w = D < kStatThreads ? D : kStatThreads;
+                    for (int rr = 0; rr < G; ++rr) v += red[rr * w + tid];
+                    iv = 1.0f / (sqrtf(v / (float)L) + 9.313225746154785e-10f);   // 2^-30
+                }
+                st[D + cb + tid] = iv;
+            }
             __syncthreads();
         }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// K2b k_norm_delta_pack: normalise, delta, delta-delta, pack the cube (L, D, 3)
+// (speechpy.feature.extract_derivative_feature, preprocess.py:86).  Tile-parallel (same tile
+// table as K1), streaming: 4 D bytes in, 12 D bytes out per frame, written with coalesced
+// 16-byte stores from a shared-memory image of the tile.
+// flags bit2: append deltas (else the output is the normalised (L, D) matrix).
+// ---------------------------------------------------------------------------
+constexpr int kPackThreads = 128;
+
+__host__ __device__ inline int k2_smem_floats(int D, int tile_frames) {
+    return 2 * D + (tile_frames + 8) * D + (tile_frames + 4) * D + tile_frames * 3 * D + 16;
+}
+
+// DT > 0: feature width known at compile time (index math by multiply-shift instead of integer division)
+template <int DT>
+__global__ void __launch_bounds__(kPackThreads)
+k_norm_delta_pack(const TileDesc* __restrict__ tiles, int n_tiles, const float* __restrict__ statics,
+                  const float* __restrict__ stats, float* __restrict__ out, int D_rt, int tile_frames,
+                  int delta_mode, int flags) {
+    const int D = DT > 0 ? DT : D_rt;
+    extern __shared__ __align__(16) float sm_p[];
+    const bool f_delta = flags & 4;
+    const int W = f_delta ? 3 : 1;
+    float* cube = sm_p;                                            // [tile_frames][D][W], 16-byte aligned
+    float* mi = cube + ((tile_frames * 3 * D + 3) & ~3);           // mean[D], inv[D]
+    float* vt = mi + 2 * D;                                        // [(rows + 8)][D]
+    float* d1 = vt + (tile_frames + 8) * D;                        // [(rows + 4)][D]
+    const int tid = threadIdx.x;
+    for (int ti = blockIdx.x; ti < n_tiles; ti += gridDim.x) {
+        const TileDesc td = tiles[ti];
+        const int nrow = td.n_frames, L = td.utt_frames, t0 = td.first_frame;
+        const float* st = stats + (long long)td.utt * 2 * D;
+        const float* x0 = statics + td.stat_off - (long long)t0 * D;          // frame 0 of the utterance
+        for (int i = tid; i < 2 * D; i += kPackThreads) mi[i] = st[i];
+        __syncthreads();
+        if (!f_delta || delta_mode == 0) {
+            // as shipped: everything is local to the frame
+            const int n = nrow * D;
+            const float* x = statics + td.stat_off;
+            for (int i = tid; i < n; i += kPackThreads) {
+                const int c = i % D;
+                vt[i] = (x[i] - mi[c]) * mi[D + c];
+            }
+            __syncthreads();
+            for (int i = tid; i < n; i += kPackThreads) {
+                const int c = i % D, rb = i - c;
+                const float v = vt[i];
+                if (!f_delta) { cube[i] = v; continue; }
+                // d1[k] = (v[k+1] + 2 v[k+2]) / 10, d2[k] = (d1[k+1] + 2 d1[k+2]) / 10, indices clamped to D-1;
+                // with ci = min(c+i, D-1): d1[c1] = (v[c2] + 2 v[c3]) / 10 and d1[c2] = (v[c3] + 2 v[c4]) / 10
+                const float v1 = vt[rb + min(c + 1, D - 1)], v2 = vt[rb + min(c + 2, D - 1)];
+                const float v3 = vt[rb + min(c + 3, D - 1)], v4 = vt[rb + min(c + 4, D - 1)];
+                const float da = (v1 + 2.f * v2) * 0.1f;
+                const float db = (v2 + 2.f * v3) * 0.1f;
+                const float dc = (v3 + 2.f * v4) * 0.1f;
+                float* q3 = cube + i * 3;
+                q3[0] = v; q3[1] = da; q3[2] = (db + 2.f * dc) * 0.1f;
+            }
+        } else {
+            // regression along time, edge replication; vt row i <-> frame clamp(t0-4+i), d1 row i <-> clamp(t0-2+i)
+            for (int i = tid; i < (nrow + 8) * D; i += kPackThreads) {
+                const int c = i % D, rr = i / D;
+                const int a = min(max(t0 - 4 + rr, 0), L - 1);
+                vt[i] = (x0[(long long)a * D + c] - mi[c]) * mi[D + c];
+            }
+            __syncthreads();
+            for (int i = tid; i < (nrow + 4) * D; i += kPackThreads) {
+                const int c = i % D, rr = i / D;
+                const int sfr = min(max(t0 - 2 + rr, 0), L - 1);
+                float acc = 0.f;
+#pragma unroll
+                for (int k = 1; k <= 2; ++k) {
+                    const int ap = min(sfr + k, L - 1) - (t0 - 4), am = max(sfr - k, 0) - (t0 - 4);
+                    acc += (float)k * (vt[ap * D + c] - vt[am * D + c]);
+                }
+                d1[i] = acc * 0.1f;
+            }
+            __syncthreads();
+            for (int i = tid; i < nrow * D; i += kPackThreads) {
+                const int c = i % D, rr = i / D, tt = t0 + rr;
+                float acc = 0.f;
+#pragma unroll
+                for (int k = 1; k <= 2; ++k) {
+                    const int ap = min(tt + k, L - 1) - (t0 - 2), am = max(tt - k, 0) - (t0 - 2);
+                    acc += (float)k * (d1[ap * D + c] - d1[am * D + c]);
+                }
+                float* q3 = cube + i * 3;
+                q3[0] = vt[(rr + 4) * D + c]; q3[1] = d1[(rr + 2) * D + c]; q3[2] = acc * 0.1f;
+            }
+        }
+        __syncthreads();
+        const int total = nrow * W * D;
+        float* dst = out + td.out_off + (long long)t0 * W * D;       // 16-byte aligned: t0 % 4 == 0
+        const int n4 = total >> 2;
+        for (int i = tid; i < n4; i += kPackThreads)
+            reinterpret_cast<float4*>(dst)[i] = reinterpret_cast<const float4*>(cube)[i];
+        for (int i = (n4 << 2) + tid; i < total; i += kPackThreads) dst[i] = cube[i];
+        __syncthreads();
     }
 }
 

@@ -218,7 +218,13 @@ def main():
     out_off, nfr = fe.plan(lens)
     frames = int(nfr.sum())
     d_out = torch.empty(int(out_off[-1]), dtype=torch.float32, device="cuda")
-    stream = torch.cuda.current_stream().cuda_stream
+    # an explicit (non-default) stream: the kernels, the timing events and the library's own
+    # per-kernel events all live on it
+    tstream = torch.cuda.Stream()
+    torch.cuda.synchronize()
+    torch.cuda.set_stream(tstream)
+    stream = tstream.cuda_stream
+    assert stream != 0
 
     def step():
         fe.run_packed(d_pcm, off, lens, out=d_out, stream=stream)
