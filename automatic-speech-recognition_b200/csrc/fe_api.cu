@@ -30,6 +30,18 @@ struct HostPinned {
 
 }  // namespace
 
+// per-run device/host scratch and the stream it is used on.  Lane 0 serves every call; lanes 1..2
+// exist only for the chunked host pipeline of fe_run (H2D / kernels / D2H of neighbouring chunks overlap).
+struct Lane {
+    cudaStream_t stream = nullptr;
+    DevBuf d_utts, d_tile_prefix, d_tiles, d_atile_prefix, d_atiles, d_statics, d_stats, d_pcm, d_out, d_scratch;
+    HostPinned h_stage;
+    std::vector<UttDesc> utts;
+    std::vector<long long> tile_prefix, atile_prefix;
+    cudaEvent_t done = nullptr;       // end of the kernels of the last run on this lane
+    bool done_valid = false;
+};
+
 struct fe_handle {
     int device = 0;
     int num_sms = 0;
@@ -47,21 +59,16 @@ struct fe_handle {
     std::vector<int> sp_up, sp_down, sp_tap_off;
     DevBuf d_sp_up, d_sp_down, d_sp_tap_off, d_taps;
 
-    // per-run scratch (grow-only)
-    DevBuf d_utts, d_tile_prefix, d_tiles, d_atile_prefix, d_atiles, d_statics, d_stats, d_pcm, d_out, d_scratch;
-    HostPinned h_stage;
-    std::vector<UttDesc> utts;
-    std::vector<long long> tile_prefix, atile_prefix;
+    Lane lane[3];
 
     int profiling = 0;
-    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // ev[5]: end of the last run
-    bool ev_valid = false;
     // profiled runs since fe_set_profiling(1): one event set per run (no sync inside the timed region)
     struct ProfSet { cudaEvent_t e[5]; bool k0, k2; };
     std::vector<ProfSet> prof;
     size_t prof_used = 0;
     int64_t launches = 0;
     size_t k1_smem[2] = {0, 0};      // [raw int16 input, float input]
+    long long pipe_chunk_bytes = 192LL << 20;   // PCM bytes per chunk of the host pipeline (FE_PIPE_CHUNK_MB overrides)
     int k1_warps = 8;                // warps per K1 CTA (8 -> 128 regs/thread, 6 -> 168); FE_K1_WARPS overrides
 };
 
@@ -121,13 +128,13 @@ struct Plan {
     bool any_scratch = false;
 };
 
-int make_plan(fe_handle* h, const int64_t* pcm_offsets, const int64_t* pcm_lengths, int32_t n,
+int make_plan(fe_handle* h, Lane& ln, const int64_t* pcm_offsets, const int64_t* pcm_lengths, int32_t n,
               const int32_t* speed_idx, const float* gain, int64_t* out_offsets, int32_t* n_frames,
               Plan& pl, bool fill_desc) {
     const fe_config& c = h->cfg;
     const int width = c.feat_dim * (c.cmvn ? 3 : 1);
     const long long align = c.pcm_dtype == FE_PCM_INT16 ? 8 : 4;
-    if (fill_desc) { h->utts.resize(n); h->tile_prefix.resize(n + 1); h->atile_prefix.resize(n + 1); }
+    if (fill_desc) { ln.utts.resize(n); ln.tile_prefix.resize(n + 1); ln.atile_prefix.resize(n + 1); }
     long long out_off = 0;
     for (int i = 0; i < n; ++i) {
         const long long len = pcm_lengths[i];
@@ -150,7 +157,7 @@ int make_plan(fe_handle* h, const int64_t* pcm_offsets, const int64_t* pcm_lengt
             return fail(h, FE_ERR_INVALID, "gain perturbation needs int16 PCM");
         const bool via_scratch = sidx >= 0 || g != 1.f || preemph;
         if (fill_desc) {
-            UttDesc& u = h->utts[i];
+            UttDesc& u = ln.utts[i];
             const long long off = pcm_offsets[i];
             if (off < 0 || off % align) return fail(h, FE_ERR_INVALID, "pcm_offsets must be multiples of 16 bytes");
             u.src_off = off;
@@ -163,8 +170,8 @@ int make_plan(fe_handle* h, const int64_t* pcm_offsets, const int64_t* pcm_lengt
             u.pcm_off = via_scratch ? pl.total_scratch : off;
             u.out_off = out_off;
             u.stat_off = c.cmvn ? pl.total_frames * c.feat_dim : out_off;
-            h->tile_prefix[i] = pl.total_tiles;
-            h->atile_prefix[i] = pl.total_atiles;
+            ln.tile_prefix[i] = pl.total_tiles;
+            ln.atile_prefix[i] = pl.total_atiles;
             pl.pcm_span = std::max(pl.pcm_span, off + len);
         }
         if (via_scratch) {
@@ -177,7 +184,7 @@ int make_plan(fe_handle* h, const int64_t* pcm_offsets, const int64_t* pcm_lengt
         out_off += round_up(L * width, 4);
     }
     if (out_offsets) out_offsets[n] = out_off;
-    if (fill_desc) { h->tile_prefix[n] = pl.total_tiles; h->atile_prefix[n] = pl.total_atiles; }
+    if (fill_desc) { ln.tile_prefix[n] = pl.total_tiles; ln.atile_prefix[n] = pl.total_atiles; }
     pl.total_out = out_off;
     return FE_OK;
 }
@@ -228,21 +235,21 @@ int launch_k1(fe_handle* h, cudaStream_t st, const void* pcm, const void* scratc
 }
 
 // K2a + K2b: per-utterance statistics, then the tile-parallel normalise / delta / pack pass
-int launch_k2(fe_handle* h, cudaStream_t st, const UttDesc* utts, int n_utts, const TileDesc* tiles, long long n_tiles,
+int launch_k2(fe_handle* h, Lane& L, cudaStream_t st, const UttDesc* utts, int n_utts, const TileDesc* tiles, long long n_tiles,
               const float* statics, float* out, int D, int tile_frames, int delta_mode, int flags) {
     int rc;
-    if ((rc = ensure(h, h->d_stats, sizeof(float) * 2 * (size_t)D * (size_t)n_utts))) return rc;
+    if ((rc = ensure(h, L.d_stats, sizeof(float) * 2 * (size_t)D * (size_t)n_utts))) return rc;
     if (flags & 3) {
         const int grid = (int)std::min<long long>(n_utts, 32LL * h->num_sms);
         k_utt_stats<<<grid, kStatThreads, (kStatThreads + std::min(D, kStatThreads)) * sizeof(float), st>>>(
-            utts, n_utts, statics, (float*)h->d_stats.p, D, flags);
+            utts, n_utts, statics, (float*)L.d_stats.p, D, flags);
         h->launches++;
     } else {
         // no normalisation: mean 0, scale 1
         std::vector<float> id((size_t)2 * D);
         for (int i = 0; i < D; ++i) { id[i] = 0.f; id[D + i] = 1.f; }
         for (int u = 0; u < n_utts; ++u)
-            FE_CUDA(h, cudaMemcpyAsync((float*)h->d_stats.p + (size_t)u * 2 * D, id.data(), sizeof(float) * 2 * D,
+            FE_CUDA(h, cudaMemcpyAsync((float*)L.d_stats.p + (size_t)u * 2 * D, id.data(), sizeof(float) * 2 * D,
                                        cudaMemcpyHostToDevice, st));
         FE_CUDA(h, cudaStreamSynchronize(st));
     }
@@ -253,7 +260,7 @@ int launch_k2(fe_handle* h, cudaStream_t st, const UttDesc* utts, int n_utts, co
         do {                                                                                                        \
             FE_CUDA(h, cudaFuncSetAttribute(k_norm_delta_pack<DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
             k_norm_delta_pack<DT><<<grid, kPackThreads, smem, st>>>(tiles, (int)n_tiles, statics,                   \
-                (const float*)h->d_stats.p, out, D, tile_frames, delta_mode, flags);                                \
+                (const float*)L.d_stats.p, out, D, tile_frames, delta_mode, flags);                                \
         } while (0)
         if (D == 13) FE_LAUNCH_PACK(13);
         else if (D == 39) FE_LAUNCH_PACK(39);
@@ -322,7 +329,12 @@ int fe_create(int device, fe_handle** out) {
     h->device = device;
     h->num_sms = prop.multiProcessorCount;
     FE_CUDA(nullptr, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
-    for (auto& ev : h->ev) FE_CUDA(nullptr, cudaEventCreate(&ev));
+    for (int i = 0; i < 3; ++i) {
+        if (i == 0) h->lane[i].stream = h->stream;
+        else FE_CUDA(nullptr, cudaStreamCreateWithFlags(&h->lane[i].stream, cudaStreamNonBlocking));
+        FE_CUDA(nullptr, cudaEventCreateWithFlags(&h->lane[i].done, cudaEventDisableTiming));
+    }
+    if (const char* e = getenv("FE_PIPE_CHUNK_MB")) { long long mb = atoll(e); if (mb > 0) h->pipe_chunk_bytes = mb << 20; }
     *out = h;
     return FE_OK;
 }
@@ -330,14 +342,18 @@ int fe_create(int device, fe_handle** out) {
 int fe_destroy(fe_handle* h) {
     if (!h) return FE_OK;
     cudaSetDevice(h->device);
-    cudaStreamSynchronize(h->stream);
+    cudaDeviceSynchronize();
     for (DevBuf* b : {&h->tw256, &h->tw512, &h->window, &h->mel_bi, &h->mel_w, &h->dct,
-                      &h->d_sp_up, &h->d_sp_down, &h->d_sp_tap_off, &h->d_taps, &h->d_utts,
-                      &h->d_tile_prefix, &h->d_tiles, &h->d_atile_prefix, &h->d_atiles, &h->d_statics, &h->d_stats,
-                      &h->d_pcm, &h->d_out, &h->d_scratch})
+                      &h->d_sp_up, &h->d_sp_down, &h->d_sp_tap_off, &h->d_taps})
         release(*b);
-    if (h->h_stage.p) cudaFreeHost(h->h_stage.p);
-    for (auto& ev : h->ev) if (ev) cudaEventDestroy(ev);
+    for (Lane& L : h->lane) {
+        for (DevBuf* b : {&L.d_utts, &L.d_tile_prefix, &L.d_tiles, &L.d_atile_prefix, &L.d_atiles, &L.d_statics,
+                          &L.d_stats, &L.d_pcm, &L.d_out, &L.d_scratch})
+            release(*b);
+        if (L.h_stage.p) cudaFreeHost(L.h_stage.p);
+        if (L.done) cudaEventDestroy(L.done);
+        if (L.stream && L.stream != h->stream) cudaStreamDestroy(L.stream);
+    }
     for (auto& p : h->prof) for (auto& e : p.e) if (e) cudaEventDestroy(e);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -419,23 +435,19 @@ int fe_plan(fe_handle* h, const int64_t* pcm_lengths, int32_t n_utts, const int3
     if (!h->configured) return fail(h, FE_ERR_STATE, "fe_configure first");
     if (n_utts < 0 || (n_utts > 0 && !pcm_lengths)) return fail(h, FE_ERR_INVALID, "bad arguments");
     Plan pl;
-    return make_plan(h, nullptr, pcm_lengths, n_utts, speed_idx, nullptr, out_offsets, n_frames, pl, false);
+    return make_plan(h, h->lane[0], nullptr, pcm_lengths, n_utts, speed_idx, nullptr, out_offsets, n_frames, pl, false);
 }
 
-int fe_run(fe_handle* h, const void* pcm, const int64_t* pcm_offsets, const int64_t* pcm_lengths,
-           int32_t n_utts, const int32_t* speed_idx, const float* gain,
-           float* out, int64_t out_capacity, int64_t* out_offsets, int32_t* n_frames, void* stream) {
-    if (!h) return FE_ERR_INVALID;
-    if (!h->configured) return fail(h, FE_ERR_STATE, "fe_configure first");
-    if (n_utts < 0) return fail(h, FE_ERR_INVALID, "n_utts < 0");
-    if (n_utts == 0) { if (out_offsets) out_offsets[0] = 0; return FE_OK; }
-    if (!pcm || !pcm_offsets || !pcm_lengths || !out) return fail(h, FE_ERR_INVALID, "NULL buffer");
+// One batch on one lane: plan, descriptor upload, (H2D), tile build, K0, K1, K2, (D2H).  Asynchronous on
+// `st` unless `final_sync`.  `pcm` / `out` may be host or device pointers.
+static int run_core(fe_handle* h, Lane& L, cudaStream_t st, const void* pcm, const int64_t* pcm_offsets,
+                    const int64_t* pcm_lengths, int32_t n_utts, const int32_t* speed_idx, const float* gain,
+                    float* out, int64_t out_capacity, int64_t* out_offsets, int32_t* n_frames,
+                    bool allow_prof, bool final_sync) {
     const fe_config& c = h->cfg;
-    FE_CUDA(h, cudaSetDevice(h->device));
-    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
 
     Plan pl;
-    int rc = make_plan(h, pcm_offsets, pcm_lengths, n_utts, speed_idx, gain, out_offsets, n_frames, pl, true);
+    int rc = make_plan(h, L, pcm_offsets, pcm_lengths, n_utts, speed_idx, gain, out_offsets, n_frames, pl, true);
     if (rc) return rc;
     if (pl.total_out > out_capacity) return fail(h, FE_ERR_CAPACITY, "out buffer too small for this batch");
     if (pl.total_tiles > 0x7fffffffLL || pl.total_atiles > 0x7fffffffLL) return fail(h, FE_ERR_INVALID, "batch too large");
@@ -445,37 +457,37 @@ int fe_run(fe_handle* h, const void* pcm, const int64_t* pcm_offsets, const int6
 
     // descriptors -> pinned staging -> device (async on st)
     const size_t b_utts = sizeof(UttDesc) * (size_t)n_utts, b_pref = sizeof(long long) * (size_t)(n_utts + 1);
-    if ((rc = ensure_pinned(h, h->h_stage, b_utts + 2 * b_pref))) return rc;
-    if ((rc = ensure(h, h->d_utts, b_utts))) return rc;
-    if ((rc = ensure(h, h->d_tile_prefix, b_pref))) return rc;
-    if ((rc = ensure(h, h->d_atile_prefix, b_pref))) return rc;
-    if ((rc = ensure(h, h->d_tiles, sizeof(TileDesc) * (size_t)std::max<long long>(pl.total_tiles, 1)))) return rc;
-    if (c.cmvn && (rc = ensure(h, h->d_statics, sizeof(float) * (size_t)std::max<long long>(pl.total_frames * c.feat_dim, 1)))) return rc;
+    if ((rc = ensure_pinned(h, L.h_stage, b_utts + 2 * b_pref))) return rc;
+    if ((rc = ensure(h, L.d_utts, b_utts))) return rc;
+    if ((rc = ensure(h, L.d_tile_prefix, b_pref))) return rc;
+    if ((rc = ensure(h, L.d_atile_prefix, b_pref))) return rc;
+    if ((rc = ensure(h, L.d_tiles, sizeof(TileDesc) * (size_t)std::max<long long>(pl.total_tiles, 1)))) return rc;
+    if (c.cmvn && (rc = ensure(h, L.d_statics, sizeof(float) * (size_t)std::max<long long>(pl.total_frames * c.feat_dim, 1)))) return rc;
     const bool preemph = c.preemph != 0.f;
     const bool k1_f32 = preemph || c.pcm_dtype == FE_PCM_FLOAT32;      // what K1's stage A reads
     if (pl.any_scratch) {
-        if ((rc = ensure(h, h->d_scratch, (preemph ? 4 : 2) * (size_t)pl.total_scratch + 64))) return rc;
-        if ((rc = ensure(h, h->d_atiles, sizeof(int2) * (size_t)pl.total_atiles))) return rc;
+        if ((rc = ensure(h, L.d_scratch, (preemph ? 4 : 2) * (size_t)pl.total_scratch + 64))) return rc;
+        if ((rc = ensure(h, L.d_atiles, sizeof(int2) * (size_t)pl.total_atiles))) return rc;
     }
     const void* d_pcm = pcm;
     float* d_out = out;
-    if (!pcm_on_dev) { if ((rc = ensure(h, h->d_pcm, esz * (size_t)pl.pcm_span))) return rc; d_pcm = h->d_pcm.p; }
-    if (!out_on_dev) { if ((rc = ensure(h, h->d_out, sizeof(float) * (size_t)std::max<long long>(pl.total_out, 1)))) return rc; d_out = (float*)h->d_out.p; }
+    if (!pcm_on_dev) { if ((rc = ensure(h, L.d_pcm, esz * (size_t)pl.pcm_span))) return rc; d_pcm = L.d_pcm.p; }
+    if (!out_on_dev) { if ((rc = ensure(h, L.d_out, sizeof(float) * (size_t)std::max<long long>(pl.total_out, 1)))) return rc; d_out = (float*)L.d_out.p; }
 
-    // the previous run on this handle may still be reading the staging area
-    if (h->ev_valid) FE_CUDA(h, cudaEventSynchronize(h->ev[5]));
-    unsigned char* hs = (unsigned char*)h->h_stage.p;
-    memcpy(hs, h->utts.data(), b_utts);
-    memcpy(hs + b_utts, h->tile_prefix.data(), b_pref);
-    memcpy(hs + b_utts + b_pref, h->atile_prefix.data(), b_pref);
-    FE_CUDA(h, cudaMemcpyAsync(h->d_utts.p, hs, b_utts, cudaMemcpyHostToDevice, st));
-    FE_CUDA(h, cudaMemcpyAsync(h->d_tile_prefix.p, hs + b_utts, b_pref, cudaMemcpyHostToDevice, st));
+    // the previous run on this lane may still be reading the staging area
+    if (L.done_valid) FE_CUDA(h, cudaEventSynchronize(L.done));
+    unsigned char* hs = (unsigned char*)L.h_stage.p;
+    memcpy(hs, L.utts.data(), b_utts);
+    memcpy(hs + b_utts, L.tile_prefix.data(), b_pref);
+    memcpy(hs + b_utts + b_pref, L.atile_prefix.data(), b_pref);
+    FE_CUDA(h, cudaMemcpyAsync(L.d_utts.p, hs, b_utts, cudaMemcpyHostToDevice, st));
+    FE_CUDA(h, cudaMemcpyAsync(L.d_tile_prefix.p, hs + b_utts, b_pref, cudaMemcpyHostToDevice, st));
     if (pl.any_scratch)
-        FE_CUDA(h, cudaMemcpyAsync(h->d_atile_prefix.p, hs + b_utts + b_pref, b_pref, cudaMemcpyHostToDevice, st));
+        FE_CUDA(h, cudaMemcpyAsync(L.d_atile_prefix.p, hs + b_utts + b_pref, b_pref, cudaMemcpyHostToDevice, st));
     if (((uintptr_t)d_pcm & 15) != 0) return fail(h, FE_ERR_INVALID, "pcm buffer must be 16-byte aligned");
-    if (!pcm_on_dev) FE_CUDA(h, cudaMemcpyAsync(h->d_pcm.p, pcm, esz * (size_t)pl.pcm_span, cudaMemcpyHostToDevice, st));
+    if (!pcm_on_dev) FE_CUDA(h, cudaMemcpyAsync(L.d_pcm.p, pcm, esz * (size_t)pl.pcm_span, cudaMemcpyHostToDevice, st));
 
-    const bool prof = h->profiling != 0 && h->prof_used < 4096;
+    const bool prof = allow_prof && h->profiling != 0 && h->prof_used < 4096;
     fe_handle::ProfSet* ps = nullptr;
     if (prof) {
         if (h->prof_used == h->prof.size()) {
@@ -489,8 +501,8 @@ int fe_run(fe_handle* h, const void* pcm, const int64_t* pcm_offsets, const int6
     }
     const int tb = 256, gb = (n_utts + tb - 1) / tb;
     if (pl.total_tiles > 0) {
-        k_build_tiles<<<gb, tb, 0, st>>>((const UttDesc*)h->d_utts.p, (const long long*)h->d_tile_prefix.p, n_utts,
-                                         c.hop, c.feat_dim, h->k1_warps * kWarpFrames, (TileDesc*)h->d_tiles.p);
+        k_build_tiles<<<gb, tb, 0, st>>>((const UttDesc*)L.d_utts.p, (const long long*)L.d_tile_prefix.p, n_utts,
+                                         c.hop, c.feat_dim, h->k1_warps * kWarpFrames, (TileDesc*)L.d_tiles.p);
         h->launches++;
     }
     if (pl.any_scratch) {
@@ -498,50 +510,103 @@ int fe_run(fe_handle* h, const void* pcm, const int64_t* pcm_offsets, const int6
         // (n_frames is not the right count there, so a dedicated tiny builder pass)
         std::vector<int2> at((size_t)pl.total_atiles);
         for (int i = 0; i < n_utts; ++i) {
-            long long b = h->atile_prefix[i], e = h->atile_prefix[i + 1];
+            long long b = L.atile_prefix[i], e = L.atile_prefix[i + 1];
             for (long long k = b; k < e; ++k) at[(size_t)k] = make_int2(i, (int)((k - b) * kK0Outputs));
         }
-        FE_CUDA(h, cudaMemcpyAsync(h->d_atiles.p, at.data(), sizeof(int2) * at.size(), cudaMemcpyHostToDevice, st));
+        FE_CUDA(h, cudaMemcpyAsync(L.d_atiles.p, at.data(), sizeof(int2) * at.size(), cudaMemcpyHostToDevice, st));
         FE_CUDA(h, cudaStreamSynchronize(st));     // `at` is pageable and dies at scope end
         if (prof) FE_CUDA(h, cudaEventRecord(ps->e[1], st));
         int grid = (int)std::min<long long>(pl.total_atiles, 16LL * h->num_sms);
         if (preemph) {
             if (c.pcm_dtype == FE_PCM_INT16)
-                k_preemph<0><<<grid, 256, 0, st>>>(d_pcm, (const UttDesc*)h->d_utts.p, (const int2*)h->d_atiles.p,
-                                                   (int)pl.total_atiles, c.preemph, (float*)h->d_scratch.p);
+                k_preemph<0><<<grid, 256, 0, st>>>(d_pcm, (const UttDesc*)L.d_utts.p, (const int2*)L.d_atiles.p,
+                                                   (int)pl.total_atiles, c.preemph, (float*)L.d_scratch.p);
             else
-                k_preemph<1><<<grid, 256, 0, st>>>(d_pcm, (const UttDesc*)h->d_utts.p, (const int2*)h->d_atiles.p,
-                                                   (int)pl.total_atiles, c.preemph, (float*)h->d_scratch.p);
+                k_preemph<1><<<grid, 256, 0, st>>>(d_pcm, (const UttDesc*)L.d_utts.p, (const int2*)L.d_atiles.p,
+                                                   (int)pl.total_atiles, c.preemph, (float*)L.d_scratch.p);
         } else {
-            k_resample<<<grid, 256, 0, st>>>((const short*)d_pcm, (const UttDesc*)h->d_utts.p, (const int2*)h->d_atiles.p,
+            k_resample<<<grid, 256, 0, st>>>((const short*)d_pcm, (const UttDesc*)L.d_utts.p, (const int2*)L.d_atiles.p,
                                              (int)pl.total_atiles, (const int*)h->d_sp_up.p, (const int*)h->d_sp_down.p,
                                              (const int*)h->d_sp_tap_off.p, (const float*)h->d_taps.p,
-                                             (short*)h->d_scratch.p, 0);
+                                             (short*)L.d_scratch.p, 0);
         }
         h->launches++;
         if (prof) ps->k0 = true;
     }
     if (prof) FE_CUDA(h, cudaEventRecord(ps->e[2], st));
     DevTables dt = dev_tables(h, k1_f32);
-    float* stat_base = c.cmvn ? (float*)h->d_statics.p : d_out;
-    if ((rc = launch_k1(h, st, d_pcm, h->d_scratch.p, k1_f32, (const TileDesc*)h->d_tiles.p,
+    float* stat_base = c.cmvn ? (float*)L.d_statics.p : d_out;
+    if ((rc = launch_k1(h, st, d_pcm, L.d_scratch.p, k1_f32, (const TileDesc*)L.d_tiles.p,
                         (int)pl.total_tiles, dt, stat_base))) return rc;
     if (prof) FE_CUDA(h, cudaEventRecord(ps->e[3], st));
     if (c.cmvn && pl.total_frames > 0) {
-        if ((rc = launch_k2(h, st, (const UttDesc*)h->d_utts.p, n_utts, (const TileDesc*)h->d_tiles.p, pl.total_tiles,
-                            (const float*)h->d_statics.p, d_out, c.feat_dim, h->k1_warps * kWarpFrames,
+        if ((rc = launch_k2(h, L, st, (const UttDesc*)L.d_utts.p, n_utts, (const TileDesc*)L.d_tiles.p, pl.total_tiles,
+                            (const float*)L.d_statics.p, d_out, c.feat_dim, h->k1_warps * kWarpFrames,
                             c.delta_mode, 7))) return rc;
         if (prof) ps->k2 = true;
     }
     FE_CUDA(h, cudaGetLastError());
     if (prof) FE_CUDA(h, cudaEventRecord(ps->e[4], st));
-    FE_CUDA(h, cudaEventRecord(h->ev[5], st));
-    h->ev_valid = true;
-    if (!out_on_dev) {
+    if (!out_on_dev)
         FE_CUDA(h, cudaMemcpyAsync(out, d_out, sizeof(float) * (size_t)pl.total_out, cudaMemcpyDeviceToHost, st));
-        FE_CUDA(h, cudaStreamSynchronize(st));
-    }
+    FE_CUDA(h, cudaEventRecord(L.done, st));
+    L.done_valid = true;
+    if (final_sync) FE_CUDA(h, cudaStreamSynchronize(st));
     return FE_OK;
+}
+
+
+
+int fe_run(fe_handle* h, const void* pcm, const int64_t* pcm_offsets, const int64_t* pcm_lengths,
+           int32_t n_utts, const int32_t* speed_idx, const float* gain,
+           float* out, int64_t out_capacity, int64_t* out_offsets, int32_t* n_frames, void* stream) {
+    if (!h) return FE_ERR_INVALID;
+    if (!h->configured) return fail(h, FE_ERR_STATE, "fe_configure first");
+    if (n_utts < 0) return fail(h, FE_ERR_INVALID, "n_utts < 0");
+    if (n_utts == 0) { if (out_offsets) out_offsets[0] = 0; return FE_OK; }
+    if (!pcm || !pcm_offsets || !pcm_lengths || !out) return fail(h, FE_ERR_INVALID, "NULL buffer");
+    FE_CUDA(h, cudaSetDevice(h->device));
+    const fe_config& c = h->cfg;
+    const bool pcm_on_dev = is_device_ptr(pcm), out_on_dev = is_device_ptr(out);
+    const long long esz = c.pcm_dtype == FE_PCM_INT16 ? 2 : 4;
+    long long span = 0;
+    bool monotonic = true;
+    for (int i = 0; i < n_utts; ++i) {
+        if (i && pcm_offsets[i] < pcm_offsets[i - 1] + pcm_lengths[i - 1]) monotonic = false;
+        span = std::max<long long>(span, pcm_offsets[i] + pcm_lengths[i]);
+    }
+    // ---- host in, host out, large batch: chunked pipeline over lanes 1 and 2 so that the H2D copy of
+    // chunk i+1, the kernels of chunk i and the D2H copy of chunk i-1 overlap (PCIe is full duplex) ----
+    if (!pcm_on_dev && !out_on_dev && monotonic && span * esz > 2 * h->pipe_chunk_bytes && out_offsets && n_frames) {
+        Plan pl;
+        int rc = make_plan(h, h->lane[0], nullptr, pcm_lengths, n_utts, speed_idx, gain, out_offsets, n_frames, pl, false);
+        if (rc) return rc;
+        if (pl.total_out > out_capacity) return fail(h, FE_ERR_CAPACITY, "out buffer too small for this batch");
+        std::vector<int64_t> loc_off, loc_out((size_t)n_utts + 1);
+        std::vector<int32_t> loc_nf((size_t)n_utts);
+        int first = 0, k = 0;
+        while (first < n_utts) {
+            int last = first;                                   // chunk = utterances [first, last]
+            const long long base = pcm_offsets[first];
+            while (last + 1 < n_utts && (pcm_offsets[last + 1] + pcm_lengths[last + 1] - base) * esz <= h->pipe_chunk_bytes) ++last;
+            const int n = last - first + 1;
+            loc_off.assign((size_t)n, 0);
+            for (int i = 0; i < n; ++i) loc_off[(size_t)i] = pcm_offsets[first + i] - base;
+            Lane& L = h->lane[1 + (k & 1)];
+            rc = run_core(h, L, L.stream, (const char*)pcm + base * esz, loc_off.data(), pcm_lengths + first, n,
+                          speed_idx ? speed_idx + first : nullptr, gain ? gain + first : nullptr,
+                          out + out_offsets[first], out_offsets[last + 1] - out_offsets[first],
+                          loc_out.data(), loc_nf.data(), false, false);
+            if (rc) return rc;
+            first = last + 1; ++k;
+        }
+        FE_CUDA(h, cudaStreamSynchronize(h->lane[1].stream));
+        FE_CUDA(h, cudaStreamSynchronize(h->lane[2].stream));
+        return FE_OK;
+    }
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    return run_core(h, h->lane[0], st, pcm, pcm_offsets, pcm_lengths, n_utts, speed_idx, gain, out, out_capacity,
+                    out_offsets, n_frames, true, !out_on_dev);
 }
 
 int fe_perturb(fe_handle* h, const int16_t* pcm, const int64_t* pcm_offsets, const int64_t* pcm_lengths,
@@ -577,17 +642,17 @@ int fe_perturb(fe_handle* h, const int16_t* pcm, const int64_t* pcm_offsets, con
     if (at.empty()) return FE_OK;
     const bool src_dev = is_device_ptr(pcm), dst_dev = is_device_ptr(dst);
     int rc;
-    if ((rc = ensure(h, h->d_utts, sizeof(UttDesc) * ut.size()))) return rc;
-    if ((rc = ensure(h, h->d_atiles, sizeof(int2) * at.size()))) return rc;
+    if ((rc = ensure(h, h->lane[0].d_utts, sizeof(UttDesc) * ut.size()))) return rc;
+    if ((rc = ensure(h, h->lane[0].d_atiles, sizeof(int2) * at.size()))) return rc;
     const short* d_src = pcm; short* d_dst = dst;
-    if (!src_dev) { if ((rc = ensure(h, h->d_pcm, 2 * (size_t)span))) return rc; d_src = (const short*)h->d_pcm.p; }
-    if (!dst_dev) { if ((rc = ensure(h, h->d_scratch, 2 * (size_t)off))) return rc; d_dst = (short*)h->d_scratch.p; }
-    FE_CUDA(h, cudaMemcpyAsync(h->d_utts.p, ut.data(), sizeof(UttDesc) * ut.size(), cudaMemcpyHostToDevice, st));
-    FE_CUDA(h, cudaMemcpyAsync(h->d_atiles.p, at.data(), sizeof(int2) * at.size(), cudaMemcpyHostToDevice, st));
-    if (!src_dev) FE_CUDA(h, cudaMemcpyAsync(h->d_pcm.p, pcm, 2 * (size_t)span, cudaMemcpyHostToDevice, st));
+    if (!src_dev) { if ((rc = ensure(h, h->lane[0].d_pcm, 2 * (size_t)span))) return rc; d_src = (const short*)h->lane[0].d_pcm.p; }
+    if (!dst_dev) { if ((rc = ensure(h, h->lane[0].d_scratch, 2 * (size_t)off))) return rc; d_dst = (short*)h->lane[0].d_scratch.p; }
+    FE_CUDA(h, cudaMemcpyAsync(h->lane[0].d_utts.p, ut.data(), sizeof(UttDesc) * ut.size(), cudaMemcpyHostToDevice, st));
+    FE_CUDA(h, cudaMemcpyAsync(h->lane[0].d_atiles.p, at.data(), sizeof(int2) * at.size(), cudaMemcpyHostToDevice, st));
+    if (!src_dev) FE_CUDA(h, cudaMemcpyAsync(h->lane[0].d_pcm.p, pcm, 2 * (size_t)span, cudaMemcpyHostToDevice, st));
     FE_CUDA(h, cudaStreamSynchronize(st));
     int grid = (int)std::min<long long>((long long)at.size(), 16LL * h->num_sms);
-    k_resample<<<grid, 256, 0, st>>>(d_src, (const UttDesc*)h->d_utts.p, (const int2*)h->d_atiles.p, (int)at.size(),
+    k_resample<<<grid, 256, 0, st>>>(d_src, (const UttDesc*)h->lane[0].d_utts.p, (const int2*)h->lane[0].d_atiles.p, (int)at.size(),
                                      (const int*)h->d_sp_up.p, (const int*)h->d_sp_down.p,
                                      (const int*)h->d_sp_tap_off.p, (const float*)h->d_taps.p, d_dst, 1);
     h->launches++;
@@ -629,22 +694,22 @@ int fe_postprocess(fe_handle* h, const float* feats, const int64_t* feat_offsets
     for (int i = 0; i < n_utts; ++i) tpref[(size_t)i + 1] = tpref[(size_t)i] + (n_frames[i] + tile_frames - 1) / tile_frames;
     const long long n_tiles = tpref[(size_t)n_utts];
     if (n_tiles > 0x7fffffffLL) return fail(h, FE_ERR_INVALID, "batch too large");
-    if ((rc = ensure(h, h->d_utts, sizeof(UttDesc) * ut.size()))) return rc;
-    if ((rc = ensure(h, h->d_tile_prefix, sizeof(long long) * tpref.size()))) return rc;
-    if ((rc = ensure(h, h->d_tiles, sizeof(TileDesc) * (size_t)std::max<long long>(n_tiles, 1)))) return rc;
+    if ((rc = ensure(h, h->lane[0].d_utts, sizeof(UttDesc) * ut.size()))) return rc;
+    if ((rc = ensure(h, h->lane[0].d_tile_prefix, sizeof(long long) * tpref.size()))) return rc;
+    if ((rc = ensure(h, h->lane[0].d_tiles, sizeof(TileDesc) * (size_t)std::max<long long>(n_tiles, 1)))) return rc;
     const float* d_in = feats; float* d_out = out;
-    if (!in_dev) { if ((rc = ensure(h, h->d_statics, sizeof(float) * (size_t)std::max<long long>(span, 1)))) return rc; d_in = (const float*)h->d_statics.p; }
-    if (!out_dev) { if ((rc = ensure(h, h->d_out, sizeof(float) * (size_t)std::max<long long>(off, 1)))) return rc; d_out = (float*)h->d_out.p; }
-    FE_CUDA(h, cudaMemcpyAsync(h->d_utts.p, ut.data(), sizeof(UttDesc) * ut.size(), cudaMemcpyHostToDevice, st));
-    FE_CUDA(h, cudaMemcpyAsync(h->d_tile_prefix.p, tpref.data(), sizeof(long long) * tpref.size(), cudaMemcpyHostToDevice, st));
-    if (!in_dev) FE_CUDA(h, cudaMemcpyAsync(h->d_statics.p, feats, sizeof(float) * (size_t)span, cudaMemcpyHostToDevice, st));
+    if (!in_dev) { if ((rc = ensure(h, h->lane[0].d_statics, sizeof(float) * (size_t)std::max<long long>(span, 1)))) return rc; d_in = (const float*)h->lane[0].d_statics.p; }
+    if (!out_dev) { if ((rc = ensure(h, h->lane[0].d_out, sizeof(float) * (size_t)std::max<long long>(off, 1)))) return rc; d_out = (float*)h->lane[0].d_out.p; }
+    FE_CUDA(h, cudaMemcpyAsync(h->lane[0].d_utts.p, ut.data(), sizeof(UttDesc) * ut.size(), cudaMemcpyHostToDevice, st));
+    FE_CUDA(h, cudaMemcpyAsync(h->lane[0].d_tile_prefix.p, tpref.data(), sizeof(long long) * tpref.size(), cudaMemcpyHostToDevice, st));
+    if (!in_dev) FE_CUDA(h, cudaMemcpyAsync(h->lane[0].d_statics.p, feats, sizeof(float) * (size_t)span, cudaMemcpyHostToDevice, st));
     FE_CUDA(h, cudaStreamSynchronize(st));
     if (n_tiles > 0) {
-        k_build_tiles<<<(n_utts + 255) / 256, 256, 0, st>>>((const UttDesc*)h->d_utts.p, (const long long*)h->d_tile_prefix.p,
-                                                            n_utts, 160, D, tile_frames, (TileDesc*)h->d_tiles.p);
+        k_build_tiles<<<(n_utts + 255) / 256, 256, 0, st>>>((const UttDesc*)h->lane[0].d_utts.p, (const long long*)h->lane[0].d_tile_prefix.p,
+                                                            n_utts, 160, D, tile_frames, (TileDesc*)h->lane[0].d_tiles.p);
         h->launches++;
     }
-    if ((rc = launch_k2(h, st, (const UttDesc*)h->d_utts.p, n_utts, (const TileDesc*)h->d_tiles.p, n_tiles, d_in, d_out,
+    if ((rc = launch_k2(h, h->lane[0], st, (const UttDesc*)h->lane[0].d_utts.p, n_utts, (const TileDesc*)h->lane[0].d_tiles.p, n_tiles, d_in, d_out,
                         D, tile_frames, delta_mode, mode))) return rc;
     if (!out_dev) {
         FE_CUDA(h, cudaMemcpyAsync(out, d_out, sizeof(float) * (size_t)off, cudaMemcpyDeviceToHost, st));
@@ -656,7 +721,7 @@ int fe_postprocess(fe_handle* h, const float* feats, const int64_t* feat_offsets
 int fe_sync(fe_handle* h) {
     if (!h) return FE_ERR_INVALID;
     FE_CUDA(h, cudaSetDevice(h->device));
-    if (h->ev_valid) FE_CUDA(h, cudaEventSynchronize(h->ev[5]));
+    for (Lane& L : h->lane) if (L.done_valid) FE_CUDA(h, cudaEventSynchronize(L.done));
     FE_CUDA(h, cudaStreamSynchronize(h->stream));
     return FE_OK;
 }
@@ -666,14 +731,14 @@ int fe_measure_fp32_peak(fe_handle* h, float* tflops) {
     FE_CUDA(h, cudaSetDevice(h->device));
     const int grid = h->num_sms * 8, block = 256, iters = 20000;
     int rc;
-    if ((rc = ensure(h, h->d_out, sizeof(float) * (size_t)grid * block))) return rc;
+    if ((rc = ensure(h, h->lane[0].d_out, sizeof(float) * (size_t)grid * block))) return rc;
     cudaEvent_t e0, e1;
     FE_CUDA(h, cudaEventCreate(&e0)); FE_CUDA(h, cudaEventCreate(&e1));
     float best = 0.f;
-    k_fp32_peak<<<grid, block, 0, h->stream>>>((float*)h->d_out.p, 200);
+    k_fp32_peak<<<grid, block, 0, h->stream>>>((float*)h->lane[0].d_out.p, 200);
     for (int rep = 0; rep < 3; ++rep) {
         FE_CUDA(h, cudaEventRecord(e0, h->stream));
-        k_fp32_peak<<<grid, block, 0, h->stream>>>((float*)h->d_out.p, iters);
+        k_fp32_peak<<<grid, block, 0, h->stream>>>((float*)h->lane[0].d_out.p, iters);
         FE_CUDA(h, cudaEventRecord(e1, h->stream));
         FE_CUDA(h, cudaEventSynchronize(e1));
         float ms = 0.f;
@@ -717,9 +782,10 @@ int64_t fe_launch_count(fe_handle* h) { return h ? h->launches : 0; }
 int64_t fe_device_bytes(fe_handle* h) {
     if (!h) return 0;
     size_t t = 0;
-    for (const DevBuf* b : {&h->d_utts, &h->d_tile_prefix, &h->d_tiles, &h->d_atile_prefix, &h->d_atiles,
-                            &h->d_statics, &h->d_pcm, &h->d_out, &h->d_scratch})
-        t += b->cap;
+    for (const Lane& L : h->lane)
+        for (const DevBuf* b : {&L.d_utts, &L.d_tile_prefix, &L.d_tiles, &L.d_atile_prefix, &L.d_atiles,
+                                &L.d_statics, &L.d_stats, &L.d_pcm, &L.d_out, &L.d_scratch})
+            t += b->cap;
     return (int64_t)t;
 }
 

@@ -460,6 +460,8 @@ k_norm_delta_pack(const TileDesc* __restrict__ tiles, int n_tiles, const float* 
         for (int i = tid; i < n4; i += kPackThreads)
             reinterpret_cast<float4*>(dst)[i] = reinterpret_cast<const float4*>(cube)[i];
         for (int i = (n4 << 2) + tid; i < total; i += kPackThreads) dst[i] = cube[i];
+        // the 0..3 pad floats that round the utterance's run up to 16 bytes are zeroed (deterministic buffers)
+        if (t0 + nrow == L && tid < ((4 - (total & 3)) & 3)) dst[total + tid] = 0.f;
         __syncthreads();
     }
 }

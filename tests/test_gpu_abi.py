@@ -75,3 +75,29 @@ def test_one_bad_utterance_does_not_poison_the_batch(pkg, ref):
         assert_close(a, ref.features_one(p), what="batch with empty utterance")
     assert np.isfinite(got[3]).all()
     fe.close()
+
+
+def test_chunked_host_pipeline_equals_single_shot(pkg, monkeypatch):
+    """host in / host out batches above 2 chunks go through the 2-lane H2D | kernels | D2H pipeline;
+    results must be bit-identical to the single-shot path (FE_PIPE_CHUNK_MB shrinks the chunk for the test)."""
+    rng = np.random.default_rng(31)
+    lens = pkg.synth.durations(300, 2, 15, rng)
+    pcm = pkg.synth.noise_corpus_fast(lens, seed=32)                  # ~80 MB of PCM
+    packed, off, ln = pkg.pack_pcm(pcm)
+    fe = pkg.Frontend(pkg.FrontendConfig())
+    ref_out, ref_off, ref_n = fe.run_packed(packed, off, ln)
+    fe.close()
+    monkeypatch.setenv("FE_PIPE_CHUNK_MB", "4")
+    fe2 = pkg.Frontend(pkg.FrontendConfig())
+    out, o2, n2 = fe2.run_packed(packed, off, ln)
+    assert np.array_equal(o2, ref_off) and np.array_equal(n2, ref_n)
+    assert np.array_equal(out[:int(o2[-1])], ref_out[:int(o2[-1])])
+    # with perturbation (scratch buffers per lane)
+    sp = np.array([(-1, 0, 1)[i % 3] for i in range(len(pcm))], np.int32)
+    a, _, _ = fe2.run_packed(packed, off, ln, speed_idx=sp)
+    fe2.close()
+    monkeypatch.delenv("FE_PIPE_CHUNK_MB")
+    fe3 = pkg.Frontend(pkg.FrontendConfig())
+    b, ob, _ = fe3.run_packed(packed, off, ln, speed_idx=sp)
+    assert np.array_equal(a[:int(ob[-1])], b[:int(ob[-1])])
+    fe3.close()
