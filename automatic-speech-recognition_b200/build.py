@@ -37,6 +37,8 @@ def build_library(force=False, verbose=False):
     if not force and not is_stale():
         return LIB_PATH
     cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else [])
+    if os.environ.get("FE_K1_PROF"):          # per-phase clock64 counters in K1 (tools/k1_phases.py); costs registers
+        cmd += ["-DFE_K1_PROF"]
     cmd += ["-o", LIB_PATH] + [os.path.join(CSRC, s) for s in SOURCES]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:

@@ -51,9 +51,11 @@ struct fe_handle {
     std::string err;
 
     // device tables
-    DevBuf tw256, tw512, window, mel_bi, mel_w, dct;
-    int mel_n4[16] = {0}, mel_e4[16] = {0};
-    int dct_stride = 0, full_spectrum = 0, mel_slots = 0, mel_entries = 0, nh = 0;
+    DevBuf tw256, tw512, window, mel_desc, mel_w, dct;
+    int dct_stride = 0, full_spectrum = 0, mel_groups = 0, p_rows = 0, nh = 0;
+    int epi_off[kEpiWarps] = {0}, epi_cnt[kEpiWarps] = {0};
+    int epi_plan = 0, epi_w_n = 0;        // specialised epilogue (fe_plans_gen.h) and its weights
+    std::vector<float> epi_w;
     bool scratch_f32 = false;     // pre-emphasis materialises float PCM in the scratch buffer
     // resampler
     std::vector<int> sp_up, sp_down, sp_tap_off;
@@ -69,7 +71,6 @@ struct fe_handle {
     int64_t launches = 0;
     size_t k1_smem[2] = {0, 0};      // [raw int16 input, float input]
     long long pipe_chunk_bytes = 192LL << 20;   // PCM bytes per chunk of the host pipeline (FE_PIPE_CHUNK_MB overrides)
-    int k1_warps = 8;                // warps per K1 CTA (8 -> 128 regs/thread, 6 -> 168); FE_K1_WARPS overrides
 };
 
 namespace {
@@ -169,7 +170,7 @@ int make_plan(fe_handle* h, Lane& ln, const int64_t* pcm_offsets, const int64_t*
             u.src_sel = via_scratch ? 1 : 0;
             u.pcm_off = via_scratch ? pl.total_scratch : off;
             u.out_off = out_off;
-            u.stat_off = c.cmvn ? pl.total_frames * c.feat_dim : out_off;
+            u.stat_off = pl.total_tiles * kTileFrames * c.feat_dim;     // K1 -> K2 statics: [D][32] blocks
             ln.tile_prefix[i] = pl.total_tiles;
             ln.atile_prefix[i] = pl.total_atiles;
             pl.pcm_span = std::max(pl.pcm_span, off + len);
@@ -180,7 +181,7 @@ int make_plan(fe_handle* h, Lane& ln, const int64_t* pcm_offsets, const int64_t*
             pl.total_atiles += (n_eff + kK0Outputs - 1) / kK0Outputs;
         }
         pl.total_frames += L;
-        pl.total_tiles += (L + h->k1_warps * kWarpFrames - 1) / (h->k1_warps * kWarpFrames);
+        pl.total_tiles += statics_tiles(L);
         out_off += round_up(L * width, 4);
     }
     if (out_offsets) out_offsets[n] = out_off;
@@ -198,75 +199,82 @@ int set_smem(fe_handle* h, K kernel, size_t bytes) {
 int launch_k1(fe_handle* h, cudaStream_t st, const void* pcm, const void* scratch, bool in_f32,
               const TileDesc* tiles, int n_tiles, const DevTables& dt, float* statics) {
     const fe_config& c = h->cfg;
-    int grid = std::min<long long>(n_tiles, 2LL * h->num_sms);
+    int grid = std::min<long long>(n_tiles, (long long)h->num_sms);        // persistent: one 16-warp CTA per SM
     if (grid <= 0) return FE_OK;
-    if (c.frame_len == 400 && c.hop == 160) {
-        K1Params P;
-        P.dt = dt;
-        P.L = k1_smem_layout(h->mel_slots, h->mel_entries, c.feat_dim, h->dct_stride, c.window != nullptr,
-                             c.frame_len, c.hop, c.feat_type == FE_FEAT_MFCC, in_f32, h->k1_warps);
-        memcpy(P.mel_n4, h->mel_n4, sizeof(P.mel_n4)); memcpy(P.mel_e4, h->mel_e4, sizeof(P.mel_e4));
-        const bool win = c.window != nullptr;
+    if (!(c.frame_len == 400 && c.hop == 160)) return fail(h, FE_ERR_INVALID, "unsupported frame geometry");
+    K1Params P;
+    P.dt = dt;
+    P.L = k1_smem_layout(c.num_filters, h->mel_groups, h->p_rows, c.feat_dim, h->dct_stride, c.window != nullptr,
+                         c.frame_len, c.hop, c.feat_type == FE_FEAT_MFCC, in_f32, h->epi_plan);
+    P.dbg = getenv("FE_K1_DBG") ? atoi(getenv("FE_K1_DBG")) : 0;
+    const bool win = c.window != nullptr;
+    memset(P.epi_w, 0, sizeof(P.epi_w));
+    if (h->epi_plan) memcpy(P.epi_w, h->epi_w.data() + (in_f32 ? (size_t)h->epi_w_n : 0), sizeof(float) * (size_t)h->epi_w_n);
+#define FE_LAUNCH_K1E(F32, WIN, EPI)                                                                       \
+    do {                                                                                                   \
+        FE_CUDA(h, cudaFuncSetAttribute(k_frames_to_statics<400, 160, F32, WIN, EPI>,                      \
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->k1_smem[F32])); \
+        k_frames_to_statics<400, 160, F32, WIN, EPI><<<grid, kK1Threads, h->k1_smem[F32], st>>>(           \
+            pcm, scratch, tiles, n_tiles, P, statics);                                                     \
+    } while (0)
 #define FE_LAUNCH_K1(F32, WIN)                                                                             \
-        do {                                                                                               \
-            if (h->k1_warps == 8) {                                                                        \
-                cudaFuncSetAttribute(k_frames_to_statics<400, 160, F32, WIN, 8>,                           \
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->k1_smem[F32]);   \
-                k_frames_to_statics<400, 160, F32, WIN, 8><<<grid, 256, h->k1_smem[F32], st>>>(            \
-                    pcm, scratch, tiles, n_tiles, P, statics);                                             \
-            } else {                                                                                       \
-                cudaFuncSetAttribute(k_frames_to_statics<400, 160, F32, WIN, 6>,                           \
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->k1_smem[F32]);   \
-                k_frames_to_statics<400, 160, F32, WIN, 6><<<grid, 192, h->k1_smem[F32], st>>>(            \
-                    pcm, scratch, tiles, n_tiles, P, statics);                                             \
-            }                                                                                              \
-        } while (0)
-        if (!in_f32 && !win) FE_LAUNCH_K1(0, 0);
-        else if (!in_f32) FE_LAUNCH_K1(0, 1);
-        else if (!win) FE_LAUNCH_K1(1, 0);
-        else FE_LAUNCH_K1(1, 1);
+    do {                                                                                                   \
+        if (h->epi_plan == 1) FE_LAUNCH_K1E(F32, WIN, 1);                                                  \
+        else if (h->epi_plan == 2) FE_LAUNCH_K1E(F32, WIN, 2);                                             \
+        else FE_LAUNCH_K1E(F32, WIN, 0);                                                                   \
+    } while (0)
+    if (!in_f32 && !win) FE_LAUNCH_K1(0, 0);
+    else if (!in_f32) FE_LAUNCH_K1(0, 1);
+    else if (!win) FE_LAUNCH_K1(1, 0);
+    else FE_LAUNCH_K1(1, 1);
+#undef FE_LAUNCH_K1E
 #undef FE_LAUNCH_K1
-    } else {
-        return fail(h, FE_ERR_INVALID, "unsupported frame geometry");
-    }
     h->launches++;
     FE_CUDA(h, cudaGetLastError());
     return FE_OK;
 }
 
-// K2a + K2b: per-utterance statistics, then the tile-parallel normalise / delta / pack pass
+// K2a + K2b: per-utterance statistics, then the tile-parallel normalise / delta / pack pass.
+// tiled: `statics` are K1's [D][32] blocks (else a row-major (L, D) matrix per utterance: fe_postprocess).
+// flags: bit0 subtract the mean, bit1 divide by the std, bit2 append deltas.
 int launch_k2(fe_handle* h, Lane& L, cudaStream_t st, const UttDesc* utts, int n_utts, const TileDesc* tiles, long long n_tiles,
-              const float* statics, float* out, int D, int tile_frames, int delta_mode, int flags) {
+              const float* statics, float* out, int D, int delta_mode, int flags, bool tiled) {
     int rc;
     if ((rc = ensure(h, L.d_stats, sizeof(float) * 2 * (size_t)D * (size_t)n_utts))) return rc;
     if (flags & 3) {
-        const int grid = (int)std::min<long long>(n_utts, 32LL * h->num_sms);
-        k_utt_stats<<<grid, kStatThreads, (kStatThreads + std::min(D, kStatThreads)) * sizeof(float), st>>>(
-            utts, n_utts, statics, (float*)L.d_stats.p, D, flags);
+        if (tiled && (flags & 3) == 3) {
+            const long long items = (long long)n_utts * D;
+            const int grid = (int)std::min<long long>((items + kStatTWarps - 1) / kStatTWarps, 32LL * h->num_sms);
+            k_utt_stats_tiled<<<grid, kStatTWarps * 32, 0, st>>>(utts, n_utts, statics, (float*)L.d_stats.p, D);
+        } else {
+            if (tiled) return fail(h, FE_ERR_INVALID, "internal: partial normalisation on tiled statics");
+            const int grid = (int)std::min<long long>(n_utts, 32LL * h->num_sms);
+            k_utt_stats<<<grid, kStatThreads, (kStatThreads + std::min(D, kStatThreads)) * sizeof(float), st>>>(
+                utts, n_utts, statics, (float*)L.d_stats.p, D, flags);
+        }
         h->launches++;
     } else {
-        // no normalisation: mean 0, scale 1
-        std::vector<float> id((size_t)2 * D);
-        for (int i = 0; i < D; ++i) { id[i] = 0.f; id[D + i] = 1.f; }
-        for (int u = 0; u < n_utts; ++u)
-            FE_CUDA(h, cudaMemcpyAsync((float*)L.d_stats.p + (size_t)u * 2 * D, id.data(), sizeof(float) * 2 * D,
-                                       cudaMemcpyHostToDevice, st));
-        FE_CUDA(h, cudaStreamSynchronize(st));
+        flags |= 8;              // no statistics: mean 0, scale 1 inside the pack kernel
     }
     if (n_tiles > 0) {
-        const size_t smem = k2_smem_floats(D, tile_frames) * sizeof(float);
+        const size_t smem = k2_smem_floats(D, kTileFrames) * sizeof(float);
         const int grid = (int)std::min<long long>(n_tiles, 12LL * h->num_sms);
-#define FE_LAUNCH_PACK(DT)                                                                                          \
+#define FE_LAUNCH_PACK(DT, TR)                                                                                      \
         do {                                                                                                        \
-            FE_CUDA(h, cudaFuncSetAttribute(k_norm_delta_pack<DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-            k_norm_delta_pack<DT><<<grid, kPackThreads, smem, st>>>(tiles, (int)n_tiles, statics,                   \
-                (const float*)L.d_stats.p, out, D, tile_frames, delta_mode, flags);                                \
+            FE_CUDA(h, cudaFuncSetAttribute(k_norm_delta_pack<DT, TR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            k_norm_delta_pack<DT, TR><<<grid, kPackThreads, smem, st>>>(tiles, (int)n_tiles, statics,               \
+                (const float*)L.d_stats.p, out, D, kTileFrames, delta_mode, flags);                                 \
         } while (0)
-        if (D == 13) FE_LAUNCH_PACK(13);
-        else if (D == 39) FE_LAUNCH_PACK(39);
-        else if (D == 40) FE_LAUNCH_PACK(40);
-        else if (D == 80) FE_LAUNCH_PACK(80);
-        else FE_LAUNCH_PACK(0);
+        if (tiled) {
+            if (D == 13) FE_LAUNCH_PACK(13, true);
+            else if (D == 40) FE_LAUNCH_PACK(40, true);
+            else if (D == 80) FE_LAUNCH_PACK(80, true);
+            else FE_LAUNCH_PACK(0, true);
+        } else {
+            if (D == 13) FE_LAUNCH_PACK(13, false);
+            else if (D == 39) FE_LAUNCH_PACK(39, false);
+            else FE_LAUNCH_PACK(0, false);
+        }
 #undef FE_LAUNCH_PACK
         h->launches++;
     }
@@ -280,10 +288,11 @@ DevTables dev_tables(const fe_handle* h, bool in_f32) {
     dt.tw256 = (const float4*)h->tw256.p;
     dt.tw512 = (const float4*)h->tw512.p;
     dt.window = c.window ? (const float2*)h->window.p : nullptr;
-    dt.mel_bi = (const int*)h->mel_bi.p;
-    dt.mel_w = (const float*)(in_f32 ? (const char*)h->mel_w.p + sizeof(float) * 8 * (size_t)h->mel_entries : (const char*)h->mel_w.p);
+    dt.mel_desc = (const int*)h->mel_desc.p;
+    dt.mel_w = (const float*)h->mel_w.p + (in_f32 ? 4 * (size_t)h->mel_groups : 0);
     dt.dctf = (const float*)h->dct.p;
-    dt.mel_slots = h->mel_slots; dt.mel_entries = h->mel_entries;
+    dt.mel_groups = h->mel_groups; dt.p_rows = h->p_rows;
+    for (int i = 0; i < kEpiWarps; ++i) { dt.epi_off[i] = h->epi_off[i]; dt.epi_cnt[i] = h->epi_cnt[i]; }
     dt.nf = c.num_filters; dt.D = c.feat_dim; dt.dct_stride = h->dct_stride; dt.nh = h->nh;
     dt.full_spectrum = h->full_spectrum;
     dt.is_mfcc = c.feat_type == FE_FEAT_MFCC;
@@ -343,7 +352,7 @@ int fe_destroy(fe_handle* h) {
     if (!h) return FE_OK;
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
-    for (DevBuf* b : {&h->tw256, &h->tw512, &h->window, &h->mel_bi, &h->mel_w, &h->dct,
+    for (DevBuf* b : {&h->tw256, &h->tw512, &h->window, &h->mel_desc, &h->mel_w, &h->dct,
                       &h->d_sp_up, &h->d_sp_down, &h->d_sp_tap_off, &h->d_taps})
         release(*b);
     for (Lane& L : h->lane) {
@@ -392,12 +401,14 @@ int fe_configure(fe_handle* h, const fe_config* c) {
     int rc;
     HostTables ht;
     build_host_tables(*c, ht);
-    h->mel_slots = ht.mel_slots; h->mel_entries = ht.mel_entries; h->nh = ht.nh; h->dct_stride = ht.dct_stride;
+    if (!ht.ok) return fail(h, FE_ERR_INVALID, "filterbank does not fit the mel plan (run too long)");
+    h->mel_groups = ht.mel_groups; h->p_rows = ht.p_rows; h->nh = ht.nh; h->dct_stride = ht.dct_stride;
+    memcpy(h->epi_off, ht.epi_off, sizeof(h->epi_off)); memcpy(h->epi_cnt, ht.epi_cnt, sizeof(h->epi_cnt));
+    h->epi_plan = ht.epi_w_n <= kEpiWCap ? ht.epi_plan : 0; h->epi_w_n = ht.epi_w_n; h->epi_w = ht.epi_w;
+    if (getenv("FE_K1_GENERIC")) h->epi_plan = 0;         // force the run-time mel plan (tests, comparisons)
     if ((rc = upload(h, h->tw256, ht.tw256.data(), ht.tw256.size() * sizeof(float)))) return rc;
     if ((rc = upload(h, h->tw512, ht.tw512.data(), ht.tw512.size() * sizeof(float)))) return rc;
-    if (ht.mel_slots > kMaxMelSlots) return fail(h, FE_ERR_INVALID, "too many mel slots");
-    memcpy(h->mel_n4, ht.mel_n4, sizeof(h->mel_n4)); memcpy(h->mel_e4, ht.mel_e4, sizeof(h->mel_e4));
-    if ((rc = upload(h, h->mel_bi, ht.mel_bi.data(), ht.mel_bi.size() * sizeof(int)))) return rc;
+    if ((rc = upload(h, h->mel_desc, ht.mel_desc.data(), ht.mel_desc.size() * sizeof(int)))) return rc;
     if ((rc = upload(h, h->mel_w, ht.mel_w.data(), ht.mel_w.size() * sizeof(float)))) return rc;
     if (c->feat_type == FE_FEAT_MFCC && (rc = upload(h, h->dct, ht.dctf.data(), ht.dctf.size() * sizeof(float)))) return rc;
     if (c->window && (rc = upload(h, h->window, ht.window.data(), ht.window.size() * sizeof(float)))) return rc;
@@ -418,12 +429,18 @@ int fe_configure(fe_handle* h, const fe_config* c) {
     }
 
     h->cfg = *c;       // pointer members are only used as "present" flags from here on
-    if (const char* e = getenv("FE_K1_WARPS")) h->k1_warps = atoi(e) == 6 ? 6 : 8;
     for (int f32 = 0; f32 < 2; ++f32) {
-        K1Smem L = k1_smem_layout(h->mel_slots, h->mel_entries, c->feat_dim, h->dct_stride, c->window != nullptr,
-                                  c->frame_len, c->hop, c->feat_type == FE_FEAT_MFCC, f32, h->k1_warps);
+        const bool used = (f32 != 0) == (c->preemph != 0.f || c->pcm_dtype == FE_PCM_FLOAT32);
+        if (!used) continue;
+        K1Smem L = k1_smem_layout(c->num_filters, h->mel_groups, h->p_rows, c->feat_dim, h->dct_stride, c->window != nullptr,
+                                  c->frame_len, c->hop, c->feat_type == FE_FEAT_MFCC, f32, h->epi_plan);
+        if (h->epi_plan && L.total > kK1SmemMax) {           // the 4-slot layout does not fit: generic epilogue
+            h->epi_plan = 0;
+            L = k1_smem_layout(c->num_filters, h->mel_groups, h->p_rows, c->feat_dim, h->dct_stride, c->window != nullptr,
+                               c->frame_len, c->hop, c->feat_type == FE_FEAT_MFCC, f32, 0);
+        }
         h->k1_smem[f32] = L.total;
-        if (L.total > 227 * 1024) return fail(h, FE_ERR_INVALID, "configuration needs too much shared memory");
+        if (L.total > kK1SmemMax) return fail(h, FE_ERR_INVALID, "configuration needs too much shared memory");
     }
     h->configured = true;
     return FE_OK;
@@ -462,7 +479,7 @@ static int run_core(fe_handle* h, Lane& L, cudaStream_t st, const void* pcm, con
     if ((rc = ensure(h, L.d_tile_prefix, b_pref))) return rc;
     if ((rc = ensure(h, L.d_atile_prefix, b_pref))) return rc;
     if ((rc = ensure(h, L.d_tiles, sizeof(TileDesc) * (size_t)std::max<long long>(pl.total_tiles, 1)))) return rc;
-    if (c.cmvn && (rc = ensure(h, L.d_statics, sizeof(float) * (size_t)std::max<long long>(pl.total_frames * c.feat_dim, 1)))) return rc;
+    if ((rc = ensure(h, L.d_statics, sizeof(float) * (size_t)std::max<long long>(pl.total_tiles * kTileFrames * c.feat_dim, 1)))) return rc;
     const bool preemph = c.preemph != 0.f;
     const bool k1_f32 = preemph || c.pcm_dtype == FE_PCM_FLOAT32;      // what K1's stage A reads
     if (pl.any_scratch) {
@@ -502,7 +519,7 @@ static int run_core(fe_handle* h, Lane& L, cudaStream_t st, const void* pcm, con
     const int tb = 256, gb = (n_utts + tb - 1) / tb;
     if (pl.total_tiles > 0) {
         k_build_tiles<<<gb, tb, 0, st>>>((const UttDesc*)L.d_utts.p, (const long long*)L.d_tile_prefix.p, n_utts,
-                                         c.hop, c.feat_dim, h->k1_warps * kWarpFrames, (TileDesc*)L.d_tiles.p);
+                                         c.hop, c.feat_dim, (TileDesc*)L.d_tiles.p);
         h->launches++;
     }
     if (pl.any_scratch) {
@@ -535,14 +552,13 @@ static int run_core(fe_handle* h, Lane& L, cudaStream_t st, const void* pcm, con
     }
     if (prof) FE_CUDA(h, cudaEventRecord(ps->e[2], st));
     DevTables dt = dev_tables(h, k1_f32);
-    float* stat_base = c.cmvn ? (float*)L.d_statics.p : d_out;
     if ((rc = launch_k1(h, st, d_pcm, L.d_scratch.p, k1_f32, (const TileDesc*)L.d_tiles.p,
-                        (int)pl.total_tiles, dt, stat_base))) return rc;
+                        (int)pl.total_tiles, dt, (float*)L.d_statics.p))) return rc;
     if (prof) FE_CUDA(h, cudaEventRecord(ps->e[3], st));
-    if (c.cmvn && pl.total_frames > 0) {
+    if (pl.total_frames > 0) {
+        // cmvn: statistics + normalise + deltas + cube; no cmvn: the same pack kernel only re-lays the blocks out as (L, D)
         if ((rc = launch_k2(h, L, st, (const UttDesc*)L.d_utts.p, n_utts, (const TileDesc*)L.d_tiles.p, pl.total_tiles,
-                            (const float*)L.d_statics.p, d_out, c.feat_dim, h->k1_warps * kWarpFrames,
-                            c.delta_mode, 7))) return rc;
+                            (const float*)L.d_statics.p, d_out, c.feat_dim, c.delta_mode, c.cmvn ? 7 : 0, true))) return rc;
         if (prof) ps->k2 = true;
     }
     FE_CUDA(h, cudaGetLastError());
@@ -689,9 +705,8 @@ int fe_postprocess(fe_handle* h, const float* feats, const int64_t* feat_offsets
     if (off > out_capacity) return fail(h, FE_ERR_CAPACITY, "out buffer too small");
     const bool in_dev = is_device_ptr(feats), out_dev = is_device_ptr(out);
     int rc;
-    const int tile_frames = 32;
     std::vector<long long> tpref((size_t)n_utts + 1, 0);
-    for (int i = 0; i < n_utts; ++i) tpref[(size_t)i + 1] = tpref[(size_t)i] + (n_frames[i] + tile_frames - 1) / tile_frames;
+    for (int i = 0; i < n_utts; ++i) tpref[(size_t)i + 1] = tpref[(size_t)i] + statics_tiles(n_frames[i]);
     const long long n_tiles = tpref[(size_t)n_utts];
     if (n_tiles > 0x7fffffffLL) return fail(h, FE_ERR_INVALID, "batch too large");
     if ((rc = ensure(h, h->lane[0].d_utts, sizeof(UttDesc) * ut.size()))) return rc;
@@ -706,11 +721,11 @@ int fe_postprocess(fe_handle* h, const float* feats, const int64_t* feat_offsets
     FE_CUDA(h, cudaStreamSynchronize(st));
     if (n_tiles > 0) {
         k_build_tiles<<<(n_utts + 255) / 256, 256, 0, st>>>((const UttDesc*)h->lane[0].d_utts.p, (const long long*)h->lane[0].d_tile_prefix.p,
-                                                            n_utts, 160, D, tile_frames, (TileDesc*)h->lane[0].d_tiles.p);
+                                                            n_utts, 160, D, (TileDesc*)h->lane[0].d_tiles.p);
         h->launches++;
     }
     if ((rc = launch_k2(h, h->lane[0], st, (const UttDesc*)h->lane[0].d_utts.p, n_utts, (const TileDesc*)h->lane[0].d_tiles.p, n_tiles, d_in, d_out,
-                        D, tile_frames, delta_mode, mode))) return rc;
+                        D, delta_mode, mode, false))) return rc;
     if (!out_dev) {
         FE_CUDA(h, cudaMemcpyAsync(out, d_out, sizeof(float) * (size_t)off, cudaMemcpyDeviceToHost, st));
     }
@@ -778,6 +793,17 @@ int fe_get_kernel_ms(fe_handle* h, float ms[4]) {
 }
 
 int64_t fe_launch_count(fe_handle* h) { return h ? h->launches : 0; }
+
+// profiling aid (FE_K1_DBG & 8): read and clear the K1 per-phase cycle counters
+int fe_debug_counters(fe_handle* h, uint64_t out[16]) {
+    if (!h || !out) return FE_ERR_INVALID;
+    FE_CUDA(h, cudaSetDevice(h->device));
+    FE_CUDA(h, cudaDeviceSynchronize());
+    FE_CUDA(h, cudaMemcpyFromSymbol(out, g_k1_prof, sizeof(uint64_t) * 16));
+    uint64_t z[16] = {0};
+    FE_CUDA(h, cudaMemcpyToSymbol(g_k1_prof, z, sizeof(z)));
+    return FE_OK;
+}
 
 int64_t fe_device_bytes(fe_handle* h) {
     if (!h) return 0;

@@ -20,6 +20,8 @@
 #pragma once
 #include <stdint.h>
 #include <math.h>
+#include <type_traits>
+#include "fe_plans_gen.h"
 
 #if defined(__CUDACC__)
 #define FE_HD __host__ __device__ __forceinline__
@@ -37,10 +39,14 @@ namespace fe {
 constexpr int kNfft = 512;
 constexpr int kBins = 257;
 constexpr int kWarpFrames = 4;          // frames per warp pass
+constexpr int kTileFrames = 32;         // frames per tile: one lane per frame in the epilogue
+constexpr int kTileGroups = kTileFrames / kWarpFrames;   // 4-frame groups (one FFT warp pass each) per tile
+constexpr int kFftWarps = 12;           // producer warps of a K1 CTA (three warpgroups)
+constexpr int kEpiWarps = 4;            // consumer warps (one warpgroup): mel / log / DCT for whole tiles
 constexpr int kERegion = 512;           // floats of exchange buffer per frame (2 KB, 2 KB aligned)
-constexpr int kPStagger = 8;            // per-frame-slot float offset of the power row
-constexpr int kLogmelOff = 288;         // log-mel row inside the frame's region (after the power row)
-constexpr int kFoldS = 0, kFoldD = 96;  // folded DCT inputs (reuse the dead power row)
+constexpr int kPStride = 36;            // floats per bin row of the CTA's power buffer: [bin][frame], stride 36 makes
+                                        // both the post-pass scatter (8 bins x 4 frames per store) and the
+                                        // epilogue's column reads (32 frames of one bin) bank-conflict free
 constexpr int kMaxFilters = 128;
 constexpr float kEpsF64 = 2.220446049250313e-16f;   // np.finfo(float).eps, as float
 
@@ -73,17 +79,14 @@ struct SmemTables {
                               //         W_256^(j k1) = W^(j 4a) * W^(j b), k1 = 4a + b
     const float4* tw512;      // [16]    cfg = Fe*8 + t: (cos rx, cos ry, sin rx, sin ry) * 2pi/512; bins r + 16 k2 by rotation
     const float2* window;     // [ROWS*16] (w[2m], w[2m+1]) per complex point m, or nullptr
-    // mel plan: S slots; slot s has mel_n4[s] float4 weight groups (weights stored
-    // [group][lane g][4], groups of all slots back to back); lane g of a frame owns filter
-    // id = mel_bi[s*8+g] >> 16 (0xffff = none) whose (padded) run starts at bin
-    // mel_bi[s*8+g] & 0xffff.  mel_n4 lives in the constant bank on the device so the trip
-    // counts are warp-uniform by construction.
-    const int*    mel_n4;         // [S]
-    const int*    mel_bi;         // [S * 8]
-    const float*  mel_w;          // [entries * 8], pre-scaled by pscale / 2048
-    const float*  dctf;           // [D][dct_stride] folded DCT rows (n < ceil(nf/2)), zero padded
-    int mel_slots;
-    int nf, D, dct_stride, nh;    // nh = ceil(nf / 2)
+    // mel plan: every epilogue warp streams its own flat list of 4-bin weight groups (its filters back to
+    // back, runs padded with zero weights to a multiple of 4): mel_desc[i] = first bin | last-group-of-
+    // filter << 10 | filter << 16, weights mel_w4[i].  A warp's slice is [off, off + cnt) (+ 8 zero groups of
+    // prefetch slack).  lane = frame, so descriptors and weights are warp-uniform loads.
+    const int*    mel_desc;
+    const float4* mel_w4;         // weight groups, pre-scaled by pscale / 2048
+    const float*  dctf;           // [D][dct_stride] folded DCT rows (n < ceil(nf/2)), zero padded to dct_stride
+    int nf, D, dct_stride, nh;    // nh = ceil(nf / 2), dct_stride = nh rounded up to 4
     int full_spectrum;        // filterbank touches bins > 128
     int is_mfcc, fbank_log, dc_elim;
     float pscale;             // 2^-30 when samples are raw int16 counts, 1 for float PCM
@@ -288,7 +291,8 @@ FE_HD void stage_b(float* e_f, LaneZ& z, int t, int fs) {
 
 // ---------------------------------------------------------------------------
 // Phase 3 (post-pass): real-FFT split, power |2X|^2 (the 1/2048 = 1/(4*512) lives in
-// the filterbank weights), scatter to the power row.
+// the filterbank weights), scatter to this frame's column of the CTA's power buffer
+// (p_f = pbuf + frame; bin k at p_f[k * kPStride]).
 //   lanes t >= 1: partner of half .x is half .y of slot 15-k2 and vice versa (free swap)
 //   lanes t == 0: rows 8 (.x) and 0 (.y) are self-paired
 // ---------------------------------------------------------------------------
@@ -322,18 +326,18 @@ FE_HD void post_pass(const LaneZ& z, float* p_f, const SmemTables& tb, int t, in
         float2 ti = pfma(s, oi, pmul(c, orr));
         float2 xr = psub(er, tr), xi = psub(ei, ti);          // 2 X[k]
         float2 plo = pfma(xi, xi, pmul(xr, xr));
-        p_f[rx + 16 * k2] = plo.x;
-        p_f[ry + 16 * k2] = plo.y;
+        p_f[(rx + 16 * k2) * kPStride] = plo.x;
+        p_f[(ry + 16 * k2) * kPStride] = plo.y;
         if (tb.full_spectrum) {
             float2 yr = padd(er, tr), yi = padd(ei, ti);      // conj(2 X[256-k])
             float2 phi = pfma(yi, yi, pmul(yr, yr));
-            p_f[256 - (rx + 16 * k2)] = phi.x;
-            p_f[256 - (ry + 16 * k2)] = phi.y;                // lane 0, k2 = 0 writes bin 256
+            p_f[(256 - (rx + 16 * k2)) * kPStride] = phi.x;
+            p_f[(256 - (ry + 16 * k2)) * kPStride] = phi.y;   // lane 0, k2 = 0 writes bin 256
         }
     }
     // bin 128 = row 0, k2 = 8 (self-paired): 2 X[128] = 2 conj(Z[128]); lane 0 holds row 0 in .y
     float zr = z.r[pos16(8)].y, zi = z.i[pos16(8)].y;
-    if (t0) p_f[128] = 4.f * (zr * zr + zi * zi);
+    if (t0) p_f[128 * kPStride] = 4.f * (zr * zr + zi * zi);
     x0 = z.r[0].y + z.i[0].y;         // X[0]   = Re Z[0] + Im Z[0]   (lane 0 only)
     x256 = z.r[0].y - z.i[0].y;       // X[256] = Re Z[0] - Im Z[0]
 }
@@ -356,145 +360,176 @@ FE_HD float fe_log(float x) {
 #endif
 }
 
-// rows inside the warp's exchange buffer e_w (kWarpFrames regions of kERegion floats)
-FE_HD float* power_row(float* e_w, int f) { return e_w + f * kERegion + f * kPStagger; }
-FE_HD float* logmel_row(float* e_w, int f) { return e_w + f * kERegion + kLogmelOff + f * kPStagger; }
-FE_HD float* fold_row(float* e_w, int f, int odd) { return e_w + f * kERegion + (odd ? kFoldD : kFoldS) + f * kPStagger; }
-
 // ---------------------------------------------------------------------------
-// Phase 4: mel filterbank, lane g of frame fs walks its slot list (uniform trip counts).
+// Epilogue (the consumer warps of K1): lane = frame of the 32-frame tile, warp = filter / coefficient
+// group.  Everything a warp reads besides its own frame column is warp-uniform (broadcast loads), every
+// column access is 32 consecutive floats (one wavefront, no conflicts).
+//   pbuf  [bins + 3][kPStride]   power columns written by the post-pass (pad rows stay zero)
+//   lm    [nf + 4][32]           (log-)mel rows of the tile (mfcc only; fbank rows go straight to out_t)
+//   out_t [D][32]                the tile's statics, coefficient-major (what K2 reads)
 // ---------------------------------------------------------------------------
-// one slot with a compile-time number of weight groups: all loads first, then the FMAs
-template <int N4>
-FE_HD float mel_slot(const float4* w, const float* p) {
-    float4 ww[N4], pv[N4];
-#pragma unroll
-    for (int q = 0; q < N4; ++q) ww[q] = w[q * 8];
-#pragma unroll
-    for (int q = 0; q < N4; ++q) pv[q] = *reinterpret_cast<const float4*>(p + 4 * q);   // runs start 16-byte aligned
-    float acc0 = 0.f, acc1 = 0.f;
-#pragma unroll
-    for (int q = 0; q < N4; ++q) {
-        acc0 = fmaf(ww[q].x, pv[q].x, acc0);
-        acc1 = fmaf(ww[q].y, pv[q].y, acc1);
-        acc0 = fmaf(ww[q].z, pv[q].z, acc0);
-        acc1 = fmaf(ww[q].w, pv[q].w, acc1);
-    }
-    return acc0 + acc1;
-}
-
-FE_HD void mel_phase(float* e_w, const SmemTables& tb, int g, int fs) {
-    const float* p_f = power_row(e_w, fs);
-    float* row = logmel_row(e_w, fs);
+// Phase 4: mel filterbank (+ zero handling, + log).  The warp's weight groups are streamed through a
+// 4-deep software pipeline (descriptors 8 groups ahead, weights and power values 4 ahead): a serial
+// load -> FMA -> log chain per filter would leave the warp idle for hundreds of cycles per filter.
+// The only loop-carried dependency is the running sum of the current filter.
+FE_HD void epi_mel(const float* pbuf, float* dst, const SmemTables& tb, int off, int G, int lane) {
+    const float* pcol = pbuf + lane;
     const bool want_log = tb.is_mfcc || tb.fbank_log;
-    const float4* w = reinterpret_cast<const float4*>(tb.mel_w) + g;
-    const int* bi = tb.mel_bi + g;
-    for (int s = 0; s < tb.mel_slots; ++s) {
-        const int n4 = tb.mel_n4[s];                 // warp-uniform (constant bank)
-        const int d = bi[s * 8];
-        const float* p = p_f + (d & 0xffff);
-        float v;
-        if (n4 == 1) v = mel_slot<1>(w, p);
-        else if (n4 == 2) v = mel_slot<2>(w, p);
-        else if (n4 == 3) v = mel_slot<3>(w, p);
-        else if (n4 == 4) v = mel_slot<4>(w, p);
-        else {
-            float acc0 = 0.f, acc1 = 0.f;
-            for (int q = 0; q < n4; ++q) {
-                const float4 ww = w[q * 8];
-                const float4 pv = *reinterpret_cast<const float4*>(p + 4 * q);
-                acc0 = fmaf(ww.x, pv.x, acc0);
-                acc1 = fmaf(ww.y, pv.y, acc1);
-                acc0 = fmaf(ww.z, pv.z, acc0);
-                acc1 = fmaf(ww.w, pv.w, acc1);
-            }
-            v = acc0 + acc1;
-        }
-        w += n4 * 8;
-        v = (v == 0.f) ? kEpsF64 : v;
-        if (want_log) v = fe_log(v);
-        const int id = d >> 16;
-        if (id != 0xffff) row[id] = v;
-    }
-}
-
-// Phase 4b (mfcc): fold the log-mel row for the DCT: s[n] = x[n] + x[nf-1-n], d[n] = x[n] - x[nf-1-n]
-FE_HD void fold_phase(float* e_w, const SmemTables& tb, int g, int fs) {
-    const float* row = logmel_row(e_w, fs);
-    float* fs_ = fold_row(e_w, fs, 0);
-    float* fd_ = fold_row(e_w, fs, 1);
-    const int nh4 = (tb.nh + 3) & ~3;
-    for (int n = g; n < nh4; n += 8) {
-        float s = 0.f, d = 0.f;
-        if (n < tb.nh) {
-            const int m = tb.nf - 1 - n;
-            float a = row[n];
-            if (m == n) { s = a; d = 0.f; }
-            else { float b = row[m]; s = a + b; d = a - b; }
-        }
-        fs_[n] = s; fd_[n] = d;
-    }
-}
-
-// Phase 5 (mfcc): lane g computes coefficients c = g, g+8, ... (same parity as g -> one input array)
-FE_HD void dct_phase(float* e_w, const float* energies, const SmemTables& tb, int g, int fs, float* dst, bool store) {
-    const float* in = fold_row(e_w, fs, g & 1);
-    const int n4 = (tb.nh + 3) >> 2;
-    for (int c0 = g; c0 < tb.D; c0 += 16) {
-        const int c1 = c0 + 8;
-        const bool has1 = c1 < tb.D;
-        const float* d0 = tb.dctf + c0 * tb.dct_stride;
-        const float* d1 = tb.dctf + (has1 ? c1 : c0) * tb.dct_stride;
-        float a0 = 0.f, a1 = 0.f;
-        for (int q = 0; q < n4; ++q) {
-            float4 x = *reinterpret_cast<const float4*>(in + 4 * q);
-            float4 u = *reinterpret_cast<const float4*>(d0 + 4 * q);
-            float4 v = *reinterpret_cast<const float4*>(d1 + 4 * q);
-            a0 = fmaf(u.x, x.x, a0); a0 = fmaf(u.y, x.y, a0); a0 = fmaf(u.z, x.z, a0); a0 = fmaf(u.w, x.w, a0);
-            a1 = fmaf(v.x, x.x, a1); a1 = fmaf(v.y, x.y, a1); a1 = fmaf(v.z, x.z, a1); a1 = fmaf(v.w, x.w, a1);
-        }
-        if (c0 == 0 && tb.dc_elim) a0 = fe_log(energies[fs]);
-        if (store) dst[c0] = a0;
-        if (store && has1) dst[c1] = a1;
-    }
-}
-
-// Phase 5 variant for nf % 8 == 0 (the reference's 40 filters): the fold
-// x[n] +- x[nf-1-n] is done on the fly from the log-mel row (16-byte loads from both ends),
-// so no separate fold phase and no extra synchronisation.
-template <int N4>
-FE_HD void dct_pair(const float* row, int nf, const float* d0, const float* d1, float sgn, int n4, float& a0, float& a1) {
-    a0 = 0.f; a1 = 0.f;
-    const int n = N4 > 0 ? N4 : n4;
+    const int* ent = tb.mel_desc + off;
+    const float4* w4 = tb.mel_w4 + off;
+    int e[4], en[4];
+    float4 w[4];
+    float pv[4][4];
 #pragma unroll
-    for (int q = 0; q < n; ++q) {
-        float4 lo = *reinterpret_cast<const float4*>(row + 4 * q);
-        float4 hi = *reinterpret_cast<const float4*>(row + nf - 4 - 4 * q);
-        float4 u = *reinterpret_cast<const float4*>(d0 + 4 * q);
-        float4 v = *reinterpret_cast<const float4*>(d1 + 4 * q);
-        const float x0 = fmaf(sgn, hi.w, lo.x), x1 = fmaf(sgn, hi.z, lo.y);
-        const float x2 = fmaf(sgn, hi.y, lo.z), x3 = fmaf(sgn, hi.x, lo.w);
-        a0 = fmaf(u.x, x0, a0); a0 = fmaf(u.y, x1, a0); a0 = fmaf(u.z, x2, a0); a0 = fmaf(u.w, x3, a0);
-        a1 = fmaf(v.x, x0, a1); a1 = fmaf(v.y, x1, a1); a1 = fmaf(v.z, x2, a1); a1 = fmaf(v.w, x3, a1);
+    for (int s = 0; s < 4; ++s) {
+        e[s] = ent[s]; en[s] = ent[4 + s]; w[s] = w4[s];
+        const float* p = pcol + (e[s] & 1023) * kPStride;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) pv[s][j] = p[j * kPStride];
+    }
+    float acc = 0.f;
+    for (int i = 0; i < G; i += 4) {
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+            const float a = fmaf(w[s].x, pv[s][0], w[s].z * pv[s][2]) + fmaf(w[s].y, pv[s][1], w[s].w * pv[s][3]);
+            acc += a;
+            const int ec = e[s];
+            // refill this stage with group i + s + 4 (the list has 8 zero groups of slack)
+            e[s] = en[s]; en[s] = ent[i + s + 8]; w[s] = w4[i + s + 4];
+            const float* p = pcol + (e[s] & 1023) * kPStride;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) pv[s][j] = p[j * kPStride];
+            if (ec & 1024) {                                    // last group of a filter (warp-uniform)
+                float v = acc == 0.f ? kEpsF64 : acc;           // speechpy.functions.zero_handling
+                if (want_log) v = fe_log(v);
+                dst[(ec >> 16) * 32 + lane] = v;
+                acc = 0.f;
+            }
+        }
     }
 }
 
-FE_HD void dct_phase_fused(float* e_w, const float* energies, const SmemTables& tb, int g, int fs, float* dst, bool store) {
-    const float* row = logmel_row(e_w, fs);
-    const float sgn = (g & 1) ? -1.f : 1.f;          // parity of every coefficient this lane owns
-    const int n4 = tb.nh >> 2;
-    for (int c0 = g; c0 < tb.D; c0 += 16) {
-        const int c1 = c0 + 8;
-        const bool has1 = c1 < tb.D;
-        const float* d0 = tb.dctf + c0 * tb.dct_stride;
-        const float* d1 = tb.dctf + (has1 ? c1 : c0) * tb.dct_stride;
-        float a0, a1;
-        if (n4 == 5) dct_pair<5>(row, tb.nf, d0, d1, sgn, n4, a0, a1);       // 40 filters (the reference)
-        else dct_pair<0>(row, tb.nf, d0, d1, sgn, n4, a0, a1);
-        if (c0 == 0 && tb.dc_elim) a0 = fe_log(energies[fs]);
-        if (store) dst[c0] = a0;
-        if (store && has1) dst[c1] = a1;
+// Phase 5 (mfcc): DCT-II (ortho), y_c = sum_{n < nh} C[c][n] (x[n] + (-1)^c x[nf-1-n]).  Warp computes
+// coefficients warp, warp + 4, ... (all of one parity -> one folded input), four at a time so that every
+// log-mel row is loaded once per four coefficients; c0 <- log(frame energy) when dc_elim.  Weights are
+// warp-uniform.  N4 > 0: number of 4-row groups known at compile time (5 for the reference's 40 filters).
+template <int N4>
+FE_HD void epi_dct_n(const float* lm, const float* energies, float* out_t, const SmemTables& tb, int warp, int lane) {
+    const int nh4 = (tb.nh + 3) & ~3, n4 = N4 > 0 ? N4 : (nh4 >> 2);
+    const float* in = lm + lane;
+    const float sgn = (warp & 1) ? -1.f : 1.f;
+    const int nf1 = tb.nf - 1;
+    for (int cb = warp; cb < tb.D; cb += 4 * kEpiWarps) {
+        const float4* d[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int c = cb + j * kEpiWarps;
+            d[j] = reinterpret_cast<const float4*>(tb.dctf + (c < tb.D ? c : cb) * tb.dct_stride);
+        }
+        float acc[4] = {0.f, 0.f, 0.f, 0.f}, bcc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int q = 0; q < n4; ++q) {
+            float x[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int n = 4 * q + j, m = nf1 - n;           // rows past nh carry zero weights; keep the reads in range
+                const float a = in[n * 32];
+                const float b = in[(m > 0 ? m : 0) * 32];
+                x[j] = (m == n) ? (sgn > 0.f ? a : 0.f) : fmaf(sgn, b, a);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float4 w = d[j][q];
+                acc[j] = fmaf(w.x, x[0], acc[j]); bcc[j] = fmaf(w.y, x[1], bcc[j]);
+                acc[j] = fmaf(w.z, x[2], acc[j]); bcc[j] = fmaf(w.w, x[3], bcc[j]);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int c = cb + j * kEpiWarps;
+            float v = acc[j] + bcc[j];
+            if (c == 0 && tb.dc_elim) v = fe_log(energies[lane]);
+            if (c < tb.D) out_t[c * 32 + lane] = v;
+        }
     }
+}
+
+FE_HD void epi_dct(const float* lm, const float* energies, float* out_t, const SmemTables& tb, int warp, int lane) {
+    if (tb.nh == 20) epi_dct_n<5>(lm, energies, out_t, tb, warp, lane);
+    else epi_dct_n<0>(lm, energies, out_t, tb, warp, lane);
+}
+
+// ---------------------------------------------------------------------------
+// Specialised epilogue for the reference's two filterbanks (fe_plans_gen.h): ONE warp takes a whole tile,
+// lane = frame.  The filterbank structure is a compile-time plan, so the whole mel -> log -> fold -> DCT
+// chain is straight-line code over registers: one shared-memory load and one FMA per non-zero weight
+// (weights and DCT rows are compile-time offsets into `w`, i.e. constant-bank operands on the device),
+// no descriptors, no barrier, no log-mel round trip through shared memory.
+//   w: [Plan::NNZ] mel weights in CSR order (pre-scaled), then [D][NF/2] folded DCT rows (mfcc)
+// ---------------------------------------------------------------------------
+template <int I, int N, class F>
+FE_HD void static_for(F&& f) {
+    if constexpr (I < N) {
+        f(std::integral_constant<int, I>{});
+        static_for<I + 1, N>(f);
+    }
+}
+
+template <class Plan, int M, bool LOG>
+FE_HD float mel_spec(const float* pcol, const float* w) {
+    constexpr int b0 = Plan::B0[M], n = Plan::N[M], off = Plan::OFF[M];
+    float a0 = 0.f, a1 = 0.f;
+    static_for<0, n>([&](auto ii) {
+        constexpr int i = decltype(ii)::value;
+        if (i & 1) a1 = fmaf(w[off + i], pcol[(b0 + i) * kPStride], a1);
+        else a0 = fmaf(w[off + i], pcol[(b0 + i) * kPStride], a0);
+    });
+    float v = a0 + a1;
+    v = v == 0.f ? kEpsF64 : v;                 // speechpy.functions.zero_handling
+    if (LOG) v = fe_log(v);
+    return v;
+}
+
+template <class Plan, int D, bool MFCC, bool LOG>
+FE_HD void epi_tile_spec(const float* pbuf, const float* energies, float* out_t, const float* w, bool dc_elim, int lane) {
+    const float* pcol = pbuf + lane;
+    if constexpr (!MFCC) {
+        static_for<0, Plan::NF>([&](auto mi) {
+            constexpr int M = decltype(mi)::value;
+            out_t[M * 32 + lane] = mel_spec<Plan, M, LOG>(pcol, w);
+        });
+    } else {
+        constexpr int NH = Plan::NF / 2;
+        static_assert(Plan::NF % 2 == 0, "the specialised plans have an even number of filters");
+        float s[NH], d[NH];                     // folded log-mel: x[n] +- x[NF-1-n]
+        static_for<0, NH>([&](auto ni) {
+            constexpr int n = decltype(ni)::value;
+            const float lo = mel_spec<Plan, n, LOG>(pcol, w), hi = mel_spec<Plan, Plan::NF - 1 - n, LOG>(pcol, w);
+            s[n] = lo + hi; d[n] = lo - hi;
+        });
+        const float* dw = w + Plan::NNZ;
+#pragma unroll
+        for (int c = 0; c < D; ++c) {
+            float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+            for (int n = 0; n < NH; n += 2) {
+                a0 = fmaf(dw[c * NH + n], (c & 1) ? d[n] : s[n], a0);
+                a1 = fmaf(dw[c * NH + n + 1], (c & 1) ? d[n + 1] : s[n + 1], a1);
+            }
+            float v = a0 + a1;
+            if (c == 0 && dc_elim) v = fe_log(energies[lane]);
+            out_t[c * 32 + lane] = v;
+        }
+    }
+}
+
+// which specialised epilogue (if any) serves a configuration: 0 = generic, 1 = mfcc 40 filters -> 13, 2 = fbank 80
+template <class Plan>
+inline bool plan_matches(const int* row_start, const int* first_bin, int nf) {
+    if (nf != Plan::NF || row_start[nf] != Plan::NNZ) return false;
+    for (int m = 0; m < nf; ++m)
+        if (first_bin[m] != Plan::B0[m] || row_start[m + 1] - row_start[m] != Plan::N[m] || row_start[m] != Plan::OFF[m]) return false;
+    return true;
 }
 
 }  // namespace fe

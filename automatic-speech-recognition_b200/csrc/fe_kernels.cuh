@@ -24,12 +24,12 @@ struct UttDesc {
     float gain;             // 1 = none
 };
 
-// one entry per tile (warps-per-CTA x 4 frames) of one utterance (48 bytes, three 16-byte loads)
+// one entry per tile (32 consecutive frames of one utterance; 48 bytes, three 16-byte loads)
 struct __align__(16) TileDesc {
     long long pcm_off;      // element offset of the tile's first sample
-    long long stat_off;     // float offset of the tile's first statics row
+    long long stat_off;     // float offset of the tile's statics block
     long long out_off;      // float offset of the utterance's output (frame 0)
-    int n_frames;           // 1..tile_frames
+    int n_frames;           // 1..32
     int src_sel;
     int utt;
     int first_frame;        // of this tile inside the utterance
@@ -41,27 +41,33 @@ struct DevTables {
     const float4* tw256;    // [6][16]
     const float4* tw512;    // [16]
     const float2* window;   // [ROWS*16] or nullptr
-    const int* mel_bi; const float* mel_w;
+    const int* mel_desc; const float* mel_w;
     const float* dctf;      // [D][dct_stride]
-    int mel_slots, mel_entries;
+    int mel_groups, p_rows;
+    int epi_off[kEpiWarps], epi_cnt[kEpiWarps];
     int nf, D, dct_stride, nh, full_spectrum, is_mfcc, fbank_log, dc_elim;
     float pscale;
 };
 
-constexpr int kMaxMelSlots = 16;     // ceil(kMaxFilters / 8)
-
 // ---------------------------------------------------------------------------
+// Statics between K1 and K2 are stored tile by tile, coefficient-major: tile j of an utterance
+// is a [D][32] block (frame 32 j + l of coefficient c at block[c * 32 + l]); the last block of
+// an utterance is padded to 32 frames.  K1's epilogue writes it with one 128-byte store per
+// (warp, coefficient); K2 reads it with the same coalescing.
+// ---------------------------------------------------------------------------
+__host__ __device__ inline long long statics_tiles(long long n_frames) { return (n_frames + kTileFrames - 1) / kTileFrames; }
+
 __global__ void k_build_tiles(const UttDesc* __restrict__ utts, const long long* __restrict__ tile_prefix,
-                              int n_utts, int hop, int D, int tile_frames, TileDesc* __restrict__ tiles) {
+                              int n_utts, int hop, int D, TileDesc* __restrict__ tiles) {
     int u = blockIdx.x * blockDim.x + threadIdx.x;
     if (u >= n_utts) return;
     const UttDesc d = utts[u];
     long long b = tile_prefix[u];
-    for (int f = 0; f < d.n_frames; f += tile_frames) {
+    for (int f = 0; f < d.n_frames; f += kTileFrames) {
         TileDesc t;
         t.pcm_off = d.pcm_off + (long long)f * hop;
-        t.stat_off = d.stat_off + (long long)f * D;
-        t.n_frames = min(tile_frames, d.n_frames - f);
+        t.stat_off = d.stat_off + (long long)f * D;        // f is a multiple of 32: whole [D][32] blocks
+        t.n_frames = min(kTileFrames, d.n_frames - f);
         t.out_off = d.out_off; t.first_frame = f; t.utt_frames = d.n_frames;
         t.src_sel = d.src_sel; t.utt = u; t.pad = 0;
         tiles[b++] = t;
@@ -73,31 +79,61 @@ __global__ void k_build_tiles(const UttDesc* __restrict__ utts, const long long*
 // The exchange regions come first so that they are 2 KB aligned (the kernel rounds
 // the dynamic shared base up to 2 KB; the host adds 2 KB of slack).
 // ---------------------------------------------------------------------------
+constexpr int kK1Threads = (kFftWarps + kEpiWarps) * 32;
+constexpr int kMaxSlots = 4;            // power-buffer slots between the FFT warps and the epilogue warps
+constexpr int kK1SmemMax = 227 * 1024;
+
 struct K1Smem {
-    int off_e, off_raw, off_scr, off_tw256, off_tw512, off_window, off_bi, off_melw, off_dct, off_bar;
+    int off_e, off_raw, off_scr, off_tw256, off_tw512, off_window, off_desc, off_melw, off_dct, off_pbuf, off_sd,
+        off_energy, off_bar;
     int raw_bytes;          // one raw buffer of one warp
+    int raw_bufs;           // 2 = double-buffered bulk copies, 1 when shared memory is short (float PCM)
+    int slots;              // power-buffer slots (3, or 2 when the full 257-bin spectrum is kept)
+    int pbuf_floats, sd_floats;     // per slot / per sd buffer
     int total;
 };
 
 __host__ __device__ inline int align16(int x) { return (x + 15) & ~15; }
 
-__host__ __device__ inline K1Smem k1_smem_layout(int mel_slots, int mel_entries, int D, int dct_stride, int has_window,
-                                                 int frame_len, int hop, int is_mfcc, int in_f32, int warps) {
+__host__ __device__ inline K1Smem k1_smem_layout_n(int nf, int mel_groups, int p_rows, int D, int dct_stride, int has_window,
+                                                   int frame_len, int hop, int is_mfcc, int in_f32, int raw_bufs, int slots,
+                                                   int spec) {
     K1Smem s;
+    s.raw_bufs = raw_bufs; s.slots = slots;
     const int rows = (frame_len + 31) / 32;
     int o = 0;
-    s.off_e = o;      o += warps * kWarpFrames * kERegion * 4;
+    s.off_e = o;      o += kFftWarps * kWarpFrames * kERegion * 4;
     s.raw_bytes = align16(((kWarpFrames - 1) * hop + rows * 32) * (in_f32 ? 4 : 2));
-    s.off_raw = o;    o += warps * 2 * s.raw_bytes;
-    s.off_scr = o;    o += warps * 64 * 4;
+    s.off_raw = o;    o += kFftWarps * raw_bufs * s.raw_bytes;
+    s.off_scr = o;    o += kFftWarps * 32 * 4;
     s.off_tw256 = o;  o += 6 * 16 * 16;
     s.off_tw512 = o;  o += 16 * 16;
     s.off_window = o; o = align16(o + (has_window ? rows * 16 * 8 : 0));
-    s.off_bi = o;     o = align16(o + mel_slots * 8 * 4);
-    s.off_melw = o;   o = align16(o + mel_entries * 8 * 4);
-    s.off_dct = o;    o = align16(o + (is_mfcc ? D * dct_stride * 4 : 0));
-    s.off_bar = o;    o += warps * 2 * 8;
+    // (the specialised epilogue reads its weights from the kernel parameters and keeps log-mel in registers)
+    s.off_desc = o;   o = align16(o + (spec ? 0 : (mel_groups > 0 ? mel_groups : 1) * 4));
+    s.off_melw = o;   o = align16(o + (spec ? 0 : (mel_groups > 0 ? mel_groups : 1) * 16));
+    s.off_dct = o;    o = align16(o + (is_mfcc && !spec ? D * dct_stride * 4 : 0));
+    s.pbuf_floats = p_rows * kPStride;
+    s.off_pbuf = o;   o = align16(o + slots * s.pbuf_floats * 4);
+    s.sd_floats = is_mfcc && !spec ? (nf + 4) * 32 : 0; // log-mel rows of one tile
+    s.off_sd = o;     o = align16(o + 2 * s.sd_floats * 4);
+    s.off_energy = o; o += kMaxSlots * kTileFrames * 4;
+    s.off_bar = o;    o += (kFftWarps * 2 + 2 * kMaxSlots) * 8;
     s.total = o + 2048;     // slack for the 2 KB round-up
+    return s;
+}
+
+// the richest buffering that fits one SM's shared memory (total > kK1SmemMax: the configuration does not fit).
+// spec: layout for a specialised epilogue -- consumer warp w owns slot w, so exactly 4 slots are needed.
+__host__ inline K1Smem k1_smem_layout(int nf, int mel_groups, int p_rows, int D, int dct_stride, int has_window,
+                                      int frame_len, int hop, int is_mfcc, int in_f32, int spec) {
+    const int gen[4][2] = {{2, 3}, {2, 2}, {1, 3}, {1, 2}}, sp[2][2] = {{2, 4}, {1, 4}};
+    K1Smem s{};
+    for (int i = 0; i < (spec ? 2 : 4); ++i) {
+        const int* o = spec ? sp[i] : gen[i];
+        s = k1_smem_layout_n(nf, mel_groups, p_rows, D, dct_stride, has_window, frame_len, hop, is_mfcc, in_f32, o[0], o[1], spec);
+        if (s.total <= kK1SmemMax) break;
+    }
     return s;
 }
 
@@ -110,6 +146,9 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, int count) {
 }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
 }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -126,19 +165,48 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         :: "r"(bar), "r"(parity) : "memory");
 }
 
-// everything K1 needs besides the data pointers; lives in the constant bank (uniform loads,
-// uniform loop bounds, nothing to rematerialise per tile)
+// everything K1 needs besides the data pointers; lives in the constant bank
+constexpr int kEpiWCap = 512;            // floats of specialised-epilogue weights carried in the kernel parameters
+
 struct K1Params {
     DevTables dt;
     K1Smem L;
-    int mel_n4[kMaxMelSlots];       // float4 weight groups per mel slot
-    int mel_e4[kMaxMelSlots];       // first float4 group of each slot
+    float epi_w[kEpiWCap];          // EPI != 0: mel CSR weights + folded DCT rows (constant-bank operands)
+    int dbg;                        // phase ablation for profiling (FE_K1_DBG): 1 = no mel/DCT
 };
 
 #define FE_OPAQUE(v) asm volatile("" : "+r"(v))
 
-template <int FRAME_LEN, int HOP, int IN_F32, int HAS_WINDOW, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32, 2)
+// FE_K1_DBG & 8: per-phase clock64 totals of lane 0 of every warp (profiling aid, read with fe_debug_counters)
+//   [0] epilogue: wait for a full slot  [1] mel  [2] named barrier  [3] DCT  [4] tiles
+//   [8] FFT: wait for raw samples  [9] stage A  [10] stage B  [11] wait for an empty slot  [12] post-pass  [13] groups
+// Compiled in only with -DFE_K1_PROF (the counters cost 14 registers in the FFT loop).
+__device__ unsigned long long g_k1_prof[16];
+#ifdef FE_K1_PROF
+#define FE_PROF_DECL(n) long long prof[n] = {0}, tick = clock64()
+#define FE_TICK(slot)                                                             \
+    do { if (P.dbg & 8) { const long long now__ = clock64(); prof[slot] += now__ - tick; tick = now__; } } while (0)
+#else
+#define FE_PROF_DECL(n)
+#define FE_TICK(slot) do { } while (0)
+#endif
+
+// ---------------------------------------------------------------------------
+// K1.  Persistent, warp-specialised: one CTA of 16 warps per SM.
+//   warps 0..11  (three warpgroups, 144 registers/thread after setmaxnreg): FFT producers.  Each pass
+//     takes one 4-frame group (8 lanes per frame): TMA bulk copy of the raw samples (double-buffered per
+//     warp) -> stage A -> exchange -> stage B -> real-FFT split -> the group's 4 columns of a [bin][frame]
+//     power-buffer slot.  No CTA barrier: producers only meet the consumers through mbarriers.
+//   warps 12..15 (one warpgroup, 80 registers/thread): epilogue consumers.  For every tile (8 groups =
+//     32 frames) lane = frame, warp = filter / coefficient group: mel (+ log) -> log-mel rows ->
+//     named barrier of the 4 warps -> DCT -> the tile's [D][32] statics block (128-byte stores).
+//   tile k of the CTA lives in slot k % 3; full[slot] (8 arrivals, one per group) / empty[slot] (4).
+// The latency-bound, LSU-heavy epilogue so runs in the issue slots the FP32-bound FFT warps leave idle.
+// ---------------------------------------------------------------------------
+// EPI: 0 = generic epilogue (run-time mel plan, the 4 consumer warps share every tile),
+//      1 / 2 = specialised for PlanMfcc40 (13 cepstra) / PlanFbank80: consumer warp w takes tiles w, w + 4, ... whole.
+template <int FRAME_LEN, int HOP, int IN_F32, int HAS_WINDOW, int EPI>
+__global__ void __launch_bounds__(kK1Threads, 1)
 k_frames_to_statics(const void* __restrict__ pcm, const void* __restrict__ scratch,
                     const TileDesc* __restrict__ tiles, int n_tiles,
                     const __grid_constant__ K1Params P, float* __restrict__ statics) {
@@ -150,127 +218,212 @@ k_frames_to_statics(const void* __restrict__ pcm, const void* __restrict__ scrat
     float4* s_tw256 = reinterpret_cast<float4*>(smem + L.off_tw256);
     float4* s_tw512 = reinterpret_cast<float4*>(smem + L.off_tw512);
     float2* s_window = reinterpret_cast<float2*>(smem + L.off_window);
-    int* s_bi = reinterpret_cast<int*>(smem + L.off_bi);
+    int* s_desc = reinterpret_cast<int*>(smem + L.off_desc);
     float* s_melw = reinterpret_cast<float*>(smem + L.off_melw);
     float* s_dct = reinterpret_cast<float*>(smem + L.off_dct);
+    float* s_pbuf = reinterpret_cast<float*>(smem + L.off_pbuf);
+    float* s_sd = reinterpret_cast<float*>(smem + L.off_sd);
+    float* s_energy = reinterpret_cast<float*>(smem + L.off_energy);
 
     const int tid = threadIdx.x;
     constexpr int ROWS = (FRAME_LEN + 31) / 32;
     for (int i = tid; i < 96; i += blockDim.x) s_tw256[i] = dt.tw256[i];
     for (int i = tid; i < 16; i += blockDim.x) s_tw512[i] = dt.tw512[i];
     if (dt.window) for (int i = tid; i < ROWS * 16; i += blockDim.x) s_window[i] = dt.window[i];
-    for (int i = tid; i < dt.mel_slots * 8; i += blockDim.x) s_bi[i] = dt.mel_bi[i];
-    for (int i = tid; i < dt.mel_entries * 8; i += blockDim.x) s_melw[i] = dt.mel_w[i];
-    if (dt.is_mfcc) for (int i = tid; i < dt.D * dt.dct_stride; i += blockDim.x) s_dct[i] = dt.dctf[i];
+    if (EPI == 0) {
+        for (int i = tid; i < dt.mel_groups; i += blockDim.x) s_desc[i] = dt.mel_desc[i];
+        for (int i = tid; i < dt.mel_groups * 4; i += blockDim.x) s_melw[i] = dt.mel_w[i];
+        if (dt.is_mfcc) for (int i = tid; i < dt.D * dt.dct_stride; i += blockDim.x) s_dct[i] = dt.dctf[i];
+    }
+    // pad rows of the power slots and of the folded rows are read (times zero weights): keep them finite
+    for (int i = tid; i < L.slots * L.pbuf_floats; i += blockDim.x) s_pbuf[i] = 0.f;
+    for (int i = tid; i < 2 * L.sd_floats; i += blockDim.x) s_sd[i] = 0.f;
+    for (int i = tid; i < kMaxSlots * kTileFrames; i += blockDim.x) s_energy[i] = 1.f;
 
-    // per-thread constants, pinned in registers (FE_OPAQUE stops the compiler from
-    // re-deriving them from threadIdx inside the tile loop)
     int lane = tid & 31, warp = tid >> 5;
-    FE_OPAQUE(lane); FE_OPAQUE(warp);
-    const int fs = lane >> 3, t = lane & 7;
-    constexpr int ESZ = IN_F32 ? 4 : 2;
-    uint32_t o_e = (uint32_t)(smem - smem_dyn) + L.off_e + warp * (kWarpFrames * kERegion * 4);   // warp's exchange buffer
-    uint32_t o_raw = (uint32_t)(smem - smem_dyn) + L.off_raw + warp * 2 * L.raw_bytes;
-    uint32_t o_scr = (uint32_t)(smem - smem_dyn) + L.off_scr + warp * 256;
-    FE_OPAQUE(o_e); FE_OPAQUE(o_raw); FE_OPAQUE(o_scr);
-    const uint32_t bar0 = smem_u32(smem + L.off_bar + warp * 16);     // two mbarriers per warp
-    if (lane == 0) { mbar_init(bar0, 1); mbar_init(bar0 + 8, 1); }
+    const uint32_t bar_base = smem_u32(smem + L.off_bar);
+    const uint32_t bar_full = bar_base + kFftWarps * 16, bar_empty = bar_full + kMaxSlots * 8;
+    if (tid == 0) {
+        for (int i = 0; i < kFftWarps * 2; ++i) mbar_init(bar_base + 8 * i, 1);
+        for (int i = 0; i < kMaxSlots; ++i) { mbar_init(bar_full + 8 * i, kTileGroups); mbar_init(bar_empty + 8 * i, EPI ? 1 : kEpiWarps); }
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
 
     SmemTables tb;
     tb.tw256 = s_tw256; tb.tw512 = s_tw512; tb.window = dt.window ? s_window : nullptr;
-    tb.mel_n4 = P.mel_n4; tb.mel_bi = s_bi; tb.mel_w = s_melw; tb.dctf = s_dct;
-    tb.mel_slots = dt.mel_slots; tb.nf = dt.nf; tb.D = dt.D; tb.dct_stride = dt.dct_stride; tb.nh = dt.nh;
+    tb.mel_desc = s_desc; tb.mel_w4 = reinterpret_cast<const float4*>(s_melw); tb.dctf = s_dct;
+    tb.nf = dt.nf; tb.D = dt.D; tb.dct_stride = dt.dct_stride; tb.nh = dt.nh;
     tb.full_spectrum = dt.full_spectrum; tb.is_mfcc = dt.is_mfcc; tb.fbank_log = dt.fbank_log;
     tb.dc_elim = dt.dc_elim; tb.pscale = dt.pscale;
-    const int D = dt.D;
 
-    // issue the bulk copy of this warp's slice of tile `td` into raw buffer `buf`
-    auto prefetch = [&](const TileDesc& td, int buf) {
-        const int nfw = min(kWarpFrames, td.n_frames - warp * kWarpFrames);
+    const int nk = (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;      // tiles of this CTA
+
+    if (warp >= kFftWarps) {
+        // =========================== epilogue warpgroup ===========================
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" :: "n"(80));
+        const int we = warp - kFftWarps;
+        if (EPI != 0) {
+            // one warp per tile: k = we, we + 4, ... in slot `we` (4 slots: a warp sees every phase of its barrier in order)
+            const int slot = we;
+            uint32_t par = 0;
+            for (int k = we; k < nk; k += kEpiWarps, par ^= 1u) {
+                float* out_t = statics + tiles[blockIdx.x + (long long)k * gridDim.x].stat_off;
+                const float* pb = s_pbuf + slot * L.pbuf_floats;
+                mbar_wait(bar_full + 8 * slot, par);
+                if (!(P.dbg & 1)) {
+                    if (EPI == 1) epi_tile_spec<PlanMfcc40, 13, true, true>(pb, s_energy + slot * kTileFrames, out_t, P.epi_w, tb.dc_elim, lane);
+                    else if (tb.fbank_log) epi_tile_spec<PlanFbank80, 80, false, true>(pb, s_energy + slot * kTileFrames, out_t, P.epi_w, false, lane);
+                    else epi_tile_spec<PlanFbank80, 80, false, false>(pb, s_energy + slot * kTileFrames, out_t, P.epi_w, false, lane);
+                } else {
+                    out_t[lane] = pb[(5 + (lane & 7)) * kPStride + lane] + s_energy[slot * kTileFrames + lane];
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_empty + 8 * slot);
+            }
+            return;
+        }
+        const int my_off = dt.epi_off[we], my_cnt = dt.epi_cnt[we];        // this warp's slice of the mel plan
+        int slot = 0;
+        uint32_t par = 0;
+        long long stat_next = tiles[blockIdx.x].stat_off;
+        FE_PROF_DECL(5);
+        for (int k = 0; k < nk; ++k) {
+            float* out_t = statics + stat_next;
+            if (k + 1 < nk) stat_next = tiles[blockIdx.x + (long long)(k + 1) * gridDim.x].stat_off;
+            float* sd = s_sd + (k & 1) * L.sd_floats;
+            const float* pb = s_pbuf + slot * L.pbuf_floats;
+            mbar_wait(bar_full + 8 * slot, par);
+            FE_TICK(0);
+            if (!(P.dbg & 1)) {
+                // ---- phase 4: mel filterbank (+ log, + fold), lane = frame ----
+                if (tb.is_mfcc) epi_mel(pb, sd, tb, my_off, my_cnt, lane);        // two calls: shared vs global stores
+                else epi_mel(pb, out_t, tb, my_off, my_cnt, lane);
+                FE_TICK(1);
+                if (tb.is_mfcc) {
+                    asm volatile("bar.sync 1, %0;" :: "n"(kEpiWarps * 32) : "memory");
+                    FE_TICK(2);
+                    // ---- phase 5: DCT, lane = frame ----
+                    epi_dct(sd, s_energy + slot * kTileFrames, out_t, tb, we, lane);
+                    FE_TICK(3);
+                }
+            } else if (we == 0) {
+                out_t[lane] = pb[(5 + (lane & 7)) * kPStride + lane] + s_energy[slot * kTileFrames + lane];
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_empty + 8 * slot);
+            if (++slot == L.slots) { slot = 0; par ^= 1u; }
+        }
+#ifdef FE_K1_PROF
+        if ((P.dbg & 8) && lane == 0) {
+            for (int i = 0; i < 4; ++i) atomicAdd(&g_k1_prof[i], (unsigned long long)prof[i]);
+            atomicAdd(&g_k1_prof[4], (unsigned long long)nk);
+        }
+#endif
+        return;
+    }
+
+    // =============================== FFT warps ===============================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" :: "n"(144));
+    // per-thread constants, pinned in registers (FE_OPAQUE stops the compiler from
+    // re-deriving them from threadIdx inside the loop)
+    FE_OPAQUE(lane); FE_OPAQUE(warp);
+    const int fs = lane >> 3, t = lane & 7;
+    constexpr int ESZ = IN_F32 ? 4 : 2;
+    uint32_t o_e = (uint32_t)(smem - smem_dyn) + L.off_e + warp * (kWarpFrames * kERegion * 4);   // warp's exchange buffer
+    uint32_t o_raw = (uint32_t)(smem - smem_dyn) + L.off_raw + warp * L.raw_bufs * L.raw_bytes;
+    const int dbl = L.raw_bufs - 1;                                    // 1: double-buffered raw samples
+    uint32_t o_scr = (uint32_t)(smem - smem_dyn) + L.off_scr + warp * 128;
+    FE_OPAQUE(o_e); FE_OPAQUE(o_raw); FE_OPAQUE(o_scr);
+    const uint32_t bar0 = bar_base + warp * 16;                        // two mbarriers per warp (raw double buffer)
+
+    // group g of this CTA: tile blockIdx.x + (g >> 3) * gridDim.x, frames 4 (g & 7) .. of it
+    const int n_groups = nk * kTileGroups;
+    auto load_desc = [&](int g, TileDesc& td) {
+        td.n_frames = 0;
+        if (g < n_groups) td = tiles[blockIdx.x + (long long)(g >> 3) * gridDim.x];
+    };
+    // issue the bulk copy of group g's samples into raw buffer `buf`
+    auto prefetch = [&](const TileDesc& td, int g, int buf) {
+        const int q = g & (kTileGroups - 1);
+        const int nfw = (P.dbg & 4) ? 0 : min(kWarpFrames, td.n_frames - q * kWarpFrames);
         if (nfw > 0 && lane == 0) {
             const unsigned char* base = reinterpret_cast<const unsigned char*>(td.src_sel ? scratch : pcm);
-            const unsigned char* src = base + (td.pcm_off + (long long)warp * kWarpFrames * HOP) * ESZ;
+            const unsigned char* src = base + (td.pcm_off + (long long)q * kWarpFrames * HOP) * ESZ;
             const uint32_t bytes = (uint32_t)(((nfw - 1) * HOP + FRAME_LEN) * ESZ);
             mbar_expect_tx(bar0 + 8 * buf, bytes);
             bulk_g2s(smem_u32(smem_dyn + o_raw + buf * L.raw_bytes), src, bytes, bar0 + 8 * buf);
         }
     };
 
-    int tile = blockIdx.x;
-    const int stride = gridDim.x;
+    int g = warp;
     TileDesc cur, next;
-    cur.n_frames = 0; next.n_frames = 0;
-    if (tile < n_tiles) { cur = tiles[tile]; prefetch(cur, 0); }
-    if (tile + stride < n_tiles) next = tiles[tile + stride];
-    uint32_t phase = 0;      // bit b = parity to wait for on barrier b
+    load_desc(g, cur);
+    prefetch(cur, g, 0);
+    load_desc(g + kFftWarps, next);
+    uint32_t phase = 0;      // bit b = parity to wait for on raw barrier b
     int buf = 0;
-    for (; tile < n_tiles; tile += stride) {
-        // descriptor two tiles ahead: in flight during this whole iteration
-        TileDesc nn;
-        nn.n_frames = 0;
-        if (tile + 2 * stride < n_tiles) nn = tiles[tile + 2 * stride];
-        const int nfw = min(kWarpFrames, cur.n_frames - warp * kWarpFrames);
+    FE_PROF_DECL(6);
+    for (; g < n_groups; g += kFftWarps) {
+        TileDesc nn;                                            // descriptor two passes ahead: in flight during this pass
+        load_desc(g + 2 * kFftWarps, nn);
+        const int k = g >> 3, q = g & (kTileGroups - 1);
+        const int slot = k % L.slots;
+        const uint32_t use = (uint32_t)(k / L.slots);           // how often the slot has been used before
+        const int nfw = (P.dbg & 4) ? 0 : min(kWarpFrames, cur.n_frames - q * kWarpFrames);
+        // the other raw buffer was last read in the previous pass's stage A
+        if (dbl) prefetch(next, g + kFftWarps, buf ^ 1);
         if (nfw > 0) {
+            float* e_w = reinterpret_cast<float*>(smem_dyn + o_e);
+            float* scr_w = reinterpret_cast<float*>(smem_dyn + o_scr);       // the lanes' partial sums of squares
+            float* e_f = e_w + fs * kERegion;
+            FE_TICK(5);
             mbar_wait(bar0 + 8 * buf, (phase >> buf) & 1u);
             phase ^= 1u << buf;
-        }
-        // the other buffer was last read in the previous iteration's stage A (several __syncwarp ago)
-        if (tile + stride < n_tiles) prefetch(next, buf ^ 1);
-        if (nfw > 0) {
-            const bool active = fs < nfw;
-            float* e_w = reinterpret_cast<float*>(smem_dyn + o_e);
-            float* scr_w = reinterpret_cast<float*>(smem_dyn + o_scr);       // [0..31] sum-of-squares, [32..35] energies
-            float* e_f = e_w + fs * kERegion;
-            const unsigned char* raw_f = smem_dyn + o_raw + buf * L.raw_bytes + fs * HOP * ESZ;
-
-            // Lanes of frame slots beyond nfw (last, partial tile of an utterance) run the same
-            // code on stale shared memory and only their global stores are masked: no divergence,
-            // no reconvergence bookkeeping inside the phases.
+            FE_TICK(0);
+            // Lanes of frame slots beyond nfw (last, partial group of an utterance) run the same code on
+            // stale shared memory: their columns of the power slot only feed their own (padding) lanes
+            // of the epilogue.
             // ---- phase 1: stage A ----
+            const unsigned char* raw_f = smem_dyn + o_raw + buf * L.raw_bytes + fs * HOP * ESZ;
             scr_w[lane] = stage_a<FRAME_LEN, IN_F32, HAS_WINDOW>(raw_f, e_f, tb, t, fs);
             __syncwarp();
+            if (!dbl) prefetch(next, g + kFftWarps, 0);          // single raw buffer: free again after stage A
+            FE_TICK(1);
             // ---- phase 2: stage B ----
             LaneZ z;
             stage_b(e_f, z, t, fs);
-            __syncwarp();
-            // ---- phase 3: post-pass, power row, frame energy ----
-            {
-                float x0, x256;
-                post_pass(z, power_row(e_w, fs), tb, t, fs, x0, x256);
-                if (t == 0) {
-                    float s = 0.f;
+            FE_TICK(2);
+            // ---- phase 3: post-pass, power columns, frame energy (the slot must have been drained) ----
+            if (use > 0) mbar_wait(bar_empty + 8 * slot, (use - 1u) & 1u);
+            FE_TICK(3);
+            float x0, x256;
+            post_pass(z, s_pbuf + slot * L.pbuf_floats + q * kWarpFrames + fs, tb, t, fs, x0, x256);
+            if (t == 0) {
+                float s = 0.f;
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) s += scr_w[fs * 8 + i];
-                    scr_w[32 + fs] = frame_energy(s, x0, x256, tb.pscale);
-                }
+                for (int i = 0; i < 8; ++i) s += scr_w[fs * 8 + i];
+                s_energy[slot * kTileFrames + q * kWarpFrames + fs] = frame_energy(s, x0, x256, tb.pscale);
             }
             __syncwarp();
-            // ---- phase 4: mel filterbank (+ log) ----
-            mel_phase(e_w, tb, t, fs);
-            __syncwarp();
-            float* dst = statics + cur.stat_off + (long long)(warp * kWarpFrames) * D;
-            if (tb.is_mfcc) {
-                if ((tb.nf & 7) == 0) {
-                    dct_phase_fused(e_w, scr_w + 32, tb, t, fs, dst + fs * D, active);
-                } else {
-                    fold_phase(e_w, tb, t, fs);
-                    __syncwarp();
-                    dct_phase(e_w, scr_w + 32, tb, t, fs, dst + fs * D, active);
-                }
-            } else {
-                for (int f = 0; f < nfw; ++f) {
-                    const float* row = logmel_row(e_w, f);
-                    for (int m = lane; m < D; m += 32) dst[f * D + m] = row[m];
-                }
-            }
-            __syncwarp();
+            FE_TICK(4);
+        } else {
+            // an empty group (partial last tile of an utterance) still has to arrive in the slot's CURRENT round
+            if (!dbl) prefetch(next, g + kFftWarps, 0);
+            if (use > 0) mbar_wait(bar_empty + 8 * slot, (use - 1u) & 1u);
         }
+        if (lane == 0) mbar_arrive(bar_full + 8 * slot);
         cur = next;
         next = nn;
-        buf ^= 1;
+        buf = (buf ^ 1) & dbl;
     }
+#ifdef FE_K1_PROF
+    if ((P.dbg & 8) && lane == 0) {
+        for (int i = 0; i < 5; ++i) atomicAdd(&g_k1_prof[8 + i], (unsigned long long)prof[i]);
+        atomicAdd(&g_k1_prof[13], (unsigned long long)((n_groups - warp + kFftWarps - 1) / kFftWarps));
+        atomicAdd(&g_k1_prof[14], (unsigned long long)prof[5]);
+    }
+#endif
 }
 
 // ---------------------------------------------------------------------------
@@ -363,12 +516,72 @@ k_utt_stats(const UttDesc* __restrict__ utts, int n_utts, const float* __restric
     }
 }
 
+// K2a for K1's tile-major statics ([D][32] blocks): one warp per (utterance, coefficient), lane = frame
+// within the block, so every load is one 128-byte line and the reduction is a fixed-order shuffle tree
+// (deterministic).  Same arithmetic as k_utt_stats: mean = x[0] + mean(x - x[0]), population variance
+// around that mean in a second pass.
+constexpr int kStatTWarps = 4;
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__global__ void __launch_bounds__(kStatTWarps * 32)
+k_utt_stats_tiled(const UttDesc* __restrict__ utts, int n_utts, const float* __restrict__ statics,
+                  float* __restrict__ stats, int D) {
+    const int lane = threadIdx.x & 31;
+    const long long n_items = (long long)n_utts * D;
+    const long long w0 = (long long)blockIdx.x * kStatTWarps + (threadIdx.x >> 5);
+    for (long long item = w0; item < n_items; item += (long long)gridDim.x * kStatTWarps) {
+        const int ui = (int)(item / D), c = (int)(item % D);
+        const int L = utts[ui].n_frames;
+        if (L <= 0) continue;
+        const float* x = statics + utts[ui].stat_off + c * 32 + lane;       // block j at x[j * 32 * D]
+        const long long bs = 32LL * D;
+        const int nb = L >> 5, tail = L & 31;
+        const float shift = __shfl_sync(0xffffffffu, x[0], 0);
+        float a[4] = {0.f, 0.f, 0.f, 0.f};
+        int j = 0;
+        for (; j + 3 < nb; j += 4) {
+            float v[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) v[k] = x[(j + k) * bs];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) a[k] += v[k] - shift;
+        }
+        for (; j < nb; ++j) a[0] += x[j * bs] - shift;
+        if (lane < tail) a[1] += x[nb * bs] - shift;
+        const float mean = shift + warp_sum((a[0] + a[1]) + (a[2] + a[3])) / (float)L;
+        float q[4] = {0.f, 0.f, 0.f, 0.f};
+        j = 0;
+        for (; j + 3 < nb; j += 4) {
+            float v[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) v[k] = x[(j + k) * bs] - mean;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) q[k] = fmaf(v[k], v[k], q[k]);
+        }
+        for (; j < nb; ++j) { const float d = x[j * bs] - mean; q[0] = fmaf(d, d, q[0]); }
+        if (lane < tail) { const float d = x[nb * bs] - mean; q[1] = fmaf(d, d, q[1]); }
+        const float var = warp_sum((q[0] + q[1]) + (q[2] + q[3])) / (float)L;
+        if (lane == 0) {
+            float* st = stats + (long long)ui * 2 * D;
+            st[c] = mean;
+            st[D + c] = 1.0f / (sqrtf(var) + 9.313225746154785e-10f);       // 2^-30
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------
 // K2b k_norm_delta_pack: normalise, delta, delta-delta, pack the cube (L, D, 3)
 // (speechpy.feature.extract_derivative_feature, preprocess.py:86).  Tile-parallel (same tile
 // table as K1), streaming: 4 D bytes in, 12 D bytes out per frame, written with coalesced
 // 16-byte stores from a shared-memory image of the tile.
-// flags bit2: append deltas (else the output is the normalised (L, D) matrix).
+// flags bit2: append deltas (else the output is the normalised (L, D) matrix); bit3: no statistics
+// (mean 0, scale 1).  TR: the input is K1's tile-major [D][32] blocks, else a row-major (L, D) matrix
+// (fe_postprocess).
 // ---------------------------------------------------------------------------
 constexpr int kPackThreads = 128;
 
@@ -377,7 +590,7 @@ __host__ __device__ inline int k2_smem_floats(int D, int tile_frames) {
 }
 
 // DT > 0: feature width known at compile time (index math by multiply-shift instead of integer division)
-template <int DT>
+template <int DT, bool TR>
 __global__ void __launch_bounds__(kPackThreads)
 k_norm_delta_pack(const TileDesc* __restrict__ tiles, int n_tiles, const float* __restrict__ statics,
                   const float* __restrict__ stats, float* __restrict__ out, int D_rt, int tile_frames,
@@ -395,26 +608,37 @@ k_norm_delta_pack(const TileDesc* __restrict__ tiles, int n_tiles, const float* 
         const TileDesc td = tiles[ti];
         const int nrow = td.n_frames, L = td.utt_frames, t0 = td.first_frame;
         const float* st = stats + (long long)td.utt * 2 * D;
-        const float* x0 = statics + td.stat_off - (long long)t0 * D;          // frame 0 of the utterance
-        for (int i = tid; i < 2 * D; i += kPackThreads) mi[i] = st[i];
+        const float* x0 = statics + td.stat_off - (long long)t0 * D;          // frame 0 of the utterance (t0 % 32 == 0)
+        if (flags & 8) { for (int i = tid; i < 2 * D; i += kPackThreads) mi[i] = i < D ? 0.f : 1.f; }
+        else { for (int i = tid; i < 2 * D; i += kPackThreads) mi[i] = st[i]; }
         __syncthreads();
         if (!f_delta || delta_mode == 0) {
             // as shipped: everything is local to the frame
             const int n = nrow * D;
             const float* x = statics + td.stat_off;
-            for (int i = tid; i < n; i += kPackThreads) {
-                const int c = i % D;
-                vt[i] = (x[i] - mi[c]) * mi[D + c];
+            // vt image: element (row r, coefficient c) at r * rs + c * cs
+            const int rs = TR ? 1 : D, cs = TR ? 33 : 1;
+            if (TR) {
+                for (int j = tid; j < 32 * D; j += kPackThreads) {            // coalesced over the [D][32] block
+                    const int c = j >> 5, r = j & 31;
+                    if (r < nrow) vt[c * 33 + r] = (x[j] - mi[c]) * mi[D + c];
+                }
+            } else {
+                for (int i = tid; i < n; i += kPackThreads) {
+                    const int c = i % D;
+                    vt[i] = (x[i] - mi[c]) * mi[D + c];
+                }
             }
             __syncthreads();
             for (int i = tid; i < n; i += kPackThreads) {
-                const int c = i % D, rb = i - c;
-                const float v = vt[i];
+                const int c = i % D, r = i / D;
+                const float* vr = vt + r * rs;
+                const float v = vr[c * cs];
                 if (!f_delta) { cube[i] = v; continue; }
                 // d1[k] = (v[k+1] + 2 v[k+2]) / 10, d2[k] = (d1[k+1] + 2 d1[k+2]) / 10, indices clamped to D-1;
                 // with ci = min(c+i, D-1): d1[c1] = (v[c2] + 2 v[c3]) / 10 and d1[c2] = (v[c3] + 2 v[c4]) / 10
-                const float v1 = vt[rb + min(c + 1, D - 1)], v2 = vt[rb + min(c + 2, D - 1)];
-                const float v3 = vt[rb + min(c + 3, D - 1)], v4 = vt[rb + min(c + 4, D - 1)];
+                const float v1 = vr[min(c + 1, D - 1) * cs], v2 = vr[min(c + 2, D - 1) * cs];
+                const float v3 = vr[min(c + 3, D - 1) * cs], v4 = vr[min(c + 4, D - 1) * cs];
                 const float da = (v1 + 2.f * v2) * 0.1f;
                 const float db = (v2 + 2.f * v3) * 0.1f;
                 const float dc = (v3 + 2.f * v4) * 0.1f;
@@ -426,7 +650,8 @@ k_norm_delta_pack(const TileDesc* __restrict__ tiles, int n_tiles, const float* 
             for (int i = tid; i < (nrow + 8) * D; i += kPackThreads) {
                 const int c = i % D, rr = i / D;
                 const int a = min(max(t0 - 4 + rr, 0), L - 1);
-                vt[i] = (x0[(long long)a * D + c] - mi[c]) * mi[D + c];
+                const float xv = TR ? x0[(long long)(a >> 5) * (32 * D) + c * 32 + (a & 31)] : x0[(long long)a * D + c];
+                vt[i] = (xv - mi[c]) * mi[D + c];
             }
             __syncthreads();
             for (int i = tid; i < (nrow + 4) * D; i += kPackThreads) {

@@ -13,11 +13,16 @@ struct HostTables {
     std::vector<float> tw256;       // [6][16][4]  twiddle bases m = 1,2,3,4,8,12; cfg = swap*8 + t
     std::vector<float> tw512;       // [16][4]     post-pass bases; cfg = flip*8 + t
     std::vector<float> window;      // [rows*32]    (w[2m], w[2m+1]) per complex point
-    std::vector<int> mel_slot_off, mel_b0, mel_id, mel_bi;    // mel_bi = id << 16 | first bin
-    std::vector<float> mel_w;       // [2][entries*8]: int16-count scale, then float scale
+    std::vector<int> mel_desc;      // [mel_groups] flat group list per epilogue warp: row | last << 10 | filter << 16
+    std::vector<float> mel_w;       // [2][mel_groups*4] weights in the same order: int16-count scale, then float scale
+    int epi_off[kEpiWarps] = {0}, epi_cnt[kEpiWarps] = {0};     // each warp's slice of the list (count % 4 == 0)
     std::vector<float> dctf;        // [D][dct_stride]
-    int mel_slots = 0, mel_entries = 0, nh = 0, dct_stride = 0;
-    int mel_n4[16] = {0}, mel_e4[16] = {0};
+    int mel_groups = 0, nh = 0, dct_stride = 0;
+    int p_rows = 0;                 // rows of the power buffer: 129 (bins 0..128) or 257, + 3 zero pad rows
+    bool ok = true;                 // false: a run does not fit the descriptor fields
+    int epi_plan = 0;               // 0 generic epilogue, 1 PlanMfcc40 (D = 13), 2 PlanFbank80 (specialised kernels)
+    std::vector<float> epi_w;       // [2][epi_w_n] specialised epilogue's weights: mel CSR (pre-scaled) + folded DCT rows
+    int epi_w_n = 0;
 };
 
 inline void build_host_tables(const fe_config& c, HostTables& t) {
@@ -42,62 +47,76 @@ inline void build_host_tables(const fe_config& c, HostTables& t) {
         o[0] = c.tw512[kx * 2];     o[1] = c.tw512[ky * 2];
         o[2] = c.tw512[kx * 2 + 1]; o[3] = c.tw512[ky * 2 + 1];
     }
-    // mel plan: filters sorted by run length, 8 per slot (one per lane of a frame); every slot
-    // is padded to the longest run in it (multiple of 4) so trip counts are lane-uniform
+    // mel plan: runs are padded to a multiple of 4 weights (zeros); reads past bin 128 / 256 land in the
+    // three zero pad rows of the power buffer
     const int nf = c.num_filters;
-    std::vector<int> order(nf);
-    for (int m = 0; m < nf; ++m) order[m] = m;
-    std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
-        return c.fb_row_start[a + 1] - c.fb_row_start[a] < c.fb_row_start[b + 1] - c.fb_row_start[b]; });
-    const int S = (nf + 7) / 8;
-    t.mel_slot_off.assign(S + 1, 0); t.mel_b0.assign(S * 8, 0); t.mel_id.assign(S * 8, -1);
-    // power-row reads are 16-byte loads: every run starts at its first bin rounded down to a
-    // multiple of 4 (weights shifted right by the remainder, zero filled)
-    for (int s = 0; s < S; ++s) {
-        int e = 0;
-        for (int g = 0; g < 8 && s * 8 + g < nf; ++g) {
-            const int m = order[s * 8 + g];
-            const int n = c.fb_row_start[m + 1] - c.fb_row_start[m];
-            e = std::max(e, n > 0 ? (c.fb_first_bin[m] & 3) + n : 0);
-        }
-        e = std::max(4, (e + 3) & ~3);
-        t.mel_slot_off[s + 1] = t.mel_slot_off[s] + e;
+    int max_bin = 0;
+    for (int m = 0; m < nf; ++m) {
+        const int n = c.fb_row_start[m + 1] - c.fb_row_start[m];
+        if (n > 0) max_bin = std::max(max_bin, c.fb_first_bin[m] + n - 1);
     }
-    const int entries = t.mel_slot_off[S];
-    t.mel_w.assign((size_t)entries * 8 * 2, 0.f);
-    for (int s = 0; s < S; ++s) {
-        const int e = t.mel_slot_off[s + 1] - t.mel_slot_off[s];
-        for (int g = 0; g < 8 && s * 8 + g < nf; ++g) {
-            const int m = order[s * 8 + g];
-            const int n = c.fb_row_start[m + 1] - c.fb_row_start[m];
-            int bin0 = n > 0 ? (c.fb_first_bin[m] & ~3) : 0;
-            int shift = n > 0 ? (c.fb_first_bin[m] & 3) : 0;
-            // keep padded reads inside the 260-float row (257 bins + 3 of slack after it)
-            while (bin0 + e > 260) { bin0 -= 4; shift += 4; }
-            t.mel_id[s * 8 + g] = m; t.mel_b0[s * 8 + g] = bin0;
-            for (int i = 0; i < n; ++i) {
-                const float v = c.fb_weights[c.fb_row_start[m] + i] * (1.0f / 2048.0f);   // rows hold |2X|^2
-                const int ee = t.mel_slot_off[s] + shift + i;       // float4 groups: [entry/4][lane][entry%4]
-                const size_t at = ((size_t)(ee >> 2) * 8 + g) * 4 + (ee & 3);
-                t.mel_w[at] = v * (1.0f / 1073741824.0f);
-                t.mel_w[(size_t)entries * 8 + at] = v;
+    t.p_rows = (max_bin > 128 ? 257 : 129) + 3;
+    // Epilogue warp w owns the filter pairs (p, nf-1-p), p = w, w + 4, ... (a narrow low filter with a wide
+    // high one: balanced work).  Its filters are flattened into one list of 4-bin weight groups, the last
+    // group of every filter flagged; the list is padded with zero groups to a multiple of 4 and followed by
+    // 8 more zero groups so that the software pipeline can prefetch past the end without bounds checks.
+    t.nh = (nf + 1) / 2;
+    t.mel_desc.clear();
+    std::vector<float> w16, wf;
+    for (int w = 0; w < kEpiWarps; ++w) {
+        t.epi_off[w] = (int)t.mel_desc.size();
+        int cnt = 0;
+        for (int p = w; p < t.nh; p += kEpiWarps) {
+            const int pair[2] = {p, nf - 1 - p};
+            for (int k = 0; k < (pair[1] != pair[0] ? 2 : 1); ++k) {
+                const int m = pair[k];
+                const int n = c.fb_row_start[m + 1] - c.fb_row_start[m];
+                const int n4 = std::max(1, (n + 3) / 4);                    // an empty filter still emits its (zero) value
+                const int b0 = n > 0 ? c.fb_first_bin[m] : 0;
+                if (b0 + 4 * n4 > t.p_rows || m > 32767) t.ok = false;
+                for (int q = 0; q < n4; ++q) {
+                    t.mel_desc.push_back((b0 + 4 * q) | ((q == n4 - 1) ? 1 << 10 : 0) | (m << 16));
+                    for (int i = 0; i < 4; ++i) {
+                        const int idx = 4 * q + i;
+                        const float v = idx < n ? c.fb_weights[c.fb_row_start[m] + idx] * (1.0f / 2048.0f) : 0.f;   // columns hold |2X|^2
+                        w16.push_back(v * (1.0f / 1073741824.0f)); wf.push_back(v);
+                    }
+                    ++cnt;
+                }
             }
         }
+        const int padded = (cnt + 3) & ~3;
+        t.epi_cnt[w] = padded;
+        for (int q = cnt; q < padded + 8; ++q) { t.mel_desc.push_back(0); for (int i = 0; i < 4; ++i) { w16.push_back(0.f); wf.push_back(0.f); } }
     }
-    t.mel_slots = S; t.mel_entries = entries;
-    for (int s = 0; s < S && s < 16; ++s) { t.mel_e4[s] = t.mel_slot_off[s] >> 2; t.mel_n4[s] = (t.mel_slot_off[s + 1] - t.mel_slot_off[s]) >> 2; }
-    t.mel_bi.assign(S * 8, 0);
-    for (int i = 0; i < S * 8; ++i) t.mel_bi[i] = ((t.mel_id[i] < 0 ? 0xffff : t.mel_id[i]) << 16) | t.mel_b0[i];
+    t.mel_groups = (int)t.mel_desc.size();
+    t.mel_w = w16;
+    t.mel_w.insert(t.mel_w.end(), wf.begin(), wf.end());
     // folded DCT: y_c = sum_{n < nh} C[c][n] * (x[n] + (-1)^c x[nf-1-n])
-    t.nh = (nf + 1) / 2;
     t.dct_stride = 0;
     t.dctf.clear();
     if (c.feat_type == FE_FEAT_MFCC) {
-        t.dct_stride = (t.nh + 3) & ~3;                  // 16-byte rows; stride/4 odd -> the 8 rows read by a
-        if (((t.dct_stride >> 2) & 1) == 0) t.dct_stride += 4;   // frame's lanes fall in distinct bank groups
+        t.dct_stride = (t.nh + 3) & ~3;                  // 16-byte groups, read warp-uniformly
         t.dctf.assign((size_t)c.feat_dim * t.dct_stride, 0.f);
         for (int k = 0; k < c.feat_dim; ++k)
             for (int m = 0; m < t.nh; ++m) t.dctf[(size_t)k * t.dct_stride + m] = c.dct[k * nf + m];
+    }
+    // specialised epilogue: only when the caller's filterbank has exactly a baked structure
+    t.epi_plan = 0; t.epi_w.clear(); t.epi_w_n = 0;
+    if (c.feat_type == FE_FEAT_MFCC && c.feat_dim == 13 && plan_matches<PlanMfcc40>(c.fb_row_start, c.fb_first_bin, nf)) t.epi_plan = 1;
+    if (c.feat_type == FE_FEAT_FBANK && plan_matches<PlanFbank80>(c.fb_row_start, c.fb_first_bin, nf)) t.epi_plan = 2;
+    if (t.epi_plan) {
+        const int nnz = c.fb_nnz, nd = t.epi_plan == 1 ? c.feat_dim * t.nh : 0;
+        t.epi_w_n = nnz + nd;
+        t.epi_w.assign((size_t)2 * t.epi_w_n, 0.f);
+        for (int i = 0; i < nnz; ++i) {
+            const float v = c.fb_weights[i] * (1.0f / 2048.0f);
+            t.epi_w[i] = v * (1.0f / 1073741824.0f);
+            t.epi_w[(size_t)t.epi_w_n + i] = v;
+        }
+        for (int k = 0; k < (t.epi_plan == 1 ? c.feat_dim : 0); ++k)
+            for (int m = 0; m < t.nh; ++m)
+                t.epi_w[nnz + k * t.nh + m] = t.epi_w[(size_t)t.epi_w_n + nnz + k * t.nh + m] = c.dct[k * nf + m];
     }
     t.window.clear();
     if (c.window) {

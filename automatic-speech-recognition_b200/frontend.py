@@ -370,6 +370,12 @@ class Frontend:
         self._check(self._lib.fe_measure_fp32_peak(self._h, C.byref(v)), "fe_measure_fp32_peak")
         return float(v.value)
 
+    def debug_counters(self):
+        """K1 per-phase clock64 totals (needs FE_K1_DBG=8); profiling aid, see tools/k1_phases.py."""
+        out = (C.c_uint64 * 16)()
+        self._check(self._lib.fe_debug_counters(self._h, out), "fe_debug_counters")
+        return [int(v) for v in out]
+
     def launch_count(self):
         return int(self._lib.fe_launch_count(self._h))
 

@@ -147,6 +147,9 @@ int fe_set_profiling(fe_handle* h, int on);
 int fe_measure_fp32_peak(fe_handle* h, float* tflops);
 int fe_get_kernel_ms(fe_handle* h, float ms[4]);
 int64_t fe_launch_count(fe_handle* h);       /* kernels launched since fe_create */
+/* profiling aid: with FE_K1_DBG=8 in the environment K1 accumulates clock64 totals per phase
+ * (lane 0 of every warp); this reads and clears them.  Layout: see g_k1_prof in fe_kernels.cuh. */
+int fe_debug_counters(fe_handle* h, uint64_t out[16]);
 int64_t fe_device_bytes(fe_handle* h);       /* scratch currently held on the device */
 
 const char* fe_last_error(fe_handle* h);     /* h may be NULL: last fe_create error */

@@ -17,10 +17,10 @@ void fill_tables(const fe_config& c, const HostTables& ht, bool in_f32, SmemTabl
     tb.tw256 = reinterpret_cast<const float4*>(ht.tw256.data());
     tb.tw512 = reinterpret_cast<const float4*>(ht.tw512.data());
     tb.window = c.window ? reinterpret_cast<const float2*>(ht.window.data()) : nullptr;
-    tb.mel_n4 = ht.mel_n4; tb.mel_bi = ht.mel_bi.data();
-    tb.mel_w = ht.mel_w.data() + (in_f32 ? (size_t)ht.mel_entries * 8 : 0);
+    tb.mel_desc = ht.mel_desc.data();
+    tb.mel_w4 = reinterpret_cast<const float4*>(ht.mel_w.data() + (in_f32 ? (size_t)ht.mel_groups * 4 : 0));
     tb.dctf = ht.dctf.data();
-    tb.mel_slots = ht.mel_slots; tb.nf = c.num_filters; tb.D = c.feat_dim; tb.dct_stride = ht.dct_stride; tb.nh = ht.nh;
+    tb.nf = c.num_filters; tb.D = c.feat_dim; tb.dct_stride = ht.dct_stride; tb.nh = ht.nh;
     int max_bin = 0;
     for (int m = 0; m < c.num_filters; ++m) {
         int w = c.fb_row_start[m + 1] - c.fb_row_start[m];
@@ -39,47 +39,50 @@ int run(const fe_config& c, const void* pcm, int n_samples, float* statics) {
     HostTables ht; build_host_tables(c, ht);
     SmemTables tb; fill_tables(c, ht, IN_F32, tb);
     const int D = c.feat_dim;
+    if (!ht.ok) return -2;
     float* e_w = static_cast<float*>(aligned_alloc(2048, kWarpFrames * kERegion * sizeof(float)));
     unsigned char* raw = static_cast<unsigned char*>(aligned_alloc(16, (3 * HOP + 13 * 32) * 4));
-    float scr_w[64];
+    std::vector<float> pbuf((size_t)ht.p_rows * kPStride, 0.f), lm((size_t)(c.num_filters + 4) * 32, 0.f), out_t((size_t)D * 32), energy(32, 1.f);
+    float scr_w[32];
     static LaneZ z[32];
-    for (int f0 = 0; f0 < L; f0 += kWarpFrames) {
-        const int nfw = (L - f0) < kWarpFrames ? (L - f0) : kWarpFrames;
-        for (int i = 0; i < kWarpFrames * kERegion; ++i) e_w[i] = 1e30f;      // poison: catches reads of unwritten words
-        memset(raw, 0x7f, (3 * HOP + 13 * 32) * 4);
-        memcpy(raw, static_cast<const unsigned char*>(pcm) + (size_t)f0 * HOP * ESZ, (size_t)((nfw - 1) * HOP + FL) * ESZ);
-        for (int lane = 0; lane < 32; ++lane) {
-            int fs = lane >> 3, t = lane & 7;
-            if (fs < nfw) scr_w[lane] = c.window ? stage_a<FL, IN_F32, 1>(raw + fs * HOP * ESZ, e_w + fs * kERegion, tb, t, fs)
-                                                 : stage_a<FL, IN_F32, 0>(raw + fs * HOP * ESZ, e_w + fs * kERegion, tb, t, fs);
-        }
-        for (int lane = 0; lane < 32; ++lane) {
-            int fs = lane >> 3, t = lane & 7;
-            if (fs < nfw) stage_b(e_w + fs * kERegion, z[lane], t, fs);
-        }
-        for (int lane = 0; lane < 32; ++lane) {
-            int fs = lane >> 3, t = lane & 7;
-            if (fs >= nfw) continue;
-            float x0, x256;
-            post_pass(z[lane], power_row(e_w, fs), tb, t, fs, x0, x256);
-            if (t == 0) {
-                float s = 0.f;
-                for (int i = 0; i < 8; ++i) s += scr_w[fs * 8 + i];
-                scr_w[32 + fs] = frame_energy(s, x0, x256, tb.pscale);
+    for (int t0 = 0; t0 < L; t0 += kTileFrames) {                       // one CTA tile
+        const int ntile = (L - t0) < kTileFrames ? (L - t0) : kTileFrames;
+        for (int r = 0; r < ht.p_rows - 3; ++r) for (int f = 0; f < 32; ++f) pbuf[(size_t)r * kPStride + f] = 1e30f;   // poison
+        for (int warp = 0; warp < kTileGroups; ++warp) {
+            const int f0 = t0 + warp * kWarpFrames;
+            const int nfw = (ntile - warp * kWarpFrames) < kWarpFrames ? (ntile - warp * kWarpFrames) : kWarpFrames;
+            if (nfw <= 0) continue;
+            for (int i = 0; i < kWarpFrames * kERegion; ++i) e_w[i] = 1e30f;      // poison: catches reads of unwritten words
+            memset(raw, 0x7f, (3 * HOP + 13 * 32) * 4);
+            memcpy(raw, static_cast<const unsigned char*>(pcm) + (size_t)f0 * HOP * ESZ, (size_t)((nfw - 1) * HOP + FL) * ESZ);
+            for (int lane = 0; lane < 32; ++lane) {
+                int fs = lane >> 3, t = lane & 7;
+                if (fs < nfw) scr_w[lane] = c.window ? stage_a<FL, IN_F32, 1>(raw + fs * HOP * ESZ, e_w + fs * kERegion, tb, t, fs)
+                                                     : stage_a<FL, IN_F32, 0>(raw + fs * HOP * ESZ, e_w + fs * kERegion, tb, t, fs);
+            }
+            for (int lane = 0; lane < 32; ++lane) {
+                int fs = lane >> 3, t = lane & 7;
+                if (fs < nfw) stage_b(e_w + fs * kERegion, z[lane], t, fs);
+            }
+            for (int lane = 0; lane < 32; ++lane) {
+                int fs = lane >> 3, t = lane & 7;
+                if (fs >= nfw) continue;
+                float x0, x256;
+                post_pass(z[lane], pbuf.data() + warp * kWarpFrames + fs, tb, t, fs, x0, x256);
+                if (t == 0) {
+                    float s = 0.f;
+                    for (int i = 0; i < 8; ++i) s += scr_w[fs * 8 + i];
+                    energy[warp * kWarpFrames + fs] = frame_energy(s, x0, x256, tb.pscale);
+                }
             }
         }
-        for (int lane = 0; lane < 32; ++lane) if ((lane >> 3) < nfw) mel_phase(e_w, tb, lane & 7, lane >> 3);
-        float* dst = statics + (long long)f0 * D;
-        if (tb.is_mfcc && (tb.nf & 7) == 0) {
-            for (int lane = 0; lane < 32; ++lane)
-                if ((lane >> 3) < nfw) dct_phase_fused(e_w, scr_w + 32, tb, lane & 7, lane >> 3, dst + (lane >> 3) * D, true);
-        } else if (tb.is_mfcc) {
-            for (int lane = 0; lane < 32; ++lane) if ((lane >> 3) < nfw) fold_phase(e_w, tb, lane & 7, lane >> 3);
-            for (int lane = 0; lane < 32; ++lane)
-                if ((lane >> 3) < nfw) dct_phase(e_w, scr_w + 32, tb, lane & 7, lane >> 3, dst + (lane >> 3) * D, true);
-        } else {
-            for (int f = 0; f < nfw; ++f) for (int m = 0; m < D; ++m) dst[f * D + m] = logmel_row(e_w, f)[m];
-        }
+        // CTA-wide epilogue: lane = frame (only the tile's real frames are replayed), warp = filter / coefficient group
+        for (int warp = 0; warp < kEpiWarps; ++warp)
+            for (int lane = 0; lane < ntile; ++lane) epi_mel(pbuf.data(), tb.is_mfcc ? lm.data() : out_t.data(), tb, ht.epi_off[warp], ht.epi_cnt[warp], lane);
+        if (tb.is_mfcc)
+            for (int warp = 0; warp < kEpiWarps; ++warp)
+                for (int lane = 0; lane < ntile; ++lane) epi_dct(lm.data(), energy.data(), out_t.data(), tb, warp, lane);
+        for (int f = 0; f < ntile; ++f) for (int m = 0; m < D; ++m) statics[(long long)(t0 + f) * D + m] = out_t[(size_t)m * 32 + f];
     }
     free(e_w); free(raw);
     return L;
