@@ -75,9 +75,10 @@ FE_HD float2 pnfma(float2 a, float2 b, float2 c) { return pfma(pneg(a), b, c); }
 struct SmemTables {
     // twiddles are generated from a few per-lane bases (shared-memory wavefronts are the scarce
     // resource of this kernel, packed FP32 issue slots are not):
-    const float4* tw256;      // [6][16] cfg = swap*8 + t: (wr(jx m), wr(jy m), wi(jx m), wi(jy m)) for m = 1,2,3,4,8,12;
-                              //         W_256^(j k1) = W^(j 4a) * W^(j b), k1 = 4a + b
-    const float4* tw512;      // [16]    cfg = Fe*8 + t: (cos rx, cos ry, sin rx, sin ry) * 2pi/512; bins r + 16 k2 by rotation
+    // twiddles come straight from tables: K1 is bound by instruction issue (a packed f32x2 instruction takes two
+    // issue cycles), so one 16-byte load per twiddle pair beats regenerating it from a base with four packed FMAs
+    const float4* tw256;      // [15][16] row k1-1, cfg = swap*8 + t: (wr(jx k1), wr(jy k1), wi(jx k1), wi(jy k1)) of W_256^(j k1)
+    const float4* tw512;      // [8][16]  row k2, cfg = flip*8 + t: (cos, cos, sin, sin) of 2 pi (rx + 16 k2) / 512 and (ry + 16 k2)
     const float2* window;     // [ROWS*16] (w[2m], w[2m+1]) per complex point m, or nullptr
     // mel plan: every epilogue warp streams its own flat list of 4-bin weight groups (its filters back to
     // back, runs padded with zero weights to a multiple of 4): mel_desc[i] = first bin | last-group-of-
@@ -202,8 +203,16 @@ FE_HD float stage_a(const void* raw_f, float* e_f, const SmemTables& tb, int t, 
             } else {
                 const uint32_t* pw = reinterpret_cast<const uint32_t*>(raw_f);
                 uint32_t u = pw[16 * a + jx], v = pw[16 * a + jy];
+#if defined(__CUDA_ARCH__) && defined(FE_I2F_HALFSEL)
+                // both halves straight from the 32-bit word (I2F.S16 with a half selector: no shift instruction)
+                asm("{\n\t.reg .b16 lo, hi;\n\tmov.b32 {lo, hi}, %2;\n\tcvt.rn.f32.s16 %0, lo;\n\tcvt.rn.f32.s16 %1, hi;\n\t}"
+                    : "=f"(vr.x), "=f"(vi.x) : "r"(u));
+                asm("{\n\t.reg .b16 lo, hi;\n\tmov.b32 {lo, hi}, %2;\n\tcvt.rn.f32.s16 %0, lo;\n\tcvt.rn.f32.s16 %1, hi;\n\t}"
+                    : "=f"(vr.y), "=f"(vi.y) : "r"(v));
+#else
                 vr = make_float2((float)(short)(u & 0xffffu), (float)(short)(v & 0xffffu));
                 vi = make_float2((float)((int)u >> 16), (float)((int)v >> 16));
+#endif
             }
             if (HAS_WINDOW) {
                 float2 w0 = tb.window[16 * a + jx], w1 = tb.window[16 * a + jy];
@@ -231,27 +240,13 @@ FE_HD float stage_a(const void* raw_f, float* e_f, const SmemTables& tb, int t, 
     const EPtr x0 = e_make(e_f, lb ^ hbx), y0 = e_make(e_f, lb ^ hby);              // pair-row 0: no slot flip
     const EPtr xF = e_make(e_f, (lb ^ hbx) | F), yF = e_make(e_f, (lb ^ hby) | F);
     const int cfg = swap * 8 + t;
-    // bases W^(j b) (b = 1..3) and W^(4 j a) (a = 1..3), packed over the two halves
-    float2 br[4], bi_[4], ar[4], ai[4];
-#pragma unroll
-    for (int m = 1; m < 4; ++m) {
-        float4 wb = tb.tw256[(m - 1) * 16 + cfg], wa = tb.tw256[(m + 2) * 16 + cfg];
-        br[m] = make_float2(wb.x, wb.y); bi_[m] = make_float2(wb.z, wb.w);
-        ar[m] = make_float2(wa.x, wa.y); ai[m] = make_float2(wa.z, wa.w);
-    }
 #pragma unroll
     for (int k1 = 0; k1 < 16; ++k1) {
         const int s = pos16(k1);
-        const int a4 = k1 >> 2, b4 = k1 & 3;
         float2 yr = re[s], yi = im[s];
         if (k1 > 0) {
-            float2 wr, wi;
-            if (a4 == 0) { wr = br[b4]; wi = bi_[b4]; }
-            else if (b4 == 0) { wr = ar[a4]; wi = ai[a4]; }
-            else {
-                wr = pnfma(ai[a4], bi_[b4], pmul(ar[a4], br[b4]));
-                wi = pfma(ar[a4], bi_[b4], pmul(ai[a4], br[b4]));
-            }
+            const float4 w = tb.tw256[(k1 - 1) * 16 + cfg];
+            const float2 wr = make_float2(w.x, w.y), wi = make_float2(w.z, w.w);
             float2 tr = pnfma(yi, wi, pmul(yr, wr));
             yi = pfma(yr, wi, pmul(yi, wr));
             yr = tr;
@@ -300,13 +295,6 @@ FE_HD void post_pass(const LaneZ& z, float* p_f, const SmemTables& tb, int t, in
     const bool t0 = (t == 0);
     const int rx = row_x(t, fs), ry = row_y(t, fs);
     const int cfg = lane_flip(t, fs) * 8 + t;
-    const float4 wb = tb.tw512[cfg];
-    const float2 c0 = make_float2(wb.x, wb.y), s0 = make_float2(wb.z, wb.w);     // angle of bins rx, ry
-    // cos / sin of pi k2 / 16 (bins advance by 16 -> angle by 2 pi 16 / 512)
-    constexpr float RC[8] = {1.f, 0.98078528040323043f, 0.92387953251128674f, 0.83146961230254524f,
-                             0.70710678118654752f, 0.55557023301960218f, 0.38268343236508977f, 0.19509032201612825f};
-    constexpr float RS[8] = {0.f, 0.19509032201612825f, 0.38268343236508977f, 0.55557023301960218f,
-                             0.70710678118654752f, 0.83146961230254524f, 0.92387953251128674f, 0.98078528040323043f};
 #pragma unroll
     for (int k2 = 0; k2 < 8; ++k2) {
         const int sa = pos16(k2), sp = pos16(15 - k2), sq = pos16((16 - k2) & 15);
@@ -315,11 +303,8 @@ FE_HD void post_pass(const LaneZ& z, float* p_f, const SmemTables& tb, int t, in
         float2 pr, pi;
         pr.x = t0 ? z.r[sp].x : z.r[sp].y;   pr.y = t0 ? z.r[sq].y : z.r[sp].x;
         pi.x = t0 ? z.i[sp].x : z.i[sp].y;   pi.y = t0 ? z.i[sq].y : z.i[sp].x;
-        float2 c = c0, s = s0;
-        if (k2 > 0) {
-            c = pnfma(s0, pbc(RS[k2]), pmul(c0, pbc(RC[k2])));
-            s = pfma(c0, pbc(RS[k2]), pmul(s0, pbc(RC[k2])));
-        }
+        const float4 wb = tb.tw512[k2 * 16 + cfg];             // angle of bins rx + 16 k2, ry + 16 k2
+        const float2 c = make_float2(wb.x, wb.y), s = make_float2(wb.z, wb.w);
         float2 er = padd(ar, pr), ei = psub(ai, pi);          // 2E  (B = conj(partner))
         float2 orr = psub(ar, pr), oi = padd(ai, pi);         // 2O
         float2 tr = pnfma(c, oi, pmul(s, orr));               // T = i w O, w = (c, -s)

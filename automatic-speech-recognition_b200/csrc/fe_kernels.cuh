@@ -38,8 +38,8 @@ struct __align__(16) TileDesc {
 };
 
 struct DevTables {
-    const float4* tw256;    // [6][16]
-    const float4* tw512;    // [16]
+    const float4* tw256;    // [15][16]
+    const float4* tw512;    // [8][16]
     const float2* window;   // [ROWS*16] or nullptr
     const int* mel_desc; const float* mel_w;
     const float* dctf;      // [D][dct_stride]
@@ -106,8 +106,8 @@ __host__ __device__ inline K1Smem k1_smem_layout_n(int nf, int mel_groups, int p
     s.raw_bytes = align16(((kWarpFrames - 1) * hop + rows * 32) * (in_f32 ? 4 : 2));
     s.off_raw = o;    o += kFftWarps * raw_bufs * s.raw_bytes;
     s.off_scr = o;    o += kFftWarps * 32 * 4;
-    s.off_tw256 = o;  o += 6 * 16 * 16;
-    s.off_tw512 = o;  o += 16 * 16;
+    s.off_tw256 = o;  o += 15 * 16 * 16;
+    s.off_tw512 = o;  o += 8 * 16 * 16;
     s.off_window = o; o = align16(o + (has_window ? rows * 16 * 8 : 0));
     // (the specialised epilogue reads its weights from the kernel parameters and keeps log-mel in registers)
     s.off_desc = o;   o = align16(o + (spec ? 0 : (mel_groups > 0 ? mel_groups : 1) * 4));
@@ -154,15 +154,21 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "WAIT_LOOP:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra WAIT_DONE;\n\t"
-        "bra WAIT_LOOP;\n\t"
-        "WAIT_DONE:\n\t}"
-        :: "r"(bar), "r"(parity) : "memory");
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+// K1 is bound by instruction issue, so a waiting warp must not spin: after a failed try it sleeps
+// (the 12 FFT warps and the other consumers keep the issue ports busy meanwhile)
+template <int NS = 128>
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    if (mbar_try(bar, parity)) return;
+    do { __nanosleep(NS); } while (!mbar_try(bar, parity));
 }
 
 // everything K1 needs besides the data pointers; lives in the constant bank
@@ -227,8 +233,8 @@ k_frames_to_statics(const void* __restrict__ pcm, const void* __restrict__ scrat
 
     const int tid = threadIdx.x;
     constexpr int ROWS = (FRAME_LEN + 31) / 32;
-    for (int i = tid; i < 96; i += blockDim.x) s_tw256[i] = dt.tw256[i];
-    for (int i = tid; i < 16; i += blockDim.x) s_tw512[i] = dt.tw512[i];
+    for (int i = tid; i < 15 * 16; i += blockDim.x) s_tw256[i] = dt.tw256[i];
+    for (int i = tid; i < 8 * 16; i += blockDim.x) s_tw512[i] = dt.tw512[i];
     if (dt.window) for (int i = tid; i < ROWS * 16; i += blockDim.x) s_window[i] = dt.window[i];
     if (EPI == 0) {
         for (int i = tid; i < dt.mel_groups; i += blockDim.x) s_desc[i] = dt.mel_desc[i];
@@ -270,7 +276,7 @@ k_frames_to_statics(const void* __restrict__ pcm, const void* __restrict__ scrat
             for (int k = we; k < nk; k += kEpiWarps, par ^= 1u) {
                 float* out_t = statics + tiles[blockIdx.x + (long long)k * gridDim.x].stat_off;
                 const float* pb = s_pbuf + slot * L.pbuf_floats;
-                mbar_wait(bar_full + 8 * slot, par);
+                mbar_wait<300>(bar_full + 8 * slot, par);
                 if (!(P.dbg & 1)) {
                     if (EPI == 1) epi_tile_spec<PlanMfcc40, 13, true, true>(pb, s_energy + slot * kTileFrames, out_t, P.epi_w, tb.dc_elim, lane);
                     else if (tb.fbank_log) epi_tile_spec<PlanFbank80, 80, false, true>(pb, s_energy + slot * kTileFrames, out_t, P.epi_w, false, lane);
@@ -293,7 +299,7 @@ k_frames_to_statics(const void* __restrict__ pcm, const void* __restrict__ scrat
             if (k + 1 < nk) stat_next = tiles[blockIdx.x + (long long)(k + 1) * gridDim.x].stat_off;
             float* sd = s_sd + (k & 1) * L.sd_floats;
             const float* pb = s_pbuf + slot * L.pbuf_floats;
-            mbar_wait(bar_full + 8 * slot, par);
+            mbar_wait<300>(bar_full + 8 * slot, par);
             FE_TICK(0);
             if (!(P.dbg & 1)) {
                 // ---- phase 4: mel filterbank (+ log, + fold), lane = frame ----
@@ -337,14 +343,21 @@ k_frames_to_statics(const void* __restrict__ pcm, const void* __restrict__ scrat
     FE_OPAQUE(o_e); FE_OPAQUE(o_raw); FE_OPAQUE(o_scr);
     const uint32_t bar0 = bar_base + warp * 16;                        // two mbarriers per warp (raw double buffer)
 
-    // group g of this CTA: tile blockIdx.x + (g >> 3) * gridDim.x, frames 4 (g & 7) .. of it
+    // group g of this CTA: tile blockIdx.x + (g >> 3) * gridDim.x, frames 4 (g & 7) .. of it.
+    // The FFT warps need three fields of a tile descriptor only (4 registers instead of 12 per descriptor in flight).
+    struct GDesc { long long pcm_off; int n_frames, src_sel; };
     const int n_groups = nk * kTileGroups;
-    auto load_desc = [&](int g, TileDesc& td) {
-        td.n_frames = 0;
-        if (g < n_groups) td = tiles[blockIdx.x + (long long)(g >> 3) * gridDim.x];
+    auto load_desc = [&](int g, GDesc& td) {
+        td.n_frames = 0; td.pcm_off = 0; td.src_sel = 0;
+        if (g < n_groups) {
+            const TileDesc* t = tiles + (blockIdx.x + (long long)(g >> 3) * gridDim.x);
+            td.pcm_off = t->pcm_off;
+            const int2 ns = *reinterpret_cast<const int2*>(&t->n_frames);       // n_frames, src_sel (8-byte aligned pair)
+            td.n_frames = ns.x; td.src_sel = ns.y;
+        }
     };
     // issue the bulk copy of group g's samples into raw buffer `buf`
-    auto prefetch = [&](const TileDesc& td, int g, int buf) {
+    auto prefetch = [&](const GDesc& td, int g, int buf) {
         const int q = g & (kTileGroups - 1);
         const int nfw = (P.dbg & 4) ? 0 : min(kWarpFrames, td.n_frames - q * kWarpFrames);
         if (nfw > 0 && lane == 0) {
@@ -356,23 +369,25 @@ k_frames_to_statics(const void* __restrict__ pcm, const void* __restrict__ scrat
         }
     };
 
+    // Raw samples run two passes ahead of the FFT when double-buffered: a buffer is refilled as soon as
+    // stage A has consumed it (with the samples of the group two passes later), descriptors three ahead.
     int g = warp;
-    TileDesc cur, next;
+    GDesc cur, next, nn;
     load_desc(g, cur);
     prefetch(cur, g, 0);
     load_desc(g + kFftWarps, next);
+    if (L.raw_bufs > 1) prefetch(next, g + kFftWarps, 1);
+    load_desc(g + 2 * kFftWarps, nn);
     uint32_t phase = 0;      // bit b = parity to wait for on raw barrier b
     int buf = 0;
     FE_PROF_DECL(6);
     for (; g < n_groups; g += kFftWarps) {
-        TileDesc nn;                                            // descriptor two passes ahead: in flight during this pass
-        load_desc(g + 2 * kFftWarps, nn);
+        GDesc n3;                                               // descriptor three passes ahead: in flight during this pass
+        load_desc(g + 3 * kFftWarps, n3);
         const int k = g >> 3, q = g & (kTileGroups - 1);
         const int slot = k % L.slots;
         const uint32_t use = (uint32_t)(k / L.slots);           // how often the slot has been used before
         const int nfw = (P.dbg & 4) ? 0 : min(kWarpFrames, cur.n_frames - q * kWarpFrames);
-        // the other raw buffer was last read in the previous pass's stage A
-        if (dbl) prefetch(next, g + kFftWarps, buf ^ 1);
         if (nfw > 0) {
             float* e_w = reinterpret_cast<float*>(smem_dyn + o_e);
             float* scr_w = reinterpret_cast<float*>(smem_dyn + o_scr);       // the lanes' partial sums of squares
@@ -388,7 +403,8 @@ k_frames_to_statics(const void* __restrict__ pcm, const void* __restrict__ scrat
             const unsigned char* raw_f = smem_dyn + o_raw + buf * L.raw_bytes + fs * HOP * ESZ;
             scr_w[lane] = stage_a<FRAME_LEN, IN_F32, HAS_WINDOW>(raw_f, e_f, tb, t, fs);
             __syncwarp();
-            if (!dbl) prefetch(next, g + kFftWarps, 0);          // single raw buffer: free again after stage A
+            // the buffer is free again: refill it (double-buffered: for the group two passes ahead)
+            if (dbl) prefetch(nn, g + 2 * kFftWarps, buf); else prefetch(next, g + kFftWarps, 0);
             FE_TICK(1);
             // ---- phase 2: stage B ----
             LaneZ z;
@@ -409,12 +425,13 @@ k_frames_to_statics(const void* __restrict__ pcm, const void* __restrict__ scrat
             FE_TICK(4);
         } else {
             // an empty group (partial last tile of an utterance) still has to arrive in the slot's CURRENT round
-            if (!dbl) prefetch(next, g + kFftWarps, 0);
+            if (dbl) prefetch(nn, g + 2 * kFftWarps, buf); else prefetch(next, g + kFftWarps, 0);
             if (use > 0) mbar_wait(bar_empty + 8 * slot, (use - 1u) & 1u);
         }
         if (lane == 0) mbar_arrive(bar_full + 8 * slot);
         cur = next;
         next = nn;
+        nn = n3;
         buf = (buf ^ 1) & dbl;
     }
 #ifdef FE_K1_PROF

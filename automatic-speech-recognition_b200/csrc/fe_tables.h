@@ -10,8 +10,8 @@
 namespace fe {
 
 struct HostTables {
-    std::vector<float> tw256;       // [6][16][4]  twiddle bases m = 1,2,3,4,8,12; cfg = swap*8 + t
-    std::vector<float> tw512;       // [16][4]     post-pass bases; cfg = flip*8 + t
+    std::vector<float> tw256;       // [15][16][4] stage-A twiddles, row k1 - 1, cfg = swap*8 + t
+    std::vector<float> tw512;       // [8][16][4]  post-pass twiddles, row k2, cfg = flip*8 + t
     std::vector<float> window;      // [rows*32]    (w[2m], w[2m+1]) per complex point
     std::vector<int> mel_desc;      // [mel_groups] flat group list per epilogue warp: row | last << 10 | filter << 16
     std::vector<float> mel_w;       // [2][mel_groups*4] weights in the same order: int16-count scale, then float scale
@@ -26,27 +26,26 @@ struct HostTables {
 };
 
 inline void build_host_tables(const fe_config& c, HostTables& t) {
-    // stage-A twiddle bases: (wr(jx m), wr(jy m), wi(jx m), wi(jy m)), jx = t + 8 swap, jy = t + 8 (1 - swap),
-    // for m = 1, 2, 3 (W^(j b)) and m = 4, 8, 12 (W^(4 j a))
-    t.tw256.assign(6 * 16 * 4, 0.f);
-    const int ms[6] = {1, 2, 3, 4, 8, 12};
-    for (int mi = 0; mi < 6; ++mi)
+    // stage-A twiddles W_256^(j k1), k1 = 1..15: (wr(jx), wr(jy), wi(jx), wi(jy)), jx = t + 8 swap, jy = t + 8 (1 - swap)
+    t.tw256.assign(15 * 16 * 4, 0.f);
+    for (int k1 = 1; k1 < 16; ++k1)
         for (int cfg = 0; cfg < 16; ++cfg) {
-            const int swap = cfg >> 3, tt = cfg & 7, m = ms[mi];
+            const int swap = cfg >> 3, tt = cfg & 7;
             const int jx = tt + 8 * swap, jy = tt + 8 * (1 - swap);
-            float* o = &t.tw256[(mi * 16 + cfg) * 4];
-            o[0] = c.tw256[(jx * 16 + m) * 2];     o[1] = c.tw256[(jy * 16 + m) * 2];
-            o[2] = c.tw256[(jx * 16 + m) * 2 + 1]; o[3] = c.tw256[(jy * 16 + m) * 2 + 1];
+            float* o = &t.tw256[((k1 - 1) * 16 + cfg) * 4];
+            o[0] = c.tw256[(jx * 16 + k1) * 2];     o[1] = c.tw256[(jy * 16 + k1) * 2];
+            o[2] = c.tw256[(jx * 16 + k1) * 2 + 1]; o[3] = c.tw256[(jy * 16 + k1) * 2 + 1];
         }
-    // post-pass twiddle bases: (cos rx, cos ry, sin rx, sin ry) (angles 2 pi r / 512); bins r + 16 k2 by rotation
-    t.tw512.assign(16 * 4, 0.f);
-    for (int cfg = 0; cfg < 16; ++cfg) {
-        const int tt = cfg & 7, fs = (cfg >> 3) << 1;
-        const int kx = row_x(tt, fs), ky = row_y(tt, fs);
-        float* o = &t.tw512[cfg * 4];
-        o[0] = c.tw512[kx * 2];     o[1] = c.tw512[ky * 2];
-        o[2] = c.tw512[kx * 2 + 1]; o[3] = c.tw512[ky * 2 + 1];
-    }
+    // post-pass twiddles: (cos, cos, sin, sin) of 2 pi k / 512 for k = rx + 16 k2 and ry + 16 k2
+    t.tw512.assign(8 * 16 * 4, 0.f);
+    for (int k2 = 0; k2 < 8; ++k2)
+        for (int cfg = 0; cfg < 16; ++cfg) {
+            const int tt = cfg & 7, fs = (cfg >> 3) << 1;
+            const int kx = row_x(tt, fs) + 16 * k2, ky = row_y(tt, fs) + 16 * k2;
+            float* o = &t.tw512[(k2 * 16 + cfg) * 4];
+            o[0] = c.tw512[kx * 2];     o[1] = c.tw512[ky * 2];
+            o[2] = c.tw512[kx * 2 + 1]; o[3] = c.tw512[ky * 2 + 1];
+        }
     // mel plan: runs are padded to a multiple of 4 weights (zeros); reads past bin 128 / 256 land in the
     // three zero pad rows of the power buffer
     const int nf = c.num_filters;
