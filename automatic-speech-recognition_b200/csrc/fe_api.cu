@@ -256,7 +256,24 @@ int launch_k2(fe_handle* h, Lane& L, cudaStream_t st, const UttDesc* utts, int n
     } else {
         flags |= 8;              // no statistics: mean 0, scale 1 inside the pack kernel
     }
-    if (n_tiles > 0) {
+    // fast path: K1's tile-major statics with the as-shipped (per-frame) deltas -- one warp per tile, no CTA barrier
+    const bool local = tiled && (delta_mode == 0 || !(flags & 4)) && (D == 13 || D == 40 || D == 80);
+    if (n_tiles > 0 && local) {
+#define FE_LAUNCH_CUBE(DT)                                                                                          \
+        do {                                                                                                        \
+            using C = CubeLocal<DT>;                                                                                \
+            FE_CUDA(h, cudaFuncSetAttribute(k_cube_local<DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes)); \
+            const int per_sm = std::max(1, std::min(8, (220 * 1024) / C::kSmemBytes));                              \
+            const int grid = (int)std::min<long long>((n_tiles + C::kWarps - 1) / C::kWarps, (long long)per_sm * h->num_sms); \
+            k_cube_local<DT><<<grid, C::kWarps * 32, C::kSmemBytes, st>>>(tiles, (int)n_tiles, statics,             \
+                (const float*)L.d_stats.p, out, flags);                                                             \
+        } while (0)
+        if (D == 13) FE_LAUNCH_CUBE(13);
+        else if (D == 40) FE_LAUNCH_CUBE(40);
+        else FE_LAUNCH_CUBE(80);
+#undef FE_LAUNCH_CUBE
+        h->launches++;
+    } else if (n_tiles > 0) {
         const size_t smem = k2_smem_floats(D, kTileFrames) * sizeof(float);
         const int grid = (int)std::min<long long>(n_tiles, 12LL * h->num_sms);
 #define FE_LAUNCH_PACK(DT, TR)                                                                                      \

@@ -171,6 +171,19 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     do { __nanosleep(NS); } while (!mbar_try(bar, parity));
 }
 
+// "slot is full" goes through hardware named barriers (ids 2 .. 2 + slots - 1): the 8 producer warps of a tile
+// bar.arrive (non-blocking), the consumer warp(s) bar.sync -- a blocked warp costs no issue slots, whereas a
+// consumer polling an mbarrier burnt ~8 % of the SM's issue cycles.  "slot is empty" stays an mbarrier: the
+// producers must not wait for each other there.
+template <int THREADS>
+__device__ __forceinline__ void full_arrive(int slot) {
+    asm volatile("bar.arrive %0, %1;" :: "r"(2 + slot), "n"(THREADS) : "memory");
+}
+template <int THREADS>
+__device__ __forceinline__ void full_wait(int slot) {
+    asm volatile("bar.sync %0, %1;" :: "r"(2 + slot), "n"(THREADS) : "memory");
+}
+
 // everything K1 needs besides the data pointers; lives in the constant bank
 constexpr int kEpiWCap = 512;            // floats of specialised-epilogue weights carried in the kernel parameters
 
@@ -263,7 +276,10 @@ k_frames_to_statics(const void* __restrict__ pcm, const void* __restrict__ scrat
     tb.full_spectrum = dt.full_spectrum; tb.is_mfcc = dt.is_mfcc; tb.fbank_log = dt.fbank_log;
     tb.dc_elim = dt.dc_elim; tb.pscale = dt.pscale;
 
-    const int nk = (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;      // tiles of this CTA
+    int bx = blockIdx.x, gx = gridDim.x;
+    FE_OPAQUE(bx); FE_OPAQUE(gx);
+    const int nk = (n_tiles - bx + gx - 1) / gx;      // tiles of this CTA
+    constexpr int kFullThreads = (kTileGroups + (EPI ? 1 : kEpiWarps)) * 32;          // producers + consumer(s) of a tile
 
     if (warp >= kFftWarps) {
         // =========================== epilogue warpgroup ===========================
@@ -276,7 +292,7 @@ k_frames_to_statics(const void* __restrict__ pcm, const void* __restrict__ scrat
             for (int k = we; k < nk; k += kEpiWarps, par ^= 1u) {
                 float* out_t = statics + tiles[blockIdx.x + (long long)k * gridDim.x].stat_off;
                 const float* pb = s_pbuf + slot * L.pbuf_floats;
-                mbar_wait<300>(bar_full + 8 * slot, par);
+                full_wait<kFullThreads>(slot);
                 if (!(P.dbg & 1)) {
                     if (EPI == 1) epi_tile_spec<PlanMfcc40, 13, true, true>(pb, s_energy + slot * kTileFrames, out_t, P.epi_w, tb.dc_elim, lane);
                     else if (tb.fbank_log) epi_tile_spec<PlanFbank80, 80, false, true>(pb, s_energy + slot * kTileFrames, out_t, P.epi_w, false, lane);
@@ -299,7 +315,7 @@ k_frames_to_statics(const void* __restrict__ pcm, const void* __restrict__ scrat
             if (k + 1 < nk) stat_next = tiles[blockIdx.x + (long long)(k + 1) * gridDim.x].stat_off;
             float* sd = s_sd + (k & 1) * L.sd_floats;
             const float* pb = s_pbuf + slot * L.pbuf_floats;
-            mbar_wait<300>(bar_full + 8 * slot, par);
+            full_wait<kFullThreads>(slot);
             FE_TICK(0);
             if (!(P.dbg & 1)) {
                 // ---- phase 4: mel filterbank (+ log, + fold), lane = frame ----
@@ -350,7 +366,7 @@ k_frames_to_statics(const void* __restrict__ pcm, const void* __restrict__ scrat
     auto load_desc = [&](int g, GDesc& td) {
         td.n_frames = 0; td.pcm_off = 0; td.src_sel = 0;
         if (g < n_groups) {
-            const TileDesc* t = tiles + (blockIdx.x + (long long)(g >> 3) * gridDim.x);
+            const TileDesc* t = tiles + (bx + (long long)(g >> 3) * gx);
             td.pcm_off = t->pcm_off;
             const int2 ns = *reinterpret_cast<const int2*>(&t->n_frames);       // n_frames, src_sel (8-byte aligned pair)
             td.n_frames = ns.x; td.src_sel = ns.y;
@@ -380,13 +396,15 @@ k_frames_to_statics(const void* __restrict__ pcm, const void* __restrict__ scrat
     load_desc(g + 2 * kFftWarps, nn);
     uint32_t phase = 0;      // bit b = parity to wait for on raw barrier b
     int buf = 0;
+    // tile k = g >> 3 lives in slot k % slots; `use` = k / slots = how often the slot has been used before.
+    // Tracked incrementally (g advances by 12 = one tile and a half): no integer division in the loop.
+    int slot = (warp >> 3) % L.slots;
+    uint32_t use = (uint32_t)((warp >> 3) / L.slots);
     FE_PROF_DECL(6);
     for (; g < n_groups; g += kFftWarps) {
         GDesc n3;                                               // descriptor three passes ahead: in flight during this pass
         load_desc(g + 3 * kFftWarps, n3);
-        const int k = g >> 3, q = g & (kTileGroups - 1);
-        const int slot = k % L.slots;
-        const uint32_t use = (uint32_t)(k / L.slots);           // how often the slot has been used before
+        const int q = g & (kTileGroups - 1);
         const int nfw = (P.dbg & 4) ? 0 : min(kWarpFrames, cur.n_frames - q * kWarpFrames);
         if (nfw > 0) {
             float* e_w = reinterpret_cast<float*>(smem_dyn + o_e);
@@ -428,11 +446,13 @@ k_frames_to_statics(const void* __restrict__ pcm, const void* __restrict__ scrat
             if (dbl) prefetch(nn, g + 2 * kFftWarps, buf); else prefetch(next, g + kFftWarps, 0);
             if (use > 0) mbar_wait(bar_empty + 8 * slot, (use - 1u) & 1u);
         }
-        if (lane == 0) mbar_arrive(bar_full + 8 * slot);
+        full_arrive<kFullThreads>(slot);
         cur = next;
         next = nn;
         nn = n3;
         buf = (buf ^ 1) & dbl;
+        slot += 1 + ((q + 4) >> 3);                             // g += 12: k advances by 1, or by 2 when q wraps
+        if (slot >= L.slots) { slot -= L.slots; ++use; }
     }
 #ifdef FE_K1_PROF
     if ((P.dbg & 8) && lane == 0) {
@@ -706,6 +726,87 @@ k_norm_delta_pack(const TileDesc* __restrict__ tiles, int n_tiles, const float* 
         if (t0 + nrow == L && tid < ((4 - (total & 3)) & 3)) dst[total + tid] = 0.f;
         __syncthreads();
     }
+}
+
+// ---------------------------------------------------------------------------
+// K2b, fast path: CMVN + as-shipped deltas + cube for K1's tile-major statics.  The as-shipped deltas run
+// along the COEFFICIENT axis, so with lane = frame everything is per-lane register arithmetic: one warp per
+// tile, no CTA barrier.  A tile's [D][32] block is read with D coalesced 128-byte loads, the (32, D, 3) cube
+// is staged through the warp's own shared-memory window (row stride 3 D is odd or padded -> conflict-free)
+// and leaves as 16-byte coalesced stores.  flags as k_norm_delta_pack (bit2 deltas, bit3 no statistics).
+// ---------------------------------------------------------------------------
+template <int D>
+struct CubeLocal {
+    static constexpr int W3 = 3 * D;
+    static constexpr int RS = (W3 & 1) ? W3 : W3 + 1;                   // staging row stride (odd: no bank conflicts)
+    static constexpr int kWarps = D <= 16 ? 8 : (D <= 40 ? 8 : 4);
+    static constexpr int kSmemBytes = kWarps * 32 * RS * 4;
+};
+
+template <int D, bool DELTA>
+__device__ __forceinline__ void cube_local_body(const TileDesc* __restrict__ tiles, int n_tiles, const float* __restrict__ statics,
+                                                const float* __restrict__ stats, float* __restrict__ out, int flags, float* sm_c) {
+    using C = CubeLocal<D>;
+    constexpr int ROWLEN = DELTA ? 3 * D : D;
+    constexpr int RS = (ROWLEN & 1) ? ROWLEN : ROWLEN + 1;               // odd row stride: conflict-free staging
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float* stage = sm_c + warp * 32 * C::RS;
+    const long long w0 = (long long)blockIdx.x * C::kWarps + warp;
+    for (long long ti = w0; ti < n_tiles; ti += (long long)gridDim.x * C::kWarps) {
+        const TileDesc td = tiles[ti];
+        const int nrow = td.n_frames;
+        const float* x = statics + td.stat_off + lane;
+        float v[D];
+#pragma unroll
+        for (int c = 0; c < D; ++c) v[c] = x[c * 32];                     // 128-byte lines; pad lanes read finite garbage
+        if (!(flags & 8)) {
+            const float* st = stats + (long long)td.utt * 2 * D;
+#pragma unroll
+            for (int c = 0; c < D; ++c) v[c] = (v[c] - __ldg(st + c)) * __ldg(st + D + c);   // warp-uniform, cached
+        }
+        float* row = stage + lane * RS;
+        if (DELTA) {
+            // d1[k] = (v[k+1] + 2 v[k+2]) / 10, d2[k] = (d1[k+1] + 2 d1[k+2]) / 10, indices clamped to D-1
+            float d1[D];
+#pragma unroll
+            for (int c = 0; c < D; ++c) {
+                const int c1 = c + 1 < D ? c + 1 : D - 1, c2 = c + 2 < D ? c + 2 : D - 1;
+                d1[c] = (v[c1] + 2.f * v[c2]) * 0.1f;
+            }
+#pragma unroll
+            for (int c = 0; c < D; ++c) {
+                const int c1 = c + 1 < D ? c + 1 : D - 1, c2 = c + 2 < D ? c + 2 : D - 1;
+                row[3 * c] = v[c]; row[3 * c + 1] = d1[c]; row[3 * c + 2] = (d1[c1] + 2.f * d1[c2]) * 0.1f;
+            }
+        } else {
+#pragma unroll
+            for (int c = 0; c < D; ++c) row[c] = v[c];
+        }
+        __syncwarp();
+        const int total = nrow * ROWLEN;
+        float* dst = out + td.out_off + (long long)td.first_frame * ROWLEN;     // 16-byte aligned: first_frame % 4 == 0
+        const int n4 = total >> 2;
+        auto at = [&](int e) { return RS == ROWLEN ? stage[e] : stage[(e / ROWLEN) * RS + e % ROWLEN]; };
+        for (int i = lane; i < n4; i += 32) {
+            float4 o;
+            if (RS == ROWLEN) o = reinterpret_cast<const float4*>(stage)[i];
+            else { const int e = 4 * i; o = make_float4(at(e), at(e + 1), at(e + 2), at(e + 3)); }
+            reinterpret_cast<float4*>(dst)[i] = o;
+        }
+        for (int i = (n4 << 2) + lane; i < total; i += 32) dst[i] = at(i);
+        // the 0..3 pad floats that round the utterance's run up to 16 bytes are zeroed (deterministic buffers)
+        if (td.first_frame + nrow == td.utt_frames && lane < ((4 - (total & 3)) & 3)) dst[total + lane] = 0.f;
+        __syncwarp();
+    }
+}
+
+template <int D>
+__global__ void __launch_bounds__(CubeLocal<D>::kWarps * 32)
+k_cube_local(const TileDesc* __restrict__ tiles, int n_tiles, const float* __restrict__ statics,
+             const float* __restrict__ stats, float* __restrict__ out, int flags) {
+    extern __shared__ __align__(16) float sm_c[];
+    if (flags & 4) cube_local_body<D, true>(tiles, n_tiles, statics, stats, out, flags, sm_c);
+    else cube_local_body<D, false>(tiles, n_tiles, statics, stats, out, flags, sm_c);
 }
 
 // ---------------------------------------------------------------------------
