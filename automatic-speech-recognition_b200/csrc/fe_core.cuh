@@ -107,6 +107,17 @@ FE_HD void bfly4(float2& r0, float2& i0, float2& r1, float2& i1, float2& r2, flo
     r3 = psub(t1r, t3i); i3 = padd(t1i, t3r);     // t1 + i t3
 }
 
+// bfly4 with a zero fourth input (the zero padding of the frame: rows 13..15 of stage A)
+FE_HD void bfly4_z3(float2& r0, float2& i0, float2& r1, float2& i1, float2& r2, float2& i2, float2& r3, float2& i3) {
+    float2 t0r = padd(r0, r2), t0i = padd(i0, i2);
+    float2 t1r = psub(r0, r2), t1i = psub(i0, i2);
+    r0 = padd(t0r, r1); i0 = padd(t0i, i1);           // t2 = t3 = x1
+    r2 = psub(t0r, r1); i2 = psub(t0i, i1);
+    float2 t3r = r1, t3i = i1;
+    r1 = padd(t1r, t3i); i1 = psub(t1i, t3r);         // t1 - i t3
+    r3 = psub(t1r, t3i); i3 = padd(t1i, t3r);         // t1 + i t3
+}
+
 // multiply (r, i) by exp(-2 pi i M / 16)
 template <int M> FE_HD void mul_w16(float2& r, float2& i) {
     constexpr float C1 = 0.92387953251128674f, S1 = 0.38268343236508977f, H = 0.70710678118654752f;
@@ -121,10 +132,15 @@ template <int M> FE_HD void mul_w16(float2& r, float2& i) {
 // In-place FFT16: input natural order x[n]; output X[k] lands at slot pos16(k).
 FE_HD constexpr int pos16(int k) { return (k >> 2) + ((k & 3) << 2); }
 
+// NZ: inputs n >= NZ are known to be zero (12 < NZ <= 16 supported: only the fourth butterfly input can vanish)
+template <int NZ = 16>
 FE_HD void fft16(float2 (&xr)[16], float2 (&xi)[16]) {
+    static_assert(NZ > 12 && NZ <= 16, "fft16: only the last three inputs may be structurally zero");
 #pragma unroll
-    for (int n1 = 0; n1 < 4; ++n1)
-        bfly4(xr[n1], xi[n1], xr[n1 + 4], xi[n1 + 4], xr[n1 + 8], xi[n1 + 8], xr[n1 + 12], xi[n1 + 12]);
+    for (int n1 = 0; n1 < 4; ++n1) {
+        if (n1 + 12 >= NZ) bfly4_z3(xr[n1], xi[n1], xr[n1 + 4], xi[n1 + 4], xr[n1 + 8], xi[n1 + 8], xr[n1 + 12], xi[n1 + 12]);
+        else bfly4(xr[n1], xi[n1], xr[n1 + 4], xi[n1 + 4], xr[n1 + 8], xi[n1 + 8], xr[n1 + 12], xi[n1 + 12]);
+    }
     // slot n1 + 4 k2 holds A[n1][k2]; twiddle W_16^(n1 k2)
     mul_w16<1>(xr[5], xi[5]);   mul_w16<2>(xr[9], xi[9]);   mul_w16<3>(xr[13], xi[13]);
     mul_w16<2>(xr[6], xi[6]);   mul_w16<4>(xr[10], xi[10]); mul_w16<6>(xr[14], xi[14]);
@@ -231,7 +247,7 @@ FE_HD float stage_a(const void* raw_f, float* e_f, const SmemTables& tb, int t, 
             re[a] = make_float2(0.f, 0.f); im[a] = make_float2(0.f, 0.f);
         }
     }
-    fft16(re, im);
+    fft16<(ROWS > 12 ? ROWS : 16)>(re, im);
     // twiddle W_256^(j k1) and scatter.  Lane part of the index (low 5 bits):
     //   4*((t>>1) ^ X ^ 4*hb) + 2*(t&1) + F   with hb = j>>3 of the half being stored
     const int X = (fs & 1) << 2, F = fs >> 1;

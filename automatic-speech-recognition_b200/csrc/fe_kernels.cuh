@@ -273,7 +273,8 @@ k_frames_to_statics(const void* __restrict__ pcm, const void* __restrict__ scrat
     tb.tw256 = s_tw256; tb.tw512 = s_tw512; tb.window = dt.window ? s_window : nullptr;
     tb.mel_desc = s_desc; tb.mel_w4 = reinterpret_cast<const float4*>(s_melw); tb.dctf = s_dct;
     tb.nf = dt.nf; tb.D = dt.D; tb.dct_stride = dt.dct_stride; tb.nh = dt.nh;
-    tb.full_spectrum = dt.full_spectrum; tb.is_mfcc = dt.is_mfcc; tb.fbank_log = dt.fbank_log;
+    tb.full_spectrum = EPI ? 0 : dt.full_spectrum;        // the baked plans only use bins <= 128
+    tb.is_mfcc = dt.is_mfcc; tb.fbank_log = dt.fbank_log;
     tb.dc_elim = dt.dc_elim; tb.pscale = dt.pscale;
 
     int bx = blockIdx.x, gx = gridDim.x;
