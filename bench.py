@@ -120,7 +120,17 @@ def run_reference(a):
         return
     import multiprocessing as mp
     cores = os.cpu_count() or 1
-    hours = a.cpu_sample_hours or min(0.35 * cores, 6.0)             # ~10-20 s of CPU work per step
+    hours = a.cpu_sample_hours
+    if not hours:
+        # size the per-step sample so that the whole --steps/--warmup run takes about 2.5 minutes:
+        # probe the host's rate on a small sample first
+        probe = host_sample(0.05 * cores, 991)
+        with mp.get_context("fork").Pool(cores) as pool:
+            cpu_pass(probe[:cores], pool, cores)
+            dt, _ = cpu_pass(probe, pool, cores)
+        rate = sum(len(p) for p in probe) / FS / 3600.0 / dt             # audio-h / s
+        per_step_s = min(30.0, max(2.0, 150.0 / (a.warmup + a.steps)))
+        hours = rate * per_step_s
     pcm = host_sample(hours, 5678)
     hours = sum(len(p) for p in pcm) / FS / 3600.0
     times = []
@@ -317,9 +327,14 @@ def main():
     cpu = None
     if world == 1 and not a.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        want_h = a.cpu_sample_hours or min(0.35 * cores, 6.0)
-        n_s = int(np.searchsorted(np.cumsum(lens), want_h * 3600 * FS)) + 1
-        sample = [d_pcm[int(off[i]):int(off[i]) + int(lens[i])].cpu().numpy() for i in range(min(n_s, len(lens)))]
+        # about 15 s of CPU work on all host cores: probe the rate on a small slice, then size the sample
+        take = lambda h: [d_pcm[int(off[i]):int(off[i]) + int(lens[i])].cpu().numpy()
+                          for i in range(min(int(np.searchsorted(np.cumsum(lens), h * 3600 * FS)) + 1, len(lens)))]
+        want_h = a.cpu_sample_hours
+        if not want_h:
+            pv, _, _, _ = cpu_baseline(take(0.05 * cores))
+            want_h = min(pv * 15.0, 0.6 * hours)
+        sample = take(want_h)
         v, cores, h_s, secs = cpu_baseline(sample)
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": "first %d utterances (%.2f audio-h) of the rank-0 shard, %.1f s on %d processes" % (len(sample), h_s, secs, cores),
