@@ -234,6 +234,43 @@ int launch_k1(fe_handle* h, cudaStream_t st, const void* pcm, const void* scratc
     return FE_OK;
 }
 
+// K0: speed / gain perturbation.  Ratios 10/9 and 10/11 (the reference's 0.9 / 1.1) go through the register-tiled
+// kernels, everything else (other ratios, gain only) through the generic one.  The tile table is grouped by
+// class on the host (class_atiles) so that no kernel walks tiles it has to skip.
+int atile_class(const fe_handle* h, const UttDesc& u) {
+    if (u.speed_idx >= 0 && h->sp_up[u.speed_idx] == 10 && h->sp_down[u.speed_idx] == 9) return 0;
+    if (u.speed_idx >= 0 && h->sp_up[u.speed_idx] == 10 && h->sp_down[u.speed_idx] == 11) return 1;
+    return 2;
+}
+
+void class_atiles(const fe_handle* h, const UttDesc* utts, std::vector<int2>& at, int counts[3]) {
+    std::vector<int2> cls[3];
+    for (const int2& t : at) cls[atile_class(h, utts[t.x])].push_back(t);
+    size_t o = 0;
+    for (int k = 0; k < 3; ++k) { counts[k] = (int)cls[k].size(); std::copy(cls[k].begin(), cls[k].end(), at.begin() + o); o += cls[k].size(); }
+}
+
+int launch_k0(fe_handle* h, cudaStream_t st, const short* src, const UttDesc* utts, const int2* atiles, const int counts[3],
+              short* dst, int use_dst_off) {
+    const int* up = (const int*)h->d_sp_up.p; const int* down = (const int*)h->d_sp_down.p;
+    const int* toff = (const int*)h->d_sp_tap_off.p; const float* taps = (const float*)h->d_taps.p;
+    auto grid = [&](int n) { return (int)std::min<long long>(n, 16LL * h->num_sms); };
+    if (counts[0] > 0) {
+        k_resample_fast<10, 9><<<grid(counts[0]), 320, 0, st>>>(src, utts, atiles, counts[0], up, down, toff, taps, dst, use_dst_off);
+        h->launches++;
+    }
+    if (counts[1] > 0) {
+        k_resample_fast<10, 11><<<grid(counts[1]), 320, 0, st>>>(src, utts, atiles + counts[0], counts[1], up, down, toff, taps, dst, use_dst_off);
+        h->launches++;
+    }
+    if (counts[2] > 0) {
+        k_resample<<<grid(counts[2]), 256, 0, st>>>(src, utts, atiles + counts[0] + counts[1], counts[2], up, down, toff, taps, dst, use_dst_off, 0);
+        h->launches++;
+    }
+    FE_CUDA(h, cudaGetLastError());
+    return FE_OK;
+}
+
 // K2a + K2b: per-utterance statistics, then the tile-parallel normalise / delta / pack pass.
 // tiled: `statics` are K1's [D][32] blocks (else a row-major (L, D) matrix per utterance: fe_postprocess).
 // flags: bit0 subtract the mean, bit1 divide by the std, bit2 append deltas.
@@ -508,6 +545,26 @@ static int run_core(fe_handle* h, Lane& L, cudaStream_t st, const void* pcm, con
     if (!pcm_on_dev) { if ((rc = ensure(h, L.d_pcm, esz * (size_t)pl.pcm_span))) return rc; d_pcm = L.d_pcm.p; }
     if (!out_on_dev) { if ((rc = ensure(h, L.d_out, sizeof(float) * (size_t)std::max<long long>(pl.total_out, 1)))) return rc; d_out = (float*)L.d_out.p; }
 
+    // K0 tile table: per-utterance start index, utterances grouped by resampler class (atile_prefix is reused
+    // for it: entry i = first tile of utterance i in the grouped table, -1 = none)
+    int k0_counts[3] = {0, 0, 0};
+    if (pl.any_scratch) {
+        long long cnt[3] = {0, 0, 0};
+        for (int i = 0; i < n_utts; ++i) {
+            const long long nt = L.atile_prefix[i + 1] - L.atile_prefix[i];
+            if (nt > 0) cnt[preemph ? 2 : atile_class(h, L.utts[i])] += nt;
+        }
+        long long base[3] = {0, cnt[0], cnt[0] + cnt[1]};
+        std::vector<long long>& as = L.atile_prefix;
+        long long prev = as[0];
+        for (int i = 0; i < n_utts; ++i) {
+            const long long nxt = as[i + 1], nt = nxt - prev;
+            prev = nxt;
+            if (nt > 0) { long long& b = base[preemph ? 2 : atile_class(h, L.utts[i])]; as[i] = b; b += nt; }
+            else as[i] = -1;
+        }
+        for (int k = 0; k < 3; ++k) k0_counts[k] = (int)cnt[k];
+    }
     // the previous run on this lane may still be reading the staging area
     if (L.done_valid) FE_CUDA(h, cudaEventSynchronize(L.done));
     unsigned char* hs = (unsigned char*)L.h_stage.p;
@@ -540,15 +597,10 @@ static int run_core(fe_handle* h, Lane& L, cudaStream_t st, const void* pcm, con
         h->launches++;
     }
     if (pl.any_scratch) {
-        // atiles: one entry per 1024 output samples; only utterances routed through scratch have atiles
-        // (n_frames is not the right count there, so a dedicated tiny builder pass)
-        std::vector<int2> at((size_t)pl.total_atiles);
-        for (int i = 0; i < n_utts; ++i) {
-            long long b = L.atile_prefix[i], e = L.atile_prefix[i + 1];
-            for (long long k = b; k < e; ++k) at[(size_t)k] = make_int2(i, (int)((k - b) * kK0Outputs));
-        }
-        FE_CUDA(h, cudaMemcpyAsync(L.d_atiles.p, at.data(), sizeof(int2) * at.size(), cudaMemcpyHostToDevice, st));
-        FE_CUDA(h, cudaStreamSynchronize(st));     // `at` is pageable and dies at scope end
+        // K0's tile table is expanded on the device from the per-utterance start indices (grouped by class)
+        k_build_atiles<<<gb, tb, 0, st>>>((const UttDesc*)L.d_utts.p, (const long long*)L.d_atile_prefix.p, n_utts,
+                                          kK0Outputs, (int2*)L.d_atiles.p);
+        h->launches++;
         if (prof) FE_CUDA(h, cudaEventRecord(ps->e[1], st));
         int grid = (int)std::min<long long>(pl.total_atiles, 16LL * h->num_sms);
         if (preemph) {
@@ -559,12 +611,9 @@ static int run_core(fe_handle* h, Lane& L, cudaStream_t st, const void* pcm, con
                 k_preemph<1><<<grid, 256, 0, st>>>(d_pcm, (const UttDesc*)L.d_utts.p, (const int2*)L.d_atiles.p,
                                                    (int)pl.total_atiles, c.preemph, (float*)L.d_scratch.p);
         } else {
-            k_resample<<<grid, 256, 0, st>>>((const short*)d_pcm, (const UttDesc*)L.d_utts.p, (const int2*)L.d_atiles.p,
-                                             (int)pl.total_atiles, (const int*)h->d_sp_up.p, (const int*)h->d_sp_down.p,
-                                             (const int*)h->d_sp_tap_off.p, (const float*)h->d_taps.p,
-                                             (short*)L.d_scratch.p, 0);
+            if ((rc = launch_k0(h, st, (const short*)d_pcm, (const UttDesc*)L.d_utts.p, (const int2*)L.d_atiles.p,
+                                k0_counts, (short*)L.d_scratch.p, 0))) return rc;
         }
-        h->launches++;
         if (prof) ps->k0 = true;
     }
     if (prof) FE_CUDA(h, cudaEventRecord(ps->e[2], st));
@@ -681,14 +730,14 @@ int fe_perturb(fe_handle* h, const int16_t* pcm, const int64_t* pcm_offsets, con
     if (!src_dev) { if ((rc = ensure(h, h->lane[0].d_pcm, 2 * (size_t)span))) return rc; d_src = (const short*)h->lane[0].d_pcm.p; }
     if (!dst_dev) { if ((rc = ensure(h, h->lane[0].d_scratch, 2 * (size_t)off))) return rc; d_dst = (short*)h->lane[0].d_scratch.p; }
     FE_CUDA(h, cudaMemcpyAsync(h->lane[0].d_utts.p, ut.data(), sizeof(UttDesc) * ut.size(), cudaMemcpyHostToDevice, st));
+    int k0_counts[3];
+    class_atiles(h, ut.data(), at, k0_counts);
     FE_CUDA(h, cudaMemcpyAsync(h->lane[0].d_atiles.p, at.data(), sizeof(int2) * at.size(), cudaMemcpyHostToDevice, st));
     if (!src_dev) FE_CUDA(h, cudaMemcpyAsync(h->lane[0].d_pcm.p, pcm, 2 * (size_t)span, cudaMemcpyHostToDevice, st));
     FE_CUDA(h, cudaStreamSynchronize(st));
     int grid = (int)std::min<long long>((long long)at.size(), 16LL * h->num_sms);
-    k_resample<<<grid, 256, 0, st>>>(d_src, (const UttDesc*)h->lane[0].d_utts.p, (const int2*)h->lane[0].d_atiles.p, (int)at.size(),
-                                     (const int*)h->d_sp_up.p, (const int*)h->d_sp_down.p,
-                                     (const int*)h->d_sp_tap_off.p, (const float*)h->d_taps.p, d_dst, 1);
-    h->launches++;
+    (void)grid;
+    if ((rc = launch_k0(h, st, d_src, (const UttDesc*)h->lane[0].d_utts.p, (const int2*)h->lane[0].d_atiles.p, k0_counts, d_dst, 1))) return rc;
     FE_CUDA(h, cudaGetLastError());
     if (!dst_dev) {
         FE_CUDA(h, cudaMemcpyAsync(dst, d_dst, 2 * (size_t)off, cudaMemcpyDeviceToHost, st));

@@ -74,6 +74,18 @@ __global__ void k_build_tiles(const UttDesc* __restrict__ utts, const long long*
     }
 }
 
+// K0's tile table (one entry per kK0Outputs output samples of a perturbed utterance), grouped by resampler
+// class on the host: a_start[u] = index of the utterance's first entry (< 0: none)
+__global__ void k_build_atiles(const UttDesc* __restrict__ utts, const long long* __restrict__ a_start, int n_utts,
+                               int tile_outputs, int2* __restrict__ atiles) {
+    int u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= n_utts) return;
+    long long b = a_start[u];
+    if (b < 0) return;
+    const int n = utts[u].n_samples;
+    for (int j = 0; j < n; j += tile_outputs) atiles[b++] = make_int2(u, j);
+}
+
 // ---------------------------------------------------------------------------
 // K1 shared-memory carve-up (bytes), shared by host (size) and device (pointers).
 // The exchange regions come first so that they are 2 KB aligned (the kernel rounds
@@ -815,19 +827,21 @@ k_cube_local(const TileDesc* __restrict__ tiles, int n_tiles, const float* __res
 // x = 0 off the ends, int16 in -> (* gain) -> round-half-even, saturate -> int16 out.
 // speed_idx < 0: gain only.
 // ---------------------------------------------------------------------------
-constexpr int kK0Outputs = 1024;
+constexpr int kK0Outputs = 1600;        // outputs per K0 tile: 32 groups of 5 x up (up = 10) same-phase outputs
 
 __global__ void __launch_bounds__(256)
 k_resample(const short* __restrict__ pcm, const UttDesc* __restrict__ utts,
            const int2* __restrict__ atiles, int n_atiles,
            const int* __restrict__ sp_up, const int* __restrict__ sp_down, const int* __restrict__ sp_tap_off,
-           const float* __restrict__ taps_all, short* __restrict__ dst, int use_dst_off) {
+           const float* __restrict__ taps_all, short* __restrict__ dst, int use_dst_off, int skip_fast) {
     for (int tile = blockIdx.x; tile < n_atiles; tile += gridDim.x) {
         const int2 te = atiles[tile];
         const UttDesc u = utts[te.x];
         const short* x = pcm + u.src_off;
         short* y = dst + (use_dst_off ? u.out_off : u.pcm_off);
         const int j1 = min(te.y + kK0Outputs, u.n_samples);
+        // ratios 10/9 and 10/11 are served by k_resample_fast
+        if (skip_fast && u.speed_idx >= 0 && sp_up[u.speed_idx] == 10 && (sp_down[u.speed_idx] == 9 || sp_down[u.speed_idx] == 11)) continue;
         if (u.speed_idx < 0) {
             for (int j = te.y + threadIdx.x; j < j1; j += blockDim.x) {
                 float v = (float)x[j];
@@ -853,6 +867,73 @@ k_resample(const short* __restrict__ pcm, const UttDesc* __restrict__ utts,
             if (u.gain != 1.f) acc *= u.gain;
             y[j] = (short)fminf(fmaxf(rintf(acc), -32768.f), 32767.f);
         }
+    }
+}
+
+// K0, fast path for a compile-time ratio (the reference's speeds 0.9 / 1.1 -> 10/9, 10/11): the tile's input span
+// and the polyphase taps sit in shared memory.  Warp p serves phase p of the tile's 32 groups of R x UP outputs
+// (lane = group): the 32 taps are warp-uniform loads, and a thread computes the R = 5 outputs j, j + UP, ...
+// of its group that share them (input windows shifted by DOWN -> a union of 4 DOWN + 32 samples).  The
+// lane stride of the window reads is R x DOWN = 45 / 55 words (odd: bank-conflict free).  Same summation order
+// per output as k_resample (bit-identical results).  Utterances of other ratios (and gain-only ones) in the
+// same batch are skipped here and served by k_resample, which skips these ratios in turn.
+template <int UP, int DOWN>
+__global__ void __launch_bounds__(UP * 32)
+k_resample_fast(const short* __restrict__ pcm, const UttDesc* __restrict__ utts,
+                const int2* __restrict__ atiles, int n_atiles,
+                const int* __restrict__ sp_up, const int* __restrict__ sp_down, const int* __restrict__ sp_tap_off,
+                const float* __restrict__ taps_all, short* __restrict__ dst, int use_dst_off) {
+    constexpr int R = kK0Outputs / (32 * UP), NX = (R - 1) * DOWN + 32;
+    static_assert(R * 32 * UP == kK0Outputs, "tile = 32 groups of R x UP outputs");
+    static_assert(((R * DOWN) & 1) == 1, "odd lane stride");
+    constexpr int SPAN = (kK0Outputs * DOWN + UP - 1) / UP + 34;            // input samples a tile can touch
+    __shared__ float xs[SPAN];
+    __shared__ float tps[UP * 32];
+    __shared__ __align__(16) short ys[kK0Outputs];
+    const int tid = threadIdx.x;
+    const int p = tid >> 5, g = tid & 31;
+    for (int tile = blockIdx.x; tile < n_atiles; tile += gridDim.x) {
+        const int2 te = atiles[tile];
+        const UttDesc u = utts[te.x];
+        if (u.speed_idx < 0 || sp_up[u.speed_idx] != UP || sp_down[u.speed_idx] != DOWN) continue;   // block-uniform
+        const short* x = pcm + u.src_off;
+        short* y = dst + (use_dst_off ? u.out_off : u.pcm_off) + te.y;
+        const int nout = min(kK0Outputs, u.n_samples - te.y);
+        const long long first = (long long)te.y * DOWN / UP - 15;          // input index of xs[0]
+        __syncthreads();                                                     // previous tile's readers are done
+        for (int i = tid; i < SPAN; i += blockDim.x) {
+            const long long n = first + i;
+            xs[i] = (n >= 0 && n < u.n_src) ? (float)__ldg(x + n) : 0.f;
+        }
+        const float* taps = taps_all + sp_tap_off[u.speed_idx];
+        for (int i = tid; i < UP * 32; i += blockDim.x) tps[i] = taps[i];
+        __syncthreads();
+        const int jl = g * (R * UP) + p;                                     // first of this thread's R outputs (tile-local)
+        const long long pos = ((long long)te.y + jl) * DOWN;
+        const int ph = (int)(pos % UP);                                      // the same for the whole warp
+        const int b0 = (int)(pos / UP - 15 - first);                        // xs index of the first window
+        float acc[R];
+#pragma unroll
+        for (int m = 0; m < R; ++m) acc[m] = 0.f;
+#pragma unroll
+        for (int k = 0; k < NX; ++k) {
+            const float xv = xs[b0 + k];
+#pragma unroll
+            for (int m = 0; m < R; ++m) {
+                const int t = k - m * DOWN;                                   // tap index of this sample in window m
+                if (t >= 0 && t < 32) acc[m] = fmaf(tps[ph * 32 + t], xv, acc[m]);
+            }
+        }
+#pragma unroll
+        for (int m = 0; m < R; ++m) {
+            float a = acc[m];
+            if (u.gain != 1.f) a *= u.gain;
+            ys[jl + m * UP] = (short)fminf(fmaxf(rintf(a), -32768.f), 32767.f);
+        }
+        __syncthreads();
+        const int n8 = nout >> 3;                                            // y is 16-byte aligned (offsets % 8 == 0, tiles of 1600)
+        for (int i = tid; i < n8; i += blockDim.x) reinterpret_cast<int4*>(y)[i] = reinterpret_cast<const int4*>(ys)[i];
+        for (int i = (n8 << 3) + tid; i < nout; i += blockDim.x) y[i] = ys[i];
     }
 }
 
