@@ -750,9 +750,10 @@ k_norm_delta_pack(const TileDesc* __restrict__ tiles, int n_tiles, const float* 
 // ---------------------------------------------------------------------------
 template <int D>
 struct CubeLocal {
-    static constexpr int W3 = 3 * D;
-    static constexpr int RS = (W3 & 1) ? W3 : W3 + 1;                   // staging row stride (odd: no bank conflicts)
-    static constexpr int kWarps = D <= 16 ? 8 : (D <= 40 ? 8 : 4);
+    static constexpr int CH = D <= 16 ? D : (D % 20 == 0 && D <= 40 ? 20 : 16);    // coefficients staged per round
+    static_assert(D % CH == 0, "feature width must be a multiple of the staging chunk");
+    static constexpr int RS = (3 * CH) | 1;                              // staging row stride (odd: no bank conflicts)
+    static constexpr int kWarps = 8;
     static constexpr int kSmemBytes = kWarps * 32 * RS * 4;
 };
 
@@ -760,10 +761,12 @@ template <int D, bool DELTA>
 __device__ __forceinline__ void cube_local_body(const TileDesc* __restrict__ tiles, int n_tiles, const float* __restrict__ statics,
                                                 const float* __restrict__ stats, float* __restrict__ out, int flags, float* sm_c) {
     using C = CubeLocal<D>;
-    constexpr int ROWLEN = DELTA ? 3 * D : D;
-    constexpr int RS = (ROWLEN & 1) ? ROWLEN : ROWLEN + 1;               // odd row stride: conflict-free staging
+    constexpr int W = DELTA ? 3 : 1;
+    constexpr int ROWLEN = W * D;                  // floats per output row
+    constexpr int SEG = W * C::CH;                 // floats of a row written per round
+    constexpr int RS = C::RS;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float* stage = sm_c + warp * 32 * C::RS;
+    float* stage = sm_c + warp * 32 * RS;
     const long long w0 = (long long)blockIdx.x * C::kWarps + warp;
     for (long long ti = w0; ti < n_tiles; ti += (long long)gridDim.x * C::kWarps) {
         const TileDesc td = tiles[ti];
@@ -777,39 +780,50 @@ __device__ __forceinline__ void cube_local_body(const TileDesc* __restrict__ til
 #pragma unroll
             for (int c = 0; c < D; ++c) v[c] = (v[c] - __ldg(st + c)) * __ldg(st + D + c);   // warp-uniform, cached
         }
-        float* row = stage + lane * RS;
-        if (DELTA) {
-            // d1[k] = (v[k+1] + 2 v[k+2]) / 10, d2[k] = (d1[k+1] + 2 d1[k+2]) / 10, indices clamped to D-1
-            float d1[D];
-#pragma unroll
-            for (int c = 0; c < D; ++c) {
-                const int c1 = c + 1 < D ? c + 1 : D - 1, c2 = c + 2 < D ? c + 2 : D - 1;
-                d1[c] = (v[c1] + 2.f * v[c2]) * 0.1f;
-            }
-#pragma unroll
-            for (int c = 0; c < D; ++c) {
-                const int c1 = c + 1 < D ? c + 1 : D - 1, c2 = c + 2 < D ? c + 2 : D - 1;
-                row[3 * c] = v[c]; row[3 * c + 1] = d1[c]; row[3 * c + 2] = (d1[c1] + 2.f * d1[c2]) * 0.1f;
-            }
-        } else {
-#pragma unroll
-            for (int c = 0; c < D; ++c) row[c] = v[c];
-        }
-        __syncwarp();
-        const int total = nrow * ROWLEN;
         float* dst = out + td.out_off + (long long)td.first_frame * ROWLEN;     // 16-byte aligned: first_frame % 4 == 0
-        const int n4 = total >> 2;
-        auto at = [&](int e) { return RS == ROWLEN ? stage[e] : stage[(e / ROWLEN) * RS + e % ROWLEN]; };
-        for (int i = lane; i < n4; i += 32) {
-            float4 o;
-            if (RS == ROWLEN) o = reinterpret_cast<const float4*>(stage)[i];
-            else { const int e = 4 * i; o = make_float4(at(e), at(e + 1), at(e + 2), at(e + 3)); }
-            reinterpret_cast<float4*>(dst)[i] = o;
+        float* row = stage + lane * RS;
+#pragma unroll
+        for (int c0 = 0; c0 < D; c0 += C::CH) {
+            if (DELTA) {
+                // d1[k] = (v[k+1] + 2 v[k+2]) / 10, d2[k] = (d1[k+1] + 2 d1[k+2]) / 10, indices clamped to D-1
+#pragma unroll
+                for (int j = 0; j < C::CH; ++j) {
+                    const int c = c0 + j;
+                    auto cl = [](int i) { return i < D ? i : D - 1; };
+                    const float d1c = (v[cl(c + 1)] + 2.f * v[cl(c + 2)]) * 0.1f;
+                    const float d1a = (v[cl(cl(c + 1) + 1)] + 2.f * v[cl(cl(c + 1) + 2)]) * 0.1f;       // d1[min(c+1, D-1)]
+                    const float d1b = (v[cl(cl(c + 2) + 1)] + 2.f * v[cl(cl(c + 2) + 2)]) * 0.1f;       // d1[min(c+2, D-1)]
+                    row[3 * j] = v[c]; row[3 * j + 1] = d1c; row[3 * j + 2] = (d1a + 2.f * d1b) * 0.1f;
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < C::CH; ++j) row[j] = v[c0 + j];
+            }
+            __syncwarp();
+            if (SEG == ROWLEN && RS == ROWLEN) {
+                // single round, contiguous staging (D = 13 with deltas): straight 16-byte copies
+                const int total = nrow * ROWLEN, n4 = total >> 2;
+                for (int i = lane; i < n4; i += 32) reinterpret_cast<float4*>(dst)[i] = reinterpret_cast<const float4*>(stage)[i];
+                for (int i = (n4 << 2) + lane; i < total; i += 32) dst[i] = stage[i];
+            } else if (SEG % 4 == 0 && ROWLEN % 4 == 0) {
+                // every row segment is a whole number of aligned 16-byte pieces
+                constexpr int Q = SEG / 4;
+                for (int i = lane; i < nrow * Q; i += 32) {
+                    const int r = i / Q, q = i - r * Q;
+                    const float* sp = stage + r * RS + 4 * q;
+                    reinterpret_cast<float4*>(dst + (long long)r * ROWLEN + W * c0)[q] = make_float4(sp[0], sp[1], sp[2], sp[3]);
+                }
+            } else {
+                for (int i = lane; i < nrow * SEG; i += 32) {
+                    const int r = i / SEG, e = i - r * SEG;
+                    dst[(long long)r * ROWLEN + W * c0 + e] = stage[r * RS + e];
+                }
+            }
+            __syncwarp();
         }
-        for (int i = (n4 << 2) + lane; i < total; i += 32) dst[i] = at(i);
         // the 0..3 pad floats that round the utterance's run up to 16 bytes are zeroed (deterministic buffers)
+        const int total = nrow * ROWLEN;
         if (td.first_frame + nrow == td.utt_frames && lane < ((4 - (total & 3)) & 3)) dst[total + lane] = 0.f;
-        __syncwarp();
     }
 }
 
