@@ -57,6 +57,32 @@ SYMBOLS = {
     "fe_last_error": (C.c_char_p, [C.c_void_p]),
 }
 
+AIO_OK, AIO_ERR_INVALID, AIO_ERR_IO, AIO_ERR_FORMAT, AIO_ERR_UNSUPPORTED, AIO_ERR_CAPACITY = 0, -1, -2, -3, -4, -5
+AIO_FMT_FLAC, AIO_FMT_WAV = 1, 2
+
+
+class AioInfo(C.Structure):
+    _fields_ = [("format", C.c_int32), ("sample_rate", C.c_int32), ("channels", C.c_int32),
+                ("bits_per_sample", C.c_int32), ("n_samples", C.c_int64)]
+
+
+_cpp = C.POINTER(C.c_char_p)
+_infop = C.POINTER(AioInfo)
+# every symbol include/asr_audio_io.h declares (host-side FLAC / WAV ingest and egress)
+AIO_SYMBOLS = {
+    "aio_probe_memory": (C.c_int, [C.c_void_p, C.c_int64, _infop]),
+    "aio_probe_file": (C.c_int, [C.c_char_p, _infop]),
+    "aio_decode_memory": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, _i64p, C.c_int]),
+    "aio_decode_file": (C.c_int, [C.c_char_p, C.c_void_p, C.c_int64, _i64p, C.c_int]),
+    "aio_probe_files": (C.c_int, [_cpp, C.c_int32, C.c_int32, _infop, _i32p]),
+    "aio_decode_files": (C.c_int, [_cpp, C.c_int32, C.c_int32, C.c_void_p, _i64p, _i64p, C.c_int, _i32p]),
+    "aio_flac_bound": (C.c_int64, [C.c_int64, C.c_int32]),
+    "aio_encode_flac": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_int64, _i64p]),
+    "aio_write_file": (C.c_int, [C.c_char_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32]),
+    "aio_write_files": (C.c_int, [_cpp, C.c_int32, C.c_int32, C.c_void_p, _i64p, _i64p, C.c_int32, C.c_int32, _i32p]),
+    "aio_strerror": (C.c_char_p, [C.c_int]),
+}
+
 _lib = None
 
 
@@ -83,7 +109,7 @@ def load():
         lib = C.CDLL(path)
     except OSError as e:
         raise FrontendLibraryError("cannot load %s: %s (no CPU fallback)" % (path, e))
-    for name, (res, args) in SYMBOLS.items():
+    for name, (res, args) in list(SYMBOLS.items()) + list(AIO_SYMBOLS.items()):
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args

@@ -3,8 +3,11 @@
 
 Same arguments, same output naming (``{target_folder}_{speed}/{id}_{speed}.{ext}``,
 ``{target_folder}/{id}_{volume}.{ext}``), same skip-if-exists rule for speed; the
-SoX subprocess per file is replaced by one batched kernel call.  The resampler is
-the one defined in DESIGN.md (SoX's own ``rate`` internals are not restated)."""
+SoX subprocess per file is replaced by: native thread-pool decode of a batch of files
+into one packed int16 buffer (``aio_decode_files``), one batched kernel call
+(``fe_perturb``), native thread-pool encode of the results (``aio_write_files``; FLAC in,
+FLAC out like SoX).  The resampler is the one defined in DESIGN.md (SoX's own ``rate``
+internals are not restated)."""
 import os
 
 import numpy as np
@@ -41,11 +44,7 @@ def SpeedAugmentation(filelist, target_folder, speed, device=0):
         try:
             for b in range(0, len(todo), _BATCH_FILES):
                 chunk = todo[b:b + _BATCH_FILES]
-                loaded = [audio_io.read_audio(src) for src, _ in chunk]
-                pcm = [_as_int16(a) for a, _ in loaded]
-                out = fe.perturb(pcm, speeds=[speed] * len(pcm))
-                for (_, dst), y, (_, fs) in zip(chunk, out, loaded):
-                    audio_io.write_audio(dst, y, fs)
+                _perturb_files(fe, [s for s, _ in chunk], [d for _, d in chunk], speeds=[speed] * len(chunk))
         finally:
             fe.close()
     return audio_path
@@ -71,14 +70,26 @@ def VolumeAugmentation(filelist, target_folder, vol_range, device=0, rng=None):
         try:
             for b in range(0, len(jobs), _BATCH_FILES):
                 chunk = jobs[b:b + _BATCH_FILES]
-                loaded = [audio_io.read_audio(src) for src, _, _ in chunk]
-                pcm = [_as_int16(a) for a, _ in loaded]
-                out = fe.perturb(pcm, gains=[g for _, _, g in chunk])
-                for (_, dst, _), y, (_, fs) in zip(chunk, out, loaded):
-                    audio_io.write_audio(dst, y, fs)
+                _perturb_files(fe, [s for s, _, _ in chunk], [d for _, d, _ in chunk], gains=[g for _, _, g in chunk])
         finally:
             fe.close()
     return audio_path
+
+
+def _perturb_files(fe, srcs, dsts, speeds=None, gains=None, n_threads=0):
+    """files -> packed int16 -> fe_perturb -> files, without per-utterance arrays when the
+    container is FLAC / WAV."""
+    native = {os.path.splitext(p)[1].lower() for p in srcs + dsts} <= {".flac", ".wav"}
+    same_out = len({os.path.splitext(p)[1].lower() for p in dsts}) == 1
+    if native and same_out:
+        packed, off, lens, fs = audio_io.read_audio_batch(srcs, n_threads)
+        dst, d_off, d_len = fe.perturb_packed(packed, off, lens, speeds=speeds, gains=gains)
+        audio_io.write_audio_batch(dsts, dst, d_off[:len(srcs)], d_len, fs, n_threads)
+        return
+    loaded = [audio_io.read_audio(src) for src in srcs]
+    out = fe.perturb([_as_int16(a) for a, _ in loaded], speeds=speeds, gains=gains)
+    for dst, y, (_, fs) in zip(dsts, out, loaded):
+        audio_io.write_audio(dst, y, fs)
 
 
 def _as_int16(a):

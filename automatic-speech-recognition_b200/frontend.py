@@ -295,29 +295,40 @@ class Frontend:
         out, out_off, nfr = self.run_packed(packed, off, lens, self.speed_indices(speeds), gains)
         return self.split(out, out_off, nfr, copy=copy)
 
-    def perturb(self, pcm_list, speeds=None, gains=None):
-        """Speed / volume perturbation only: int16 in -> list of int16 arrays."""
-        if len(pcm_list) == 0:
-            return []
-        packed, off, lens = pack_pcm(pcm_list, np.int16)
+    def perturb_packed(self, packed, off, lens, speeds=None, gains=None):
+        """Speed / volume perturbation of a packed int16 batch (host in, host out).
+        Returns (dst, dst_offsets[n + 1], dst_lengths[n]); utterance i is
+        dst[dst_offsets[i] : dst_offsets[i] + dst_lengths[i]], starts 16-byte aligned."""
+        packed = np.ascontiguousarray(packed, dtype=np.int16)
+        off = np.ascontiguousarray(off, dtype=np.int64)
+        lens = np.ascontiguousarray(lens, dtype=np.int64)
         n = lens.size
         sp = self.speed_indices(speeds)
         gn = None if gains is None else np.ascontiguousarray(gains, dtype=np.float32)
+        by_index = {v: k for k, v in self._speed_index.items()}
         cap = 0
         for i in range(n):
             m = int(lens[i])
             if sp is not None and sp[i] >= 0:
-                m = tables.resampled_length(m, [k for k, v in self._speed_index.items() if v == sp[i]][0])
+                m = tables.resampled_length(m, by_index[int(sp[i])])
             cap += (m + 7) // 8 * 8
         dst = np.zeros(max(cap, 8), dtype=np.int16)
         d_off = np.zeros(n + 1, dtype=np.int64)
-        d_len = np.zeros(n, dtype=np.int64)
+        d_len = np.zeros(max(n, 1), dtype=np.int64)
         self._check(self._lib.fe_perturb(
             self._h, C.c_void_p(packed.ctypes.data), _ptr(off, C.c_int64), _ptr(lens, C.c_int64), n,
             None if sp is None else _ptr(sp, C.c_int32), None if gn is None else _ptr(gn, C.c_float),
             C.c_void_p(dst.ctypes.data), dst.size, _ptr(d_off, C.c_int64), _ptr(d_len, C.c_int64), None),
             "fe_perturb")
-        return [dst[int(d_off[i]):int(d_off[i]) + int(d_len[i])].copy() for i in range(n)]
+        return dst, d_off, d_len[:n]
+
+    def perturb(self, pcm_list, speeds=None, gains=None):
+        """Speed / volume perturbation only: int16 in -> list of int16 arrays."""
+        if len(pcm_list) == 0:
+            return []
+        packed, off, lens = pack_pcm(pcm_list, np.int16)
+        dst, d_off, d_len = self.perturb_packed(packed, off, lens, speeds, gains)
+        return [dst[int(d_off[i]):int(d_off[i]) + int(d_len[i])].copy() for i in range(lens.size)]
 
     def postprocess(self, mats, mean=True, var=True, deltas=True, delta_mode=None):
         """CMVN and/or delta cube for a list of (L, D) float matrices (host in, host out):

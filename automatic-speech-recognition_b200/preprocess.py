@@ -73,19 +73,64 @@ def process_pcm(pcm_list, args, fs=16000, device=0, speeds=None, gains=None, **s
     return to_object_array(cubes), featlen
 
 
-def process_audios(audio_path, args, device=0, **switches):
-    """Same signature and return value as the reference (preprocess.py:50-91)."""
-    pcm_list, fs_seen = [], None
-    for p in audio_path:
-        audio, fs = audio_io.read_audio(p)
-        if fs_seen is None:
-            fs_seen = fs
-        elif fs != fs_seen:
-            raise ValueError("mixed sample rates in one call: %d vs %d (%s)" % (fs_seen, fs, p))
-        pcm_list.append(audio)
-    if not pcm_list:
+def _plan_file_batches(lengths, limit=_BATCH_SAMPLES):
+    """Consecutive [start, stop) ranges of at most ~limit samples each (at least one file)."""
+    ranges, start, acc = [], 0, 0
+    for i, n in enumerate(lengths):
+        acc += int(n)
+        if acc >= limit or i == len(lengths) - 1:
+            ranges.append((start, i + 1))
+            start, acc = i + 1, 0
+    return ranges
+
+
+def process_audios(audio_path, args, device=0, n_threads=0, **switches):
+    """Same signature and return value as the reference (preprocess.py:50-91).
+
+    FLAC / WAV lists take the batch path: headers are probed once, then each ~1-audio-hour
+    batch is decoded by the native thread pool straight into a packed int16 buffer
+    (``aio_decode_files``) while the GPU works on the previous batch, and handed to ``fe_run``
+    as is -- no per-utterance array exists between the file and the device."""
+    audio_path = list(audio_path)
+    if not audio_path:
         return to_object_array([]), []
-    return process_pcm(pcm_list, args, fs=fs_seen, device=device, **switches)
+    exts = {os.path.splitext(p)[1].lower() for p in audio_path}
+    if not exts <= {".flac", ".wav"}:
+        pcm_list, fs_seen = [], None
+        for p in audio_path:
+            audio, fs = audio_io.read_audio(p)
+            if fs_seen is None:
+                fs_seen = fs
+            elif fs != fs_seen:
+                raise ValueError("mixed sample rates in one call: %d vs %d (%s)" % (fs_seen, fs, p))
+            pcm_list.append(audio)
+        return process_pcm(pcm_list, args, fs=fs_seen, device=device, **switches)
+
+    from concurrent.futures import ThreadPoolExecutor
+    infos = [audio_io.probe(p) for p in audio_path] if len(audio_path) < 64 else audio_io.probe_batch(audio_path, n_threads)
+    fs = infos[0]["sample_rate"]
+    cfg = FrontendConfig.from_args(args, sample_rate=fs, pcm_dtype="int16", **switches)
+    fe = get_frontend(cfg, device)
+    for p, inf in zip(audio_path, infos):
+        if inf["channels"] != 1:
+            raise ValueError("%s: mono audio expected" % p)
+        if 0 <= inf["n_samples"] < cfg.frame_len:
+            raise ValueError("negative dimensions are not allowed")      # what speechpy's stack_frames raises
+    ranges = _plan_file_batches([max(inf["n_samples"], 0) for inf in infos])
+    cubes, featlen = [], []
+    with ThreadPoolExecutor(max_workers=1) as pool:
+        nxt = pool.submit(audio_io.read_audio_batch, audio_path[ranges[0][0]:ranges[0][1]], n_threads)
+        for b, (lo, hi) in enumerate(ranges):
+            packed, off, lens, fs_b = nxt.result()
+            if b + 1 < len(ranges):
+                nxt = pool.submit(audio_io.read_audio_batch, audio_path[ranges[b + 1][0]:ranges[b + 1][1]], n_threads)
+            if fs_b != fs:
+                raise ValueError("mixed sample rates in one call: %d vs %d" % (fs, fs_b))
+            out, out_off, nfr = fe.run_packed(packed, off, lens)
+            got = fe.split(out, out_off, nfr)
+            cubes.extend(got)
+            featlen.extend(int(L) for L in nfr)
+    return to_object_array(cubes), featlen
 
 
 def process_libri_feats(audio_path, cat, k, args, device=0, **switches):

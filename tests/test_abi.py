@@ -9,10 +9,10 @@ import pytest
 from conftest import ROOT, PKG, _has_gpu
 
 
-def header_symbols():
-    txt = open(os.path.join(ROOT, "include", "asr_frontend.h")).read()
+def header_symbols(header="asr_frontend.h", prefix="fe_"):
+    txt = open(os.path.join(ROOT, "include", header)).read()
     txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
-    return sorted(set(re.findall(r"\b(fe_[a-z_0-9]+)\s*\(", txt)))
+    return sorted(set(re.findall(r"\b(%s[a-z_0-9]+)\s*\(" % prefix, txt)))
 
 
 def test_library_exports_every_declared_symbol(pkg):
@@ -24,6 +24,12 @@ def test_library_exports_every_declared_symbol(pkg):
         assert hasattr(lib, n), "missing export %s" % n
     assert sorted(_lib.SYMBOLS) == names, "ctypes table and header disagree"
     assert _lib.load().fe_abi_version() == _lib.FE_ABI_VERSION
+    aio = header_symbols("asr_audio_io.h", "aio_")
+    assert len(aio) >= 10
+    for n in aio:
+        assert hasattr(lib, n), "missing export %s" % n
+    assert sorted(_lib.AIO_SYMBOLS) == aio, "ctypes table and asr_audio_io.h disagree"
+    assert ctypes.sizeof(_lib.AioInfo) == 24
 
 
 def test_pure_host_entry_points(pkg, golden):

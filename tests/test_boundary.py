@@ -60,16 +60,22 @@ def test_augmentation_file_interface(pkg, sox, tmp_path, monkeypatch):
                 return [sox.speed_perturb(p, s) for p, s in zip(pcm, speeds)]
             return [sox.volume_perturb(p, g) for p, g in zip(pcm, gains)]
 
+        def perturb_packed(self, packed, off, lens, speeds=None, gains=None):
+            ys = self.perturb([packed[o:o + n] for o, n in zip(off, lens)], speeds, gains)
+            fr = importlib.import_module(PKG + ".frontend")
+            dst, d_off, d_len = fr.pack_pcm(ys)
+            return dst, np.concatenate((d_off, [dst.size])), d_len
+
         def close(self):
             pass
     monkeypatch.setattr(aug, "_frontend", lambda speed=None, device=0: Fake())
     src = []
     for i, x in enumerate(pkg.synth.corpus(2, 0.2, 0.3, seed=2)):
-        p = str(tmp_path / ("1-2-%04d.wav" % i))
+        p = str(tmp_path / ("1-2-%04d.flac" % i))
         pkg.audio_io.write_audio(p, x, 16000)
         src.append(p)
     out = aug.SpeedAugmentation(src, str(tmp_path / "LibriSpeech_speed_aug"), 0.9)
-    assert out == [str(tmp_path / "LibriSpeech_speed_aug_0.9" / ("1-2-%04d_0.9.wav" % i)) for i in range(2)]
+    assert out == [str(tmp_path / "LibriSpeech_speed_aug_0.9" / ("1-2-%04d_0.9.flac" % i)) for i in range(2)]
     y, _ = pkg.audio_io.read_audio(out[0])
     x, _ = pkg.audio_io.read_audio(src[0])
     assert len(y) == -(-len(x) * 10 // 9)
@@ -77,7 +83,7 @@ def test_augmentation_file_interface(pkg, sox, tmp_path, monkeypatch):
     aug.SpeedAugmentation(src, str(tmp_path / "LibriSpeech_speed_aug"), 0.9)          # existing files are skipped
     assert os.path.getmtime(out[0]) == 1
     vout = aug.VolumeAugmentation(src, str(tmp_path / "vol"), [0.8, 1.5], rng=np.random.default_rng(3))
-    g = float(os.path.basename(vout[0]).rsplit("_", 1)[1][:-4])
+    g = float(os.path.basename(vout[0]).rsplit("_", 1)[1][:-5])
     assert 0.8 <= g <= 1.5 and round(g, 2) == g
     assert np.array_equal(pkg.audio_io.read_audio(vout[0])[0], sox.volume_perturb(x, g))
 

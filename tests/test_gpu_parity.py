@@ -3,10 +3,13 @@ oracle on the same seeded inputs (sizes the oracle finishes in seconds), against
 vectors, and -- at BASELINE.json's full sizes -- through size-independent properties.
 
 Tolerance (BASELINE.json north_star): frame counts bit-exact; features max-abs <= 1e-3 OR rel <= 1e-4."""
+import importlib
+import os
+
 import numpy as np
 import pytest
 
-from conftest import assert_close, make_args
+from conftest import PKG, assert_close, make_args
 
 pytestmark = pytest.mark.gpu
 
@@ -195,18 +198,50 @@ def test_speechpy_shims(pkg, ref, corpus1):
         sp.mfcc(x, 16000)                                              # speechpy default 20 ms frames: unsupported
 
 
-def test_process_audios_files_and_pickles(pkg, ref, tmp_path, corpus1, args):
+def test_process_audios_files_and_pickles(pkg, ref, tmp_path, corpus1, args, monkeypatch):
     paths = []
     for i, p in enumerate(corpus1[:4]):
-        path = str(tmp_path / ("utt%d.wav" % i))
+        path = str(tmp_path / ("utt%d.%s" % (i, "flac" if i % 2 == 0 else "wav")))   # LibriSpeech ships FLAC
         pkg.audio_io.write_audio(path, p, 16000)
         paths.append(path)
     feats, featlen = pkg.process_audios(paths, args)                   # the reference signature
     for a, p in zip(feats, corpus1):
         assert_close(a, ref.features_one(p), what="process_audios")
+    monkeypatch.setattr(importlib.import_module(PKG + ".preprocess"), "_BATCH_SAMPLES", 200_000)
+    feats2, featlen2 = pkg.process_audios(paths, args)                 # several decode batches, prefetch thread
+    assert featlen2 == featlen and all(np.array_equal(a, b) for a, b in zip(feats, feats2))
+    short = str(tmp_path / "short.flac")
+    pkg.audio_io.write_audio(short, np.zeros(399, np.int16), 16000)
+    with pytest.raises(ValueError, match="negative dimensions"):
+        pkg.process_audios(paths[:1] + [short], args)
     import joblib
     args.feat_dir = str(tmp_path / "feats")
     pkg.process_libri_feats(paths, "dev", 1, args)
     back = joblib.load(args.feat_dir + "/dev-feats.pkl")
     assert all(np.array_equal(a, b) for a, b in zip(back, feats))
     assert np.load(args.feat_dir + "/dev-featlen.npy").tolist() == featlen
+
+
+@pytest.mark.gpu
+def test_augmentation_files_flac_in_flac_out(pkg, sox, tmp_path):
+    """utils/augmentation.py:6-31, 33-56 end to end on FLAC files: native decode -> fe_perturb -> native encode."""
+    aug = importlib.import_module(PKG + ".augmentation")
+    pcm = pkg.synth.corpus(3, 0.5, 1.5, seed=21)
+    src = []
+    for i, x in enumerate(pcm):
+        p = str(tmp_path / ("103-1240-%04d.flac" % i))
+        pkg.audio_io.write_audio(p, x, 16000)
+        src.append(p)
+    for speed in (0.9, 1.1):
+        out = aug.SpeedAugmentation(src, str(tmp_path / "LibriSpeech_speed_aug"), speed)
+        assert out == [str(tmp_path / ("LibriSpeech_speed_aug_%s" % speed) / ("103-1240-%04d_%s.flac" % (i, speed)))
+                       for i in range(3)]
+        for x, p in zip(pcm, out):
+            y, fs = pkg.audio_io.read_audio(p)
+            want = sox.speed_perturb(x, speed)
+            assert fs == 16000 and y.shape == want.shape
+            assert np.abs(y.astype(np.int32) - want.astype(np.int32)).max() <= 1       # float32 taps vs float64 oracle
+    vout = aug.VolumeAugmentation(src, str(tmp_path / "vol"), [0.8, 1.5], rng=np.random.default_rng(3))
+    for x, p in zip(pcm, vout):
+        g = float(os.path.basename(p).rsplit("_", 1)[1][:-5])
+        assert np.array_equal(pkg.audio_io.read_audio(p)[0], sox.volume_perturb(x, g))
