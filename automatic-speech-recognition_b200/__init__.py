@@ -8,7 +8,9 @@ from .frontend import Frontend, FrontendConfig, pack_pcm, num_frames   # noqa: F
 from .preprocess import process_audios, process_pcm, process_libri_feats, to_object_array  # noqa: F401
 from .augmentation import SpeedAugmentation, VolumeAugmentation        # noqa: F401
 from . import speechpy_shim                                            # noqa: F401
+from . import tfrecord                                                 # noqa: F401  (create_tfrecord.py drop-in)
+from .tfrecord import create_tfrecords                                 # noqa: F401
 
 __all__ = ["Frontend", "FrontendConfig", "pack_pcm", "num_frames", "process_audios", "process_pcm",
            "process_libri_feats", "to_object_array", "SpeedAugmentation", "VolumeAugmentation",
-           "tables", "synth", "sharding", "audio_io", "speechpy_shim", "FrontendLibraryError", "library_path"]
+           "tables", "synth", "sharding", "audio_io", "speechpy_shim", "tfrecord", "create_tfrecords", "FrontendLibraryError", "library_path"]

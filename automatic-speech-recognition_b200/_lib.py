@@ -83,6 +83,22 @@ AIO_SYMBOLS = {
     "aio_strerror": (C.c_char_p, [C.c_int]),
 }
 
+RIO_OK, RIO_ERR_INVALID, RIO_ERR_IO, RIO_ERR_FORMAT, RIO_ERR_CAPACITY = 0, -1, -2, -3, -4
+# every symbol include/asr_record_io.h declares (TFRecord / tf.train.Example writer and reader)
+RIO_SYMBOLS = {
+    "rio_crc32c": (C.c_uint32, [C.c_void_p, C.c_int64]),
+    "rio_masked_crc32c": (C.c_uint32, [C.c_void_p, C.c_int64]),
+    "rio_example_size": (C.c_int64, [C.c_int64, _i64p, C.c_int32, _i64p, C.c_int64]),
+    "rio_example_serialize": (C.c_int, [C.c_void_p, C.c_int64, _i64p, C.c_int32, _i64p, C.c_int64, C.c_void_p, C.c_int64, _i64p]),
+    "rio_write_tfrecord": (C.c_int, [C.c_char_p, C.c_int32, C.c_void_p, _i64p, _i32p, C.c_int32, C.c_int32,
+                                     _i64p, _i64p, _i32p]),
+    "rio_write_tfrecords": (C.c_int, [_cpp, C.c_int32, _i32p, C.c_int32, C.c_void_p, _i64p, _i32p, C.c_int32, C.c_int32,
+                                      _i64p, _i64p, _i32p, _i32p]),
+    "rio_index_tfrecord": (C.c_int64, [C.c_char_p, C.c_int64, _i64p, _i64p, _i64p]),
+    "rio_read_tfrecord": (C.c_int, [C.c_char_p, C.c_int64, C.c_void_p, _i64p, _i64p, _i64p]),
+    "rio_strerror": (C.c_char_p, [C.c_int]),
+}
+
 _lib = None
 
 
@@ -109,7 +125,7 @@ def load():
         lib = C.CDLL(path)
     except OSError as e:
         raise FrontendLibraryError("cannot load %s: %s (no CPU fallback)" % (path, e))
-    for name, (res, args) in list(SYMBOLS.items()) + list(AIO_SYMBOLS.items()):
+    for name, (res, args) in list(SYMBOLS.items()) + list(AIO_SYMBOLS.items()) + list(RIO_SYMBOLS.items()):
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args

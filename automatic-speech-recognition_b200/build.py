@@ -7,9 +7,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_NAME = "libasr_frontend.so"
 LIB_PATH = os.path.join(HERE, LIB_NAME)
-SOURCES = ["fe_api.cu", "audio_codec.cpp"]
+SOURCES = ["fe_api.cu", "audio_codec.cpp", "record_io.cpp"]
 HEADERS = ["fe_core.cuh", "fe_kernels.cuh", os.path.join("..", "..", "include", "asr_frontend.h"),
-           os.path.join("..", "..", "include", "asr_audio_io.h")]
+           os.path.join("..", "..", "include", "asr_audio_io.h"), os.path.join("..", "..", "include", "asr_record_io.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

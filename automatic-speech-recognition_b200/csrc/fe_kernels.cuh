@@ -889,8 +889,17 @@ k_resample(const short* __restrict__ pcm, const UttDesc* __restrict__ utts,
 // (lane = group): the 32 taps are warp-uniform loads, and a thread computes the R = 5 outputs j, j + UP, ...
 // of its group that share them (input windows shifted by DOWN -> a union of 4 DOWN + 32 samples).  The
 // lane stride of the window reads is R x DOWN = 45 / 55 words (odd: bank-conflict free).  Same summation order
-// per output as k_resample (bit-identical results).  Utterances of other ratios (and gain-only ones) in the
-// same batch are skipped here and served by k_resample, which skips these ratios in turn.
+// per output as k_resample (bit-identical results).
+// Staging: the span is fetched as 16-byte vectors (8 int16 samples, one vector per thread: the span is at most
+// 226 vectors), one tile AHEAD of the arithmetic -- the vector for tile i + 1 is in flight in a register while
+// tile i is computed -- so the HBM latency of the descriptor -> sample chain is off the critical path.
+struct K0Stage {
+    uint4 v;            // 8 samples: utterance indices [n0, n0 + 8)
+    long long n0;
+    int n_src;
+    bool live;
+};
+
 template <int UP, int DOWN>
 __global__ void __launch_bounds__(UP * 32)
 k_resample_fast(const short* __restrict__ pcm, const UttDesc* __restrict__ utts,
@@ -901,31 +910,68 @@ k_resample_fast(const short* __restrict__ pcm, const UttDesc* __restrict__ utts,
     static_assert(R * 32 * UP == kK0Outputs, "tile = 32 groups of R x UP outputs");
     static_assert(((R * DOWN) & 1) == 1, "odd lane stride");
     constexpr int SPAN = (kK0Outputs * DOWN + UP - 1) / UP + 34;            // input samples a tile can touch
-    __shared__ float xs[SPAN];
+    constexpr int NV = (SPAN + 7 + 7) / 8;                                   // 16-byte vectors covering it from an aligned start
+    static_assert(NV <= UP * 32, "one staging vector per thread");
+    __shared__ __align__(16) float xs[NV * 8];
     __shared__ float tps[UP * 32];
     __shared__ __align__(16) short ys[kK0Outputs];
     const int tid = threadIdx.x;
     const int p = tid >> 5, g = tid & 31;
+    int taps_of = -1;                                                        // speed index whose taps are in tps
+
+    // issue the staging load of a tile (nothing is waited for here)
+    auto fetch = [&](int tile, K0Stage& sg, int2& te, UttDesc& u) {
+        sg.live = false;
+        if (tile >= n_atiles) return;
+        te = atiles[tile];
+        u = utts[te.x];
+        const long long first = (long long)te.y * DOWN / UP - 15;          // first input sample of the tile
+        const long long a0 = first & ~7LL;                                   // aligned down (two's complement: also for first < 0)
+        sg.n0 = a0 + 8LL * tid;
+        sg.n_src = u.n_src;
+        sg.v = make_uint4(0u, 0u, 0u, 0u);
+        if (tid < NV && sg.n0 + 8 > 0 && sg.n0 < u.n_src) {                  // at least one valid sample: the vector lies inside the buffer
+            sg.v = __ldg(reinterpret_cast<const uint4*>(pcm + u.src_off + sg.n0));
+            sg.live = true;
+        }
+    };
+
+    K0Stage sg;
+    int2 te_n = make_int2(0, 0);
+    UttDesc u_n;
+    fetch(blockIdx.x, sg, te_n, u_n);
     for (int tile = blockIdx.x; tile < n_atiles; tile += gridDim.x) {
-        const int2 te = atiles[tile];
-        const UttDesc u = utts[te.x];
-        if (u.speed_idx < 0 || sp_up[u.speed_idx] != UP || sp_down[u.speed_idx] != DOWN) continue;   // block-uniform
-        const short* x = pcm + u.src_off;
+        const int2 te = te_n;
+        const UttDesc u = u_n;
         short* y = dst + (use_dst_off ? u.out_off : u.pcm_off) + te.y;
         const int nout = min(kK0Outputs, u.n_samples - te.y);
-        const long long first = (long long)te.y * DOWN / UP - 15;          // input index of xs[0]
-        __syncthreads();                                                     // previous tile's readers are done
-        for (int i = tid; i < SPAN; i += blockDim.x) {
-            const long long n = first + i;
-            xs[i] = (n >= 0 && n < u.n_src) ? (float)__ldg(x + n) : 0.f;
+        const long long first = (long long)te.y * DOWN / UP - 15;
+        const long long a0 = first & ~7LL;
+        __syncthreads();                                                     // previous tile's readers of xs / ys are done
+        if (tid < NV) {                                                      // int16 -> float, samples off the ends are zero
+            const unsigned w[4] = {sg.v.x, sg.v.y, sg.v.z, sg.v.w};
+            float f[8];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const long long n = sg.n0 + 2 * q;
+                const bool ok0 = sg.live && n >= 0 && n < sg.n_src, ok1 = sg.live && n + 1 >= 0 && n + 1 < sg.n_src;
+                f[2 * q] = ok0 ? (float)(short)(w[q] & 0xffffu) : 0.f;
+                f[2 * q + 1] = ok1 ? (float)(short)(w[q] >> 16) : 0.f;
+            }
+            reinterpret_cast<float4*>(xs)[2 * tid] = make_float4(f[0], f[1], f[2], f[3]);
+            reinterpret_cast<float4*>(xs)[2 * tid + 1] = make_float4(f[4], f[5], f[6], f[7]);
         }
-        const float* taps = taps_all + sp_tap_off[u.speed_idx];
-        for (int i = tid; i < UP * 32; i += blockDim.x) tps[i] = taps[i];
+        if (taps_of != u.speed_idx) {                                        // block-uniform
+            const float* taps = taps_all + sp_tap_off[u.speed_idx];
+            for (int i = tid; i < UP * 32; i += blockDim.x) tps[i] = taps[i];
+            taps_of = u.speed_idx;
+        }
         __syncthreads();
+        fetch(tile + gridDim.x, sg, te_n, u_n);                              // next tile's samples fly during the arithmetic
         const int jl = g * (R * UP) + p;                                     // first of this thread's R outputs (tile-local)
         const long long pos = ((long long)te.y + jl) * DOWN;
         const int ph = (int)(pos % UP);                                      // the same for the whole warp
-        const int b0 = (int)(pos / UP - 15 - first);                        // xs index of the first window
+        const int b0 = (int)(pos / UP - 15 - a0);                           // xs index of the first window
         float acc[R];
 #pragma unroll
         for (int m = 0; m < R; ++m) acc[m] = 0.f;

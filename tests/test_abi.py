@@ -30,6 +30,11 @@ def test_library_exports_every_declared_symbol(pkg):
         assert hasattr(lib, n), "missing export %s" % n
     assert sorted(_lib.AIO_SYMBOLS) == aio, "ctypes table and asr_audio_io.h disagree"
     assert ctypes.sizeof(_lib.AioInfo) == 24
+    rio = header_symbols("asr_record_io.h", "rio_")
+    assert len(rio) >= 9
+    for n in rio:
+        assert hasattr(lib, n), "missing export %s" % n
+    assert sorted(_lib.RIO_SYMBOLS) == rio, "ctypes table and asr_record_io.h disagree"
 
 
 def test_pure_host_entry_points(pkg, golden):
