@@ -841,7 +841,7 @@ k_cube_local(const TileDesc* __restrict__ tiles, int n_tiles, const float* __res
 // x = 0 off the ends, int16 in -> (* gain) -> round-half-even, saturate -> int16 out.
 // speed_idx < 0: gain only.
 // ---------------------------------------------------------------------------
-constexpr int kK0Outputs = 1600;        // outputs per K0 tile: 32 groups of 5 x up (up = 10) same-phase outputs
+constexpr int kK0Outputs = 2880;        // outputs per K0 tile: 32 groups of 9 x up (up = 10) same-phase outputs
 
 __global__ void __launch_bounds__(256)
 k_resample(const short* __restrict__ pcm, const UttDesc* __restrict__ utts,
@@ -886,22 +886,30 @@ k_resample(const short* __restrict__ pcm, const UttDesc* __restrict__ utts,
 
 // K0, fast path for a compile-time ratio (the reference's speeds 0.9 / 1.1 -> 10/9, 10/11): the tile's input span
 // and the polyphase taps sit in shared memory.  Warp p serves phase p of the tile's 32 groups of R x UP outputs
-// (lane = group): the 32 taps are warp-uniform loads, and a thread computes the R = 5 outputs j, j + UP, ...
-// of its group that share them (input windows shifted by DOWN -> a union of 4 DOWN + 32 samples).  The
-// lane stride of the window reads is R x DOWN = 45 / 55 words (odd: bank-conflict free).  Same summation order
+// (lane = group): the 32 taps are warp-uniform loads, and a thread computes the R = 9 outputs j, j + UP, ...
+// of its group that share them (input windows shifted by DOWN -> a union of 8 DOWN + 32 samples: 0.36 shared-
+// memory loads per FMA).  The lane stride of the window reads is R x DOWN = 81 / 99 words (odd: bank-conflict free).  Same summation order
 // per output as k_resample (bit-identical results).
-// Staging: the span is fetched as 16-byte vectors (8 int16 samples, one vector per thread: the span is at most
-// 226 vectors), one tile AHEAD of the arithmetic -- the vector for tile i + 1 is in flight in a register while
-// tile i is computed -- so the HBM latency of the descriptor -> sample chain is off the critical path.
+// Staging: the span is fetched as 16-byte vectors (8 int16 samples, at most two vectors per thread), one tile
+// AHEAD of the arithmetic -- the vectors for tile i + 1 are in flight in registers while tile i is computed --
+// so the HBM latency of the descriptor -> sample chain is off the critical path.  Tiles start at multiples of
+// kK0Outputs, i.e. at phase 0 and at a whole number of input samples: all index math is 32-bit, no division.
+template <int VPT>
 struct K0Stage {
-    uint4 v;            // 8 samples: utterance indices [n0, n0 + 8)
-    long long n0;
+    uint4 v[VPT];       // vector q holds 8 samples: utterance indices [n0 + 8 q THREADS, + 8)
+    int n0;
     int n_src;
-    bool live;
 };
 
+// float -> int16, round half to even, saturating: one F2I instead of rint + min + max + cast (same result; NaN -> 0)
+__device__ __forceinline__ short f2s16_rn_sat(float a) {
+    short r;
+    asm("cvt.rni.sat.s16.f32 %0, %1;" : "=h"(r) : "f"(a));
+    return r;
+}
+
 template <int UP, int DOWN>
-__global__ void __launch_bounds__(UP * 32)
+__global__ void __launch_bounds__(UP * 32, 3)
 k_resample_fast(const short* __restrict__ pcm, const UttDesc* __restrict__ utts,
                 const int2* __restrict__ atiles, int n_atiles,
                 const int* __restrict__ sp_up, const int* __restrict__ sp_down, const int* __restrict__ sp_tap_off,
@@ -911,32 +919,36 @@ k_resample_fast(const short* __restrict__ pcm, const UttDesc* __restrict__ utts,
     static_assert(((R * DOWN) & 1) == 1, "odd lane stride");
     constexpr int SPAN = (kK0Outputs * DOWN + UP - 1) / UP + 34;            // input samples a tile can touch
     constexpr int NV = (SPAN + 7 + 7) / 8;                                   // 16-byte vectors covering it from an aligned start
-    static_assert(NV <= UP * 32, "one staging vector per thread");
-    __shared__ __align__(16) float xs[NV * 8];
+    constexpr int THREADS = UP * 32, VPT = (NV + THREADS - 1) / THREADS;
+    constexpr int TILE_IN = kK0Outputs * DOWN / UP;                           // input samples a tile advances by (tiles start at
+    static_assert(TILE_IN * UP == kK0Outputs * DOWN, "tile starts are phase 0");   // multiples of kK0Outputs: 32-bit index math)
+    static_assert(kK0Outputs % 8 == 0, "16-byte aligned output tiles");
+    __shared__ __align__(16) float xs[VPT * THREADS * 8];
     __shared__ float tps[UP * 32];
     __shared__ __align__(16) short ys[kK0Outputs];
     const int tid = threadIdx.x;
     const int p = tid >> 5, g = tid & 31;
     int taps_of = -1;                                                        // speed index whose taps are in tps
 
-    // issue the staging load of a tile (nothing is waited for here)
-    auto fetch = [&](int tile, K0Stage& sg, int2& te, UttDesc& u) {
-        sg.live = false;
+    // issue the staging loads of a tile (nothing is waited for here)
+    auto fetch = [&](int tile, K0Stage<VPT>& sg, int2& te, UttDesc& u) {
         if (tile >= n_atiles) return;
         te = atiles[tile];
         u = utts[te.x];
-        const long long first = (long long)te.y * DOWN / UP - 15;          // first input sample of the tile
-        const long long a0 = first & ~7LL;                                   // aligned down (two's complement: also for first < 0)
-        sg.n0 = a0 + 8LL * tid;
+        const int first = (te.y / kK0Outputs) * TILE_IN - 15;               // first input sample of the tile
+        const int a0 = first & ~7;                                           // aligned down (two's complement: also for first < 0)
+        sg.n0 = a0 + 8 * tid;
         sg.n_src = u.n_src;
-        sg.v = make_uint4(0u, 0u, 0u, 0u);
-        if (tid < NV && sg.n0 + 8 > 0 && sg.n0 < u.n_src) {                  // at least one valid sample: the vector lies inside the buffer
-            sg.v = __ldg(reinterpret_cast<const uint4*>(pcm + u.src_off + sg.n0));
-            sg.live = true;
+#pragma unroll
+        for (int q = 0; q < VPT; ++q) {
+            const int n = sg.n0 + q * (8 * THREADS);
+            sg.v[q] = make_uint4(0u, 0u, 0u, 0u);
+            if (tid + q * THREADS < NV && n >= 0 && n < u.n_src)             // >= 1 valid sample: the vector lies inside the buffer
+                sg.v[q] = __ldg(reinterpret_cast<const uint4*>(pcm + u.src_off + n));
         }
     };
 
-    K0Stage sg;
+    K0Stage<VPT> sg;
     int2 te_n = make_int2(0, 0);
     UttDesc u_n;
     fetch(blockIdx.x, sg, te_n, u_n);
@@ -945,21 +957,28 @@ k_resample_fast(const short* __restrict__ pcm, const UttDesc* __restrict__ utts,
         const UttDesc u = u_n;
         short* y = dst + (use_dst_off ? u.out_off : u.pcm_off) + te.y;
         const int nout = min(kK0Outputs, u.n_samples - te.y);
-        const long long first = (long long)te.y * DOWN / UP - 15;
-        const long long a0 = first & ~7LL;
+        const int first = (te.y / kK0Outputs) * TILE_IN - 15;
+        const int a0 = first & ~7;
         __syncthreads();                                                     // previous tile's readers of xs / ys are done
-        if (tid < NV) {                                                      // int16 -> float, samples off the ends are zero
-            const unsigned w[4] = {sg.v.x, sg.v.y, sg.v.z, sg.v.w};
-            float f[8];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const long long n = sg.n0 + 2 * q;
-                const bool ok0 = sg.live && n >= 0 && n < sg.n_src, ok1 = sg.live && n + 1 >= 0 && n + 1 < sg.n_src;
-                f[2 * q] = ok0 ? (float)(short)(w[q] & 0xffffu) : 0.f;
-                f[2 * q + 1] = ok1 ? (float)(short)(w[q] >> 16) : 0.f;
+        for (int qv = 0; qv < VPT; ++qv) {                                   // int16 -> float, samples off the ends are zero
+            const int vi = tid + qv * THREADS;
+            if (vi < NV) {
+                const unsigned w[4] = {sg.v[qv].x, sg.v[qv].y, sg.v[qv].z, sg.v[qv].w};
+                const int nb = sg.n0 + qv * (8 * THREADS);
+                float f[8];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {                                 // zeros were loaded for dead vectors (n < 0 or n >= n_src)
+                    f[2 * q] = (float)(short)(w[q] & 0xffffu);
+                    f[2 * q + 1] = (float)(short)(w[q] >> 16);
+                }
+                if (nb + 8 > sg.n_src) {                                      // the vector straddles the utterance's end
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) f[q] = (nb + q < sg.n_src) ? f[q] : 0.f;
+                }
+                reinterpret_cast<float4*>(xs)[2 * vi] = make_float4(f[0], f[1], f[2], f[3]);
+                reinterpret_cast<float4*>(xs)[2 * vi + 1] = make_float4(f[4], f[5], f[6], f[7]);
             }
-            reinterpret_cast<float4*>(xs)[2 * tid] = make_float4(f[0], f[1], f[2], f[3]);
-            reinterpret_cast<float4*>(xs)[2 * tid + 1] = make_float4(f[4], f[5], f[6], f[7]);
         }
         if (taps_of != u.speed_idx) {                                        // block-uniform
             const float* taps = taps_all + sp_tap_off[u.speed_idx];
@@ -969,9 +988,8 @@ k_resample_fast(const short* __restrict__ pcm, const UttDesc* __restrict__ utts,
         __syncthreads();
         fetch(tile + gridDim.x, sg, te_n, u_n);                              // next tile's samples fly during the arithmetic
         const int jl = g * (R * UP) + p;                                     // first of this thread's R outputs (tile-local)
-        const long long pos = ((long long)te.y + jl) * DOWN;
-        const int ph = (int)(pos % UP);                                      // the same for the whole warp
-        const int b0 = (int)(pos / UP - 15 - a0);                           // xs index of the first window
+        const int ph = (p * DOWN) % UP;                                      // phase of output jl: the same for the whole warp
+        const int b0 = g * (R * DOWN) + (p * DOWN) / UP + (first - a0);      // xs index of the first window
         float acc[R];
 #pragma unroll
         for (int m = 0; m < R; ++m) acc[m] = 0.f;
@@ -985,13 +1003,9 @@ k_resample_fast(const short* __restrict__ pcm, const UttDesc* __restrict__ utts,
             }
         }
 #pragma unroll
-        for (int m = 0; m < R; ++m) {
-            float a = acc[m];
-            if (u.gain != 1.f) a *= u.gain;
-            ys[jl + m * UP] = (short)fminf(fmaxf(rintf(a), -32768.f), 32767.f);
-        }
+        for (int m = 0; m < R; ++m) ys[jl + m * UP] = f2s16_rn_sat(acc[m] * u.gain);     // gain 1 = exact identity
         __syncthreads();
-        const int n8 = nout >> 3;                                            // y is 16-byte aligned (offsets % 8 == 0, tiles of 1600)
+        const int n8 = nout >> 3;                                            // y is 16-byte aligned (offsets % 8 == 0, tiles % 8 == 0)
         for (int i = tid; i < n8; i += blockDim.x) reinterpret_cast<int4*>(y)[i] = reinterpret_cast<const int4*>(ys)[i];
         for (int i = (n8 << 3) + tid; i < nout; i += blockDim.x) y[i] = ys[i];
     }
