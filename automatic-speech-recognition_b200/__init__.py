@@ -10,7 +10,8 @@ from .augmentation import SpeedAugmentation, VolumeAugmentation        # noqa: F
 from . import speechpy_shim                                            # noqa: F401
 from . import tfrecord                                                 # noqa: F401  (create_tfrecord.py drop-in)
 from .tfrecord import create_tfrecords                                 # noqa: F401
+from . import bucketing                                                # noqa: F401  (tfrecord_data_loader.py batching)
 
 __all__ = ["Frontend", "FrontendConfig", "pack_pcm", "num_frames", "process_audios", "process_pcm",
            "process_libri_feats", "to_object_array", "SpeedAugmentation", "VolumeAugmentation",
-           "tables", "synth", "sharding", "audio_io", "speechpy_shim", "tfrecord", "create_tfrecords", "FrontendLibraryError", "library_path"]
+           "tables", "synth", "sharding", "audio_io", "speechpy_shim", "tfrecord", "create_tfrecords", "bucketing", "FrontendLibraryError", "library_path"]

@@ -47,6 +47,9 @@ SYMBOLS = {
                              C.c_void_p, C.c_int64, _i64p, _i64p, C.c_void_p]),
     "fe_postprocess": (C.c_int, [C.c_void_p, C.c_void_p, _i64p, _i32p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                  C.c_void_p, C.c_int64, _i64p, C.c_void_p]),
+    "fe_pad_batches": (C.c_int, [C.c_void_p, C.c_void_p, _i64p, _i32p, _i64p, _i32p, C.c_int32, C.c_void_p, C.c_int64,
+                                 C.c_void_p]),
+    "fe_get_pad_ms": (C.c_int, [C.c_void_p, _f32p]),
     "fe_sync": (C.c_int, [C.c_void_p]),
     "fe_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
     "fe_measure_fp32_peak": (C.c_int, [C.c_void_p, _f32p]),

@@ -60,6 +60,9 @@ struct fe_handle {
     // resampler
     std::vector<int> sp_up, sp_down, sp_tap_off;
     DevBuf d_sp_up, d_sp_down, d_sp_tap_off, d_taps;
+    // bucketed batches (fe_pad_batches): slot table, time of the last profiled launch
+    DevBuf d_pad;
+    float pad_ms = 0.f;
 
     Lane lane[3];
 
@@ -407,7 +410,7 @@ int fe_destroy(fe_handle* h) {
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
     for (DevBuf* b : {&h->tw256, &h->tw512, &h->window, &h->mel_desc, &h->mel_w, &h->dct,
-                      &h->d_sp_up, &h->d_sp_down, &h->d_sp_tap_off, &h->d_taps})
+                      &h->d_sp_up, &h->d_sp_down, &h->d_sp_tap_off, &h->d_taps, &h->d_pad})
         release(*b);
     for (Lane& L : h->lane) {
         for (DevBuf* b : {&L.d_utts, &L.d_tile_prefix, &L.d_tiles, &L.d_atile_prefix, &L.d_atiles, &L.d_statics,
@@ -796,6 +799,59 @@ int fe_postprocess(fe_handle* h, const float* feats, const int64_t* feat_offsets
         FE_CUDA(h, cudaMemcpyAsync(out, d_out, sizeof(float) * (size_t)off, cudaMemcpyDeviceToHost, st));
     }
     FE_CUDA(h, cudaStreamSynchronize(st));
+    return FE_OK;
+}
+
+int fe_pad_batches(fe_handle* h, const float* feats, const int64_t* src_offsets, const int32_t* valid_floats,
+                   const int64_t* dst_offsets, const int32_t* slot_floats, int32_t n_slots, float* dst,
+                   int64_t dst_capacity, void* stream) {
+    if (!h) return FE_ERR_INVALID;
+    if (n_slots < 0) return fail(h, FE_ERR_INVALID, "bad n_slots");
+    if (n_slots == 0) return FE_OK;
+    if (!feats || !src_offsets || !valid_floats || !dst_offsets || !slot_floats || !dst) return fail(h, FE_ERR_INVALID, "NULL buffer");
+    FE_CUDA(h, cudaSetDevice(h->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    std::vector<PadSlot> sl((size_t)n_slots);
+    long long span_src = 0, span_dst = 0;
+    for (int i = 0; i < n_slots; ++i) {
+        if (src_offsets[i] < 0 || dst_offsets[i] < 0 || valid_floats[i] < 0 || slot_floats[i] < 0)
+            return fail(h, FE_ERR_INVALID, "negative offset / length");
+        if (valid_floats[i] > slot_floats[i]) return fail(h, FE_ERR_INVALID, "utterance longer than its slot (bucket boundary)");
+        sl[(size_t)i] = PadSlot{src_offsets[i], dst_offsets[i], valid_floats[i], slot_floats[i]};
+        span_src = std::max<long long>(span_src, src_offsets[i] + valid_floats[i]);
+        span_dst = std::max<long long>(span_dst, dst_offsets[i] + slot_floats[i]);
+    }
+    if (span_dst > dst_capacity) return fail(h, FE_ERR_CAPACITY, "batch buffer too small");
+    const bool in_dev = is_device_ptr(feats), out_dev = is_device_ptr(dst);
+    int rc;
+    Lane& L = h->lane[0];
+    if ((rc = ensure(h, h->d_pad, sizeof(PadSlot) * sl.size()))) return rc;
+    const float* d_in = feats; float* d_out = dst;
+    if (!in_dev) { if ((rc = ensure(h, L.d_statics, sizeof(float) * (size_t)std::max<long long>(span_src, 1)))) return rc; d_in = (const float*)L.d_statics.p; }
+    if (!out_dev) { if ((rc = ensure(h, L.d_out, sizeof(float) * (size_t)std::max<long long>(span_dst, 1)))) return rc; d_out = (float*)L.d_out.p; }
+    FE_CUDA(h, cudaMemcpyAsync(h->d_pad.p, sl.data(), sizeof(PadSlot) * sl.size(), cudaMemcpyHostToDevice, st));
+    if (!in_dev) FE_CUDA(h, cudaMemcpyAsync(L.d_statics.p, feats, sizeof(float) * (size_t)span_src, cudaMemcpyHostToDevice, st));
+    FE_CUDA(h, cudaStreamSynchronize(st));                   // sl / feats may be freed by the caller after return
+    const int grid = (int)std::min<long long>(n_slots, 8LL * h->num_sms);
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (h->profiling) { FE_CUDA(h, cudaEventCreate(&e0)); FE_CUDA(h, cudaEventCreate(&e1)); FE_CUDA(h, cudaEventRecord(e0, st)); }
+    k_pad_slots<<<grid, 256, 0, st>>>(d_in, (const PadSlot*)h->d_pad.p, n_slots, d_out);
+    h->launches++;
+    FE_CUDA(h, cudaGetLastError());
+    if (h->profiling) {
+        FE_CUDA(h, cudaEventRecord(e1, st));
+        FE_CUDA(h, cudaEventSynchronize(e1));
+        FE_CUDA(h, cudaEventElapsedTime(&h->pad_ms, e0, e1));
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+    }
+    if (!out_dev) FE_CUDA(h, cudaMemcpyAsync(dst, d_out, sizeof(float) * (size_t)span_dst, cudaMemcpyDeviceToHost, st));
+    if (!out_dev || !in_dev) FE_CUDA(h, cudaStreamSynchronize(st));
+    return FE_OK;
+}
+
+int fe_get_pad_ms(fe_handle* h, float* ms) {
+    if (!h || !ms) return FE_ERR_INVALID;
+    *ms = h->pad_ms;
     return FE_OK;
 }
 

@@ -1035,6 +1035,53 @@ k_preemph(const void* __restrict__ pcm, const UttDesc* __restrict__ utts, const 
     }
 }
 
+// ---------------------------------------------------------------------------
+// K3: bucketed batches.  Slot = one utterance inside a dense [B, T_pad, D, planes] batch tensor: the
+// utterance's n_valid floats are copied, the rest of the slot (padding up to the bucket boundary,
+// tfrecord_data_loader.py:88-92 pad_to_bucket_boundary=True) is zero-filled.  Pure HBM traffic:
+// 4 (n_valid + n_slot) bytes per slot.  One CTA per slot (grid-stride), 16-byte stores on the
+// destination's alignment; loads are 16-byte when source and destination are congruent mod 16 bytes
+// (always for 80-dim fbank rows, every other slot for MFCC-39 rows of 39 floats), else scalar but
+// still fully coalesced.
+// ---------------------------------------------------------------------------
+struct __align__(8) PadSlot {
+    long long src_off;      // float offset of the utterance's cube in the feature buffer
+    long long dst_off;      // float offset of the slot in the batch buffer
+    int n_valid;            // floats to copy (n_frames * D * planes)
+    int n_slot;             // floats in the slot (T_pad * D * planes)
+};
+
+__global__ void __launch_bounds__(256)
+k_pad_slots(const float* __restrict__ src, const PadSlot* __restrict__ slots, int n_slots, float* __restrict__ dst) {
+    const int tid = threadIdx.x;
+    for (int it = blockIdx.x; it < n_slots; it += gridDim.x) {
+        const PadSlot p = slots[it];
+        const float* s = src + p.src_off;
+        float* d = dst + p.dst_off;
+        const int head = min((int)((4 - (p.dst_off & 3)) & 3), p.n_slot);    // scalars up to the first 16-byte boundary of dst
+        if (tid < head) d[tid] = tid < p.n_valid ? s[tid] : 0.f;
+        const int nbody = (p.n_slot - head) >> 2;
+        const bool congruent = ((p.src_off + head) & 3) == 0;
+        const int full = p.n_valid >= head ? (p.n_valid - head) >> 2 : 0;     // body vectors made of valid floats only
+#pragma unroll 4
+        for (int j = tid; j < nbody; j += 256) {
+            const int e = head + 4 * j;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (j < full) {
+                if (congruent) v = __ldcs(reinterpret_cast<const float4*>(s + e));
+                else v = make_float4(__ldcs(s + e), __ldcs(s + e + 1), __ldcs(s + e + 2), __ldcs(s + e + 3));
+            } else if (e < p.n_valid) {                                       // the vector straddles the end of the data
+                v.x = s[e];
+                if (e + 1 < p.n_valid) v.y = s[e + 1];
+                if (e + 2 < p.n_valid) v.z = s[e + 2];
+            }
+            __stcs(reinterpret_cast<float4*>(d + e), v);
+        }
+        const int e = head + 4 * nbody + tid;
+        if (e < p.n_slot) d[e] = e < p.n_valid ? s[e] : 0.f;
+    }
+}
+
 // FP32 roofline denominator measured on the spot: independent packed FFMA2 chains, no memory.
 __global__ void __launch_bounds__(256) k_fp32_peak(float* __restrict__ out, int iters) {
     float2 x[8];

@@ -135,6 +135,18 @@ int fe_postprocess(fe_handle* h, const float* feats, const int64_t* feat_offsets
                    int32_t n_utts, int32_t feat_dim, int32_t mode, int32_t delta_mode,
                    float* out, int64_t out_capacity, int64_t* out_offsets, void* stream);
 
+/* Bucketed, padded batches: what tf.data's bucket_by_sequence_length(..., pad_to_bucket_boundary=True)
+ * hands the model (tfrecord_data_loader.py:75-94), built on the device from the cubes fe_run left in HBM.
+ * Slot i of the batch buffer (dst + dst_offsets[i], slot_floats[i] = T_pad * D * planes floats) receives the
+ * valid_floats[i] = L_i * D * planes floats at feats + src_offsets[i] followed by zeros.  Which utterance goes
+ * to which slot (bucket by length, batch size per bucket, drop L >= 1710) is the caller's plan -- the host
+ * mirror builds it with the reference's boundaries.  One launch for any number of batches; host or device
+ * pointers; asynchronous on the stream when both are device pointers.  Needs no fe_configure. */
+int fe_pad_batches(fe_handle* h, const float* feats, const int64_t* src_offsets, const int32_t* valid_floats,
+                   const int64_t* dst_offsets, const int32_t* slot_floats, int32_t n_slots,
+                   float* dst, int64_t dst_capacity, void* stream);
+int fe_get_pad_ms(fe_handle* h, float* ms);    /* duration of the last fe_pad_batches launch (profiling on) */
+
 int fe_sync(fe_handle* h);
 
 /* Measurement hooks.  With profiling on, every kernel of every fe_run is bracketed by CUDA
