@@ -32,6 +32,11 @@ class FeConfig(C.Structure):
     ]
 
 
+class FeFlacFile(C.Structure):
+    _fields_ = [("byte_offset", C.c_int64), ("pcm_offset", C.c_int64), ("n_bytes", C.c_int32), ("first_frame", C.c_int32),
+                ("n_samples", C.c_int32), ("block_size", C.c_int32), ("bits_per_sample", C.c_int32), ("reserved", C.c_int32)]
+
+
 # every symbol include/asr_frontend.h declares: name -> (restype, argtypes)
 SYMBOLS = {
     "fe_abi_version": (C.c_int, []),
@@ -50,6 +55,9 @@ SYMBOLS = {
     "fe_pad_batches": (C.c_int, [C.c_void_p, C.c_void_p, _i64p, _i32p, _i64p, _i32p, C.c_int32, C.c_void_p, C.c_int64,
                                  C.c_void_p]),
     "fe_get_pad_ms": (C.c_int, [C.c_void_p, _f32p]),
+    "fe_decode_flac": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(FeFlacFile), C.c_int32, C.c_void_p, C.c_int64,
+                                 _i32p, C.c_void_p]),
+    "fe_get_flac_ms": (C.c_int, [C.c_void_p, _f32p]),
     "fe_sync": (C.c_int, [C.c_void_p]),
     "fe_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
     "fe_measure_fp32_peak": (C.c_int, [C.c_void_p, _f32p]),
@@ -69,6 +77,11 @@ class AioInfo(C.Structure):
                 ("bits_per_sample", C.c_int32), ("n_samples", C.c_int64)]
 
 
+class AioFlacLayout(C.Structure):
+    _fields_ = [("n_samples", C.c_int64), ("first_frame", C.c_int32), ("min_block", C.c_int32), ("max_block", C.c_int32),
+                ("sample_rate", C.c_int32), ("channels", C.c_int32), ("bits_per_sample", C.c_int32)]
+
+
 _cpp = C.POINTER(C.c_char_p)
 _infop = C.POINTER(AioInfo)
 # every symbol include/asr_audio_io.h declares (host-side FLAC / WAV ingest and egress)
@@ -79,6 +92,9 @@ AIO_SYMBOLS = {
     "aio_decode_file": (C.c_int, [C.c_char_p, C.c_void_p, C.c_int64, _i64p, C.c_int]),
     "aio_probe_files": (C.c_int, [_cpp, C.c_int32, C.c_int32, _infop, _i32p]),
     "aio_decode_files": (C.c_int, [_cpp, C.c_int32, C.c_int32, C.c_void_p, _i64p, _i64p, C.c_int, _i32p]),
+    "aio_flac_layout": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(AioFlacLayout)]),
+    "aio_file_sizes": (C.c_int, [_cpp, C.c_int32, _i64p]),
+    "aio_read_files": (C.c_int, [_cpp, C.c_int32, C.c_int32, C.c_void_p, _i64p, _i64p, _i32p]),
     "aio_flac_bound": (C.c_int64, [C.c_int64, C.c_int32]),
     "aio_encode_flac": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_int64, _i64p]),
     "aio_write_file": (C.c_int, [C.c_char_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32]),

@@ -151,6 +151,68 @@ def read_audio_batch(paths, n_threads=0, check_md5=True, out=None):
     return out, offsets, lengths, fs
 
 
+def flac_layout(data):
+    """Stream layout of FLAC bytes (for the device decoder) -> dict."""
+    buf = np.frombuffer(data, dtype=np.uint8)
+    lay = _lib.AioFlacLayout()
+    _check(_lib.load().aio_flac_layout(C.c_void_p(buf.ctypes.data), buf.size, C.byref(lay)), "flac_layout")
+    return {k: getattr(lay, k) for k, _ in _lib.AioFlacLayout._fields_}
+
+
+def load_flac_batch(paths, n_threads=0, out=None):
+    """Raw bytes of mono FLAC files in ONE buffer for ``Frontend.decode_flac`` (the GPU decoder): file i
+    starts at a 16-byte aligned offset.  No sample is decoded on the host -- only the metadata blocks are
+    parsed.  Returns (buf uint8, files: ctypes array of fe_flac_file with pcm offsets planned, pcm_offsets[n],
+    lengths[n], fs, total_bytes).  ``out`` may be a caller-owned (e.g. pinned) uint8 array."""
+    lib = _lib.load()
+    n = len(paths)
+    arr = _paths_array(paths)
+    sizes = np.zeros(max(n, 1), dtype=np.int64)
+    if lib.aio_file_sizes(arr, n, sizes.ctypes.data_as(C.POINTER(C.c_int64))) != 0:
+        bad = int(np.flatnonzero(sizes[:n] < 0)[0])
+        _check(_lib.AIO_ERR_IO, paths[bad])
+    sizes = sizes[:n]
+    if np.any(sizes >= 2 ** 31):
+        raise AudioFormatError("file larger than 2 GB")
+    offsets = np.zeros(n, dtype=np.int64)
+    if n > 1:
+        np.cumsum((sizes[:-1] + 15) // 16 * 16, out=offsets[1:])
+    total = int(offsets[-1] + sizes[-1]) if n else 0
+    if out is None:
+        out = np.zeros(total + 16, dtype=np.uint8)
+    elif out.dtype != np.uint8 or out.size < total or not out.flags.c_contiguous:
+        raise ValueError("out must be a C-contiguous uint8 array of at least %d bytes" % total)
+    status = np.zeros(max(n, 1), dtype=np.int32)
+    rc = lib.aio_read_files(arr, n, int(n_threads), C.c_void_p(out.ctypes.data), offsets.ctypes.data_as(C.POINTER(C.c_int64)),
+                            sizes.ctypes.data_as(C.POINTER(C.c_int64)), status.ctypes.data_as(C.POINTER(C.c_int32)))
+    if rc != 0:
+        bad = int(np.flatnonzero(status)[0])
+        _check(int(status[bad]), paths[bad])
+    files = (_lib.FeFlacFile * max(n, 1))()
+    lengths = np.zeros(n, dtype=np.int64)
+    lay = _lib.AioFlacLayout()
+    fs = DEFAULT_FS
+    for i in range(n):
+        _check(lib.aio_flac_layout(C.c_void_p(out.ctypes.data + int(offsets[i])), int(sizes[i]), C.byref(lay)), paths[i])
+        if lay.channels != 1:
+            raise ValueError("%s: mono audio expected" % paths[i])
+        if i == 0:
+            fs = lay.sample_rate
+        elif lay.sample_rate != fs:
+            raise ValueError("mixed sample rates in one call: %d vs %d (%s)" % (fs, lay.sample_rate, paths[i]))
+        if lay.min_block != lay.max_block or lay.n_samples <= 0 or lay.max_block % 8 or lay.bits_per_sample > 16:
+            raise AudioFormatError("%s: the device decoder takes fixed-block-size streams (multiple of 8) of at most "
+                                   "16 bits with a sample count; use read_audio_batch" % paths[i])
+        lengths[i] = lay.n_samples
+        f = files[i]
+        f.byte_offset, f.n_bytes, f.first_frame = int(offsets[i]), int(sizes[i]), lay.first_frame
+        f.n_samples, f.block_size, f.bits_per_sample = int(lay.n_samples), lay.max_block, lay.bits_per_sample
+    pcm_offsets, _ = plan_batch(lengths)
+    for i in range(n):
+        files[i].pcm_offset = int(pcm_offsets[i])
+    return out, files, pcm_offsets, lengths, fs, total
+
+
 def encode_flac(pcm16, fs=DEFAULT_FS, channels=1):
     """int16 samples (interleaved if channels > 1) -> FLAC bytes."""
     lib = _lib.load()

@@ -892,6 +892,54 @@ int aio_decode_files(const char* const* paths, int32_t n, int32_t n_threads, int
     return first;
 }
 
+int aio_flac_layout(const uint8_t* data, int64_t n_bytes, aio_flac_layout_t* out) {
+    if (!data || !out) return AIO_ERR_INVALID;
+    StreamInfo si;
+    int rc = parse_flac_header(data, n_bytes, &si);
+    if (rc) return rc;
+    out->n_samples = si.total;
+    out->first_frame = (int32_t)si.first_frame;
+    out->min_block = si.min_block;
+    out->max_block = si.max_block;
+    out->sample_rate = si.sample_rate;
+    out->channels = si.channels;
+    out->bits_per_sample = si.bps;
+    return AIO_OK;
+}
+
+int aio_file_sizes(const char* const* paths, int32_t n, int64_t* sizes) {
+    if (n < 0 || (n > 0 && (!paths || !sizes))) return AIO_ERR_INVALID;
+    int first = 0;
+    for (int32_t i = 0; i < n; ++i) {
+        FILE* f = fopen(paths[i], "rb");
+        long sz = -1;
+        if (f) { if (fseek(f, 0, SEEK_END) == 0) sz = ftell(f); fclose(f); }
+        sizes[i] = sz;
+        if (sz < 0 && !first) first = AIO_ERR_IO;
+    }
+    return first;
+}
+
+int aio_read_files(const char* const* paths, int32_t n, int32_t n_threads, uint8_t* buf, const int64_t* offsets,
+                   const int64_t* sizes, int32_t* status) {
+    if (n < 0 || (n > 0 && (!paths || !buf || !offsets || !sizes))) return AIO_ERR_INVALID;
+    std::vector<int32_t> st((size_t)n, 0);
+    parallel_for(n, n_threads, [&](int32_t i) {
+        FILE* f = fopen(paths[i], "rb");
+        if (!f) { st[(size_t)i] = AIO_ERR_IO; return; }
+        size_t want = (size_t)sizes[i];
+        size_t got = want ? fread(buf + offsets[i], 1, want, f) : 0;
+        fclose(f);
+        st[(size_t)i] = got == want ? AIO_OK : AIO_ERR_IO;
+    });
+    int first = 0;
+    for (int32_t i = 0; i < n; ++i) {
+        if (status) status[i] = st[(size_t)i];
+        if (!first && st[(size_t)i]) first = st[(size_t)i];
+    }
+    return first;
+}
+
 int64_t aio_flac_bound(int64_t n_samples, int32_t channels) {
     if (n_samples < 0 || channels < 1) return -1;
     int64_t frames = (n_samples + kBlock - 1) / kBlock;

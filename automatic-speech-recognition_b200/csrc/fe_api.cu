@@ -10,6 +10,7 @@
 
 #include "../../include/asr_frontend.h"
 #include "fe_kernels.cuh"
+#include "flac_gpu.cuh"
 #include "fe_tables.h"
 
 using namespace fe;
@@ -63,6 +64,9 @@ struct fe_handle {
     // bucketed batches (fe_pad_batches): slot table, time of the last profiled launch
     DevBuf d_pad;
     float pad_ms = 0.f;
+    // FLAC decode on the device (fe_decode_flac)
+    DevBuf d_flac_bytes, d_flac_files, d_flac_frames, d_flac_cands, d_flac_ctr, d_flac_pcm;
+    float flac_ms[3] = {0.f, 0.f, 0.f};
 
     Lane lane[3];
 
@@ -410,7 +414,8 @@ int fe_destroy(fe_handle* h) {
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
     for (DevBuf* b : {&h->tw256, &h->tw512, &h->window, &h->mel_desc, &h->mel_w, &h->dct,
-                      &h->d_sp_up, &h->d_sp_down, &h->d_sp_tap_off, &h->d_taps, &h->d_pad})
+                      &h->d_sp_up, &h->d_sp_down, &h->d_sp_tap_off, &h->d_taps, &h->d_pad,
+                      &h->d_flac_bytes, &h->d_flac_files, &h->d_flac_frames, &h->d_flac_cands, &h->d_flac_ctr, &h->d_flac_pcm})
         release(*b);
     for (Lane& L : h->lane) {
         for (DevBuf* b : {&L.d_utts, &L.d_tile_prefix, &L.d_tiles, &L.d_atile_prefix, &L.d_atiles, &L.d_statics,
@@ -846,6 +851,119 @@ int fe_pad_batches(fe_handle* h, const float* feats, const int64_t* src_offsets,
     }
     if (!out_dev) FE_CUDA(h, cudaMemcpyAsync(dst, d_out, sizeof(float) * (size_t)span_dst, cudaMemcpyDeviceToHost, st));
     if (!out_dev || !in_dev) FE_CUDA(h, cudaStreamSynchronize(st));
+    return FE_OK;
+}
+
+int fe_decode_flac(fe_handle* h, const uint8_t* bytes, int64_t total_bytes, const fe_flac_file* files, int32_t n_files,
+                   int16_t* pcm, int64_t pcm_capacity, int32_t* status, void* stream) {
+    if (!h) return FE_ERR_INVALID;
+    if (n_files < 0 || total_bytes < 0) return fail(h, FE_ERR_INVALID, "bad n_files / total_bytes");
+    if (n_files == 0) return FE_OK;
+    if (!bytes || !files || !pcm || !status) return fail(h, FE_ERR_INVALID, "NULL buffer");
+    FE_CUDA(h, cudaSetDevice(h->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    std::vector<FlacFile> ff((size_t)n_files);
+    long long frames_total = 0, pcm_span = 0;
+    for (int i = 0; i < n_files; ++i) {
+        const fe_flac_file& s = files[i];
+        if (s.byte_offset < 0 || (s.byte_offset & 15) || s.n_bytes < 0 || s.byte_offset + s.n_bytes > total_bytes)
+            return fail(h, FE_ERR_INVALID, "file byte ranges must be 16-byte aligned and inside the buffer");
+        if (i > 0 && s.byte_offset < files[i - 1].byte_offset + files[i - 1].n_bytes)
+            return fail(h, FE_ERR_INVALID, "files must be laid out in ascending, non-overlapping byte ranges");
+        if (s.pcm_offset < 0 || (s.pcm_offset & 7)) return fail(h, FE_ERR_INVALID, "pcm_offset must be a multiple of 8 samples");
+        if (s.n_samples < 0 || s.first_frame < 0 || s.first_frame > s.n_bytes) return fail(h, FE_ERR_INVALID, "bad stream layout");
+        if (s.block_size < 16 || (s.block_size & 7) || s.block_size > 65535)
+            return fail(h, FE_ERR_INVALID, "unsupported FLAC block size (fixed block size, multiple of 8, expected)");
+        if (s.bits_per_sample < 4 || s.bits_per_sample > 16) return fail(h, FE_ERR_INVALID, "unsupported bits per sample (4..16)");
+        FlacFile& f = ff[(size_t)i];
+        f.byte_off = s.byte_offset; f.pcm_off = s.pcm_offset; f.n_bytes = s.n_bytes; f.first_frame = s.first_frame;
+        f.n_samples = s.n_samples; f.block_size = s.block_size; f.bps = s.bits_per_sample;
+        f.frame_base = (int)frames_total;
+        f.n_frames = (s.n_samples + s.block_size - 1) / s.block_size;
+        f.pad = 0;
+        frames_total += f.n_frames;
+        if (frames_total > 0x7fffffffLL) return fail(h, FE_ERR_INVALID, "batch too large");
+        pcm_span = std::max<long long>(pcm_span, s.pcm_offset + s.n_samples);
+    }
+    if (pcm_span > pcm_capacity) return fail(h, FE_ERR_CAPACITY, "pcm buffer too small");
+    const bool in_dev = is_device_ptr(bytes), out_dev = is_device_ptr(pcm);
+    const int cap = (int)std::min<long long>(frames_total + frames_total / 64 + 1024, 0x7fffffffLL);
+    const size_t ctr_ints = 1 + 2 * (size_t)n_files;                      // n_cands, cand_per_file[n], status[n]
+    int rc;
+    if ((rc = ensure(h, h->d_flac_files, sizeof(FlacFile) * ff.size()))) return rc;
+    if ((rc = ensure(h, h->d_flac_frames, sizeof(FlacFrame) * (size_t)std::max<long long>(frames_total, 1)))) return rc;
+    if ((rc = ensure(h, h->d_flac_cands, sizeof(int4) * (size_t)cap))) return rc;
+    if ((rc = ensure(h, h->d_flac_ctr, sizeof(int) * ctr_ints))) return rc;
+    const uint8_t* d_bytes = bytes;
+    if (!in_dev) {                                                        // the kernels read up to 4 KB past the last file
+        if ((rc = ensure(h, h->d_flac_bytes, (size_t)total_bytes + kFlacPadBytes))) return rc;
+        FE_CUDA(h, cudaMemcpyAsync(h->d_flac_bytes.p, bytes, (size_t)total_bytes, cudaMemcpyHostToDevice, st));
+        FE_CUDA(h, cudaMemsetAsync((char*)h->d_flac_bytes.p + total_bytes, 0, kFlacPadBytes, st));
+        d_bytes = (const uint8_t*)h->d_flac_bytes.p;
+    }
+    short* d_pcm = pcm;
+    if (!out_dev) {
+        if ((rc = ensure(h, h->d_flac_pcm, sizeof(short) * (size_t)std::max<long long>(pcm_span, 8)))) return rc;
+        d_pcm = (short*)h->d_flac_pcm.p;
+    }
+    int* d_ncand = (int*)h->d_flac_ctr.p;
+    int* d_cpf = d_ncand + 1;
+    int* d_status = d_cpf + n_files;
+    FE_CUDA(h, cudaMemcpyAsync(h->d_flac_files.p, ff.data(), sizeof(FlacFile) * ff.size(), cudaMemcpyHostToDevice, st));
+    FE_CUDA(h, cudaMemsetAsync(h->d_flac_frames.p, 0, sizeof(FlacFrame) * (size_t)std::max<long long>(frames_total, 1), st));
+    FE_CUDA(h, cudaMemsetAsync(h->d_flac_ctr.p, 0, sizeof(int) * ctr_ints, st));
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    if (h->profiling) { for (auto& e : ev) FE_CUDA(h, cudaEventCreate(&e)); FE_CUDA(h, cudaEventRecord(ev[0], st)); }
+    const long long nvec = (total_bytes + 15) >> 4;
+    const int g_scan = (int)std::min<long long>((nvec + 255) / 256, 32LL * h->num_sms);
+    if (nvec > 0) {
+        k_flac_scan<<<std::max(g_scan, 1), 256, 0, st>>>(d_bytes, total_bytes, (const FlacFile*)h->d_flac_files.p, n_files,
+                                                         (int4*)h->d_flac_cands.p, d_ncand, cap, d_cpf);
+        h->launches++;
+    }
+    if (h->profiling) FE_CUDA(h, cudaEventRecord(ev[1], st));
+    const int g_dec = (int)std::min<long long>((frames_total + 127) / 128 + 1, 64LL * h->num_sms);
+    k_flac_decode<<<g_dec, 128, 0, st>>>(d_bytes, (const FlacFile*)h->d_flac_files.p, (const int4*)h->d_flac_cands.p, d_ncand, cap,
+                                         (FlacFrame*)h->d_flac_frames.p, d_pcm, d_status, 0);
+    h->launches++;
+    if (h->profiling) FE_CUDA(h, cudaEventRecord(ev[2], st));
+    k_flac_validate<<<(n_files + 255) / 256, 256, 0, st>>>((const FlacFile*)h->d_flac_files.p, n_files, (const FlacFrame*)h->d_flac_frames.p,
+                                                           d_cpf, d_status);
+    h->launches++;
+    if (h->profiling) FE_CUDA(h, cudaEventRecord(ev[3], st));
+    FE_CUDA(h, cudaGetLastError());
+    std::vector<int> hs((size_t)n_files);
+    FE_CUDA(h, cudaMemcpyAsync(hs.data(), d_status, sizeof(int) * (size_t)n_files, cudaMemcpyDeviceToHost, st));
+    FE_CUDA(h, cudaStreamSynchronize(st));
+    if (h->profiling) {
+        for (int k = 0; k < 3; ++k) FE_CUDA(h, cudaEventElapsedTime(&h->flac_ms[k], ev[k], ev[k + 1]));
+        for (auto& e : ev) cudaEventDestroy(e);
+    }
+    bool redo = false;
+    for (int v : hs) redo |= (v == kFlacRedo);
+    if (redo) {                                                           // a stray header-like byte run: decode chain positions again
+        k_flac_decode<<<g_dec, 128, 0, st>>>(d_bytes, (const FlacFile*)h->d_flac_files.p, (const int4*)h->d_flac_cands.p, d_ncand, cap,
+                                             (FlacFrame*)h->d_flac_frames.p, d_pcm, d_status, 1);
+        h->launches++;
+        FE_CUDA(h, cudaGetLastError());
+        FE_CUDA(h, cudaStreamSynchronize(st));
+    }
+    int n_bad = 0;
+    for (int i = 0; i < n_files; ++i) {
+        status[i] = (hs[(size_t)i] == kFlacCorrupt) ? FE_ERR_INVALID : FE_OK;
+        n_bad += status[i] != 0;
+    }
+    if (!out_dev) {
+        FE_CUDA(h, cudaMemcpyAsync(pcm, d_pcm, sizeof(short) * (size_t)pcm_span, cudaMemcpyDeviceToHost, st));
+        FE_CUDA(h, cudaStreamSynchronize(st));
+    }
+    if (n_bad) return fail(h, FE_ERR_INVALID, "FLAC decode: " + std::to_string(n_bad) + " file(s) corrupt, truncated or not fixed-block-size mono (see status[])");
+    return FE_OK;
+}
+
+int fe_get_flac_ms(fe_handle* h, float ms[3]) {
+    if (!h || !ms) return FE_ERR_INVALID;
+    for (int k = 0; k < 3; ++k) ms[k] = h->flac_ms[k];
     return FE_OK;
 }
 

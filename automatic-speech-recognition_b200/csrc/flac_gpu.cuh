@@ -1,0 +1,363 @@
+// FLAC decode on the GPU: the file boundary of the front-end (sf.read, /root/reference/preprocess.py:69)
+// moved behind the PCIe link -- compressed bytes go up, int16 PCM is produced in HBM where K1 frames it.
+//
+// FLAC frames are independently decodable and, in a fixed-block-size stream (what libFLAC / SoX write and
+// LibriSpeech ships), frame number n starts at sample n x block_size.  So:
+//   k_flac_scan      every byte position is tested for a frame header of ITS file (sync code, fixed
+//                    blocking, mono, the stream's block size / sample size, UTF-8 frame number in range,
+//                    CRC-8): ~2^-37 false positives per byte.  Hits are appended to a candidate list.
+//   k_flac_decode    one thread per candidate: Rice / Rice2 residual decode fused with the fixed / LPC
+//                    recurrence (and constant / verbatim subframes, wasted bits), samples staged through
+//                    lane-interleaved local memory and stored as 16-byte vectors, then CRC-16 of the frame.
+//                    A candidate that decodes cleanly registers (start, end) in the file's frame table.
+//   k_flac_validate  one thread per file: every frame number present exactly once, frames tile the byte
+//                    range from the first frame to the last one's end.  A file that also saw a non-chain
+//                    candidate (a false positive that may have written samples) is flagged for a second
+//                    decode pass restricted to chain positions; any other defect marks the file corrupt.
+// Integer work throughout; results are bit-identical to the host decoder (audio_codec.cpp), which is pinned
+// by FFmpeg-encoded fixtures.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace fe {
+
+struct FlacFile {
+    long long byte_off;     // first byte of the file in the batch buffer (16-byte aligned)
+    long long pcm_off;      // int16 element offset of sample 0 in the output (16-byte aligned)
+    int n_bytes;
+    int first_frame;        // byte offset of the first audio frame inside the file
+    int n_samples;
+    int block_size;         // fixed block size of the stream
+    int bps;                // bits per sample (4..16), mono
+    int frame_base;         // index of this file's frame 0 in the frame table
+    int n_frames;           // ceil(n_samples / block_size)
+    int pad;
+};
+
+struct FlacFrame {
+    int start, end;         // byte range [start, end) inside the file, valid when hits == 1
+    int hits;               // candidates that decoded cleanly with a good CRC-16 for this frame number
+    int pad;
+};
+
+constexpr int kFlacOk = 0, kFlacCorrupt = 1, kFlacRedo = 2;
+constexpr int kFlacPadBytes = 4096;     // readable bytes the kernels may touch past the end of the batch buffer
+
+__device__ __forceinline__ unsigned flac_crc8_step(unsigned c, unsigned byte) {
+    c ^= byte;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) c = (c & 0x80u) ? ((c << 1) ^ 0x07u) & 0xffu : (c << 1) & 0xffu;
+    return c;
+}
+
+// ---------------------------------------------------------------------------------------------- scan
+// Header test at byte p of file f.  Returns the header length (including the CRC-8 byte) or 0.
+__device__ __forceinline__ int flac_header_at(const uint8_t* __restrict__ fb, int p, const FlacFile& f, int* frame_no) {
+    if (p + 6 > f.n_bytes) return 0;
+    const unsigned b1 = fb[p + 1], b2 = fb[p + 2], b3 = fb[p + 3];
+    if (b1 != 0xF8u) return 0;                                        // sync + reserved 0 + fixed block size
+    const int bs_code = b2 >> 4, sr_code = b2 & 15, ch = b3 >> 4, ss_code = (b3 >> 1) & 7;
+    if (bs_code == 0 || sr_code == 15 || ch != 0 || (b3 & 1)) return 0;      // mono only, reserved bit
+    static const int kBits[8] = {0, 8, 12, -1, 16, 20, 24, 32};
+    const int bits = kBits[ss_code];
+    if (bits < 0 || (bits != 0 && bits != f.bps)) return 0;
+    int q = p + 4;
+    const unsigned c0 = fb[q++];                                      // UTF-8 style frame number
+    int extra = 0;
+    unsigned long long num = c0;
+    if (c0 & 0x80u) {
+        if ((c0 & 0xE0u) == 0xC0u) { extra = 1; num = c0 & 0x1Fu; }
+        else if ((c0 & 0xF0u) == 0xE0u) { extra = 2; num = c0 & 0x0Fu; }
+        else if ((c0 & 0xF8u) == 0xF0u) { extra = 3; num = c0 & 0x07u; }
+        else if ((c0 & 0xFCu) == 0xF8u) { extra = 4; num = c0 & 0x03u; }
+        else if ((c0 & 0xFEu) == 0xFCu) { extra = 5; num = c0 & 0x01u; }
+        else return 0;
+    }
+    if (q + extra + 3 > f.n_bytes) return 0;
+    for (int i = 0; i < extra; ++i) {
+        const unsigned c = fb[q++];
+        if ((c & 0xC0u) != 0x80u) return 0;
+        num = (num << 6) | (c & 0x3Fu);
+    }
+    if (num >= (unsigned long long)f.n_frames) return 0;
+    int bs;
+    if (bs_code == 1) bs = 192;
+    else if (bs_code <= 5) bs = 576 << (bs_code - 2);
+    else if (bs_code == 6) { bs = (int)fb[q] + 1; q += 1; }
+    else if (bs_code == 7) { bs = (((int)fb[q] << 8) | (int)fb[q + 1]) + 1; q += 2; }
+    else bs = 256 << (bs_code - 8);
+    const int want = ((int)num == f.n_frames - 1) ? f.n_samples - (int)num * f.block_size : f.block_size;
+    if (bs != want) return 0;
+    if (sr_code == 12) q += 1;
+    else if (sr_code == 13 || sr_code == 14) q += 2;
+    if (q + 1 > f.n_bytes) return 0;
+    unsigned c = 0;
+    for (int i = p; i < q; ++i) c = flac_crc8_step(c, fb[i]);
+    if (c != fb[q]) return 0;
+    *frame_no = (int)num;
+    return q + 1 - p;
+}
+
+// One thread per 16 consecutive bytes of the batch buffer (a 16-byte vector load; the sync byte pair may
+// straddle vectors, so byte 16 is fetched too).  cands: (file, byte position in file, frame number, header length).
+__global__ void __launch_bounds__(256)
+k_flac_scan(const uint8_t* __restrict__ bytes, long long total_bytes, const FlacFile* __restrict__ files, int n_files,
+            int4* __restrict__ cands, int* __restrict__ n_cands, int cap, int* __restrict__ cand_per_file) {
+    const long long nvec = (total_bytes + 15) >> 4;
+    for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += (long long)gridDim.x * blockDim.x) {
+        const uint4 w = __ldg(reinterpret_cast<const uint4*>(bytes) + v);        // buffer is padded to 16 bytes + 16
+        const unsigned ws[5] = {w.x, w.y, w.z, w.w, (unsigned)bytes[(v << 4) + 16]};
+        // any 0xFF byte followed by 0xF8?
+        unsigned hit = 0;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const unsigned a = (ws[i >> 2] >> (8 * (i & 3))) & 0xffu;
+            const unsigned b = (ws[(i + 1) >> 2] >> (8 * ((i + 1) & 3))) & 0xffu;
+            hit |= (a == 0xFFu && b == 0xF8u) ? (1u << i) : 0u;
+        }
+        while (hit) {
+            const int i = __ffs(hit) - 1;
+            hit &= hit - 1;
+            const long long p = (v << 4) + i;
+            int lo = 0, hi = n_files - 1;                                        // last file with byte_off <= p
+            while (lo < hi) {
+                const int mid = (lo + hi + 1) >> 1;
+                if (files[mid].byte_off <= p) lo = mid; else hi = mid - 1;
+            }
+            const FlacFile f = files[lo];
+            const long long rel = p - f.byte_off;
+            if (rel < f.first_frame || rel >= f.n_bytes) continue;
+            int frame_no = 0;
+            const int hl = flac_header_at(bytes + f.byte_off, (int)rel, f, &frame_no);
+            if (!hl) continue;
+            const int slot = atomicAdd(n_cands, 1);
+            atomicAdd(cand_per_file + lo, 1);
+            if (slot < cap) cands[slot] = make_int4(lo, (int)rel, frame_no, hl);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- decode
+struct FlacBits {
+    const unsigned* words;      // 4-byte aligned view of the file (file starts are 16-byte aligned)
+    int widx;                   // next word to load
+    int limit_bits;             // file length in bits
+    unsigned long long acc;     // valid bits are the top cnt, zeros below
+    int cnt;
+    __device__ __forceinline__ void init(const uint8_t* file, int byte_pos, int n_bytes) {
+        words = reinterpret_cast<const unsigned*>(file);
+        widx = byte_pos >> 2;
+        limit_bits = n_bytes * 8;
+        const unsigned w = __byte_perm(__ldg(words + widx), 0, 0x0123);          // big-endian bit order
+        widx++;
+        const int skip = (byte_pos & 3) * 8;
+        acc = ((unsigned long long)w << 32) << skip;
+        cnt = 32 - skip;
+    }
+    __device__ __forceinline__ void refill() {                                    // needs cnt <= 32
+        const unsigned w = __byte_perm(__ldg(words + widx), 0, 0x0123);
+        widx++;
+        acc |= (unsigned long long)w << (32 - cnt);
+        cnt += 32;
+    }
+    __device__ __forceinline__ int bit_pos() const { return widx * 32 - cnt; }   // bits consumed from the file start
+    __device__ __forceinline__ bool overrun() const { return bit_pos() > limit_bits; }
+    __device__ __forceinline__ unsigned get(int n) {                              // 0 <= n <= 32
+        if (n == 0) return 0u;
+        if (cnt < n) refill();
+        const unsigned v = (unsigned)(acc >> (64 - n));
+        acc <<= n;
+        cnt -= n;
+        return v;
+    }
+    __device__ __forceinline__ int get_signed(int n) {                            // 1 <= n <= 32
+        const unsigned v = get(n);
+        const unsigned m = 1u << (n - 1);
+        return n < 32 ? (int)((v ^ m) - m) : (int)v;
+    }
+    // zeros before the next one bit (which is consumed); stops at the end of the file (overrun() then holds)
+    __device__ __forceinline__ unsigned unary() {
+        unsigned q = 0;
+        for (;;) {
+            if (cnt < 32) refill();
+            if (acc != 0ull) {
+                const int z = __clzll((long long)acc);
+                q += (unsigned)z;
+                acc = (z == 63) ? 0ull : acc << (z + 1);
+                cnt -= z + 1;
+                return q;
+            }
+            q += (unsigned)cnt;
+            cnt = 0;
+            if (overrun()) return q;
+        }
+    }
+};
+
+// eight staged samples -> one 16-byte vector of int16 (scaled by 2^up)
+__device__ __forceinline__ int4 flac_pack8(const int* stage, int up) {
+    unsigned w[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const unsigned a = (unsigned)stage[2 * q] << up, b = (unsigned)stage[2 * q + 1] << up;
+        w[q] = (a & 0xffffu) | (b << 16);
+    }
+    return make_int4((int)w[0], (int)w[1], (int)w[2], (int)w[3]);
+}
+
+__device__ __forceinline__ unsigned flac_crc16_bytes(const uint8_t* __restrict__ fb, int lo, int hi, const unsigned short* tab) {
+    unsigned c = 0;
+    for (int i = lo; i < hi; ++i) c = ((c << 8) ^ tab[((c >> 8) ^ fb[i]) & 0xffu]) & 0xffffu;
+    return c;
+}
+
+// mode 0: every candidate.  mode 1: only chain positions of files flagged kFlacRedo (second pass).
+__global__ void __launch_bounds__(128)
+k_flac_decode(const uint8_t* __restrict__ bytes, const FlacFile* __restrict__ files, const int4* __restrict__ cands,
+              const int* __restrict__ n_cands_p, int cap, FlacFrame* __restrict__ frames, short* __restrict__ pcm,
+              const int* __restrict__ file_status, int mode) {
+    __shared__ unsigned short crc_tab[256];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+        unsigned c = (unsigned)i << 8;
+        for (int k = 0; k < 8; ++k) c = (c & 0x8000u) ? ((c << 1) ^ 0x8005u) & 0xffffu : (c << 1) & 0xffffu;
+        crc_tab[i] = (unsigned short)c;
+    }
+    __syncthreads();
+    const int n_cands = min(*n_cands_p, cap);
+    for (int ci = blockIdx.x * blockDim.x + threadIdx.x; ci < n_cands; ci += gridDim.x * blockDim.x) {
+        const int4 cd = cands[ci];
+        const FlacFile f = files[cd.x];
+        FlacFrame* fr = frames + f.frame_base + cd.z;
+        if (mode == 1 && (file_status[cd.x] != kFlacRedo || fr->hits != 1 || fr->start != cd.y)) continue;
+        const uint8_t* fb = bytes + f.byte_off;
+        const int bs = (cd.z == f.n_frames - 1) ? f.n_samples - cd.z * f.block_size : f.block_size;
+        short* out = pcm + f.pcm_off + (long long)cd.z * f.block_size;           // 16-byte aligned (block sizes % 8 == 0)
+        FlacBits br;
+        br.init(fb, cd.y + cd.w, f.n_bytes);
+        bool bad = false;
+        // ---- subframe header
+        if (br.get(1) != 0u) bad = true;
+        const int type = (int)br.get(6);
+        int wasted = 0;
+        if (br.get(1)) wasted = (int)br.unary() + 1;
+        const int bps = f.bps - wasted;
+        if (bps < 1) bad = true;
+        const int up = 16 - f.bps + wasted;                                       // scale to the int16 range + wasted bits
+        int hist[32];                                                             // ring of the last 32 samples (local memory)
+        int coef[32];
+        int stage[8];
+        int order = 0, shift = 0, porder = 0, pbits = 4;
+        bool residual = false;
+        if (!bad) {
+            if (type == 0) {                                                      // CONSTANT
+                const short v = (short)((unsigned)br.get_signed(bps) << up);
+                const int pair = ((int)(unsigned short)v) | ((int)(unsigned short)v << 16);
+                const int4 q = make_int4(pair, pair, pair, pair);
+                const int n8 = bs >> 3;
+                for (int i = 0; i < n8; ++i) reinterpret_cast<int4*>(out)[i] = q;
+                for (int i = n8 << 3; i < bs; ++i) out[i] = v;
+            } else if (type == 1) {                                               // VERBATIM
+                for (int i = 0; i < bs; ++i) {
+                    out[i] = (short)((unsigned)br.get_signed(bps) << up);
+                    if ((i & 63) == 63 && br.overrun()) { bad = true; break; }
+                }
+            } else if (type >= 8 && type <= 12) {                                 // FIXED = LPC with binomial coefficients
+                order = type - 8;
+                coef[0] = order == 1 ? 1 : order == 2 ? 2 : order == 3 ? 3 : 4;
+                coef[1] = order == 2 ? -1 : order == 3 ? -3 : -6;
+                coef[2] = order == 3 ? 1 : 4;
+                coef[3] = -1;
+                residual = true;
+            } else if (type >= 32) {                                              // LPC
+                order = type - 31;
+                residual = true;
+            } else {
+                bad = true;
+            }
+        }
+        if (residual && order > bs) bad = true;
+        if (residual && !bad) {
+            for (int i = 0; i < order; ++i) {                                     // warm-up samples
+                const int s = br.get_signed(bps);
+                hist[i & 31] = s;
+                stage[i & 7] = s;
+                if ((i & 7) == 7) reinterpret_cast<int4*>(out)[i >> 3] = flac_pack8(stage, up);
+            }
+            if (type >= 32) {
+                const int prec = (int)br.get(4) + 1;
+                if (prec == 16) bad = true;
+                shift = br.get_signed(5);
+                if (shift < 0) bad = true;
+                for (int i = 0; i < order; ++i) coef[i] = br.get_signed(prec);
+            }
+            const int method = (int)br.get(2);
+            if (method > 1) bad = true;
+            pbits = method ? 5 : 4;
+            porder = (int)br.get(4);
+            const int per = bs >> porder;
+            if (porder > 0 && ((per << porder) != bs || per < order)) bad = true;
+            if (!bad) {
+                const int esc = method ? 31 : 15;
+                int i = order;
+                for (int part = 0; part < (1 << porder) && !bad; ++part) {
+                    const int pend = (part + 1) * per;                            // partition = samples [part * per, pend)
+                    const int k = (int)br.get(pbits);
+                    const int raw = (k == esc) ? (int)br.get(5) : -1;
+                    for (; i < pend; ++i) {
+                        int r;
+                        if (raw >= 0) {
+                            r = raw ? br.get_signed(raw) : 0;
+                        } else {
+                            const unsigned hi = br.unary();
+                            const unsigned u = (hi << k) | br.get(k);
+                            r = (int)(u >> 1) ^ -(int)(u & 1u);
+                        }
+                        long long acc = 0;
+                        for (int j = 0; j < order; ++j) acc += (long long)coef[j] * hist[(i - 1 - j) & 31];
+                        const int s = r + (int)(acc >> shift);
+                        hist[i & 31] = s;
+                        stage[i & 7] = s;
+                        if ((i & 7) == 7) reinterpret_cast<int4*>(out)[i >> 3] = flac_pack8(stage, up);
+                        if ((i & 63) == 63 && br.overrun()) { bad = true; break; }    // bounds the reads past a bad frame
+                    }
+                    if (br.overrun()) bad = true;
+                }
+                if (!bad) {                                                       // the last 1..7 samples of a short final block
+                    for (int t = bs & ~7; t < bs; ++t) out[t] = (short)((unsigned)stage[t & 7] << up);
+                }
+            }
+        }
+        if (bad || br.overrun()) continue;
+        // ---- frame footer: zero padding to the byte boundary, CRC-16 over [start, here)
+        const int bits = br.bit_pos();
+        const int body_end = (bits + 7) >> 3;
+        if (body_end + 2 > f.n_bytes) continue;
+        const unsigned want = ((unsigned)fb[body_end] << 8) | fb[body_end + 1];
+        if (flac_crc16_bytes(fb, cd.y, body_end, crc_tab) != want) continue;
+        if (mode == 0) {
+            if (atomicAdd(&fr->hits, 1) == 0) { fr->start = cd.y; fr->end = body_end + 2; }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- validate
+__global__ void __launch_bounds__(256)
+k_flac_validate(const FlacFile* __restrict__ files, int n_files, const FlacFrame* __restrict__ frames,
+                const int* __restrict__ cand_per_file, int* __restrict__ file_status) {
+    for (int fi = blockIdx.x * blockDim.x + threadIdx.x; fi < n_files; fi += gridDim.x * blockDim.x) {
+        const FlacFile f = files[fi];
+        int st = kFlacOk;
+        int expect = f.first_frame;
+        for (int k = 0; k < f.n_frames; ++k) {
+            const FlacFrame fr = frames[f.frame_base + k];
+            if (fr.hits != 1 || fr.start != expect) { st = kFlacCorrupt; break; }
+            expect = fr.end;
+        }
+        if (st == kFlacOk && expect > f.n_bytes) st = kFlacCorrupt;
+        if (st == kFlacOk && cand_per_file[fi] != f.n_frames) st = kFlacRedo;     // a stray candidate may have written samples
+        file_status[fi] = st;
+    }
+}
+
+}  // namespace fe

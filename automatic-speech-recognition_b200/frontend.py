@@ -273,6 +273,32 @@ class Frontend:
             C.c_void_p(int(stream)) if stream else None), "fe_run")
         return out, out_off, nfr[:n]
 
+    def decode_flac(self, buf, files, n_files, total_bytes, pcm_total, pcm=None, stream=None):
+        """FLAC bytes -> int16 PCM on the GPU (``fe_decode_flac``).  ``buf``: numpy uint8 (host) or a CUDA
+        uint8 tensor padded by 4096 bytes; ``files``: the fe_flac_file array ``audio_io.load_flac_batch``
+        planned.  ``pcm``: optional destination (CUDA int16 tensor or numpy int16); by default a CUDA tensor
+        is allocated, so the samples stay in HBM for ``run_packed``.  Returns pcm."""
+        dev = _device_ptr(buf)
+        in_ptr = dev if dev is not None else buf.ctypes.data
+        if pcm is None:
+            import torch
+            pcm = torch.zeros(max(int(pcm_total), 8), dtype=torch.int16, device="cuda:%d" % self.device)
+        pdev = _device_ptr(pcm)
+        out_ptr = pdev if pdev is not None else pcm.ctypes.data
+        cap = int(pcm.numel()) if hasattr(pcm, "numel") else int(pcm.size)
+        status = np.zeros(max(n_files, 1), dtype=np.int32)
+        rc = self._lib.fe_decode_flac(self._h, C.c_void_p(in_ptr), int(total_bytes), files, int(n_files),
+                                      C.c_void_p(out_ptr), cap, _ptr(status, C.c_int32),
+                                      C.c_void_p(int(stream)) if stream else None)
+        self.flac_status = status[:n_files]
+        self._check(rc, "fe_decode_flac")
+        return pcm
+
+    def flac_ms(self):
+        ms = (C.c_float * 3)()
+        self._check(self._lib.fe_get_flac_ms(self._h, ms), "fe_get_flac_ms")
+        return {"scan": ms[0], "decode": ms[1], "validate": ms[2]}
+
     def split(self, out, out_offsets, n_frames, copy=False):
         """Flat output -> list of per-utterance arrays, (L, D, 3) with cmvn else (L, D)."""
         if _device_ptr(out) is not None:

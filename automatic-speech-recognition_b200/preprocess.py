@@ -84,8 +84,41 @@ def _plan_file_batches(lengths, limit=_BATCH_SAMPLES):
     return ranges
 
 
-def process_audios(audio_path, args, device=0, n_threads=0, **switches):
+def _process_flac_on_device(audio_path, args, device, n_threads, switches):
+    """FLAC files -> features with the decode on the GPU: raw file bytes are read into one buffer per
+    ~1-audio-hour batch (host threads, no decoding), uploaded, decoded by ``fe_decode_flac`` into HBM and
+    framed there by ``fe_run``; only the cubes come back."""
+    from concurrent.futures import ThreadPoolExecutor
+    sizes = [os.path.getsize(p) for p in audio_path]
+    ranges = _plan_file_batches([s * 2 for s in sizes], _BATCH_SAMPLES * 2)      # ~2 bytes of PCM per FLAC byte
+    cubes, featlen, fe = [], [], None
+    with ThreadPoolExecutor(max_workers=1) as pool:
+        nxt = pool.submit(audio_io.load_flac_batch, audio_path[ranges[0][0]:ranges[0][1]], n_threads)
+        for b, (lo, hi) in enumerate(ranges):
+            buf, files, pcm_off, lens, fs, total = nxt.result()
+            if b + 1 < len(ranges):
+                nxt = pool.submit(audio_io.load_flac_batch, audio_path[ranges[b + 1][0]:ranges[b + 1][1]], n_threads)
+            if fe is None:
+                cfg = FrontendConfig.from_args(args, sample_rate=fs, pcm_dtype="int16", **switches)
+                fe = get_frontend(cfg, device)
+            if np.any(lens < fe.config.frame_len):
+                raise ValueError("negative dimensions are not allowed")          # what speechpy's stack_frames raises
+            pcm_total = int(pcm_off[-1] + (lens[-1] + 7) // 8 * 8) if len(lens) else 0
+            try:
+                d_pcm = fe.decode_flac(buf, files, hi - lo, total, pcm_total)
+            except RuntimeError as e:
+                bad = [audio_path[lo + int(i)] for i in np.flatnonzero(fe.flac_status)]
+                raise audio_io.AudioFormatError("%s: %s" % (", ".join(bad[:4]), e))
+            out, out_off, nfr = fe.run_packed(d_pcm, pcm_off, lens)
+            cubes.extend(fe.split(out, out_off, nfr))
+            featlen.extend(int(L) for L in nfr)
+    return to_object_array(cubes), featlen
+
+
+def process_audios(audio_path, args, device=0, n_threads=0, device_decode=False, **switches):
     """Same signature and return value as the reference (preprocess.py:50-91).
+
+    ``device_decode=True`` (FLAC lists only) moves the FLAC decode itself to the GPU.
 
     FLAC / WAV lists take the batch path: headers are probed once, then each ~1-audio-hour
     batch is decoded by the native thread pool straight into a packed int16 buffer
@@ -95,6 +128,10 @@ def process_audios(audio_path, args, device=0, n_threads=0, **switches):
     if not audio_path:
         return to_object_array([]), []
     exts = {os.path.splitext(p)[1].lower() for p in audio_path}
+    if device_decode:
+        if exts != {".flac"}:
+            raise ValueError("device_decode=True takes .flac files only")
+        return _process_flac_on_device(audio_path, args, device, n_threads, switches)
     if not exts <= {".flac", ".wav"}:
         pcm_list, fs_seen = [], None
         for p in audio_path:

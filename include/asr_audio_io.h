@@ -64,6 +64,20 @@ int aio_probe_files(const char* const* paths, int32_t n, int32_t n_threads, aio_
 int aio_decode_files(const char* const* paths, int32_t n, int32_t n_threads, int16_t* out,
                      const int64_t* offsets, const int64_t* lengths, int check_md5, int32_t* status);
 
+/* Device-side FLAC decode support (fe_decode_flac, asr_frontend.h): the stream layout the GPU kernels
+ * need from the metadata -- byte offset of the first audio frame and the stream's block sizes -- and a
+ * thread-pooled raw file read into one buffer (file i at buf + offsets[i], sizes[i] bytes; no decoding). */
+typedef struct aio_flac_layout_t {
+    int64_t n_samples;         /* per channel (0 if unknown) */
+    int32_t first_frame;       /* byte offset of the first audio frame */
+    int32_t min_block, max_block;
+    int32_t sample_rate, channels, bits_per_sample;
+} aio_flac_layout_t;
+int aio_flac_layout(const uint8_t* data, int64_t n_bytes, aio_flac_layout_t* out);
+int aio_file_sizes(const char* const* paths, int32_t n, int64_t* sizes);
+int aio_read_files(const char* const* paths, int32_t n, int32_t n_threads, uint8_t* buf, const int64_t* offsets,
+                   const int64_t* sizes, int32_t* status);
+
 /* Encoders (mono or interleaved multi-channel int16).  FLAC: fixed block size
  * 4096; constant / verbatim / fixed-predictor (order 0..4) subframes with
  * partitioned Rice coding, frame CRCs and the STREAMINFO MD5 -- a subset of the

@@ -147,6 +147,29 @@ int fe_pad_batches(fe_handle* h, const float* feats, const int64_t* src_offsets,
                    float* dst, int64_t dst_capacity, void* stream);
 int fe_get_pad_ms(fe_handle* h, float* ms);    /* duration of the last fe_pad_batches launch (profiling on) */
 
+/* FLAC decode on the device: sf.read (preprocess.py:69) behind the PCIe link.  The caller uploads (or
+ * passes host memory holding) the raw bytes of n FLAC files, each starting at a 16-byte aligned offset
+ * of one buffer, with the stream layout the host probe reports (aio_flac_layout, asr_audio_io.h); the
+ * int16 samples of file i appear at pcm + pcm_offset (host or device memory), ready for fe_run.
+ * Streams must be mono, <= 16 bits, fixed block size (a multiple of 8) -- what libFLAC, SoX and this
+ * library's encoder write.  Every frame's CRC-8 / CRC-16 and the frame chain of every file are
+ * verified on the device; status[i] = 0 or FE_ERR_INVALID (corrupt, truncated, unsupported layout) and
+ * the call returns FE_ERR_INVALID if any file failed (the others are decoded).  A device `bytes` buffer
+ * must be readable for 4096 bytes past total_bytes.  Synchronous. */
+typedef struct fe_flac_file {
+    int64_t byte_offset;      /* of the file's first byte in `bytes`, multiple of 16 */
+    int64_t pcm_offset;       /* int16 element offset of its first sample in `pcm`, multiple of 8 */
+    int32_t n_bytes;
+    int32_t first_frame;      /* byte offset of the first audio frame inside the file */
+    int32_t n_samples;        /* STREAMINFO total samples */
+    int32_t block_size;       /* STREAMINFO min == max block size */
+    int32_t bits_per_sample;
+    int32_t reserved;
+} fe_flac_file;
+int fe_decode_flac(fe_handle* h, const uint8_t* bytes, int64_t total_bytes, const fe_flac_file* files, int32_t n_files,
+                   int16_t* pcm, int64_t pcm_capacity, int32_t* status, void* stream);
+int fe_get_flac_ms(fe_handle* h, float ms[3]);   /* scan, decode, validate of the last call (profiling on) */
+
 int fe_sync(fe_handle* h);
 
 /* Measurement hooks.  With profiling on, every kernel of every fe_run is bracketed by CUDA
