@@ -93,6 +93,7 @@ AIO_SYMBOLS = {
     "aio_probe_files": (C.c_int, [_cpp, C.c_int32, C.c_int32, _infop, _i32p]),
     "aio_decode_files": (C.c_int, [_cpp, C.c_int32, C.c_int32, C.c_void_p, _i64p, _i64p, C.c_int, _i32p]),
     "aio_flac_layout": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(AioFlacLayout)]),
+    "aio_flac_layouts": (C.c_int, [C.c_void_p, _i64p, _i64p, C.c_int32, C.c_int32, C.POINTER(AioFlacLayout), _i32p]),
     "aio_file_sizes": (C.c_int, [_cpp, C.c_int32, _i64p]),
     "aio_read_files": (C.c_int, [_cpp, C.c_int32, C.c_int32, C.c_void_p, _i64p, _i64p, _i32p]),
     "aio_flac_bound": (C.c_int64, [C.c_int64, C.c_int32]),

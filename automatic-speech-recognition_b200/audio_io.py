@@ -189,27 +189,31 @@ def load_flac_batch(paths, n_threads=0, out=None):
         bad = int(np.flatnonzero(status)[0])
         _check(int(status[bad]), paths[bad])
     files = (_lib.FeFlacFile * max(n, 1))()
-    lengths = np.zeros(n, dtype=np.int64)
-    lay = _lib.AioFlacLayout()
-    fs = DEFAULT_FS
-    for i in range(n):
-        _check(lib.aio_flac_layout(C.c_void_p(out.ctypes.data + int(offsets[i])), int(sizes[i]), C.byref(lay)), paths[i])
-        if lay.channels != 1:
-            raise ValueError("%s: mono audio expected" % paths[i])
-        if i == 0:
-            fs = lay.sample_rate
-        elif lay.sample_rate != fs:
-            raise ValueError("mixed sample rates in one call: %d vs %d (%s)" % (fs, lay.sample_rate, paths[i]))
-        if lay.min_block != lay.max_block or lay.n_samples <= 0 or lay.max_block % 8 or lay.bits_per_sample > 16:
-            raise AudioFormatError("%s: the device decoder takes fixed-block-size streams (multiple of 8) of at most "
-                                   "16 bits with a sample count; use read_audio_batch" % paths[i])
-        lengths[i] = lay.n_samples
-        f = files[i]
-        f.byte_offset, f.n_bytes, f.first_frame = int(offsets[i]), int(sizes[i]), lay.first_frame
-        f.n_samples, f.block_size, f.bits_per_sample = int(lay.n_samples), lay.max_block, lay.bits_per_sample
+    lays = (_lib.AioFlacLayout * max(n, 1))()
+    rc = lib.aio_flac_layouts(C.c_void_p(out.ctypes.data), offsets.ctypes.data_as(C.POINTER(C.c_int64)),
+                              sizes.ctypes.data_as(C.POINTER(C.c_int64)), n, int(n_threads), lays,
+                              status.ctypes.data_as(C.POINTER(C.c_int32)))
+    if rc != 0:
+        bad = int(np.flatnonzero(status)[0])
+        _check(int(status[bad]), paths[bad])
+    L = np.ctypeslib.as_array(lays)[:n]                                   # structured views: no per-file Python work
+    F = np.ctypeslib.as_array(files)[:n]
+    fs = int(L["sample_rate"][0]) if n else DEFAULT_FS
+    if np.any(L["channels"] != 1):
+        raise ValueError("%s: mono audio expected" % paths[int(np.flatnonzero(L["channels"] != 1)[0])])
+    if np.any(L["sample_rate"] != fs):
+        i = int(np.flatnonzero(L["sample_rate"] != fs)[0])
+        raise ValueError("mixed sample rates in one call: %d vs %d (%s)" % (fs, L["sample_rate"][i], paths[i]))
+    unsup = ((L["min_block"] != L["max_block"]) | (L["n_samples"] <= 0) | (L["max_block"] % 8 != 0) |
+             (L["bits_per_sample"] > 16) | (L["n_samples"] >= 2 ** 31))
+    if np.any(unsup):
+        raise AudioFormatError("%s: the device decoder takes fixed-block-size streams (multiple of 8) of at most "
+                               "16 bits with a sample count; use read_audio_batch" % paths[int(np.flatnonzero(unsup)[0])])
+    lengths = L["n_samples"].astype(np.int64)
     pcm_offsets, _ = plan_batch(lengths)
-    for i in range(n):
-        files[i].pcm_offset = int(pcm_offsets[i])
+    F["byte_offset"], F["n_bytes"], F["first_frame"] = offsets, sizes, L["first_frame"]
+    F["n_samples"], F["block_size"], F["bits_per_sample"] = lengths, L["max_block"], L["bits_per_sample"]
+    F["pcm_offset"] = pcm_offsets
     return out, files, pcm_offsets, lengths, fs, total
 
 

@@ -111,6 +111,8 @@ class BucketBatcher:
             self.fe._h, C.c_void_p(in_ptr), _ptr(src_off, C.c_int64), _ptr(valid, C.c_int32), _ptr(dst, C.c_int64),
             _ptr(slot, C.c_int32), int(src.size), C.c_void_p(out_ptr), cap,
             C.c_void_p(int(stream)) if stream else None), "fe_pad_batches")
+        if stream is None:
+            self.fe.sync()                 # device in / device out runs asynchronously on the handle's own stream
         views = []
         for (b, idx), base in zip(plan, bases):
             T = self.boundaries[b] - 1

@@ -907,6 +907,19 @@ int aio_flac_layout(const uint8_t* data, int64_t n_bytes, aio_flac_layout_t* out
     return AIO_OK;
 }
 
+int aio_flac_layouts(const uint8_t* buf, const int64_t* offsets, const int64_t* sizes, int32_t n, int32_t n_threads,
+                     aio_flac_layout_t* out, int32_t* status) {
+    if (n < 0 || (n > 0 && (!buf || !offsets || !sizes || !out))) return AIO_ERR_INVALID;
+    std::vector<int32_t> st((size_t)n, 0);
+    parallel_for(n, n_threads, [&](int32_t i) { st[(size_t)i] = aio_flac_layout(buf + offsets[i], sizes[i], &out[i]); });
+    int first = 0;
+    for (int32_t i = 0; i < n; ++i) {
+        if (status) status[i] = st[(size_t)i];
+        if (!first && st[(size_t)i]) first = st[(size_t)i];
+    }
+    return first;
+}
+
 int aio_file_sizes(const char* const* paths, int32_t n, int64_t* sizes) {
     if (n < 0 || (n > 0 && (!paths || !sizes))) return AIO_ERR_INVALID;
     int first = 0;

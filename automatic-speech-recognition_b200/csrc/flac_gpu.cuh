@@ -212,6 +212,72 @@ __device__ __forceinline__ unsigned flac_crc16_bytes(const uint8_t* __restrict__
     return c;
 }
 
+// Residual decode fused with the prediction recurrence, samples [order, bs) of a subframe.
+//   MODE 0  any order (<= 32): history ring and coefficients in lane-interleaved local memory, 64-bit sums
+//   MODE 1  order <= 12, sums fit 32 bits (bps + precision + ceil(log2(order)) <= 32: every libFLAC stream
+//           at <= 16 bits): history and zero-padded coefficients in registers -- the same straight-line
+//           code for every lane of the warp whatever its frame's order
+//   MODE 2  order <= 12, 64-bit sums (e.g. FFmpeg's 15-bit coefficients)
+// Returns true if the frame is bad.
+constexpr int kFlacRegOrder = 12;
+
+template <int MODE>
+__device__ __forceinline__ bool flac_residual(FlacBits& br, int bs, int order, int shift, int porder, int pbits, int esc,
+                                              int* hist, const int* coef, int* stage, short* out, int up) {
+    int h[kFlacRegOrder], c[kFlacRegOrder];
+    if (MODE != 0) {
+#pragma unroll
+        for (int j = 0; j < kFlacRegOrder; ++j) {                                 // h[0] = newest sample
+            h[j] = j < order ? hist[order - 1 - j] : 0;
+            c[j] = j < order ? coef[j] : 0;
+        }
+    }
+    const int per = bs >> porder;
+    int i = order;
+    for (int part = 0; part < (1 << porder); ++part) {
+        const int pend = (part + 1) * per;                                        // partition = samples [part * per, pend)
+        const int k = (int)br.get(pbits);
+        const int raw = (k == esc) ? (int)br.get(5) : -1;
+        for (; i < pend; ++i) {
+            int r;
+            if (raw >= 0) {
+                r = raw ? br.get_signed(raw) : 0;
+            } else {
+                const unsigned hi = br.unary();
+                const unsigned u = (hi << k) | br.get(k);
+                r = (int)(u >> 1) ^ -(int)(u & 1u);
+            }
+            int s;
+            if (MODE == 0) {
+                long long acc = 0;
+                for (int j = 0; j < order; ++j) acc += (long long)coef[j] * hist[(i - 1 - j) & 31];
+                s = r + (int)(acc >> shift);
+                hist[i & 31] = s;
+            } else {
+                if (MODE == 1) {
+                    int a0 = 0, a1 = 0;
+#pragma unroll
+                    for (int j = 0; j < kFlacRegOrder; j += 2) { a0 += c[j] * h[j]; a1 += c[j + 1] * h[j + 1]; }
+                    s = r + ((a0 + a1) >> shift);
+                } else {
+                    long long a0 = 0, a1 = 0;
+#pragma unroll
+                    for (int j = 0; j < kFlacRegOrder; j += 2) { a0 += (long long)c[j] * h[j]; a1 += (long long)c[j + 1] * h[j + 1]; }
+                    s = r + (int)((a0 + a1) >> shift);
+                }
+#pragma unroll
+                for (int j = kFlacRegOrder - 1; j > 0; --j) h[j] = h[j - 1];
+                h[0] = s;
+            }
+            stage[i & 7] = s;
+            if ((i & 7) == 7) reinterpret_cast<int4*>(out)[i >> 3] = flac_pack8(stage, up);
+            if ((i & 63) == 63 && br.overrun()) return true;                      // bounds the reads past a bad frame
+        }
+        if (br.overrun()) return true;
+    }
+    return false;
+}
+
 // mode 0: every candidate.  mode 1: only chain positions of files flagged kFlacRedo (second pass).
 __global__ void __launch_bounds__(128)
 k_flac_decode(const uint8_t* __restrict__ bytes, const FlacFile* __restrict__ files, const int4* __restrict__ cands,
@@ -247,7 +313,7 @@ k_flac_decode(const uint8_t* __restrict__ bytes, const FlacFile* __restrict__ fi
         int hist[32];                                                             // ring of the last 32 samples (local memory)
         int coef[32];
         int stage[8];
-        int order = 0, shift = 0, porder = 0, pbits = 4;
+        int order = 0, shift = 0, porder = 0, pbits = 4, prec = 4;                 // fixed predictors: |coefficient| <= 6
         bool residual = false;
         if (!bad) {
             if (type == 0) {                                                      // CONSTANT
@@ -285,7 +351,7 @@ k_flac_decode(const uint8_t* __restrict__ bytes, const FlacFile* __restrict__ fi
                 if ((i & 7) == 7) reinterpret_cast<int4*>(out)[i >> 3] = flac_pack8(stage, up);
             }
             if (type >= 32) {
-                const int prec = (int)br.get(4) + 1;
+                prec = (int)br.get(4) + 1;
                 if (prec == 16) bad = true;
                 shift = br.get_signed(5);
                 if (shift < 0) bad = true;
@@ -299,30 +365,10 @@ k_flac_decode(const uint8_t* __restrict__ bytes, const FlacFile* __restrict__ fi
             if (porder > 0 && ((per << porder) != bs || per < order)) bad = true;
             if (!bad) {
                 const int esc = method ? 31 : 15;
-                int i = order;
-                for (int part = 0; part < (1 << porder) && !bad; ++part) {
-                    const int pend = (part + 1) * per;                            // partition = samples [part * per, pend)
-                    const int k = (int)br.get(pbits);
-                    const int raw = (k == esc) ? (int)br.get(5) : -1;
-                    for (; i < pend; ++i) {
-                        int r;
-                        if (raw >= 0) {
-                            r = raw ? br.get_signed(raw) : 0;
-                        } else {
-                            const unsigned hi = br.unary();
-                            const unsigned u = (hi << k) | br.get(k);
-                            r = (int)(u >> 1) ^ -(int)(u & 1u);
-                        }
-                        long long acc = 0;
-                        for (int j = 0; j < order; ++j) acc += (long long)coef[j] * hist[(i - 1 - j) & 31];
-                        const int s = r + (int)(acc >> shift);
-                        hist[i & 31] = s;
-                        stage[i & 7] = s;
-                        if ((i & 7) == 7) reinterpret_cast<int4*>(out)[i >> 3] = flac_pack8(stage, up);
-                        if ((i & 63) == 63 && br.overrun()) { bad = true; break; }    // bounds the reads past a bad frame
-                    }
-                    if (br.overrun()) bad = true;
-                }
+                const int lg = order <= 1 ? 0 : 32 - __clz(order - 1);             // ceil(log2(order))
+                if (order > kFlacRegOrder) bad = flac_residual<0>(br, bs, order, shift, porder, pbits, esc, hist, coef, stage, out, up);
+                else if (bps + prec + lg <= 32) bad = flac_residual<1>(br, bs, order, shift, porder, pbits, esc, hist, coef, stage, out, up);
+                else bad = flac_residual<2>(br, bs, order, shift, porder, pbits, esc, hist, coef, stage, out, up);
                 if (!bad) {                                                       // the last 1..7 samples of a short final block
                     for (int t = bs & ~7; t < bs; ++t) out[t] = (short)((unsigned)stage[t & 7] << up);
                 }

@@ -283,6 +283,7 @@ class Frontend:
         if pcm is None:
             import torch
             pcm = torch.zeros(max(int(pcm_total), 8), dtype=torch.int16, device="cuda:%d" % self.device)
+            torch.cuda.current_stream(self.device).synchronize()      # the handle's stream does not wait for torch's
         pdev = _device_ptr(pcm)
         out_ptr = pdev if pdev is not None else pcm.ctypes.data
         cap = int(pcm.numel()) if hasattr(pcm, "numel") else int(pcm.size)
@@ -302,6 +303,7 @@ class Frontend:
     def split(self, out, out_offsets, n_frames, copy=False):
         """Flat output -> list of per-utterance arrays, (L, D, 3) with cmvn else (L, D)."""
         if _device_ptr(out) is not None:
+            self.sync()                    # fe_run on device buffers is asynchronous on the handle's stream
             out = out.cpu().numpy()
         c = self.config
         res = []

@@ -109,7 +109,9 @@ def _process_flac_on_device(audio_path, args, device, n_threads, switches):
             except RuntimeError as e:
                 bad = [audio_path[lo + int(i)] for i in np.flatnonzero(fe.flac_status)]
                 raise audio_io.AudioFormatError("%s: %s" % (", ".join(bad[:4]), e))
-            out, out_off, nfr = fe.run_packed(d_pcm, pcm_off, lens)
+            plan_off, _ = fe.plan(lens)
+            host_out = np.empty(max(int(plan_off[-1]), 1), dtype=np.float32)     # cubes come back through fe_run's pinned D2H lanes
+            out, out_off, nfr = fe.run_packed(d_pcm, pcm_off, lens, out=host_out)
             cubes.extend(fe.split(out, out_off, nfr))
             featlen.extend(int(L) for L in nfr)
     return to_object_array(cubes), featlen

@@ -74,6 +74,8 @@ typedef struct aio_flac_layout_t {
     int32_t sample_rate, channels, bits_per_sample;
 } aio_flac_layout_t;
 int aio_flac_layout(const uint8_t* data, int64_t n_bytes, aio_flac_layout_t* out);
+int aio_flac_layouts(const uint8_t* buf, const int64_t* offsets, const int64_t* sizes, int32_t n, int32_t n_threads,
+                     aio_flac_layout_t* out, int32_t* status);     /* batch form: file i at buf + offsets[i] */
 int aio_file_sizes(const char* const* paths, int32_t n, int64_t* sizes);
 int aio_read_files(const char* const* paths, int32_t n, int32_t n_threads, uint8_t* buf, const int64_t* offsets,
                    const int64_t* sizes, int32_t* status);

@@ -6,7 +6,7 @@
 Two directions, both against code we did not write:
 
 * ``ffmpeg_*.flac`` -- seeded PCM encoded by FFmpeg's FLAC encoder (LPC subframes,
-  partitioned Rice, mid/side stereo; compression levels 0 / 5 / 8 / 12): the
+  partitioned Rice, mid/side stereo; compression levels 0 / 5 / 8 / 12, LPC orders up to 32): the
   committed files pin OUR decoder (aio_decode_*) -- the manifest holds the SHA-256
   of the PCM that went in, tests regenerate it from the seed.
 * our encoder's output (aio_encode_flac) is demuxed and decoded by FFmpeg here and
@@ -228,6 +228,15 @@ def main():
             assert got.size == pcm.size and (got == pcm).all(), fn
             manifest["ffmpeg_encoded"][fn] = {"signal": name, "channels": ch, "samples": int(pcm.size // ch),
                                               "level": lv, "frame_size": fsize, "pcm_sha256": sha,
+                                              "bytes": os.path.getsize(os.path.join(OUT, fn))}
+        if name == "tone_plus_noise":          # LPC orders 20..32: beyond the FLAC "subset" limit of 12
+            fn = "ffmpeg_%s_o32.flac" % name
+            opts = (("min_prediction_order", 20), ("max_prediction_order", 32), ("prediction_order_method", "estimation"))
+            fsize = ffmpeg_encode(ff, pcm, ch, 8, os.path.join(OUT, fn), tmp, opts=opts)
+            got, _, _ = ffmpeg_decode(ff, os.path.join(OUT, fn))
+            assert got.size == pcm.size and (got == pcm).all(), fn
+            manifest["ffmpeg_encoded"][fn] = {"signal": name, "channels": ch, "samples": int(pcm.size // ch), "level": 8,
+                                              "options": dict(opts), "frame_size": fsize, "pcm_sha256": sha,
                                               "bytes": os.path.getsize(os.path.join(OUT, fn))}
         ours = os.path.join(tmp, "ours_%s.flac" % name)
         pkg.audio_io.write_flac(ours, pcm, FS, channels=ch)

@@ -4,6 +4,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import asr_b200 as A
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 600
+rep = int(sys.argv[2]) if len(sys.argv) > 2 else 1                    # every file is listed rep times (bigger batch, same disk set)
 pcm = A.synth.corpus(n, 2.0, 15.0, seed=4567)
 pcm = [(p // 16).astype(np.int16) for p in pcm]                      # LibriSpeech-like level: FLAC ratio ~0.56
 hours = sum(len(p) for p in pcm) / 16000 / 3600
@@ -12,6 +13,7 @@ try:
     paths = [os.path.join(root, "%05d.flac" % i) for i in range(n)]
     packed, off, lens = A.pack_pcm(pcm)
     A.audio_io.write_audio_batch(paths, packed, off, lens, 16000)
+    paths = paths * rep; pcm = pcm * rep; hours *= rep; n *= rep
     t = time.time(); buf, files, pcm_off, lens2, fs, total = A.audio_io.load_flac_batch(paths); t_load = time.time() - t
     fe = A.Frontend(A.FrontendConfig()); fe.set_profiling(True)
     pcm_total = int(pcm_off[-1] + (lens2[-1] + 7) // 8 * 8)

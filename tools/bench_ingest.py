@@ -7,6 +7,7 @@ import numpy as np
 import asr_b200 as A
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 400
 threads = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+rep = int(sys.argv[3]) if len(sys.argv) > 3 else 1                    # list every file rep times for the process_audios runs
 pcm = A.synth.corpus(n, 2.0, 15.0, seed=4567)
 hours = sum(len(p) for p in pcm) / 16000 / 3600
 root = tempfile.mkdtemp(dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
@@ -28,8 +29,15 @@ try:
             if torch.cuda.is_available():
                 args = types.SimpleNamespace(frame_step=10, frame_length=25, feat_dim=13, feat_type="mfcc", cmvn=True)
                 A.process_audios(paths[:8], args)                                   # warm-up (handle, tables)
-                t = time.time(); feats, featlen = A.process_audios(paths, args, n_threads=threads); t_e2e = time.time() - t
-                r["process_audios_files_h_per_s"] = hours / t_e2e
+                big = paths * rep
+                t = time.time(); feats, featlen = A.process_audios(big, args, n_threads=threads); t_e2e = time.time() - t
+                r["process_audios_files_h_per_s"] = hours * rep / t_e2e
+                A.process_audios(paths[:8], args, device_decode=True)
+                A.process_audios(big, args, n_threads=threads, device_decode=True)          # grows the device buffers once
+                t = time.time(); feats2, featlen2 = A.process_audios(big, args, n_threads=threads, device_decode=True); t_dev = time.time() - t
+                assert featlen2 == featlen and all(np.array_equal(a, b) for a, b in zip(feats, feats2))
+                r["process_audios_files_device_decode_h_per_s"] = hours * rep / t_dev
+                r["process_audios_audio_hours"] = hours * rep
         except ImportError:
             pass
         res[tag] = r
