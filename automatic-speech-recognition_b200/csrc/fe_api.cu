@@ -817,12 +817,14 @@ int fe_pad_batches(fe_handle* h, const float* feats, const int64_t* src_offsets,
     FE_CUDA(h, cudaSetDevice(h->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
     std::vector<PadSlot> sl((size_t)n_slots);
-    long long span_src = 0, span_dst = 0;
+    long long span_src = 0, span_dst = 0, n_chunks = 0;
     for (int i = 0; i < n_slots; ++i) {
         if (src_offsets[i] < 0 || dst_offsets[i] < 0 || valid_floats[i] < 0 || slot_floats[i] < 0)
             return fail(h, FE_ERR_INVALID, "negative offset / length");
         if (valid_floats[i] > slot_floats[i]) return fail(h, FE_ERR_INVALID, "utterance longer than its slot (bucket boundary)");
-        sl[(size_t)i] = PadSlot{src_offsets[i], dst_offsets[i], valid_floats[i], slot_floats[i]};
+        sl[(size_t)i] = PadSlot{src_offsets[i], dst_offsets[i], valid_floats[i], slot_floats[i], (int)n_chunks, 0};
+        n_chunks += std::max(1, (slot_floats[i] / 4 + kPadChunk / 4 - 1) / (kPadChunk / 4));      // >= 1: head / tail scalars
+        if (n_chunks > 0x7fffffffLL) return fail(h, FE_ERR_INVALID, "batch too large");
         span_src = std::max<long long>(span_src, src_offsets[i] + valid_floats[i]);
         span_dst = std::max<long long>(span_dst, dst_offsets[i] + slot_floats[i]);
     }
@@ -837,10 +839,10 @@ int fe_pad_batches(fe_handle* h, const float* feats, const int64_t* src_offsets,
     FE_CUDA(h, cudaMemcpyAsync(h->d_pad.p, sl.data(), sizeof(PadSlot) * sl.size(), cudaMemcpyHostToDevice, st));
     if (!in_dev) FE_CUDA(h, cudaMemcpyAsync(L.d_statics.p, feats, sizeof(float) * (size_t)span_src, cudaMemcpyHostToDevice, st));
     FE_CUDA(h, cudaStreamSynchronize(st));                   // sl / feats may be freed by the caller after return
-    const int grid = (int)std::min<long long>(n_slots, 8LL * h->num_sms);
+    const int grid = (int)std::min<long long>(n_chunks, 8LL * h->num_sms);
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (h->profiling) { FE_CUDA(h, cudaEventCreate(&e0)); FE_CUDA(h, cudaEventCreate(&e1)); FE_CUDA(h, cudaEventRecord(e0, st)); }
-    k_pad_slots<<<grid, 256, 0, st>>>(d_in, (const PadSlot*)h->d_pad.p, n_slots, d_out);
+    k_pad_slots<<<grid, 256, 0, st>>>(d_in, (const PadSlot*)h->d_pad.p, n_slots, (int)n_chunks, d_out);
     h->launches++;
     FE_CUDA(h, cudaGetLastError());
     if (h->profiling) {

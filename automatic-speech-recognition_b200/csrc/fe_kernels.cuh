@@ -1049,22 +1049,34 @@ struct __align__(8) PadSlot {
     long long dst_off;      // float offset of the slot in the batch buffer
     int n_valid;            // floats to copy (n_frames * D * planes)
     int n_slot;             // floats in the slot (T_pad * D * planes)
+    int chunk_base;         // index of the slot's first work item (chunks of kPadChunk floats)
+    int pad;
 };
 
+constexpr int kPadChunk = 8192;     // floats per work item (32 KB written): fine-grained enough to balance 148 SMs
+
 __global__ void __launch_bounds__(256)
-k_pad_slots(const float* __restrict__ src, const PadSlot* __restrict__ slots, int n_slots, float* __restrict__ dst) {
+k_pad_slots(const float* __restrict__ src, const PadSlot* __restrict__ slots, int n_slots, int n_chunks,
+            float* __restrict__ dst) {
     const int tid = threadIdx.x;
-    for (int it = blockIdx.x; it < n_slots; it += gridDim.x) {
-        const PadSlot p = slots[it];
+    for (int w = blockIdx.x; w < n_chunks; w += gridDim.x) {
+        int lo = 0, hi = n_slots - 1;                                         // last slot with chunk_base <= w (block-uniform)
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (slots[mid].chunk_base <= w) lo = mid; else hi = mid - 1;
+        }
+        const PadSlot p = slots[lo];
         const float* s = src + p.src_off;
         float* d = dst + p.dst_off;
         const int head = min((int)((4 - (p.dst_off & 3)) & 3), p.n_slot);    // scalars up to the first 16-byte boundary of dst
-        if (tid < head) d[tid] = tid < p.n_valid ? s[tid] : 0.f;
+        const int c = w - p.chunk_base;                                       // chunk c covers body vectors [c, c + 1) * kPadChunk / 4
+        if (c == 0 && tid < head) d[tid] = tid < p.n_valid ? s[tid] : 0.f;
         const int nbody = (p.n_slot - head) >> 2;
         const bool congruent = ((p.src_off + head) & 3) == 0;
         const int full = p.n_valid >= head ? (p.n_valid - head) >> 2 : 0;     // body vectors made of valid floats only
+        const int j1 = min(nbody, (c + 1) * (kPadChunk / 4));
 #pragma unroll 4
-        for (int j = tid; j < nbody; j += 256) {
+        for (int j = c * (kPadChunk / 4) + tid; j < j1; j += 256) {
             const int e = head + 4 * j;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             if (j < full) {
@@ -1077,8 +1089,10 @@ k_pad_slots(const float* __restrict__ src, const PadSlot* __restrict__ slots, in
             }
             __stcs(reinterpret_cast<float4*>(d + e), v);
         }
-        const int e = head + 4 * nbody + tid;
-        if (e < p.n_slot) d[e] = e < p.n_valid ? s[e] : 0.f;
+        if (j1 == nbody) {                                                    // the slot's last chunk also writes the tail scalars
+            const int e = head + 4 * nbody + tid;
+            if (e < p.n_slot) d[e] = e < p.n_valid ? s[e] : 0.f;
+        }
     }
 }
 

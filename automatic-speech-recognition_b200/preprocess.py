@@ -84,7 +84,11 @@ def _plan_file_batches(lengths, limit=_BATCH_SAMPLES):
     return ranges
 
 
-def _process_flac_on_device(audio_path, args, device, n_threads, switches):
+def _uniform(value, n):
+    return None if value is None else [value] * n
+
+
+def _process_flac_on_device(audio_path, args, device, n_threads, switches, speed=None, gain=None):
     """FLAC files -> features with the decode on the GPU: raw file bytes are read into one buffer per
     ~1-audio-hour batch (host threads, no decoding), uploaded, decoded by ``fe_decode_flac`` into HBM and
     framed there by ``fe_run``; only the cubes come back."""
@@ -109,18 +113,22 @@ def _process_flac_on_device(audio_path, args, device, n_threads, switches):
             except RuntimeError as e:
                 bad = [audio_path[lo + int(i)] for i in np.flatnonzero(fe.flac_status)]
                 raise audio_io.AudioFormatError("%s: %s" % (", ".join(bad[:4]), e))
-            plan_off, _ = fe.plan(lens)
-            host_out = np.empty(max(int(plan_off[-1]), 1), dtype=np.float32)     # cubes come back through fe_run's pinned D2H lanes
-            out, out_off, nfr = fe.run_packed(d_pcm, pcm_off, lens, out=host_out)
+            # cubes come back into a host array (device PCM in, host features out)
+            plan_off, _ = fe.plan(lens, fe.speed_indices(_uniform(speed, len(lens))))
+            host_out = np.empty(max(int(plan_off[-1]), 1), dtype=np.float32)
+            out, out_off, nfr = fe.run_packed(d_pcm, pcm_off, lens, speed_idx=fe.speed_indices(_uniform(speed, len(lens))),
+                                              gain=_uniform(gain, len(lens)), out=host_out)
             cubes.extend(fe.split(out, out_off, nfr))
             featlen.extend(int(L) for L in nfr)
     return to_object_array(cubes), featlen
 
 
-def process_audios(audio_path, args, device=0, n_threads=0, device_decode=False, **switches):
+def process_audios(audio_path, args, device=0, n_threads=0, device_decode=False, speed=None, gain=None, **switches):
     """Same signature and return value as the reference (preprocess.py:50-91).
 
     ``device_decode=True`` (FLAC lists only) moves the FLAC decode itself to the GPU.
+    ``speed`` / ``gain`` perturb every file of the call on the fly (K0 in front of the framing): the
+    features of ``SpeedAugmentation(files, ..., speed)`` without the intermediate audio files.
 
     FLAC / WAV lists take the batch path: headers are probed once, then each ~1-audio-hour
     batch is decoded by the native thread pool straight into a packed int16 buffer
@@ -133,7 +141,7 @@ def process_audios(audio_path, args, device=0, n_threads=0, device_decode=False,
     if device_decode:
         if exts != {".flac"}:
             raise ValueError("device_decode=True takes .flac files only")
-        return _process_flac_on_device(audio_path, args, device, n_threads, switches)
+        return _process_flac_on_device(audio_path, args, device, n_threads, switches, speed, gain)
     if not exts <= {".flac", ".wav"}:
         pcm_list, fs_seen = [], None
         for p in audio_path:
@@ -143,7 +151,8 @@ def process_audios(audio_path, args, device=0, n_threads=0, device_decode=False,
             elif fs != fs_seen:
                 raise ValueError("mixed sample rates in one call: %d vs %d (%s)" % (fs_seen, fs, p))
             pcm_list.append(audio)
-        return process_pcm(pcm_list, args, fs=fs_seen, device=device, **switches)
+        return process_pcm(pcm_list, args, fs=fs_seen, device=device, speeds=_uniform(speed, len(pcm_list)),
+                           gains=_uniform(gain, len(pcm_list)), **switches)
 
     from concurrent.futures import ThreadPoolExecutor
     infos = [audio_io.probe(p) for p in audio_path] if len(audio_path) < 64 else audio_io.probe_batch(audio_path, n_threads)
@@ -165,11 +174,21 @@ def process_audios(audio_path, args, device=0, n_threads=0, device_decode=False,
                 nxt = pool.submit(audio_io.read_audio_batch, audio_path[ranges[b + 1][0]:ranges[b + 1][1]], n_threads)
             if fs_b != fs:
                 raise ValueError("mixed sample rates in one call: %d vs %d" % (fs, fs_b))
-            out, out_off, nfr = fe.run_packed(packed, off, lens)
+            out, out_off, nfr = fe.run_packed(packed, off, lens, speed_idx=fe.speed_indices(_uniform(speed, len(lens))),
+                                              gain=_uniform(gain, len(lens)))
             got = fe.split(out, out_off, nfr)
             cubes.extend(got)
             featlen.extend(int(L) for L in nfr)
     return to_object_array(cubes), featlen
+
+
+def process_speed_augmented(audio_path, args, speed_list=(0.9, 1.1), k=4, device=0, **switches):
+    """preprocess.py:158-167 without the detour over disk: for each speed the reference writes a resampled
+    copy of every training file (SpeedAugmentation) and extracts ``speed_{s}`` features from the copies;
+    here the resampler runs in front of the framing inside the same batch call.  Same output files
+    (``speed_{s}-feats[-i].pkl``, ``speed_{s}-featlen.npy``)."""
+    return {s: process_libri_feats(audio_path, "speed_{}".format(s), k, args, device, speed=s, **switches)
+            for s in speed_list}
 
 
 def process_libri_feats(audio_path, cat, k, args, device=0, **switches):

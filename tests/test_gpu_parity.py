@@ -245,3 +245,32 @@ def test_augmentation_files_flac_in_flac_out(pkg, sox, tmp_path):
     for x, p in zip(pcm, vout):
         g = float(os.path.basename(p).rsplit("_", 1)[1][:-5])
         assert np.array_equal(pkg.audio_io.read_audio(p)[0], sox.volume_perturb(x, g))
+
+
+@pytest.mark.gpu
+def test_on_the_fly_speed_features_equal_file_level_augmentation(pkg, ref, sox, tmp_path):
+    """preprocess.py:158-167: speed_{s} features.  The fused call (resampler in front of the framing) must give
+    what the reference's detour gives: SpeedAugmentation writes copies, process_audios reads them back."""
+    import joblib
+    aug = importlib.import_module(PKG + ".augmentation")
+    pcm = pkg.synth.corpus(4, 1.0, 4.0, seed=55)
+    src = []
+    for i, x in enumerate(pcm):
+        p = str(tmp_path / ("1272-128104-%04d.flac" % i))
+        pkg.audio_io.write_audio(p, x, 16000)
+        src.append(p)
+    args = make_args(feat_dir=str(tmp_path / "features"))
+    for dev in (False, True):
+        fused, flen = pkg.process_audios(src, args, speed=0.9, device_decode=dev)
+        copies = aug.SpeedAugmentation(src, str(tmp_path / ("aug%d" % dev)), 0.9)
+        via_files, vlen = pkg.process_audios(copies, args)
+        assert flen == vlen and all(np.array_equal(a, b) for a, b in zip(fused, via_files))      # same kernels, same bits
+    for a, x in zip(fused, pcm):
+        assert_close(a, ref.features_one(sox.speed_perturb(x, 0.9)), what="speed 0.9 features")
+    lens = importlib.import_module(PKG + ".preprocess").process_speed_augmented(src, args, speed_list=(0.9, 1.1), k=4)
+    assert sorted(lens) == [0.9, 1.1]
+    back = joblib.load(args.feat_dir + "/speed_1.1-feats.pkl")
+    assert np.load(args.feat_dir + "/speed_1.1-featlen.npy").tolist() == lens[1.1] == [len(b) for b in back]
+    louder, _ = pkg.process_audios(src, args, gain=1.3)
+    for a, x in zip(louder, pcm):
+        assert_close(a, ref.features_one(sox.volume_perturb(x, 1.3)), what="gain 1.3 features")
