@@ -15,6 +15,7 @@ import numpy as np
 from . import _lib
 
 DEFAULT_FS = 16000
+_MAX_SAMPLES_PER_BYTE = 8192      # a constant subframe holds 65 535 samples in ~9 bytes; more than that is a damaged header
 _FORMATS = {".flac": _lib.AIO_FMT_FLAC, ".wav": _lib.AIO_FMT_WAV}
 
 
@@ -63,17 +64,19 @@ def decode_bytes(data, check_md5=True):
     buf = np.frombuffer(data, dtype=np.uint8)
     info = _lib.AioInfo()
     _check(lib.aio_probe_memory(C.c_void_p(buf.ctypes.data), buf.size, C.byref(info)), "probe")
-    n, ch = info.n_samples, info.channels
-    unknown = n < 0                 # FLAC stream without total_samples: grow the buffer until it fits
-    if unknown:
-        n = max(buf.size * 4 // ch, 4096)
+    claimed, ch = info.n_samples, info.channels
+    # The sample count is a header field: never trust it for the allocation.  Start from what the bytes
+    # plausibly hold and grow while the decoder reports a full buffer, up to the claimed count.
+    n = max(buf.size * 16 // max(ch, 1), 65536)
+    if claimed >= 0:
+        n = min(n, claimed)
     while True:
         out = np.empty(max(n * ch, 1), dtype=np.int16)
         got = C.c_int64()
         rc = lib.aio_decode_memory(C.c_void_p(buf.ctypes.data), buf.size, C.c_void_p(out.ctypes.data), n * ch,
                                    C.byref(got), int(bool(check_md5)))
-        if rc == _lib.AIO_ERR_CAPACITY and unknown and n < (1 << 33):
-            n *= 4
+        if rc == _lib.AIO_ERR_CAPACITY and (claimed < 0 or n < claimed) and n < (1 << 36):
+            n = n * 4 if claimed < 0 else min(n * 4, claimed)
             continue
         _check(rc, "decode")
         break
@@ -136,6 +139,8 @@ def read_audio_batch(paths, n_threads=0, check_md5=True, out=None):
             raise ValueError("mixed sample rates in one call: %d vs %d (%s)" % (fs, info[i].sample_rate, paths[i]))
         if info[i].n_samples < 0:
             raise AudioFormatError("%s: FLAC stream without a sample count; use read_audio" % paths[i])
+        if info[i].n_samples > _MAX_SAMPLES_PER_BYTE * max(os.path.getsize(paths[i]), 1):
+            raise AudioFormatError("%s: implausible sample count %d in the header" % (paths[i], info[i].n_samples))
         lengths[i] = info[i].n_samples
     offsets, total = plan_batch(lengths)
     if out is None:
@@ -204,8 +209,8 @@ def load_flac_batch(paths, n_threads=0, out=None):
     if np.any(L["sample_rate"] != fs):
         i = int(np.flatnonzero(L["sample_rate"] != fs)[0])
         raise ValueError("mixed sample rates in one call: %d vs %d (%s)" % (fs, L["sample_rate"][i], paths[i]))
-    unsup = ((L["min_block"] != L["max_block"]) | (L["n_samples"] <= 0) | (L["max_block"] % 8 != 0) |
-             (L["bits_per_sample"] > 16) | (L["n_samples"] >= 2 ** 31))
+    unsup = ((L["min_block"] != L["max_block"]) | (L["n_samples"] <= 0) | (L["max_block"] % 8 != 0) | (L["max_block"] < 16) |
+             (L["bits_per_sample"] > 16) | (L["n_samples"] >= 2 ** 31) | (L["n_samples"] > _MAX_SAMPLES_PER_BYTE * np.maximum(sizes, 1)))
     if np.any(unsup):
         raise AudioFormatError("%s: the device decoder takes fixed-block-size streams (multiple of 8) of at most "
                                "16 bits with a sample count; use read_audio_batch" % paths[int(np.flatnonzero(unsup)[0])])

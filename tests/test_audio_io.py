@@ -126,3 +126,36 @@ def test_stereo_and_rate_errors(pkg, tmp_path):
     pkg.audio_io.write_audio(b, np.zeros(800, np.int16), 8000)
     with pytest.raises(ValueError, match="mixed sample rates"):
         pkg.audio_io.read_audio_batch([a, b])
+
+
+def test_decoder_survives_mutated_streams(pkg):
+    """Hand-written parser hygiene: byte flips, truncations and garbage never crash or over-run the decoder --
+    every outcome is either the exact PCM (mutation hit padding / a metadata block) or AudioFormatError."""
+    rng = np.random.default_rng(2026)
+    x = pkg.synth.corpus(1, 0.6, 0.6, seed=12)[0]
+    clean = np.frombuffer(pkg.audio_io.encode_flac(x), dtype=np.uint8)
+    ff = np.frombuffer(open(os.path.join(FLAC_DIR, "ffmpeg_tone_plus_noise_l8.flac"), "rb").read(), dtype=np.uint8)
+    outcomes = {"ok": 0, "rejected": 0}
+    for trial in range(600):
+        src = clean if trial % 2 == 0 else ff
+        buf = src.copy()
+        kind = trial % 5
+        if kind == 0:                                      # flip 1..4 random bits
+            for _ in range(rng.integers(1, 5)):
+                buf[rng.integers(0, buf.size)] ^= 1 << rng.integers(0, 8)
+        elif kind == 1:                                    # overwrite a run with random bytes
+            a = int(rng.integers(0, buf.size - 64)); buf[a:a + 64] = rng.integers(0, 256, 64, dtype=np.uint8)
+        elif kind == 2:                                    # truncate
+            buf = buf[:int(rng.integers(1, buf.size))]
+        elif kind == 3:                                    # all-ones / all-zeros run (long unary codes)
+            a = int(rng.integers(42, buf.size - 256)); buf[a:a + 256] = 0xFF if trial % 2 else 0
+        else:                                              # header field damage
+            buf[int(rng.integers(4, 42))] = rng.integers(0, 256)
+        try:
+            got, fs = pkg.audio_io.decode_bytes(buf.tobytes(), check_md5=True)
+            outcomes["ok"] += 1
+        except pkg.audio_io.AudioFormatError:
+            outcomes["rejected"] += 1
+    assert outcomes["rejected"] > 400 and outcomes["ok"] + outcomes["rejected"] == 600
+    with pytest.raises(pkg.audio_io.AudioFormatError):
+        pkg.audio_io.decode_bytes(rng.integers(0, 256, 5000, dtype=np.uint8).tobytes())

@@ -126,3 +126,45 @@ def test_process_audios_device_decode_equals_host_decode(pkg, tmp_path, monkeypa
     assert alen == blen and all(np.array_equal(u, v) for u, v in zip(a, b))
     with pytest.raises(ValueError, match="flac files only"):
         pkg.process_audios([str(tmp_path / "x.wav")], args, device_decode=True)
+
+
+def test_mutated_streams_never_hang_or_corrupt_neighbours(pkg, tmp_path):
+    """64 files, half of them damaged (bit flips, random runs, zero / one runs, truncation): the GPU decoder must
+    return, flag exactly the files the host decoder rejects, and decode the intact ones bit-exactly."""
+    rng = np.random.default_rng(77)
+    pcm = pkg.synth.corpus(64, 0.5, 1.5, seed=13)
+    paths, expect_bad = [], []
+    for i, x in enumerate(pcm):
+        data = bytearray(pkg.audio_io.encode_flac(x))
+        lay = pkg.audio_io.flac_layout(bytes(data))
+        if i % 2:
+            kind = (i // 2) % 4
+            a = int(rng.integers(lay["first_frame"] + 8, len(data) - 300))
+            if kind == 0:
+                data[a] ^= 1 << int(rng.integers(0, 8))
+            elif kind == 1:
+                data[a:a + 64] = bytes(rng.integers(0, 256, 64, dtype=np.uint8))
+            elif kind == 2:
+                data[a:a + 256] = bytes([0xFF if i % 4 == 1 else 0]) * 256
+            else:
+                data = data[:a]
+        p = str(tmp_path / ("m%02d.flac" % i))
+        open(p, "wb").write(bytes(data))
+        paths.append(p)
+        try:
+            pkg.audio_io.decode_bytes(bytes(data))
+            expect_bad.append(0)
+        except pkg.audio_io.AudioFormatError:
+            expect_bad.append(-1)
+    assert sum(expect_bad) <= -28
+    fe = pkg.Frontend(pkg.FrontendConfig())
+    buf, files, pcm_off, lens, fs, total = pkg.audio_io.load_flac_batch(paths)
+    pcm_total = int(pcm_off[-1] + (lens[-1] + 7) // 8 * 8)
+    dst = np.zeros(pcm_total, np.int16)
+    with pytest.raises(RuntimeError, match="file"):
+        fe.decode_flac(buf, files, len(paths), total, pcm_total, pcm=dst)
+    assert fe.flac_status.tolist() == expect_bad
+    for i, x in enumerate(pcm):
+        if expect_bad[i] == 0:
+            assert np.array_equal(dst[pcm_off[i]:pcm_off[i] + lens[i]], x), i
+    fe.close()
