@@ -274,3 +274,151 @@ def test_on_the_fly_speed_features_equal_file_level_augmentation(pkg, ref, sox, 
     louder, _ = pkg.process_audios(src, args, gain=1.3)
     for a, x in zip(louder, pcm):
         assert_close(a, ref.features_one(sox.volume_perturb(x, 1.3)), what="gain 1.3 features")
+
+
+@pytest.mark.gpu
+def test_full_size_properties_config4_100k_sharded_bucketed(pkg, tmp_path):
+    """BASELINE config 4 at full size: 100 000 utterances of U(2,15) s (236 audio-hours, 27 GB of int16) resident in
+    HBM, sharded 2 / 8 ways, bucketed, and handed to the create_tfrecord.py drop-in -- size-independent checks."""
+    import torch
+    bk = importlib.import_module(PKG + ".bucketing")
+    rng = np.random.default_rng(4567)
+    lens = pkg.synth.durations(100_000, 2, 15, rng)
+    pad = (lens + 7) // 8 * 8
+    off = np.concatenate(([0], np.cumsum(pad)))[:-1].astype(np.int64)
+    total = int(pad.sum())
+    assert 230 < lens.sum() / 16000 / 3600 < 242
+    g = torch.Generator(device="cuda"); g.manual_seed(4567)
+    d = torch.empty(total, dtype=torch.int16, device="cuda")
+    for s in range(0, total, 1 << 27):
+        e = min(total, s + (1 << 27))
+        d[s:e] = (torch.randn(e - s, device="cuda", generator=g) * 3000.0).clamp_(-32768, 32767).to(torch.int16)
+    torch.cuda.synchronize()
+    fe = pkg.Frontend(pkg.FrontendConfig())
+    out, out_off, nfr = fe.run_packed(d, off, lens)
+    fe.sync()
+    assert np.array_equal(nfr, (lens - 400) // 160)                                       # frame counts bit-exact
+    assert int(out_off[-1]) * 4 > 13e9
+    # per-utterance CMVN moments and the delta identity, on the device, for every 97th utterance
+    idx13 = torch.arange(13, device="cuda")
+    for i in range(0, 100_000, 97):
+        c = out[int(out_off[i]):int(out_off[i]) + int(nfr[i]) * 39].view(int(nfr[i]), 13, 3).double()
+        st = c[:, :, 0]
+        assert float(st.mean(0).abs().max()) < 2e-4 and float((st.std(0, unbiased=False) - 1).abs().max()) < 2e-4
+        d1 = (st[:, torch.clamp(idx13 + 1, max=12)] + 2 * st[:, torch.clamp(idx13 + 2, max=12)]) / 10
+        assert float((c[:, :, 1] - d1).abs().max()) < 1e-5
+    # sharding: a rank's shard processed on its own equals the same utterances of the unsharded run, bit for bit
+    sh = pkg.sharding
+    for world, rank in ((2, 1), (8, 3)):
+        mine = sh.shard_indices(lens, rank, world)
+        assert abs(len(mine) - 100_000 / world) < 0.2 * 100_000 / world and sh.imbalance(lens, world) < 0.01
+        spad = pad[mine]
+        soff = np.concatenate(([0], np.cumsum(spad)))[:-1].astype(np.int64)
+        sd = torch.empty(int(spad.sum()), dtype=torch.int16, device="cuda")
+        src_idx = torch.cat([torch.arange(int(off[i]), int(off[i]) + int(pad[i]), device="cuda") for i in mine[:200]])
+        sd[:src_idx.numel()] = d[src_idx]                                                  # first 200 utterances of the shard
+        n_chk = 200
+        so, so_off, snfr = fe.run_packed(sd, soff[:n_chk], lens[mine[:n_chk]])
+        fe.sync()
+        for k in range(0, n_chk, 7):
+            i = int(mine[k])
+            a = so[int(so_off[k]):int(so_off[k]) + int(snfr[k]) * 39]
+            b = out[int(out_off[i]):int(out_off[i]) + int(nfr[i]) * 39]
+            assert torch.equal(a, b)
+        del sd, so
+    # bucketing: every utterance lands in exactly one slot of a batch of its bucket, padding is zero
+    plan = bk.plan_batches(nfr)
+    assert sum(len(ix) for _, ix in plan) == 100_000 and max(int(nfr.max()), 0) < 1710
+    bb = bk.BucketBatcher(fe)
+    views, flat = bb.pad(out, out_off[:-1], nfr, 39, plan)
+    for bi in range(0, len(plan), 211):
+        b, ix = plan[bi]
+        v = views[bi]
+        assert v.shape == (len(ix), bk.BUCKETS_TRAIN[b] - 1, 39)
+        k = len(ix) // 2
+        i = int(ix[k])
+        assert torch.equal(v[k, :int(nfr[i])].reshape(-1), out[int(out_off[i]):int(out_off[i]) + int(nfr[i]) * 39])
+        assert not bool(v[k, int(nfr[i]):].any())
+    del views, flat
+    # consumer: create_tfrecords (create_tfrecord.py:43-97) on 300 of the cubes, read back
+    tfr = importlib.import_module(PKG + ".tfrecord")
+    pick = np.arange(0, 100_000, 334)[:300]
+    cubes = [out[int(out_off[i]):int(out_off[i]) + int(nfr[i]) * 39].cpu().numpy().reshape(int(nfr[i]), 13, 3) for i in pick]
+    X = pkg.to_object_array(cubes)
+    y = pkg.to_object_array([[int(i) % 5000, 1, 2] for i in pick])
+    paths = tfr.create_tfrecords(X, y, str(tmp_path / "train-100"), num_files=3)
+    back = [r for p in paths for r in tfr.read_tfrecord(p)]
+    assert len(back) == 300 and all(np.array_equal(f, c) and t.tolist() == list(t0) for (f, t), c, t0 in zip(back, cubes, y))
+    fe.close()
+
+
+def _device_noise(lens, seed):
+    import torch
+    pad = (lens + 7) // 8 * 8
+    off = np.concatenate(([0], np.cumsum(pad)))[:-1].astype(np.int64)
+    g = torch.Generator(device="cuda"); g.manual_seed(seed)
+    d = (torch.randn(int(pad.sum()), device="cuda", generator=g) * 3000.0).clamp_(-32768, 32767).to(torch.int16)
+    torch.cuda.synchronize()
+    return d, off
+
+
+@pytest.mark.gpu
+def test_full_size_properties_config2_fbank80(pkg, ref):
+    """BASELINE config 2 at full size: 2 000 utterances, clip(N(12.3, 3.8^2), 2, 35) s, 80 mel energies + CMVN."""
+    import torch
+    rng = np.random.default_rng(2345)
+    lens = pkg.synth.durations(2000, 2, 35, rng, "librispeech")
+    d, off = _device_noise(lens, 2345)
+    idx = torch.arange(80, device="cuda")
+    for log in (False, True):
+        fe = pkg.Frontend(pkg.FrontendConfig(feat_type="fbank", feat_dim=80, fbank_log=log))
+        out, out_off, nfr = fe.run_packed(d, off, lens)
+        fe.sync()
+        assert np.array_equal(nfr, (lens - 400) // 160)
+        for i in range(0, 2000, 41):
+            c = out[int(out_off[i]):int(out_off[i]) + int(nfr[i]) * 240].view(int(nfr[i]), 80, 3).double()
+            st = c[:, :, 0]
+            assert float(st.mean(0).abs().max()) < 5e-4 and float((st.std(0, unbiased=False) - 1).abs().max()) < 5e-4
+            d1 = (st[:, torch.clamp(idx + 1, max=79)] + 2 * st[:, torch.clamp(idx + 2, max=79)]) / 10
+            assert float((c[:, :, 1] - d1).abs().max()) < 1e-5
+        for i in (0, 1999):                                                               # spot parity against the oracle
+            p = d[int(off[i]):int(off[i]) + int(lens[i])].cpu().numpy()
+            got = out[int(out_off[i]):int(out_off[i]) + int(nfr[i]) * 240].cpu().numpy().reshape(int(nfr[i]), 80, 3)
+            assert_close(got, ref.features_one(p, feat_dim=80, feat_type="fbank", fbank_log=log), what="config2 full spot")
+        fe.close()
+
+
+@pytest.mark.gpu
+def test_full_size_properties_config3_three_speeds(pkg, ref, sox):
+    """BASELINE config 3 at full size: 1 000 utterances x speeds 0.9 / 1.0 / 1.1 in ONE batch call."""
+    tables = importlib.import_module(PKG + ".tables")
+    rng = np.random.default_rng(3456)
+    base = pkg.synth.durations(1000, 2, 15, rng)
+    lens = np.repeat(base, 3)
+    d1, off1 = _device_noise(base, 3456)
+    import torch
+    pad = (lens + 7) // 8 * 8
+    off = np.concatenate(([0], np.cumsum(pad)))[:-1].astype(np.int64)
+    d = torch.zeros(int(pad.sum()), dtype=torch.int16, device="cuda")
+    for i in range(1000):                                                                 # three copies of every utterance
+        src = d1[int(off1[i]):int(off1[i]) + int(base[i])]
+        for k in range(3):
+            d[int(off[3 * i + k]):int(off[3 * i + k]) + int(base[i])] = src
+    torch.cuda.synchronize()
+    speeds = [0.9, 1.0, 1.1] * 1000
+    fe = pkg.Frontend(pkg.FrontendConfig())
+    out, out_off, nfr = fe.run_packed(d, off, lens, speed_idx=fe.speed_indices(speeds))
+    plain, plain_off, plain_nfr = fe.run_packed(d1, off1, base)
+    fe.sync()
+    want_len = np.array([tables.resampled_length(int(n), s) for n, s in zip(lens, speeds)])
+    assert want_len[0] == -(-int(base[0]) * 10 // 9) and want_len[2] == -(-int(base[0]) * 10 // 11)
+    assert np.array_equal(nfr, np.maximum((want_len - 400) // 160, 0))                    # lengths and frame counts bit-exact
+    for i in range(0, 1000, 13):                                                          # the speed-1.0 copy is untouched
+        a = out[int(out_off[3 * i + 1]):int(out_off[3 * i + 1]) + int(nfr[3 * i + 1]) * 39]
+        b = plain[int(plain_off[i]):int(plain_off[i]) + int(plain_nfr[i]) * 39]
+        assert torch.equal(a, b)
+    for j in (0, 2, 2999):                                                                # spot parity: oracle resampler + oracle features
+        p = d[int(off[j]):int(off[j]) + int(lens[j])].cpu().numpy()
+        got = out[int(out_off[j]):int(out_off[j]) + int(nfr[j]) * 39].cpu().numpy().reshape(int(nfr[j]), 13, 3)
+        assert_close(got, ref.features_one(sox.speed_perturb(p, speeds[j])), what="config3 full spot")
+    fe.close()
