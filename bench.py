@@ -142,7 +142,7 @@ def run_reference(a):
     ms = 1e3 * sum(times) / len(times)
     value = hours / (ms * 1e-3)
     sample = "%.2f audio-h (%d utterances) of the same LibriSpeech-length distribution per step" % (hours, len(pcm))
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
         "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
@@ -153,7 +153,7 @@ def run_reference(a):
                                  "installable here); multiprocessing over all host cores; decode excluded"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-    }))
+    })
 
 
 # ----------------------------------------------------------------------------------------
@@ -192,8 +192,28 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(reasons), "samples": len(self.samples)}
 
 
+_REAL_STDOUT = None
+
+
+def _guard_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version line to fd 1
+    when the environment sets NCCL_DEBUG), so everything but the final line is routed to stderr at the fd level."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    if _REAL_STDOUT is not None:
+        os.dup2(_REAL_STDOUT, 1)
+    print(json.dumps(line), flush=True)
+
+
 def main():
     a = parse()
+    _guard_stdout()
     if a.impl == "reference":
         return run_reference(a)
 
@@ -410,7 +430,7 @@ def main():
         "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
         "clocks": sampler.summary(), "parity_check": parity,
     }
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.barrier(); dist.destroy_process_group()
 
