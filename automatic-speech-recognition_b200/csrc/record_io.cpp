@@ -292,7 +292,7 @@ int64_t for_each_record(const char* path, F fn) {
         uint32_t lcrc;
         memcpy(&len, hdr, 8);
         memcpy(&lcrc, hdr + 8, 4);
-        if (mask_crc(crc32c(hdr, 8)) != lcrc || len > (1ull << 34)) { fclose(f); return RIO_ERR_FORMAT; }
+        if (mask_crc(crc32c(hdr, 8)) != lcrc || len > (1ull << 31)) { fclose(f); return RIO_ERR_FORMAT; }   // protobuf's own limit
         buf.resize((size_t)len + 4);
         if (fread(buf.data(), 1, (size_t)len + 4, f) != (size_t)len + 4) { fclose(f); return RIO_ERR_FORMAT; }
         uint32_t dcrc;

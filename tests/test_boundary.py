@@ -102,3 +102,17 @@ def test_lpt_partition(pkg):
     merged = sh.merge_shards(parts, [[int(i) * 10 for i in p] for p in parts], 5000)
     assert merged == [i * 10 for i in range(5000)]
     assert sh.frame_counts([399, 400, 559, 560, 16000]).tolist() == [0, 0, 0, 1, 97]
+
+
+def test_file_batch_planning(pkg):
+    """Host batching of process_audios: consecutive ranges, every file exactly once, ~one audio-hour per batch."""
+    pp = importlib.import_module(PKG + ".preprocess")
+    rng = np.random.default_rng(0)
+    lens = rng.integers(32000, 560000, 1000).tolist()
+    ranges = pp._plan_file_batches(lens, 57_600_000)
+    assert ranges[0][0] == 0 and ranges[-1][1] == 1000 and all(a[1] == b[0] for a, b in zip(ranges, ranges[1:]))
+    sums = [sum(lens[lo:hi]) for lo, hi in ranges]
+    assert all(s >= 57_600_000 for s in sums[:-1]) and all(s < 57_600_000 + 560000 for s in sums)
+    assert pp._plan_file_batches([10], 100) == [(0, 1)] and pp._plan_file_batches([200, 5], 100) == [(0, 1), (1, 2)]
+    off, total = pkg.audio_io.plan_batch([5, 8, 9])
+    assert off.tolist() == [0, 8, 16] and total == 32
