@@ -54,37 +54,53 @@ struct Md5 {
     }
     static inline uint32_t rol(uint32_t x, int c) { return (x << c) | (x >> (32 - c)); }
     void block(const uint8_t* p) {
-        static const uint32_t K[64] = {
-            0xd76aa478, 0xe8c7b756, 0x242070db, 0xc1bdceee, 0xf57c0faf, 0x4787c62a, 0xa8304613, 0xfd469501,
-            0x698098d8, 0x8b44f7af, 0xffff5bb1, 0x895cd7be, 0x6b901122, 0xfd987193, 0xa679438e, 0x49b40821,
-            0xf61e2562, 0xc040b340, 0x265e5a51, 0xe9b6c7aa, 0xd62f105d, 0x02441453, 0xd8a1e681, 0xe7d3fbc8,
-            0x21e1cde6, 0xc33707d6, 0xf4d50d87, 0x455a14ed, 0xa9e3e905, 0xfcefa3f8, 0x676f02d9, 0x8d2a4c8a,
-            0xfffa3942, 0x8771f681, 0x6d9d6122, 0xfde5380c, 0xa4beea44, 0x4bdecfa9, 0xf6bb4b60, 0xbebfbc70,
-            0x289b7ec6, 0xeaa127fa, 0xd4ef3085, 0x04881d05, 0xd9d4d039, 0xe6db99e5, 0x1fa27cf8, 0xc4ac5665,
-            0xf4292244, 0x432aff97, 0xab9423a7, 0xfc93a039, 0x655b59c3, 0x8f0ccc92, 0xffeff47d, 0x85845dd1,
-            0x6fa87e4f, 0xfe2ce6e0, 0xa3014314, 0x4e0811a1, 0xf7537e82, 0xbd3af235, 0x2ad7d2bb, 0xeb86d391};
-        static const int R[64] = {7, 12, 17, 22, 7, 12, 17, 22, 7, 12, 17, 22, 7, 12, 17, 22,
-                                  5, 9,  14, 20, 5, 9,  14, 20, 5, 9,  14, 20, 5, 9,  14, 20,
-                                  4, 11, 16, 23, 4, 11, 16, 23, 4, 11, 16, 23, 4, 11, 16, 23,
-                                  6, 10, 15, 21, 6, 10, 15, 21, 6, 10, 15, 21, 6, 10, 15, 21};
         uint32_t w[16];
         for (int i = 0; i < 16; ++i)
             w[i] = (uint32_t)p[4 * i] | ((uint32_t)p[4 * i + 1] << 8) | ((uint32_t)p[4 * i + 2] << 16) |
                    ((uint32_t)p[4 * i + 3] << 24);
         uint32_t a = s[0], b = s[1], c = s[2], d = s[3];
-        for (int i = 0; i < 64; ++i) {
-            uint32_t f;
-            int g;
-            if (i < 16) { f = (b & c) | (~b & d); g = i; }
-            else if (i < 32) { f = (d & b) | (~d & c); g = (5 * i + 1) & 15; }
-            else if (i < 48) { f = b ^ c ^ d; g = (3 * i + 5) & 15; }
-            else { f = c ^ (b | ~d); g = (7 * i) & 15; }
-            uint32_t t = d;
-            d = c;
-            c = b;
-            b = b + rol(a + f + K[i] + w[g], R[i]);
-            a = t;
-        }
+#define MD5_F(x, y, z) ((z) ^ ((x) & ((y) ^ (z))))
+#define MD5_G(x, y, z) ((y) ^ ((z) & ((x) ^ (y))))
+#define MD5_H(x, y, z) ((x) ^ (y) ^ (z))
+#define MD5_I(x, y, z) ((y) ^ ((x) | ~(z)))
+#define MD5_STEP(f, a, b, c, d, g, k, r) a += f(b, c, d) + w[g] + k; a = rol(a, r) + b;
+        MD5_STEP(MD5_F, a, b, c, d, 0, 0xd76aa478u, 7)   MD5_STEP(MD5_F, d, a, b, c, 1, 0xe8c7b756u, 12)
+        MD5_STEP(MD5_F, c, d, a, b, 2, 0x242070dbu, 17)  MD5_STEP(MD5_F, b, c, d, a, 3, 0xc1bdceeeu, 22)
+        MD5_STEP(MD5_F, a, b, c, d, 4, 0xf57c0fafu, 7)   MD5_STEP(MD5_F, d, a, b, c, 5, 0x4787c62au, 12)
+        MD5_STEP(MD5_F, c, d, a, b, 6, 0xa8304613u, 17)  MD5_STEP(MD5_F, b, c, d, a, 7, 0xfd469501u, 22)
+        MD5_STEP(MD5_F, a, b, c, d, 8, 0x698098d8u, 7)   MD5_STEP(MD5_F, d, a, b, c, 9, 0x8b44f7afu, 12)
+        MD5_STEP(MD5_F, c, d, a, b, 10, 0xffff5bb1u, 17) MD5_STEP(MD5_F, b, c, d, a, 11, 0x895cd7beu, 22)
+        MD5_STEP(MD5_F, a, b, c, d, 12, 0x6b901122u, 7)  MD5_STEP(MD5_F, d, a, b, c, 13, 0xfd987193u, 12)
+        MD5_STEP(MD5_F, c, d, a, b, 14, 0xa679438eu, 17) MD5_STEP(MD5_F, b, c, d, a, 15, 0x49b40821u, 22)
+        MD5_STEP(MD5_G, a, b, c, d, 1, 0xf61e2562u, 5)   MD5_STEP(MD5_G, d, a, b, c, 6, 0xc040b340u, 9)
+        MD5_STEP(MD5_G, c, d, a, b, 11, 0x265e5a51u, 14) MD5_STEP(MD5_G, b, c, d, a, 0, 0xe9b6c7aau, 20)
+        MD5_STEP(MD5_G, a, b, c, d, 5, 0xd62f105du, 5)   MD5_STEP(MD5_G, d, a, b, c, 10, 0x02441453u, 9)
+        MD5_STEP(MD5_G, c, d, a, b, 15, 0xd8a1e681u, 14) MD5_STEP(MD5_G, b, c, d, a, 4, 0xe7d3fbc8u, 20)
+        MD5_STEP(MD5_G, a, b, c, d, 9, 0x21e1cde6u, 5)   MD5_STEP(MD5_G, d, a, b, c, 14, 0xc33707d6u, 9)
+        MD5_STEP(MD5_G, c, d, a, b, 3, 0xf4d50d87u, 14)  MD5_STEP(MD5_G, b, c, d, a, 8, 0x455a14edu, 20)
+        MD5_STEP(MD5_G, a, b, c, d, 13, 0xa9e3e905u, 5)  MD5_STEP(MD5_G, d, a, b, c, 2, 0xfcefa3f8u, 9)
+        MD5_STEP(MD5_G, c, d, a, b, 7, 0x676f02d9u, 14)  MD5_STEP(MD5_G, b, c, d, a, 12, 0x8d2a4c8au, 20)
+        MD5_STEP(MD5_H, a, b, c, d, 5, 0xfffa3942u, 4)   MD5_STEP(MD5_H, d, a, b, c, 8, 0x8771f681u, 11)
+        MD5_STEP(MD5_H, c, d, a, b, 11, 0x6d9d6122u, 16) MD5_STEP(MD5_H, b, c, d, a, 14, 0xfde5380cu, 23)
+        MD5_STEP(MD5_H, a, b, c, d, 1, 0xa4beea44u, 4)   MD5_STEP(MD5_H, d, a, b, c, 4, 0x4bdecfa9u, 11)
+        MD5_STEP(MD5_H, c, d, a, b, 7, 0xf6bb4b60u, 16)  MD5_STEP(MD5_H, b, c, d, a, 10, 0xbebfbc70u, 23)
+        MD5_STEP(MD5_H, a, b, c, d, 13, 0x289b7ec6u, 4)  MD5_STEP(MD5_H, d, a, b, c, 0, 0xeaa127fau, 11)
+        MD5_STEP(MD5_H, c, d, a, b, 3, 0xd4ef3085u, 16)  MD5_STEP(MD5_H, b, c, d, a, 6, 0x04881d05u, 23)
+        MD5_STEP(MD5_H, a, b, c, d, 9, 0xd9d4d039u, 4)   MD5_STEP(MD5_H, d, a, b, c, 12, 0xe6db99e5u, 11)
+        MD5_STEP(MD5_H, c, d, a, b, 15, 0x1fa27cf8u, 16) MD5_STEP(MD5_H, b, c, d, a, 2, 0xc4ac5665u, 23)
+        MD5_STEP(MD5_I, a, b, c, d, 0, 0xf4292244u, 6)   MD5_STEP(MD5_I, d, a, b, c, 7, 0x432aff97u, 10)
+        MD5_STEP(MD5_I, c, d, a, b, 14, 0xab9423a7u, 15) MD5_STEP(MD5_I, b, c, d, a, 5, 0xfc93a039u, 21)
+        MD5_STEP(MD5_I, a, b, c, d, 12, 0x655b59c3u, 6)  MD5_STEP(MD5_I, d, a, b, c, 3, 0x8f0ccc92u, 10)
+        MD5_STEP(MD5_I, c, d, a, b, 10, 0xffeff47du, 15) MD5_STEP(MD5_I, b, c, d, a, 1, 0x85845dd1u, 21)
+        MD5_STEP(MD5_I, a, b, c, d, 8, 0x6fa87e4fu, 6)   MD5_STEP(MD5_I, d, a, b, c, 15, 0xfe2ce6e0u, 10)
+        MD5_STEP(MD5_I, c, d, a, b, 6, 0xa3014314u, 15)  MD5_STEP(MD5_I, b, c, d, a, 13, 0x4e0811a1u, 21)
+        MD5_STEP(MD5_I, a, b, c, d, 4, 0xf7537e82u, 6)   MD5_STEP(MD5_I, d, a, b, c, 11, 0xbd3af235u, 10)
+        MD5_STEP(MD5_I, c, d, a, b, 2, 0x2ad7d2bbu, 15)  MD5_STEP(MD5_I, b, c, d, a, 9, 0xeb86d391u, 21)
+#undef MD5_STEP
+#undef MD5_F
+#undef MD5_G
+#undef MD5_H
+#undef MD5_I
         s[0] += a; s[1] += b; s[2] += c; s[3] += d;
     }
     void update(const uint8_t* p, size_t n) {
@@ -110,6 +126,9 @@ struct Md5 {
             for (int k = 0; k < 4; ++k) out[4 * i + k] = (uint8_t)(s[i] >> (8 * k));
     }
 };
+
+const uint16_t kEndianProbe = 1;
+const bool kLittleEndian = *(const uint8_t*)&kEndianProbe == 1;
 
 // ----------------------------------------------------------------------------- bit reader
 struct BitReader {
@@ -279,6 +298,83 @@ int read_frame_header(BitReader& br, const StreamInfo& si, FrameHeader* fh) {
     return AIO_OK;
 }
 
+// One Rice partition of n residuals with parameter k, on a local copy of the bit window.  The window is topped up
+// eight bytes at a time (bits below `cnt` may then hold look-ahead data: they are the true next bits, OR-ing them
+// again on the next top-up is idempotent); a code that does not fit the window, and the last bytes of the
+// stream, go through the generic reader.
+inline void rice_partition(BitReader& br, int k, int n, int32_t* res) {
+    uint64_t acc = br.acc;
+    int cnt = br.cnt;
+    const uint8_t* p = br.p;
+    const uint8_t* const end = br.end;
+    int i = 0;
+    for (; i < n; ++i) {
+        if (cnt < 48) {
+            if (end - p < 8) break;
+            uint64_t w;
+            memcpy(&w, p, 8);
+            w = __builtin_bswap64(w);
+            acc |= w >> cnt;
+            p += (63 - cnt) >> 3;
+            cnt |= 56;
+        }
+        const uint64_t valid = acc & (~0ull << (64 - cnt));           // cnt >= 48 here
+        if (valid == 0) break;
+        const int z = __builtin_clzll(valid);
+        if (z + 1 + k > cnt) break;
+        acc <<= z + 1;                                                // z + 1 <= 48
+        cnt -= z + 1;
+        uint32_t u = (uint32_t)z << k;
+        if (k) {
+            u |= (uint32_t)(acc >> (64 - k));
+            acc <<= k;
+            cnt -= k;
+        }
+        res[i] = (int32_t)(u >> 1) ^ -(int32_t)(u & 1);
+    }
+    br.acc = cnt ? acc & (~0ull << (64 - cnt)) : 0;                   // restore the reader's invariant: zeros below cnt
+    br.cnt = cnt;
+    br.p = p;
+    for (; i < n; ++i) {                                              // generic path: window edge cases, end of stream
+        uint32_t hi = br.unary();
+        uint32_t u = (hi << k) | br.get(k);
+        res[i] = (int32_t)(u >> 1) ^ -(int32_t)(u & 1);
+        if (br.bad) return;
+    }
+}
+
+// Prediction recurrence out[i] = r[i - ORDER] + (sum_j coef[j] out[i-1-j] >> shift) with a compile-time order.
+// ACC = int32_t when the sums fit 32 bits (bps + precision + ceil(log2 order) <= 32), else int64_t.
+template <int ORDER, class ACC>
+void lpc_restore(const int32_t* r, int n, const int32_t* coef, int shift, int32_t* out) {
+    ACC c[ORDER];
+    for (int j = 0; j < ORDER; ++j) c[j] = coef[j];
+    for (int i = ORDER; i < n; ++i) {
+        ACC sum = 0;
+        for (int j = 0; j < ORDER; ++j) sum += c[j] * (ACC)out[i - 1 - j];
+        out[i] = (int32_t)((ACC)r[i - ORDER] + (sum >> shift));
+    }
+}
+
+template <class ACC>
+bool lpc_restore_dispatch(int order, const int32_t* r, int n, const int32_t* coef, int shift, int32_t* out) {
+    switch (order) {
+        case 1: lpc_restore<1, ACC>(r, n, coef, shift, out); return true;
+        case 2: lpc_restore<2, ACC>(r, n, coef, shift, out); return true;
+        case 3: lpc_restore<3, ACC>(r, n, coef, shift, out); return true;
+        case 4: lpc_restore<4, ACC>(r, n, coef, shift, out); return true;
+        case 5: lpc_restore<5, ACC>(r, n, coef, shift, out); return true;
+        case 6: lpc_restore<6, ACC>(r, n, coef, shift, out); return true;
+        case 7: lpc_restore<7, ACC>(r, n, coef, shift, out); return true;
+        case 8: lpc_restore<8, ACC>(r, n, coef, shift, out); return true;
+        case 9: lpc_restore<9, ACC>(r, n, coef, shift, out); return true;
+        case 10: lpc_restore<10, ACC>(r, n, coef, shift, out); return true;
+        case 11: lpc_restore<11, ACC>(r, n, coef, shift, out); return true;
+        case 12: lpc_restore<12, ACC>(r, n, coef, shift, out); return true;
+        default: return false;
+    }
+}
+
 int read_residual(BitReader& br, int blocksize, int order, int32_t* res) {
     int method = (int)br.get(2);
     if (method > 1) return AIO_ERR_FORMAT;
@@ -297,11 +393,8 @@ int read_residual(BitReader& br, int blocksize, int order, int32_t* res) {
             int raw = (int)br.get(5);
             for (int i = 0; i < n; ++i) res[idx++] = raw ? br.get_signed(raw) : 0;
         } else {
-            for (int i = 0; i < n; ++i) {
-                uint32_t hi = br.unary();
-                uint32_t u = (hi << k) | br.get(k);
-                res[idx++] = (int32_t)(u >> 1) ^ -(int32_t)(u & 1);
-            }
+            rice_partition(br, k, n, res + idx);
+            idx += n;
         }
         if (br.bad) return AIO_ERR_FORMAT;
     }
@@ -357,10 +450,17 @@ int read_subframe(BitReader& br, int blocksize, int bps, int32_t* out, std::vect
         int rc = read_residual(br, blocksize, order, scratch.data());
         if (rc) return rc;
         const int32_t* r = scratch.data();
-        for (int i = order; i < blocksize; ++i) {
-            int64_t acc = 0;
-            for (int j = 0; j < order; ++j) acc += (int64_t)coef[j] * out[i - 1 - j];
-            out[i] = (int32_t)((int64_t)r[i - order] + (acc >> shift));
+        int lg = 0;
+        while ((1 << lg) < order) ++lg;
+        const bool narrow = bps + prec + lg <= 32;                   // every libFLAC stream at <= 16 bits
+        const bool done = narrow ? lpc_restore_dispatch<int32_t>(order, r, blocksize, coef, shift, out)
+                                 : lpc_restore_dispatch<int64_t>(order, r, blocksize, coef, shift, out);
+        if (!done) {
+            for (int i = order; i < blocksize; ++i) {
+                int64_t acc = 0;
+                for (int j = 0; j < order; ++j) acc += (int64_t)coef[j] * out[i - 1 - j];
+                out[i] = (int32_t)((int64_t)r[i - order] + (acc >> shift));
+            }
         }
     } else {
         return AIO_ERR_FORMAT;                              // reserved subframe type
@@ -418,7 +518,7 @@ int decode_flac(const uint8_t* d, int64_t n, int16_t* out, int64_t capacity, int
                 chan[1][i] = (mid - side) >> 1;
             }
         }
-        if (do_md5) {                                                  // MD5 is over the un-scaled samples
+        if (do_md5 && !(C == 1 && up == 0 && kLittleEndian)) {         // MD5 is over the un-scaled samples
             const int bytes = (si.bps + 7) / 8;
             md5buf.resize((size_t)bs * C * bytes);
             uint8_t* m = md5buf.data();
@@ -434,6 +534,7 @@ int decode_flac(const uint8_t* d, int64_t n, int16_t* out, int64_t capacity, int
         if (C == 1) {
             const int32_t* s = chan[0].data();
             for (int i = 0; i < bs; ++i) o[i] = (int16_t)(s[i] * (1 << up));
+            if (do_md5 && up == 0 && kLittleEndian) md5.update((const uint8_t*)o, (size_t)bs * 2);   // 16-bit mono: the output IS the hashed byte stream
         } else {
             for (int i = 0; i < bs; ++i)
                 for (int c = 0; c < C; ++c) o[(size_t)i * C + c] = (int16_t)(chan[c][i] * (1 << up));
