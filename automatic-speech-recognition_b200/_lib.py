@@ -58,6 +58,8 @@ SYMBOLS = {
     "fe_decode_flac": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(FeFlacFile), C.c_int32, C.c_void_p, C.c_int64,
                                  _i32p, C.c_void_p]),
     "fe_get_flac_ms": (C.c_int, [C.c_void_p, _f32p]),
+    "fe_host_alloc": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(C.c_void_p)]),
+    "fe_host_free": (C.c_int, [C.c_void_p, C.c_void_p]),
     "fe_sync": (C.c_int, [C.c_void_p]),
     "fe_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
     "fe_measure_fp32_peak": (C.c_int, [C.c_void_p, _f32p]),

@@ -975,6 +975,19 @@ int fe_get_pad_ms(fe_handle* h, float* ms) {
     return FE_OK;
 }
 
+int fe_host_alloc(fe_handle* h, int64_t n_bytes, void** out) {
+    if (!h || !out || n_bytes <= 0) return h ? fail(h, FE_ERR_INVALID, "bad size / NULL out") : FE_ERR_INVALID;
+    FE_CUDA(h, cudaSetDevice(h->device));
+    FE_CUDA(h, cudaHostAlloc(out, (size_t)n_bytes, cudaHostAllocDefault));
+    return FE_OK;
+}
+
+int fe_host_free(fe_handle* h, void* p) {
+    if (!h) return FE_ERR_INVALID;
+    if (p) FE_CUDA(h, cudaFreeHost(p));
+    return FE_OK;
+}
+
 int fe_sync(fe_handle* h) {
     if (!h) return FE_ERR_INVALID;
     FE_CUDA(h, cudaSetDevice(h->device));

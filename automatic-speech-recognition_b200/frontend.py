@@ -173,15 +173,29 @@ class Frontend:
         self.device = device
         self._lib = _lib.load()
         self._h = C.c_void_p()
+        self._pinned_ptrs = []
         rc = self._lib.fe_create(int(device), C.byref(self._h))
         if rc != 0:
             msg = self._lib.fe_last_error(None)
             raise RuntimeError("fe_create(device=%d) failed (%d): %s" % (device, rc, msg.decode() if msg else ""))
         self._configure()
 
+    # -- pinned host staging ---------------------------------------------------
+    def pinned(self, n, dtype=np.uint8):
+        """A page-locked numpy array of n elements owned by this handle (freed in close())."""
+        dt = np.dtype(dtype)
+        ptr = C.c_void_p()
+        self._check(self._lib.fe_host_alloc(self._h, int(max(n, 1)) * dt.itemsize, C.byref(ptr)), "fe_host_alloc")
+        self._pinned_ptrs.append(ptr.value)
+        raw = (C.c_uint8 * (int(max(n, 1)) * dt.itemsize)).from_address(ptr.value)
+        return np.frombuffer(raw, dtype=dt, count=int(max(n, 1)))
+
     # -- lifecycle ---------------------------------------------------------
     def close(self):
         if getattr(self, "_h", None) is not None and self._h.value:
+            for p in getattr(self, "_pinned_ptrs", []):
+                self._lib.fe_host_free(self._h, C.c_void_p(p))
+            self._pinned_ptrs = []
             self._lib.fe_destroy(self._h)
             self._h = C.c_void_p()
 

@@ -96,12 +96,23 @@ def _process_flac_on_device(audio_path, args, device, n_threads, switches, speed
     sizes = [os.path.getsize(p) for p in audio_path]
     ranges = _plan_file_batches([s * 2 for s in sizes], _BATCH_SAMPLES * 2)      # ~2 bytes of PCM per FLAC byte
     cubes, featlen, fe = [], [], None
+    # two page-locked staging buffers for the file bytes (batch b uploads while b + 1 is being read)
+    fe0 = get_frontend(FrontendConfig.from_args(args, sample_rate=audio_io.DEFAULT_FS, pcm_dtype="int16", **switches), device)
+    need = max(sum(sizes[lo:hi]) + 16 * (hi - lo) for lo, hi in ranges) + 64
+    stage = getattr(fe0, "_flac_stage", None)
+    if stage is None or stage[0].size < need:
+        stage = fe0._flac_stage = [fe0.pinned(need + need // 4), fe0.pinned(need + need // 4)]
+    trace = {"wait_files": 0.0, "decode": 0.0, "features": 0.0, "views": 0.0} if os.environ.get("FE_TRACE_INGEST") else None
+    import time
     with ThreadPoolExecutor(max_workers=1) as pool:
-        nxt = pool.submit(audio_io.load_flac_batch, audio_path[ranges[0][0]:ranges[0][1]], n_threads)
+        nxt = pool.submit(audio_io.load_flac_batch, audio_path[ranges[0][0]:ranges[0][1]], n_threads, stage[0])
         for b, (lo, hi) in enumerate(ranges):
+            t0 = time.perf_counter()
             buf, files, pcm_off, lens, fs, total = nxt.result()
+            t1 = time.perf_counter()
             if b + 1 < len(ranges):
-                nxt = pool.submit(audio_io.load_flac_batch, audio_path[ranges[b + 1][0]:ranges[b + 1][1]], n_threads)
+                nxt = pool.submit(audio_io.load_flac_batch, audio_path[ranges[b + 1][0]:ranges[b + 1][1]], n_threads,
+                                  stage[(b + 1) & 1])
             if fe is None:
                 cfg = FrontendConfig.from_args(args, sample_rate=fs, pcm_dtype="int16", **switches)
                 fe = get_frontend(cfg, device)
@@ -113,13 +124,22 @@ def _process_flac_on_device(audio_path, args, device, n_threads, switches, speed
             except RuntimeError as e:
                 bad = [audio_path[lo + int(i)] for i in np.flatnonzero(fe.flac_status)]
                 raise audio_io.AudioFormatError("%s: %s" % (", ".join(bad[:4]), e))
+            t2 = time.perf_counter()
             # cubes come back into a host array (device PCM in, host features out)
             plan_off, _ = fe.plan(lens, fe.speed_indices(_uniform(speed, len(lens))))
             host_out = np.empty(max(int(plan_off[-1]), 1), dtype=np.float32)
             out, out_off, nfr = fe.run_packed(d_pcm, pcm_off, lens, speed_idx=fe.speed_indices(_uniform(speed, len(lens))),
                                               gain=_uniform(gain, len(lens)), out=host_out)
+            t3 = time.perf_counter()
             cubes.extend(fe.split(out, out_off, nfr))
             featlen.extend(int(L) for L in nfr)
+            if trace is not None:
+                t4 = time.perf_counter()
+                for k, v in zip(("wait_files", "decode", "features", "views"), (t1 - t0, t2 - t1, t3 - t2, t4 - t3)):
+                    trace[k] += v
+    if trace is not None:
+        import sys
+        sys.stderr.write("ingest trace (s): %s over %d batches\n" % ({k: round(v, 4) for k, v in trace.items()}, len(ranges)))
     return to_object_array(cubes), featlen
 
 

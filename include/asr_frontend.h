@@ -170,6 +170,12 @@ int fe_decode_flac(fe_handle* h, const uint8_t* bytes, int64_t total_bytes, cons
                    int16_t* pcm, int64_t pcm_capacity, int32_t* status, void* stream);
 int fe_get_flac_ms(fe_handle* h, float ms[3]);   /* scan, decode, validate of the last call (profiling on) */
 
+/* Page-locked host memory for the caller's staging buffers (file bytes, PCM, cubes): transfers from / to such
+ * buffers run at the PCIe rate and asynchronously, pageable ones at a fraction of it.  Freed with fe_host_free
+ * (or by fe_destroy of a still-live handle is NOT implied: the caller owns these). */
+int fe_host_alloc(fe_handle* h, int64_t n_bytes, void** out);
+int fe_host_free(fe_handle* h, void* p);
+
 int fe_sync(fe_handle* h);
 
 /* Measurement hooks.  With profiling on, every kernel of every fe_run is bracketed by CUDA
