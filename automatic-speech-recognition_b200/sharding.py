@@ -91,3 +91,80 @@ def process_pcm_sharded(pcm_list, args, fs=16000, gather_to=0, extract_fn=None, 
         return None, None
     merged = merge_shards(parts, gathered, len(pcm_list))
     return to_object_array(merged), [len(m) for m in merged]
+
+
+def _dist():
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            return dist, dist.get_rank(), dist.get_world_size()
+    except ImportError:
+        pass
+    return None, 0, 1
+
+
+def process_audios_sharded(audio_path, args, gather_to=0, process_fn=None, lengths=None, **kw):
+    """File-list variant of ``process_pcm_sharded``: every rank calls it with the SAME ``audio_path``; the
+    files are LPT-partitioned by their sample counts (header probe, no decoding), each rank runs
+    ``process_audios`` on its shard on its own GPU, rank ``gather_to`` receives (feats, featlen) in input
+    order, the others (None, None).  ``process_fn`` / ``lengths`` let tests stand in for the GPU call and
+    the probe."""
+    import os
+    from . import audio_io
+    from .preprocess import process_audios, to_object_array
+    dist, rank, world = _dist()
+    device = int(os.environ.get("LOCAL_RANK", 0))
+    fn = process_fn or process_audios
+    if world == 1:
+        return fn(list(audio_path), args, device=device, **kw)
+    if lengths is None:
+        lengths = [max(i["n_samples"], 0) for i in audio_io.probe_batch(list(audio_path))]
+    parts = lpt_partition(frame_counts(lengths) + 1, world)
+    mine = [audio_path[int(i)] for i in parts[rank]]
+    feats, _ = fn(mine, args, device=device, **kw) if mine else (to_object_array([]), [])
+    gathered = [None] * world if rank == gather_to else None
+    dist.gather_object(list(feats), gathered, dst=gather_to)
+    if rank != gather_to:
+        return None, None
+    merged = merge_shards(parts, gathered, len(audio_path))
+    return to_object_array(merged), [len(m) for m in merged]
+
+
+def process_libri_feats_sharded(audio_path, cat, k, args, process_fn=None, threshold=None, **kw):
+    """preprocess.py:112-130 over several GPUs with the SAME files on disk as the single-process run.
+
+    Sets above the reference's 30 000-file threshold are written as k chunk pickles with the reference's
+    boundaries (``n = len // k + 1``): rank r extracts and writes chunks r, r + world, ... -- no feature
+    leaves its rank; only the per-chunk frame counts (ints) are exchanged so that rank 0 can write
+    ``{cat}-featlen.npy`` in file order.  Smaller sets become one ``{cat}-feats.pkl`` written by rank 0
+    from the LPT-sharded, gathered result.  Returns featlen on rank 0, None elsewhere."""
+    import os
+    import joblib
+    from . import preprocess as pp
+    dist, rank, world = _dist()
+    device = int(os.environ.get("LOCAL_RANK", 0))
+    fn = process_fn or pp.process_audios
+    threshold = pp._SAMPLE_THRESHOLD if threshold is None else threshold
+    os.makedirs(args.feat_dir, exist_ok=True)
+    if len(audio_path) <= threshold:
+        feats, featlen = process_audios_sharded(audio_path, args, 0, process_fn, **kw)
+        if rank == 0:
+            joblib.dump(feats, args.feat_dir + "/{}-feats.pkl".format(cat))
+            np.save(args.feat_dir + "/{}-featlen.npy".format(cat), featlen)
+            return featlen
+        return None
+    n = len(audio_path) // k + 1
+    mine = {}
+    for i in range(rank, k, world):
+        feats, flen = fn(audio_path[i * n:(i + 1) * n], args, device=device, **kw)
+        joblib.dump(feats, args.feat_dir + "/{}-feats-{}.pkl".format(cat, i))
+        mine[i] = list(flen)
+    if world > 1:
+        allc = [None] * world if rank == 0 else None
+        dist.gather_object(mine, allc, dst=0)
+        if rank != 0:
+            return None
+        mine = {i: v for d in allc for i, v in d.items()}
+    featlen = [x for i in range(k) for x in mine[i]]
+    np.save(args.feat_dir + "/{}-featlen.npy".format(cat), featlen)
+    return featlen
