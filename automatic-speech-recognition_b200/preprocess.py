@@ -89,35 +89,50 @@ def _uniform(value, n):
 
 
 def _process_flac_on_device(audio_path, args, device, n_threads, switches, speed=None, gain=None):
-    """FLAC files -> features with the decode on the GPU: raw file bytes are read into one buffer per
-    ~1-audio-hour batch (host threads, no decoding), uploaded, decoded by ``fe_decode_flac`` into HBM and
-    framed there by ``fe_run``; only the cubes come back."""
-    from concurrent.futures import ThreadPoolExecutor
-    sizes = [os.path.getsize(p) for p in audio_path]
-    ranges = _plan_file_batches([s * 2 for s in sizes], _BATCH_SAMPLES * 2)      # ~2 bytes of PCM per FLAC byte
-    cubes, featlen, fe = [], [], None
-    # two page-locked staging buffers for the file bytes (batch b uploads while b + 1 is being read)
-    fe0 = get_frontend(FrontendConfig.from_args(args, sample_rate=audio_io.DEFAULT_FS, pcm_dtype="int16", **switches), device)
-    need = max(sum(sizes[lo:hi]) + 16 * (hi - lo) for lo, hi in ranges) + 64
-    stage = getattr(fe0, "_flac_stage", None)
-    if stage is None or stage[0].size < need:
-        stage = fe0._flac_stage = [fe0.pinned(need + need // 4), fe0.pinned(need + need // 4)]
-    trace = {"wait_files": 0.0, "decode": 0.0, "features": 0.0, "views": 0.0} if os.environ.get("FE_TRACE_INGEST") else None
+    """FLAC files -> features with the decode on the GPU: raw file bytes are read into page-locked staging
+    buffers per ~1-audio-hour batch (host threads, no decoding), uploaded, decoded by ``fe_decode_flac`` into
+    HBM and framed there by ``fe_run``; only the cubes come back -- into ONE result array for the whole call,
+    whose pages a helper thread touches a batch ahead so that first-touch faults overlap the GPU work."""
     import time
-    with ThreadPoolExecutor(max_workers=1) as pool:
+    from concurrent.futures import ThreadPoolExecutor
+    infos = audio_io.probe_batch(audio_path, n_threads)
+    fs = infos[0]["sample_rate"]
+    cfg = FrontendConfig.from_args(args, sample_rate=fs, pcm_dtype="int16", **switches)
+    fe = get_frontend(cfg, device)
+    all_lens = np.asarray([max(i["n_samples"], 0) for i in infos], dtype=np.int64)
+    if np.any(all_lens < fe.config.frame_len):
+        raise ValueError("negative dimensions are not allowed")              # what speechpy's stack_frames raises
+    ranges = _plan_file_batches(all_lens.tolist())
+    sizes = [os.path.getsize(p) for p in audio_path]
+    # two page-locked staging buffers for the file bytes (batch b uploads while b + 1 is being read)
+    need = max(sum(sizes[lo:hi]) + 16 * (hi - lo) for lo, hi in ranges) + 64
+    stage = getattr(fe, "_flac_stage", None)
+    if stage is None or stage[0].size < need:
+        stage = fe._flac_stage = [fe.pinned(need + need // 4), fe.pinned(need + need // 4)]
+    # the result array of the whole call, one slice per batch
+    out_sizes = [int(fe.plan(all_lens[lo:hi], fe.speed_indices(_uniform(speed, hi - lo)))[0][-1]) for lo, hi in ranges]
+    out_base = np.concatenate(([0], np.cumsum(out_sizes))).astype(np.int64)
+    result = np.empty(max(int(out_base[-1]), 1), dtype=np.float32)
+    trace = {"wait_files": 0.0, "decode": 0.0, "features": 0.0, "views": 0.0} if os.environ.get("FE_TRACE_INGEST") else None
+    cubes, featlen = [], []
+
+    def touch(b):
+        result[out_base[b]:out_base[b + 1]].fill(0.0)                         # first-touch page faults off the critical path
+
+    with ThreadPoolExecutor(max_workers=1) as pool, ThreadPoolExecutor(max_workers=1) as toucher:
         nxt = pool.submit(audio_io.load_flac_batch, audio_path[ranges[0][0]:ranges[0][1]], n_threads, stage[0])
+        touched = [toucher.submit(touch, b) for b in range(min(2, len(ranges)))]
         for b, (lo, hi) in enumerate(ranges):
             t0 = time.perf_counter()
-            buf, files, pcm_off, lens, fs, total = nxt.result()
+            buf, files, pcm_off, lens, fs_b, total = nxt.result()
             t1 = time.perf_counter()
             if b + 1 < len(ranges):
                 nxt = pool.submit(audio_io.load_flac_batch, audio_path[ranges[b + 1][0]:ranges[b + 1][1]], n_threads,
                                   stage[(b + 1) & 1])
-            if fe is None:
-                cfg = FrontendConfig.from_args(args, sample_rate=fs, pcm_dtype="int16", **switches)
-                fe = get_frontend(cfg, device)
-            if np.any(lens < fe.config.frame_len):
-                raise ValueError("negative dimensions are not allowed")          # what speechpy's stack_frames raises
+            if b + 2 < len(ranges):
+                touched.append(toucher.submit(touch, b + 2))
+            if fs_b != fs:
+                raise ValueError("mixed sample rates in one call: %d vs %d" % (fs, fs_b))
             pcm_total = int(pcm_off[-1] + (lens[-1] + 7) // 8 * 8) if len(lens) else 0
             try:
                 d_pcm = fe.decode_flac(buf, files, hi - lo, total, pcm_total)
@@ -125,11 +140,9 @@ def _process_flac_on_device(audio_path, args, device, n_threads, switches, speed
                 bad = [audio_path[lo + int(i)] for i in np.flatnonzero(fe.flac_status)]
                 raise audio_io.AudioFormatError("%s: %s" % (", ".join(bad[:4]), e))
             t2 = time.perf_counter()
-            # cubes come back into a host array (device PCM in, host features out)
-            plan_off, _ = fe.plan(lens, fe.speed_indices(_uniform(speed, len(lens))))
-            host_out = np.empty(max(int(plan_off[-1]), 1), dtype=np.float32)
+            touched[b].result()
             out, out_off, nfr = fe.run_packed(d_pcm, pcm_off, lens, speed_idx=fe.speed_indices(_uniform(speed, len(lens))),
-                                              gain=_uniform(gain, len(lens)), out=host_out)
+                                              gain=_uniform(gain, len(lens)), out=result[out_base[b]:out_base[b + 1]])
             t3 = time.perf_counter()
             cubes.extend(fe.split(out, out_off, nfr))
             featlen.extend(int(L) for L in nfr)
