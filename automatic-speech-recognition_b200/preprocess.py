@@ -20,6 +20,9 @@ from .frontend import Frontend, FrontendConfig
 _SAMPLE_THRESHOLD = 30000
 # host-side batching: PCM samples handed to the GPU per call (~1 audio-hour at 16 kHz)
 _BATCH_SAMPLES = 57_600_000
+# the device-decode path wants bigger batches: the GPU decoder runs one thread per FLAC frame (14 k frames per
+# audio-hour) and the per-batch synchronisations amortise; measured optimum ~4 audio-hours (tools/bench_ingest.py)
+_DEVICE_BATCH_SAMPLES = 4 * 57_600_000
 
 _frontends = {}
 
@@ -90,38 +93,36 @@ def _uniform(value, n):
 
 def _process_flac_on_device(audio_path, args, device, n_threads, switches, speed=None, gain=None):
     """FLAC files -> features with the decode on the GPU: raw file bytes are read into page-locked staging
-    buffers per ~1-audio-hour batch (host threads, no decoding), uploaded, decoded by ``fe_decode_flac`` into
-    HBM and framed there by ``fe_run``; only the cubes come back -- into ONE result array for the whole call,
-    whose pages a helper thread touches a batch ahead so that first-touch faults overlap the GPU work."""
+    buffers per ~4-audio-hour batch (host threads, no decoding), uploaded, decoded by ``fe_decode_flac`` into
+    HBM and framed there by ``fe_run``; only the cubes come back -- through page-locked bounce buffers into one
+    result array per batch, filled (and first-touched) by helper threads while the GPU works on the next batch.
+    Nothing is probed up front: a batch's sample counts come out of the bytes the reader thread just loaded."""
     import time
     from concurrent.futures import ThreadPoolExecutor
-    infos = audio_io.probe_batch(audio_path, n_threads)
-    fs = infos[0]["sample_rate"]
-    cfg = FrontendConfig.from_args(args, sample_rate=fs, pcm_dtype="int16", **switches)
-    fe = get_frontend(cfg, device)
-    all_lens = np.asarray([max(i["n_samples"], 0) for i in infos], dtype=np.int64)
-    if np.any(all_lens < fe.config.frame_len):
-        raise ValueError("negative dimensions are not allowed")              # what speechpy's stack_frames raises
-    ranges = _plan_file_batches(all_lens.tolist())
     sizes = [os.path.getsize(p) for p in audio_path]
+    ranges = _plan_file_batches(sizes, int(_DEVICE_BATCH_SAMPLES * 1.1))      # ~0.55 x 2 bytes of FLAC per sample
+    fe = None
     # two page-locked staging buffers for the file bytes (batch b uploads while b + 1 is being read)
+    fe0 = get_frontend(FrontendConfig.from_args(args, sample_rate=audio_io.DEFAULT_FS, pcm_dtype="int16", **switches), device)
     need = max(sum(sizes[lo:hi]) + 16 * (hi - lo) for lo, hi in ranges) + 64
-    stage = getattr(fe, "_flac_stage", None)
+    stage = getattr(fe0, "_flac_stage", None)
     if stage is None or stage[0].size < need:
-        stage = fe._flac_stage = [fe.pinned(need + need // 4), fe.pinned(need + need // 4)]
-    # the result array of the whole call, one slice per batch
-    out_sizes = [int(fe.plan(all_lens[lo:hi], fe.speed_indices(_uniform(speed, hi - lo)))[0][-1]) for lo, hi in ranges]
-    out_base = np.concatenate(([0], np.cumsum(out_sizes))).astype(np.int64)
-    result = np.empty(max(int(out_base[-1]), 1), dtype=np.float32)
+        stage = fe0._flac_stage = [fe0.pinned(need + need // 4), fe0.pinned(need + need // 4)]
     trace = {"wait_files": 0.0, "decode": 0.0, "features": 0.0, "views": 0.0} if os.environ.get("FE_TRACE_INGEST") else None
     cubes, featlen = [], []
+    # cubes leave the GPU through two page-locked bounce buffers (PCIe rate instead of the pageable-copy rate);
+    # helper threads move a finished batch into that batch's result array -- which is also its first touch --
+    # while the next batch is decoded and framed
+    n_copy = 4
+    results = []
 
-    def touch(b):
-        result[out_base[b]:out_base[b + 1]].fill(0.0)                         # first-touch page faults off the critical path
+    def copy_out(dst, src):
+        cuts = np.linspace(0, dst.size, n_copy + 1).astype(np.int64)
+        return [copier.submit(np.copyto, dst[cuts[k]:cuts[k + 1]], src[cuts[k]:cuts[k + 1]]) for k in range(n_copy)]
 
-    with ThreadPoolExecutor(max_workers=1) as pool, ThreadPoolExecutor(max_workers=1) as toucher:
+    with ThreadPoolExecutor(max_workers=1) as pool, ThreadPoolExecutor(max_workers=n_copy) as copier:
         nxt = pool.submit(audio_io.load_flac_batch, audio_path[ranges[0][0]:ranges[0][1]], n_threads, stage[0])
-        touched = [toucher.submit(touch, b) for b in range(min(2, len(ranges)))]
+        copies = []
         for b, (lo, hi) in enumerate(ranges):
             t0 = time.perf_counter()
             buf, files, pcm_off, lens, fs_b, total = nxt.result()
@@ -129,10 +130,13 @@ def _process_flac_on_device(audio_path, args, device, n_threads, switches, speed
             if b + 1 < len(ranges):
                 nxt = pool.submit(audio_io.load_flac_batch, audio_path[ranges[b + 1][0]:ranges[b + 1][1]], n_threads,
                                   stage[(b + 1) & 1])
-            if b + 2 < len(ranges):
-                touched.append(toucher.submit(touch, b + 2))
+            if fe is None:
+                fs = fs_b
+                fe = get_frontend(FrontendConfig.from_args(args, sample_rate=fs, pcm_dtype="int16", **switches), device)
             if fs_b != fs:
                 raise ValueError("mixed sample rates in one call: %d vs %d" % (fs, fs_b))
+            if np.any(lens < fe.config.frame_len):
+                raise ValueError("negative dimensions are not allowed")      # what speechpy's stack_frames raises
             pcm_total = int(pcm_off[-1] + (lens[-1] + 7) // 8 * 8) if len(lens) else 0
             try:
                 d_pcm = fe.decode_flac(buf, files, hi - lo, total, pcm_total)
@@ -140,16 +144,32 @@ def _process_flac_on_device(audio_path, args, device, n_threads, switches, speed
                 bad = [audio_path[lo + int(i)] for i in np.flatnonzero(fe.flac_status)]
                 raise audio_io.AudioFormatError("%s: %s" % (", ".join(bad[:4]), e))
             t2 = time.perf_counter()
-            touched[b].result()
-            out, out_off, nfr = fe.run_packed(d_pcm, pcm_off, lens, speed_idx=fe.speed_indices(_uniform(speed, len(lens))),
-                                              gain=_uniform(gain, len(lens)), out=result[out_base[b]:out_base[b + 1]])
+            sp = fe.speed_indices(_uniform(speed, len(lens)))
+            n_out = max(int(fe.plan(lens, sp)[0][-1]), 1)
+            bounce = getattr(fe, "_out_stage", None)
+            if bounce is None or bounce[0].size < n_out:
+                for fs_ in copies:                                            # old buffers may still be read by the copy threads
+                    for f in fs_:
+                        f.result()
+                bounce = fe._out_stage = [fe.pinned(n_out + n_out // 4, np.float32), fe.pinned(n_out + n_out // 4, np.float32)]
+            if b >= 2:
+                for f in copies[b - 2]:                                       # the bounce buffer of batch b - 2 is free again
+                    f.result()
+            src = bounce[b & 1][:n_out]
+            out, out_off, nfr = fe.run_packed(d_pcm, pcm_off, lens, speed_idx=sp, gain=_uniform(gain, len(lens)), out=src)
+            res_b = np.empty(n_out, dtype=np.float32)
+            results.append(res_b)
+            copies.append(copy_out(res_b, src))
             t3 = time.perf_counter()
-            cubes.extend(fe.split(out, out_off, nfr))
+            cubes.extend(fe.split(res_b, out_off, nfr))                       # views; filled by the copy threads
             featlen.extend(int(L) for L in nfr)
             if trace is not None:
                 t4 = time.perf_counter()
                 for k, v in zip(("wait_files", "decode", "features", "views"), (t1 - t0, t2 - t1, t3 - t2, t4 - t3)):
                     trace[k] += v
+        for fs_ in copies:
+            for f in fs_:
+                f.result()
     if trace is not None:
         import sys
         sys.stderr.write("ingest trace (s): %s over %d batches\n" % ({k: round(v, 4) for k, v in trace.items()}, len(ranges)))

@@ -121,7 +121,7 @@ def test_process_audios_device_decode_equals_host_decode(pkg, tmp_path, monkeypa
         paths.append(p)
     args = make_args()
     a, alen = pkg.process_audios(paths, args)
-    monkeypatch.setattr(importlib.import_module(PKG + ".preprocess"), "_BATCH_SAMPLES", 150_000)   # several batches
+    monkeypatch.setattr(importlib.import_module(PKG + ".preprocess"), "_DEVICE_BATCH_SAMPLES", 150_000)   # several batches
     b, blen = pkg.process_audios(paths, args, device_decode=True)
     assert alen == blen and all(np.array_equal(u, v) for u, v in zip(a, b))
     with pytest.raises(ValueError, match="flac files only"):
