@@ -38,6 +38,8 @@ def build_library(force=False, verbose=False):
     if not force and not is_stale():
         return LIB_PATH
     cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else [])
+    if os.environ.get("FE_I2F_HALFSEL"):      # experiment: both int16 halves through I2F.S16 half selectors (no SHF)
+        cmd += ["-DFE_I2F_HALFSEL"]
     if os.environ.get("FE_K1_PROF"):          # per-phase clock64 counters in K1 (tools/k1_phases.py); costs registers
         cmd += ["-DFE_K1_PROF"]
     cmd += ["-o", LIB_PATH] + [os.path.join(CSRC, s) for s in SOURCES]
