@@ -97,3 +97,37 @@ def _as_int16(a):
     if a.dtype == np.int16:
         return a
     return np.clip(np.rint(a.astype(np.float64) * 32768.0), -32768, 32767).astype(np.int16)
+
+
+class EpochAugmenter:
+    """On-the-fly perturbation instead of the reference's three static copies of the training set
+    (preprocess.py:158-167 writes speed 0.9 / 1.1 copies once; README.md:31 lists speed perturbation as the
+    key improvement): every epoch draws a speed from ``speeds`` and, if ``vol_range`` is given, a gain
+    ``np.around(U(lo, hi), 2)`` (utils/augmentation.py:48-49) per utterance, reproducibly from
+    ``(seed, epoch)``, and the features come out of the same batch call (K0 in front of the framing).
+
+    ``draw(n, epoch)`` is pure host logic; ``extract(...)`` runs the batch on the GPU."""
+
+    def __init__(self, frontend, speeds=(0.9, 1.0, 1.1), vol_range=None, seed=0):
+        self.fe = frontend
+        self.speeds = tuple(float(s) for s in speeds)
+        self.vol_range = None if vol_range is None else (float(vol_range[0]), float(vol_range[1]))
+        self.seed = int(seed)
+        if frontend is not None:
+            frontend.speed_indices(self.speeds)          # raises if a speed is not configured in the handle
+
+    def draw(self, n, epoch):
+        """-> (speeds[n] float64, gains[n] float32 or None), a function of (seed, epoch, n) only."""
+        rng = np.random.default_rng([self.seed, int(epoch)])
+        sp = np.asarray(self.speeds)[rng.integers(0, len(self.speeds), n)]
+        gains = None
+        if self.vol_range is not None:
+            gains = np.around(rng.uniform(self.vol_range[0], self.vol_range[1], n), 2).astype(np.float32)
+        return sp, gains
+
+    def extract(self, packed, offsets, lengths, epoch, out=None, stream=None):
+        """One epoch's view of a packed PCM batch (host or device): (out, out_offsets, n_frames, speeds, gains)."""
+        sp, gains = self.draw(len(lengths), epoch)
+        out, out_off, nfr = self.fe.run_packed(packed, offsets, lengths, speed_idx=self.fe.speed_indices(sp), gain=gains,
+                                               out=out, stream=stream)
+        return out, out_off, nfr, sp, gains

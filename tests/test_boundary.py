@@ -116,3 +116,15 @@ def test_file_batch_planning(pkg):
     assert pp._plan_file_batches([10], 100) == [(0, 1)] and pp._plan_file_batches([200, 5], 100) == [(0, 1), (1, 2)]
     off, total = pkg.audio_io.plan_batch([5, 8, 9])
     assert off.tolist() == [0, 8, 16] and total == 32
+
+
+def test_epoch_augmenter_draws_are_reproducible(pkg):
+    aug = importlib.import_module(PKG + ".augmentation")
+    a = aug.EpochAugmenter(None, speeds=(0.9, 1.0, 1.1), vol_range=(0.8, 1.5), seed=7)
+    s0, g0 = a.draw(1000, epoch=0)
+    s0b, g0b = a.draw(1000, epoch=0)
+    s1, g1 = a.draw(1000, epoch=1)
+    assert np.array_equal(s0, s0b) and np.array_equal(g0, g0b) and not np.array_equal(s0, s1)
+    assert set(np.unique(s0)) == {0.9, 1.0, 1.1} and abs((s0 == 1.0).mean() - 1 / 3) < 0.06
+    assert g0.min() >= 0.8 and g0.max() <= 1.5 and np.array_equal(np.around(g0, 2), g0)     # utils/augmentation.py:48-49
+    assert aug.EpochAugmenter(None, seed=7).draw(5, 3)[1] is None

@@ -422,3 +422,28 @@ def test_full_size_properties_config3_three_speeds(pkg, ref, sox):
         got = out[int(out_off[j]):int(out_off[j]) + int(nfr[j]) * 39].cpu().numpy().reshape(int(nfr[j]), 13, 3)
         assert_close(got, ref.features_one(sox.speed_perturb(p, speeds[j])), what="config3 full spot")
     fe.close()
+
+
+@pytest.mark.gpu
+def test_epoch_augmenter_features(pkg, ref, sox):
+    aug = importlib.import_module(PKG + ".augmentation")
+    pcm = pkg.synth.corpus(9, 1.0, 3.0, seed=91)
+    packed, off, lens = pkg.pack_pcm(pcm)
+    fe = pkg.Frontend(pkg.FrontendConfig())
+    ea = aug.EpochAugmenter(fe, vol_range=(0.8, 1.5), seed=3)
+    out, out_off, nfr, sp, gains = ea.extract(packed, off, lens, epoch=2)
+    out2, _, _, sp2, gains2 = ea.extract(packed, off, lens, epoch=2)
+    assert np.array_equal(out, out2) and np.array_equal(sp, sp2)                             # an epoch is reproducible
+    out3, _, nfr3, sp3, _ = ea.extract(packed, off, lens, epoch=3)
+    assert not np.array_equal(sp, sp3)
+    for i, x in enumerate(pcm):
+        y = sox.volume_perturb(sox.speed_perturb(x, float(sp[i])) if sp[i] != 1.0 else x, float(gains[i]))
+        got = out[int(out_off[i]):int(out_off[i]) + int(nfr[i]) * 39].reshape(int(nfr[i]), 13, 3)
+        want = ref.features_one(y)
+        assert got.shape == want.shape
+        # gain is applied inside the resampler's rounding (one quantisation) in the kernel, after it in the oracle
+        # chain above (two quantisations): +-1 LSB differences are expected, the features agree to tolerance
+        assert_close(got, want, abs_tol=3e-3, rel_tol=1e-3, what="epoch augmenter")
+    with pytest.raises(ValueError, match="not in FrontendConfig.speeds"):
+        aug.EpochAugmenter(fe, speeds=(0.8,))
+    fe.close()
