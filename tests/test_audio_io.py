@@ -159,3 +159,41 @@ def test_decoder_survives_mutated_streams(pkg):
     assert outcomes["rejected"] > 400 and outcomes["ok"] + outcomes["rejected"] == 600
     with pytest.raises(pkg.audio_io.AudioFormatError):
         pkg.audio_io.decode_bytes(rng.integers(0, 256, 5000, dtype=np.uint8).tobytes())
+
+
+def test_flac_round_trip_property(pkg):
+    """Property test (hypothesis): any int16 signal -- noise, ramps, constant runs, clipped rails, odd lengths and
+    sample rates -- survives encode -> decode bit-exactly, with the MD5 of STREAMINFO verified on the way."""
+    from hypothesis import given, settings, strategies as st, HealthCheck
+
+    @st.composite
+    def signals(draw):
+        parts = []
+        for _ in range(draw(st.integers(1, 4))):
+            n = draw(st.integers(0, 6000))
+            kind = draw(st.sampled_from(["noise", "small", "const", "ramp", "rail", "sine"]))
+            seed = draw(st.integers(0, 2 ** 31 - 1))
+            rng = np.random.default_rng(seed)
+            if kind == "noise":
+                x = rng.integers(-32768, 32768, n)
+            elif kind == "small":
+                x = rng.integers(-3, 4, n)
+            elif kind == "const":
+                x = np.full(n, draw(st.integers(-32768, 32767)))
+            elif kind == "ramp":
+                x = np.clip(np.arange(n) * draw(st.integers(-40, 40)) + draw(st.integers(-20000, 20000)), -32768, 32767)
+            elif kind == "rail":
+                x = rng.choice([-32768, 32767], n)
+            else:
+                x = np.sin(np.arange(n) * draw(st.floats(0.001, 3.0))) * draw(st.integers(1, 32767))
+            parts.append(np.asarray(x).astype(np.int16))
+        return np.concatenate(parts) if parts else np.zeros(0, np.int16)
+
+    @settings(max_examples=60, deadline=None, suppress_health_check=[HealthCheck.too_slow, HealthCheck.data_too_large])
+    @given(signals(), st.sampled_from([8000, 16000, 22050, 44100, 12345]))
+    def check(x, fs):
+        data = pkg.audio_io.encode_flac(x, fs)
+        back, fs2 = pkg.audio_io.decode_bytes(data, check_md5=True)
+        assert fs2 == fs and back.dtype == np.int16 and np.array_equal(back, x)
+        assert len(data) <= 2 * x.size + 64 + 24 * (x.size // 4096 + 1)          # never worse than verbatim + framing
+    check()
