@@ -23,6 +23,11 @@ class AudioFormatError(RuntimeError):
     pass
 
 
+class UnsupportedStreamError(AudioFormatError):
+    """A valid stream that the DEVICE decoder does not take (stereo, > 16 bit, variable block size, no sample
+    count); the host decoder reads it."""
+
+
 def _check(rc, what):
     if rc != 0:
         msg = _lib.load().aio_strerror(int(rc))
@@ -212,8 +217,8 @@ def load_flac_batch(paths, n_threads=0, out=None):
     unsup = ((L["min_block"] != L["max_block"]) | (L["n_samples"] <= 0) | (L["max_block"] % 8 != 0) | (L["max_block"] < 16) |
              (L["bits_per_sample"] > 16) | (L["n_samples"] >= 2 ** 31) | (L["n_samples"] > _MAX_SAMPLES_PER_BYTE * np.maximum(sizes, 1)))
     if np.any(unsup):
-        raise AudioFormatError("%s: the device decoder takes fixed-block-size streams (multiple of 8) of at most "
-                               "16 bits with a sample count; use read_audio_batch" % paths[int(np.flatnonzero(unsup)[0])])
+        raise UnsupportedStreamError("%s: the device decoder takes fixed-block-size streams (multiple of 8) of at most "
+                                     "16 bits with a sample count; use read_audio_batch" % paths[int(np.flatnonzero(unsup)[0])])
     lengths = L["n_samples"].astype(np.int64)
     pcm_offsets, _ = plan_batch(lengths)
     F["byte_offset"], F["n_bytes"], F["first_frame"] = offsets, sizes, L["first_frame"]

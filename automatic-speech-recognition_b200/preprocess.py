@@ -176,10 +176,13 @@ def _process_flac_on_device(audio_path, args, device, n_threads, switches, speed
     return to_object_array(cubes), featlen
 
 
-def process_audios(audio_path, args, device=0, n_threads=0, device_decode=False, speed=None, gain=None, **switches):
+def process_audios(audio_path, args, device=0, n_threads=0, device_decode=None, speed=None, gain=None, **switches):
     """Same signature and return value as the reference (preprocess.py:50-91).
 
-    ``device_decode=True`` (FLAC lists only) moves the FLAC decode itself to the GPU.
+    ``device_decode``: True moves the FLAC decode itself to the GPU (FLAC lists only), False keeps it on the
+    host thread pool.  The default (None) picks the GPU decoder for an all-FLAC list and says so in the log; if
+    the FIRST batch turns out to hold a stream the device decoder does not take (stereo, > 16 bit, variable block
+    size), the call continues on the host decoder -- logged, and only for that reason: corrupt files raise.
     ``speed`` / ``gain`` perturb every file of the call on the fly (K0 in front of the framing): the
     features of ``SpeedAugmentation(files, ..., speed)`` without the intermediate audio files.
 
@@ -195,6 +198,12 @@ def process_audios(audio_path, args, device=0, n_threads=0, device_decode=False,
         if exts != {".flac"}:
             raise ValueError("device_decode=True takes .flac files only")
         return _process_flac_on_device(audio_path, args, device, n_threads, switches, speed, gain)
+    if device_decode is None and exts == {".flac"}:
+        try:
+            logging.info("process_audios: %d FLAC files, decoding on the GPU", len(audio_path))
+            return _process_flac_on_device(audio_path, args, device, n_threads, switches, speed, gain)
+        except audio_io.UnsupportedStreamError as e:
+            logging.info("process_audios: host FLAC decoder instead (%s)", e)
     if not exts <= {".flac", ".wav"}:
         pcm_list, fs_seen = [], None
         for p in audio_path:

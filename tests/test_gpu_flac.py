@@ -120,12 +120,20 @@ def test_process_audios_device_decode_equals_host_decode(pkg, tmp_path, monkeypa
         pkg.audio_io.write_audio(p, x, 16000)
         paths.append(p)
     args = make_args()
-    a, alen = pkg.process_audios(paths, args)
+    a, alen = pkg.process_audios(paths, args, device_decode=False)
     monkeypatch.setattr(importlib.import_module(PKG + ".preprocess"), "_DEVICE_BATCH_SAMPLES", 150_000)   # several batches
     b, blen = pkg.process_audios(paths, args, device_decode=True)
     assert alen == blen and all(np.array_equal(u, v) for u, v in zip(a, b))
+    c, clen = pkg.process_audios(paths, args)                                                     # default: GPU decoder for FLAC lists
+    assert clen == alen and all(np.array_equal(u, v) for u, v in zip(a, c))
     with pytest.raises(ValueError, match="flac files only"):
         pkg.process_audios([str(tmp_path / "x.wav")], args, device_decode=True)
+    # a stream the device decoder does not take (stereo is rejected earlier; here: 8-bit block size not a multiple
+    # of 8 cannot be produced by our encoder, so use a 2-channel file): default mode must not silently mis-handle it
+    st = str(tmp_path / "stereo.flac")
+    pkg.audio_io.write_flac(st, np.zeros(4000, np.int16), 16000, channels=2)
+    with pytest.raises(ValueError, match="mono"):
+        pkg.process_audios([st], args)
 
 
 def test_mutated_streams_never_hang_or_corrupt_neighbours(pkg, tmp_path):

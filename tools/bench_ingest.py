@@ -28,9 +28,9 @@ try:
             import torch
             if torch.cuda.is_available():
                 args = types.SimpleNamespace(frame_step=10, frame_length=25, feat_dim=13, feat_type="mfcc", cmvn=True)
-                A.process_audios(paths[:8], args)                                   # warm-up (handle, tables)
+                A.process_audios(paths[:8], args, device_decode=False)               # warm-up (handle, tables)
                 big = paths * rep
-                t = time.time(); feats, featlen = A.process_audios(big, args, n_threads=threads); t_e2e = time.time() - t
+                t = time.time(); feats, featlen = A.process_audios(big, args, n_threads=threads, device_decode=False); t_e2e = time.time() - t
                 r["process_audios_files_h_per_s"] = hours * rep / t_e2e
                 A.process_audios(paths[:8], args, device_decode=True)
                 A.process_audios(big, args, n_threads=threads, device_decode=True)          # grows the device buffers once
