@@ -388,6 +388,16 @@ def main():
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": "first %d utterances (%.2f audio-h) of the rank-0 shard, %.1f s on %d processes" % (len(sample), h_s, secs, cores),
                "cpu": cpu_model()}
+        # how the reference actually runs (preprocess.py:67: one process, one file at a time): ~3 s on one core
+        try:
+            one = take(max(v / cores * 3.0, 0.01))
+            t1 = time.perf_counter()
+            _cpu_worker(one)
+            dt1 = time.perf_counter() - t1
+            h1 = sum(len(p) for p in one) / FS / 3600.0
+            cpu["single_process"] = {"value": h1 / dt1, "unit": UNIT, "sample": "%d utterances (%.3f audio-h), %.1f s, 1 BLAS thread" % (len(one), h1, dt1)}
+        except Exception as ex:
+            cpu["single_process"] = {"error": str(ex)[:120]}
 
     peaks = {}
     try:
