@@ -63,3 +63,29 @@ def test_no_cpu_fallback(pkg):
     import numpy as np
     with pytest.raises(RuntimeError):
         pkg.process_pcm([np.zeros(1000, np.int16)], make_args())
+
+
+def _struct_fields(header, name):
+    txt = open(os.path.join(ROOT, "include", header)).read()
+    body = txt[txt.index("typedef struct %s {" % name):]
+    body = body[:body.index("}")]
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    out = []
+    for decl in body.split(";"):
+        m = re.match(r"\s*(?:typedef struct \w+ \{)?\s*(int32_t|int64_t|float)\s+([\w\s,]+)$", decl.strip())
+        if m:
+            out += [(m.group(1), n.strip()) for n in m.group(2).split(",")]
+    return out
+
+
+def test_plain_structs_match_headers(pkg):
+    """fe_flac_file / aio_info / aio_flac_layout_t: field order, types and sizes of the ctypes mirrors."""
+    _lib = importlib.import_module(PKG + "._lib")
+    ctype = {"int32_t": ctypes.c_int32, "int64_t": ctypes.c_int64, "float": ctypes.c_float}
+    for header, cname, mirror, size in (("asr_frontend.h", "fe_flac_file", _lib.FeFlacFile, 40),
+                                        ("asr_audio_io.h", "aio_info", _lib.AioInfo, 24),
+                                        ("asr_audio_io.h", "aio_flac_layout_t", _lib.AioFlacLayout, 32)):
+        fields = _struct_fields(header, cname)
+        assert [n for _, n in fields] == [f[0] for f in mirror._fields_], cname
+        assert [ctype[t] for t, _ in fields] == [f[1] for f in mirror._fields_], cname
+        assert ctypes.sizeof(mirror) == size, cname
