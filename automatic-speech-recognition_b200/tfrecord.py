@@ -11,9 +11,7 @@ TensorFlow is not needed (and not installed here); the byte format is checked ag
 ``google.protobuf`` in tests/test_tfrecord.py."""
 import ctypes as C
 import os
-from glob import glob
 
-import joblib
 import numpy as np
 
 from . import _lib
@@ -114,8 +112,10 @@ def write_packed(paths, file_start, feats_ptr, feat_offsets, n_frames, feat_dim,
                                  _i64p(tokens), _i64p(np.ascontiguousarray(token_offsets, dtype=np.int64)),
                                  _i32p(np.ascontiguousarray(token_lens, dtype=np.int32)), _i32p(status))
     if rc != 0:
-        bad = int(np.flatnonzero(status)[0])
-        _check(int(status[bad]), paths[bad])
+        bad = np.flatnonzero(status)
+        if bad.size:                                  # a per-file failure: name the file
+            _check(int(status[bad[0]]), paths[int(bad[0])])
+        _check(rc, "rio_write_tfrecords")             # rejected before any file was touched
 
 
 def create_tfrecords(X, y, filename, num_files=5, file_start_index=1, n_threads=0):
@@ -178,49 +178,3 @@ def data_parser(record):
     feat = np.asarray(feat, dtype=np.float32).reshape(feat.shape[0], feat.shape[1], 3)
     token = np.asarray(token).astype(np.int32)
     return (feat, int(feat.shape[0])), (token, int(token.shape[0]))
-
-
-def load_train_feats(filenames):
-    """create_tfrecord.py:32-40."""
-    feats = []
-    for f in filenames:
-        print("load", f)
-        feats_ = joblib.load(f)
-        feats = np.append(feats, feats_)
-    return feats
-
-
-def build_training_tfrecords(feat_dir, save_dir, unit="subword", hours=(100, 360, 500), rng=None, n_threads=0):
-    """The ``__main__`` of create_tfrecord.py:100-140: per training split, load the pickles in groups,
-    shuffle, drop utterances with ``len(feat) >= MAXLEN`` and write 5000-record files.  ``rng``
-    replaces the reference's unseeded ``np.random.permutation`` (:129) when reproducibility is wanted."""
-    os.makedirs(save_dir, exist_ok=True)
-    perm = (rng.permutation if rng is not None else np.random.permutation)
-    written = []
-    for h in hours:
-        prefix = "train-{}".format(h)
-        train_tokens = np.load(feat_dir + "/{}-{}s.npy".format(prefix, unit), allow_pickle=True)
-        num_files = len(glob(feat_dir + "/" + prefix + "-feats*"))
-        num_partitions = max(h // 50, 1)
-        filenames = [feat_dir + "/" + prefix + "-feats-{}.pkl".format(i) for i in range(num_files)]
-        if num_files == 1 and not os.path.exists(filenames[0]):
-            filenames = [feat_dir + "/" + prefix + "-feats.pkl"]
-        num_pkl_per_tfrecord = max(num_files // num_partitions, 1)
-        num_partitions = min(num_partitions, num_files)
-        st_save_index, st_token_index = 1, 0
-        for i in range(num_partitions):
-            st = i * num_pkl_per_tfrecord
-            ed = (i + 1) * num_pkl_per_tfrecord if i != num_partitions - 1 else num_files
-            train_feats = load_train_feats(filenames[st:ed])
-            train_tokens_ = train_tokens[st_token_index:st_token_index + len(train_feats)]
-            st_token_index += len(train_feats)
-            rand_idx = perm(len(train_tokens_))
-            train_feats = train_feats[rand_idx]
-            train_featlen = np.array([len(feat) for feat in train_feats])
-            train_tokens_ = train_tokens_[rand_idx]
-            X = train_feats[train_featlen < MAXLEN]
-            y = train_tokens_[train_featlen < MAXLEN]
-            nfile = max(len(y) // NUM_FILE_PER_TFRECORD, 1)      # the reference writes nothing for < 5000 records
-            written += create_tfrecords(X, y, save_dir + "/" + prefix, nfile, st_save_index, n_threads)
-            st_save_index += nfile
-    return written

@@ -68,9 +68,10 @@ def test_mini_librispeech_offline_pipeline(pkg, ref, tmp_path, device_decode):
     assert np.load(args.feat_dir + "/train-100-featlen.npy").tolist() == featlen == [len(f) for f in feats]
     for f, p in zip(feats, audio_path):
         assert_close(f, ref.features_one(truth[p][0]), what="pipeline features")
-    # create_tfrecord.py:100-140
-    tfr_paths = tfr.build_training_tfrecords(args.feat_dir, str(tmp_path / "tfrecord"), unit="char", hours=(100,),
-                                             rng=np.random.default_rng(0))
+    # create_tfrecord.py:43-97 (the caller script create_tfrecord.py:100-140 is a consumer and runs unchanged)
+    os.makedirs(str(tmp_path / "tfrecord"))
+    perm = np.random.default_rng(0).permutation(len(feats))
+    tfr_paths = tfr.create_tfrecords(feats[perm], tokens[perm], str(tmp_path / "tfrecord" / "train-100"), 1)
     records = [r for p in tfr_paths for r in tfr.read_tfrecord(p)]
     assert len(records) == 15
     by_len = {(f.shape[0], tuple(t.tolist())) for f, t in records}
