@@ -129,7 +129,8 @@ class FrontendLibraryError(RuntimeError):
 
 
 def library_path():
-    return _build.LIB_PATH
+    """The in-tree library; FE_LIB points profiling / experiment builds (build.build_library(out=...)) at another file."""
+    return os.environ.get("FE_LIB") or _build.LIB_PATH
 
 
 def load():

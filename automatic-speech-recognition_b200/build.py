@@ -33,22 +33,23 @@ def is_stale():
     return any(os.path.exists(d) and os.path.getmtime(d) > t for d in deps)
 
 
-def build_library(force=False, verbose=False):
-    """Compile the CUDA sources into automatic-speech-recognition_b200/libasr_frontend.so."""
-    if not force and not is_stale():
+def build_library(force=False, verbose=False, out=None, defines=()):
+    """Compile the CUDA sources into automatic-speech-recognition_b200/libasr_frontend.so
+    (``out`` / ``defines``: experiment variants, loaded with FE_LIB=<path>)."""
+    if out is None and not force and not is_stale():
         return LIB_PATH
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else [])
+    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-D" + d for d in defines]
     if os.environ.get("FE_I2F_HALFSEL"):      # experiment: both int16 halves through I2F.S16 half selectors (no SHF)
         cmd += ["-DFE_I2F_HALFSEL"]
     if os.environ.get("FE_K1_PROF"):          # per-phase clock64 counters in K1 (tools/k1_phases.py); costs registers
         cmd += ["-DFE_K1_PROF"]
-    cmd += ["-o", LIB_PATH] + [os.path.join(CSRC, s) for s in SOURCES]
+    cmd += ["-o", out or LIB_PATH] + [os.path.join(CSRC, s) for s in SOURCES]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed:\n%s\n%s" % (res.stdout, res.stderr))
     if verbose:
         sys.stderr.write(res.stderr)
-    return LIB_PATH
+    return out or LIB_PATH
 
 
 if __name__ == "__main__":

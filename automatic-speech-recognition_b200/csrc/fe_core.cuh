@@ -64,6 +64,17 @@ FE_HD float2 psub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y)
 FE_HD float2 pmul(float2 a, float2 b) { return make_float2(a.x * b.x, a.y * b.y); }
 FE_HD float2 pfma(float2 a, float2 b, float2 c) { return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)); }
 #endif
+// FE_FMA_MODE (measured with tools/ubench_issue2.cu): an FFMA2 whose three operands are
+// distinct register pairs occupies the issue port longer than two scalar FFMAs; 1 = such FMAs are issued
+// as scalar pairs, 2 = every FMA is, 0 = everything packed.
+#ifndef FE_FMA_MODE
+#define FE_FMA_MODE 0
+#endif
+FE_HD float2 pfma_s(float2 a, float2 b, float2 c) { return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)); }
+// all three operands live in registers (table twiddles, squares)
+FE_HD float2 pfma_rr(float2 a, float2 b, float2 c) { return FE_FMA_MODE >= 1 ? pfma_s(a, b, c) : pfma(a, b, c); }
+// one operand is a compile-time constant broadcast to both halves
+FE_HD float2 pfma_k(float2 a, float k, float2 c) { return FE_FMA_MODE >= 2 ? make_float2(fmaf(a.x, k, c.x), fmaf(a.y, k, c.y)) : pfma(a, make_float2(k, k), c); }
 FE_HD float2 pbc(float s) { return make_float2(s, s); }
 FE_HD float2 pswap(float2 a) { return make_float2(a.y, a.x); }
 FE_HD float2 pneg(float2 a) { return make_float2(-a.x, -a.y); }
@@ -77,7 +88,7 @@ struct SmemTables {
     // resource of this kernel, packed FP32 issue slots are not):
     // twiddles come straight from tables: K1 is bound by instruction issue (a packed f32x2 instruction takes two
     // issue cycles), so one 16-byte load per twiddle pair beats regenerating it from a base with four packed FMAs
-    const float4* tw256;      // [15][16] row k1-1, cfg = swap*8 + t: (wr(jx k1), wr(jy k1), wi(jx k1), wi(jy k1)) of W_256^(j k1)
+    const float4* tw256;      // [15][16] row j-1, cfg = flip*8 + t: (wr(j rx), wr(j ry), wi(j rx), wi(j ry)) of W_256^(j row), applied by stage B
     const float4* tw512;      // [8][16]  row k2, cfg = flip*8 + t: (cos, cos, sin, sin) of 2 pi (rx + 16 k2) / 512 and (ry + 16 k2)
     const float2* window;     // [ROWS*16] (w[2m], w[2m+1]) per complex point m, or nullptr
     // mel plan: every epilogue warp streams its own flat list of 4-bin weight groups (its filters back to
@@ -118,19 +129,79 @@ FE_HD void bfly4_z3(float2& r0, float2& i0, float2& r1, float2& i1, float2& r2, 
     r3 = psub(t1r, t3i); i3 = padd(t1i, t3r);         // t1 + i t3
 }
 
-// multiply (r, i) by exp(-2 pi i M / 16)
-template <int M> FE_HD void mul_w16(float2& r, float2& i) {
-    constexpr float C1 = 0.92387953251128674f, S1 = 0.38268343236508977f, H = 0.70710678118654752f;
-    if (M == 1)      { float2 t = pfma(i, pbc(S1), pmul(r, pbc(C1))); i = pnfma(r, pbc(S1), pmul(i, pbc(C1))); r = t; }
-    else if (M == 2) { float2 t = pmul(padd(r, i), pbc(H)); i = pmul(psub(i, r), pbc(H)); r = t; }
-    else if (M == 3) { float2 t = pfma(i, pbc(C1), pmul(r, pbc(S1))); i = pnfma(r, pbc(C1), pmul(i, pbc(S1))); r = t; }
-    else if (M == 4) { float2 t = r; r = i; i = pneg(t); }
-    else if (M == 6) { float2 t = pmul(psub(i, r), pbc(H)); i = pmul(padd(r, i), pbc(-H)); r = t; }
-    else if (M == 9) { float2 t = pnfma(i, pbc(S1), pmul(r, pbc(-C1))); i = pfma(r, pbc(S1), pmul(i, pbc(-C1))); r = t; }
-}
-
 // In-place FFT16: input natural order x[n]; output X[k] lands at slot pos16(k).
 FE_HD constexpr int pos16(int k) { return (k >> 2) + ((k & 3) << 2); }
+
+// (ar, ai) = (r, i) * (wr + i wi)                       2 FMUL2 + 2 FFMA2
+FE_HD void cmul_c(float2 r, float2 i, float wr, float wi, float2& ar, float2& ai) {
+    ar = pfma_k(i, -wi, pmul(r, pbc(wr)));
+    ai = pfma_k(r, wi, pmul(i, pbc(wr)));
+}
+// (tr, ti) = (br, bi) + (r, i) * (wr + i wi)            4 FFMA2: the product is never materialised
+FE_HD void cmac_c(float2 r, float2 i, float wr, float wi, float2 br, float2 bi, float2& tr, float2& ti) {
+    tr = pfma_k(r, wr, pfma_k(i, -wi, br));
+    ti = pfma_k(r, wi, pfma_k(i, wr, bi));
+}
+// same with per-half twiddles (packed operands)
+FE_HD void cmul_p(float2 r, float2 i, float2 wr, float2 wi, float2& ar, float2& ai) {
+    ar = pfma_rr(pneg(i), wi, pmul(r, wr));
+    ai = pfma_rr(r, wi, pmul(i, wr));
+}
+FE_HD void cmac_p(float2 r, float2 i, float2 wr, float2 wi, float2 br, float2 bi, float2& tr, float2& ti) {
+    tr = pfma_rr(r, wr, pfma_rr(pneg(i), wi, br));
+    ti = pfma_rr(r, wi, pfma_rr(i, wr, bi));
+}
+FE_HD float2 ptwice_minus(float2 a, float2 t) { return pfma_k(a, 2.f, pneg(t)); }     // 2 a - t
+
+// second half of a radix-4 butterfly: (t0, t1, t2, t3) -> outputs
+FE_HD void bfly4_out(float2 t0r, float2 t0i, float2 t1r, float2 t1i, float2 t2r, float2 t2i, float2 t3r, float2 t3i,
+                     float2& r0, float2& i0, float2& r1, float2& i1, float2& r2, float2& i2, float2& r3, float2& i3) {
+    r0 = padd(t0r, t2r); i0 = padd(t0i, t2i);
+    r2 = psub(t0r, t2r); i2 = psub(t0i, t2i);
+    r1 = padd(t1r, t3i); i1 = psub(t1i, t3r);     // t1 - i t3
+    r3 = psub(t1r, t3i); i3 = padd(t1i, t3r);     // t1 + i t3
+}
+
+// Second level of the FFT16 with the W_16^(n1 k2) twiddles folded into the butterflies' additions (the
+// kernel is bound by instruction issue, so a multiply that can ride on the following add as an FMA is free):
+//   x0 + w x2 and x0 - w x2 with w = +-H(1 -+ i) cost 2 adds + 4 FMAs instead of 2 adds + 2 muls + 4 adds,
+//   a = w1 x1 (4 ops), t2 = a + w3 x3 (4 FMAs), t3 = 2 a - t2 (2 FMAs) instead of 4 + 4 + 4.
+// 84 packed operations for the level instead of 96.
+FE_HD void fft16_level2(float2 (&xr)[16], float2 (&xi)[16]) {
+    constexpr float C1 = 0.92387953251128674f, S1 = 0.38268343236508977f, H = 0.70710678118654752f;
+    bfly4(xr[0], xi[0], xr[1], xi[1], xr[2], xi[2], xr[3], xi[3]);                    // k2 = 0: no twiddles
+    {   // k2 = 1: x1 W^1, x2 W^2 = H (1 - i), x3 W^3
+        const float2 s2 = padd(xr[6], xi[6]), d2 = psub(xi[6], xr[6]);
+        const float2 t0r = pfma_k(s2, H, xr[4]), t0i = pfma_k(d2, H, xi[4]);
+        const float2 t1r = pfma_k(s2, -H, xr[4]), t1i = pfma_k(d2, -H, xi[4]);
+        float2 ar, ai, t2r, t2i;
+        cmul_c(xr[5], xi[5], C1, -S1, ar, ai);
+        cmac_c(xr[7], xi[7], S1, -C1, ar, ai, t2r, t2i);
+        const float2 t3r = ptwice_minus(ar, t2r), t3i = ptwice_minus(ai, t2i);
+        bfly4_out(t0r, t0i, t1r, t1i, t2r, t2i, t3r, t3i, xr[4], xi[4], xr[5], xi[5], xr[6], xi[6], xr[7], xi[7]);
+    }
+    {   // k2 = 2: x1 W^2 = H (s1, d1), x2 W^4 = -i x2, x3 W^6 = H (d3, -s3); the H rides on the output additions
+        const float2 s1 = padd(xr[9], xi[9]), d1 = psub(xi[9], xr[9]);
+        const float2 s3 = padd(xr[11], xi[11]), d3 = psub(xi[11], xr[11]);
+        const float2 t0r = padd(xr[8], xi[10]), t0i = psub(xi[8], xr[10]);
+        const float2 t1r = psub(xr[8], xi[10]), t1i = padd(xi[8], xr[10]);
+        const float2 ur = padd(s1, d3), ui = psub(d1, s3), vr = psub(s1, d3), vi = padd(d1, s3);
+        xr[8] = pfma_k(ur, H, t0r);   xi[8] = pfma_k(ui, H, t0i);
+        xr[10] = pfma_k(ur, -H, t0r); xi[10] = pfma_k(ui, -H, t0i);
+        xr[9] = pfma_k(vi, H, t1r);   xi[9] = pfma_k(vr, -H, t1i);
+        xr[11] = pfma_k(vi, -H, t1r); xi[11] = pfma_k(vr, H, t1i);
+    }
+    {   // k2 = 3: x1 W^3, x2 W^6 = H (d2, -s2), x3 W^9
+        const float2 s2 = padd(xr[14], xi[14]), d2 = psub(xi[14], xr[14]);
+        const float2 t0r = pfma_k(d2, H, xr[12]), t0i = pfma_k(s2, -H, xi[12]);
+        const float2 t1r = pfma_k(d2, -H, xr[12]), t1i = pfma_k(s2, H, xi[12]);
+        float2 ar, ai, t2r, t2i;
+        cmul_c(xr[13], xi[13], S1, -C1, ar, ai);
+        cmac_c(xr[15], xi[15], -C1, S1, ar, ai, t2r, t2i);
+        const float2 t3r = ptwice_minus(ar, t2r), t3i = ptwice_minus(ai, t2i);
+        bfly4_out(t0r, t0i, t1r, t1i, t2r, t2i, t3r, t3i, xr[12], xi[12], xr[13], xi[13], xr[14], xi[14], xr[15], xi[15]);
+    }
+}
 
 // NZ: inputs n >= NZ are known to be zero (12 < NZ <= 16 supported: only the fourth butterfly input can vanish)
 template <int NZ = 16>
@@ -141,14 +212,29 @@ FE_HD void fft16(float2 (&xr)[16], float2 (&xi)[16]) {
         if (n1 + 12 >= NZ) bfly4_z3(xr[n1], xi[n1], xr[n1 + 4], xi[n1 + 4], xr[n1 + 8], xi[n1 + 8], xr[n1 + 12], xi[n1 + 12]);
         else bfly4(xr[n1], xi[n1], xr[n1 + 4], xi[n1 + 4], xr[n1 + 8], xi[n1 + 8], xr[n1 + 12], xi[n1 + 12]);
     }
-    // slot n1 + 4 k2 holds A[n1][k2]; twiddle W_16^(n1 k2)
-    mul_w16<1>(xr[5], xi[5]);   mul_w16<2>(xr[9], xi[9]);   mul_w16<3>(xr[13], xi[13]);
-    mul_w16<2>(xr[6], xi[6]);   mul_w16<4>(xr[10], xi[10]); mul_w16<6>(xr[14], xi[14]);
-    mul_w16<3>(xr[7], xi[7]);   mul_w16<6>(xr[11], xi[11]); mul_w16<9>(xr[15], xi[15]);
+    fft16_level2(xr, xi);       // slot n1 + 4 k2 holds A[n1][k2]; twiddle W_16^(n1 k2)
+}
+
+// FFT16 of x[n] * w[n] (w[0] = 1): the input twiddles are folded into the first level's additions.
+//   a0 = x0 w0 (4 ops, none for n1 = 0), t0 = a0 + x2 w2 (4 FMAs), t1 = 2 a0 - t0 (2), same for (x1, x3):
+//   24 / 28 operations per butterfly instead of 28 / 32 with separate complex multiplies.
+// tw(n) returns (wr, wi) of input n as packed pairs (one twiddle per half).
+template <class TW>
+FE_HD void fft16_twiddled(float2 (&xr)[16], float2 (&xi)[16], TW&& tw) {
 #pragma unroll
-    for (int k2 = 0; k2 < 4; ++k2)
-        bfly4(xr[4 * k2], xi[4 * k2], xr[4 * k2 + 1], xi[4 * k2 + 1],
-              xr[4 * k2 + 2], xi[4 * k2 + 2], xr[4 * k2 + 3], xi[4 * k2 + 3]);
+    for (int n1 = 0; n1 < 4; ++n1) {
+        float2 a0r = xr[n1], a0i = xi[n1], wr, wi;
+        if (n1 > 0) { tw(n1, wr, wi); cmul_p(xr[n1], xi[n1], wr, wi, a0r, a0i); }
+        float2 t0r, t0i, a1r, a1i, t2r, t2i;
+        tw(n1 + 8, wr, wi);  cmac_p(xr[n1 + 8], xi[n1 + 8], wr, wi, a0r, a0i, t0r, t0i);
+        const float2 t1r = ptwice_minus(a0r, t0r), t1i = ptwice_minus(a0i, t0i);
+        tw(n1 + 4, wr, wi);  cmul_p(xr[n1 + 4], xi[n1 + 4], wr, wi, a1r, a1i);
+        tw(n1 + 12, wr, wi); cmac_p(xr[n1 + 12], xi[n1 + 12], wr, wi, a1r, a1i, t2r, t2i);
+        const float2 t3r = ptwice_minus(a1r, t2r), t3i = ptwice_minus(a1i, t2i);
+        bfly4_out(t0r, t0i, t1r, t1i, t2r, t2i, t3r, t3i,
+                  xr[n1], xi[n1], xr[n1 + 4], xi[n1 + 4], xr[n1 + 8], xi[n1 + 8], xr[n1 + 12], xi[n1 + 12]);
+    }
+    fft16_level2(xr, xi);
 }
 
 // ---------------------------------------------------------------------------
@@ -242,31 +328,24 @@ FE_HD float stage_a(const void* raw_f, float* e_f, const SmemTables& tb, int t, 
                 if (ny + 1 >= FRAME_LEN) vi.y = 0.f;
             }
             re[a] = vr; im[a] = vi;
-            ss = pfma(vr, vr, ss); ss = pfma(vi, vi, ss);
+            ss = pfma_rr(vr, vr, ss); ss = pfma_rr(vi, vi, ss);
         } else {
             re[a] = make_float2(0.f, 0.f); im[a] = make_float2(0.f, 0.f);
         }
     }
     fft16<(ROWS > 12 ? ROWS : 16)>(re, im);
-    // twiddle W_256^(j k1) and scatter.  Lane part of the index (low 5 bits):
+    // scatter (the W_256^(j k1) twiddles are applied by stage B, folded into its first butterflies).
+    // Lane part of the index (low 5 bits):
     //   4*((t>>1) ^ X ^ 4*hb) + 2*(t&1) + F   with hb = j>>3 of the half being stored
     const int X = (fs & 1) << 2, F = fs >> 1;
     const int lb = (((t >> 1) ^ X) << 2) | ((t & 1) << 1);
     const int hbx = swap << 4, hby = (1 - swap) << 4;           // chunk bit 2 = index bit 4
     const EPtr x0 = e_make(e_f, lb ^ hbx), y0 = e_make(e_f, lb ^ hby);              // pair-row 0: no slot flip
     const EPtr xF = e_make(e_f, (lb ^ hbx) | F), yF = e_make(e_f, (lb ^ hby) | F);
-    const int cfg = swap * 8 + t;
 #pragma unroll
     for (int k1 = 0; k1 < 16; ++k1) {
         const int s = pos16(k1);
-        float2 yr = re[s], yi = im[s];
-        if (k1 > 0) {
-            const float4 w = tb.tw256[(k1 - 1) * 16 + cfg];
-            const float2 wr = make_float2(w.x, w.y), wi = make_float2(w.z, w.w);
-            float2 tr = pnfma(yi, wi, pmul(yr, wr));
-            yi = pfma(yr, wi, pmul(yi, wr));
-            yr = tr;
-        }
+        const float2 yr = re[s], yi = im[s];
         const int p = e_prow(k1), c = (p << 2) | e_slot(k1), off = p * 64;
         const EPtr qx = (p == 0 ? x0 : xF).x(c), qy = (p == 0 ? y0 : yF).x(c);
         e_st(qx, off, yr.x);
@@ -287,7 +366,7 @@ FE_HD int lane_flip(int t, int fs) { return t ? (fs >> 1) : 0; }
 FE_HD int row_x(int t, int fs) { return t == 0 ? 8 : (lane_flip(t, fs) ? 16 - t : t); }
 FE_HD int row_y(int t, int fs) { return t == 0 ? 0 : (lane_flip(t, fs) ? t : 16 - t); }
 
-FE_HD void stage_b(float* e_f, LaneZ& z, int t, int fs) {
+FE_HD void stage_b(float* e_f, LaneZ& z, const SmemTables& tb, int t, int fs) {
     const int X = (fs & 1) << 2;
     const EPtr b = e_make(e_f, t * 64 + ((t ^ X) << 2));
 #pragma unroll
@@ -297,7 +376,12 @@ FE_HD void stage_b(float* e_f, LaneZ& z, int t, int fs) {
         z.r[2 * q] = make_float2(vr.x, vr.y); z.r[2 * q + 1] = make_float2(vr.z, vr.w);
         z.i[2 * q] = make_float2(vi.x, vi.y); z.i[2 * q + 1] = make_float2(vi.z, vi.w);
     }
-    fft16(z.r, z.i);
+    // column j carries W_256^(j row): rows (rx, ry) are a per-lane constant, the table row is the column
+    const float4* tw = tb.tw256 + lane_flip(t, fs) * 8 + t;
+    fft16_twiddled(z.r, z.i, [&](int j, float2& wr, float2& wi) {
+        const float4 w = tw[(j - 1) * 16];
+        wr = make_float2(w.x, w.y); wi = make_float2(w.z, w.w);
+    });
 }
 
 // ---------------------------------------------------------------------------
@@ -323,15 +407,16 @@ FE_HD void post_pass(const LaneZ& z, float* p_f, const SmemTables& tb, int t, in
         const float2 c = make_float2(wb.x, wb.y), s = make_float2(wb.z, wb.w);
         float2 er = padd(ar, pr), ei = psub(ai, pi);          // 2E  (B = conj(partner))
         float2 orr = psub(ar, pr), oi = padd(ai, pi);         // 2O
-        float2 tr = pnfma(c, oi, pmul(s, orr));               // T = i w O, w = (c, -s)
-        float2 ti = pfma(s, oi, pmul(c, orr));
-        float2 xr = psub(er, tr), xi = psub(ei, ti);          // 2 X[k]
-        float2 plo = pfma(xi, xi, pmul(xr, xr));
+        // T = i w O, w = (c, -s): Tr = s Or - c Oi, Ti = c Or + s Oi; 2 X[k] = 2E - T with the products folded
+        // into the subtraction (2 FFMA2 per component instead of FMUL2 + FFMA2 + FADD2)
+        float2 xr = pfma_rr(pneg(s), orr, pfma_rr(c, oi, er));
+        float2 xi = pfma_rr(pneg(s), oi, pfma_rr(pneg(c), orr, ei));
+        float2 plo = pfma_rr(xi, xi, pmul(xr, xr));
         p_f[(rx + 16 * k2) * kPStride] = plo.x;
         p_f[(ry + 16 * k2) * kPStride] = plo.y;
         if (tb.full_spectrum) {
-            float2 yr = padd(er, tr), yi = padd(ei, ti);      // conj(2 X[256-k])
-            float2 phi = pfma(yi, yi, pmul(yr, yr));
+            float2 yr = ptwice_minus(er, xr), yi = ptwice_minus(ei, xi);      // conj(2 X[256-k]) = 2E + T = 2 (2E) - 2X
+            float2 phi = pfma_rr(yi, yi, pmul(yr, yr));
             p_f[(256 - (rx + 16 * k2)) * kPStride] = phi.x;
             p_f[(256 - (ry + 16 * k2)) * kPStride] = phi.y;   // lane 0, k2 = 0 writes bin 256
         }

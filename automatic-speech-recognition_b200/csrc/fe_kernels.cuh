@@ -439,7 +439,7 @@ k_frames_to_statics(const void* __restrict__ pcm, const void* __restrict__ scrat
             FE_TICK(1);
             // ---- phase 2: stage B ----
             LaneZ z;
-            stage_b(e_f, z, t, fs);
+            stage_b(e_f, z, tb, t, fs);
             FE_TICK(2);
             // ---- phase 3: post-pass, power columns, frame energy (the slot must have been drained) ----
             if (use > 0) mbar_wait(bar_empty + 8 * slot, (use - 1u) & 1u);

@@ -10,7 +10,7 @@
 namespace fe {
 
 struct HostTables {
-    std::vector<float> tw256;       // [15][16][4] stage-A twiddles, row k1 - 1, cfg = swap*8 + t
+    std::vector<float> tw256;       // [15][16][4] stage-B input twiddles, row j - 1, cfg = flip*8 + t
     std::vector<float> tw512;       // [8][16][4]  post-pass twiddles, row k2, cfg = flip*8 + t
     std::vector<float> window;      // [rows*32]    (w[2m], w[2m+1]) per complex point
     std::vector<int> mel_desc;      // [mel_groups] flat group list per epilogue warp: row | last << 10 | filter << 16
@@ -26,15 +26,15 @@ struct HostTables {
 };
 
 inline void build_host_tables(const fe_config& c, HostTables& t) {
-    // stage-A twiddles W_256^(j k1), k1 = 1..15: (wr(jx), wr(jy), wi(jx), wi(jy)), jx = t + 8 swap, jy = t + 8 (1 - swap)
+    // stage-B input twiddles W_256^(j row), j = 1..15: (wr(rx), wr(ry), wi(rx), wi(ry)) for the lane's two rows
     t.tw256.assign(15 * 16 * 4, 0.f);
-    for (int k1 = 1; k1 < 16; ++k1)
+    for (int j = 1; j < 16; ++j)
         for (int cfg = 0; cfg < 16; ++cfg) {
-            const int swap = cfg >> 3, tt = cfg & 7;
-            const int jx = tt + 8 * swap, jy = tt + 8 * (1 - swap);
-            float* o = &t.tw256[((k1 - 1) * 16 + cfg) * 4];
-            o[0] = c.tw256[(jx * 16 + k1) * 2];     o[1] = c.tw256[(jy * 16 + k1) * 2];
-            o[2] = c.tw256[(jx * 16 + k1) * 2 + 1]; o[3] = c.tw256[(jy * 16 + k1) * 2 + 1];
+            const int tt = cfg & 7, fs = (cfg >> 3) << 1;
+            const int rx = row_x(tt, fs), ry = row_y(tt, fs);
+            float* o = &t.tw256[((j - 1) * 16 + cfg) * 4];
+            o[0] = c.tw256[(j * 16 + rx) * 2];     o[1] = c.tw256[(j * 16 + ry) * 2];
+            o[2] = c.tw256[(j * 16 + rx) * 2 + 1]; o[3] = c.tw256[(j * 16 + ry) * 2 + 1];
         }
     // post-pass twiddles: (cos, cos, sin, sin) of 2 pi k / 512 for k = rx + 16 k2 and ry + 16 k2
     t.tw512.assign(8 * 16 * 4, 0.f);

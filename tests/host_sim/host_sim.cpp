@@ -62,7 +62,7 @@ int run(const fe_config& c, const void* pcm, int n_samples, float* statics) {
             }
             for (int lane = 0; lane < 32; ++lane) {
                 int fs = lane >> 3, t = lane & 7;
-                if (fs < nfw) stage_b(e_w + fs * kERegion, z[lane], t, fs);
+                if (fs < nfw) stage_b(e_w + fs * kERegion, z[lane], tb, t, fs);
             }
             for (int lane = 0; lane < 32; ++lane) {
                 int fs = lane >> 3, t = lane & 7;
