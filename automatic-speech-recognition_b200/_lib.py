@@ -7,7 +7,7 @@ import os
 
 from . import build as _build
 
-FE_ABI_VERSION = 1
+FE_ABI_VERSION = 2
 FE_OK, FE_ERR_INVALID, FE_ERR_CUDA, FE_ERR_CAPACITY, FE_ERR_STATE = 0, -1, -2, -3, -4
 FE_FEAT_MFCC, FE_FEAT_FBANK = 0, 1
 FE_DELTA_SPEECHPY, FE_DELTA_TIME_REGRESSION = 0, 1
@@ -29,6 +29,7 @@ class FeConfig(C.Structure):
         ("fb_row_start", _i32p), ("fb_first_bin", _i32p), ("fb_weights", _f32p),
         ("dct", _f32p), ("window", _f32p), ("tw256", _f32p), ("tw512", _f32p),
         ("n_speeds", C.c_int32), ("speed_up", _i32p), ("speed_down", _i32p), ("speed_taps", _f32p),
+        ("speed_ntaps", C.c_int32),
     ]
 
 

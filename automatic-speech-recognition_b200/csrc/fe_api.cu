@@ -60,6 +60,8 @@ struct fe_handle {
     bool scratch_f32 = false;     // pre-emphasis materialises float PCM in the scratch buffer
     // resampler
     std::vector<int> sp_up, sp_down, sp_tap_off;
+    std::vector<float> sp_taps;       // host copy: the fast kernels take their table as a kernel parameter
+    int sp_ntaps = 0;                 // taps per phase
     DevBuf d_sp_up, d_sp_down, d_sp_tap_off, d_taps;
     // bucketed batches (fe_pad_batches): slot table, time of the last profiled launch
     DevBuf d_pad;
@@ -245,9 +247,12 @@ int launch_k1(fe_handle* h, cudaStream_t st, const void* pcm, const void* scratc
 // kernels, everything else (other ratios, gain only) through the generic one.  The tile table is grouped by
 // class on the host (class_atiles) so that no kernel walks tiles it has to skip.
 int atile_class(const fe_handle* h, const UttDesc& u) {
-    if (u.speed_idx >= 0 && h->sp_up[u.speed_idx] == 10 && h->sp_down[u.speed_idx] == 9) return 0;
-    if (u.speed_idx >= 0 && h->sp_up[u.speed_idx] == 10 && h->sp_down[u.speed_idx] == 11) return 1;
-    return 2;
+    if (u.speed_idx < 0 || h->sp_ntaps != kK0Taps) return 2;
+    const int up = h->sp_up[u.speed_idx], down = h->sp_down[u.speed_idx];
+    if (up != 10 || (down != 9 && down != 11)) return 2;
+    // two entries with the same ratio could carry different taps: only the first one rides the fast kernel
+    for (int i = 0; i < u.speed_idx; ++i) if (h->sp_up[i] == up && h->sp_down[i] == down) return 2;
+    return down == 9 ? 0 : 1;
 }
 
 void class_atiles(const fe_handle* h, const UttDesc* utts, std::vector<int2>& at, int counts[3]) {
@@ -257,21 +262,32 @@ void class_atiles(const fe_handle* h, const UttDesc* utts, std::vector<int2>& at
     for (int k = 0; k < 3; ++k) { counts[k] = (int)cls[k].size(); std::copy(cls[k].begin(), cls[k].end(), at.begin() + o); o += cls[k].size(); }
 }
 
+// first configured speed with this ratio (-1: none)
+int speed_with_ratio(const fe_handle* h, int up, int down) {
+    for (size_t i = 0; i < h->sp_up.size(); ++i) if (h->sp_up[i] == up && h->sp_down[i] == down) return (int)i;
+    return -1;
+}
+
 int launch_k0(fe_handle* h, cudaStream_t st, const short* src, const UttDesc* utts, const int2* atiles, const int counts[3],
               short* dst, int use_dst_off) {
     const int* up = (const int*)h->d_sp_up.p; const int* down = (const int*)h->d_sp_down.p;
     const int* toff = (const int*)h->d_sp_tap_off.p; const float* taps = (const float*)h->d_taps.p;
     auto grid = [&](int n) { return (int)std::min<long long>(n, 16LL * h->num_sms); };
     if (counts[0] > 0) {
-        k_resample_fast<10, 9><<<grid(counts[0]), 320, 0, st>>>(src, utts, atiles, counts[0], up, down, toff, taps, dst, use_dst_off);
+        K0Taps<10, kK0Taps> W;
+        memcpy(W.w, h->sp_taps.data() + h->sp_tap_off[speed_with_ratio(h, 10, 9)], sizeof(W.w));
+        k_resample_fast<10, 9, kK0Taps><<<grid(counts[0]), kK0Outputs / 10, 0, st>>>(src, utts, atiles, counts[0], W, dst, use_dst_off);
         h->launches++;
     }
     if (counts[1] > 0) {
-        k_resample_fast<10, 11><<<grid(counts[1]), 320, 0, st>>>(src, utts, atiles + counts[0], counts[1], up, down, toff, taps, dst, use_dst_off);
+        K0Taps<10, kK0Taps> W;
+        memcpy(W.w, h->sp_taps.data() + h->sp_tap_off[speed_with_ratio(h, 10, 11)], sizeof(W.w));
+        k_resample_fast<10, 11, kK0Taps><<<grid(counts[1]), kK0Outputs / 10, 0, st>>>(src, utts, atiles + counts[0], counts[1], W, dst, use_dst_off);
         h->launches++;
     }
     if (counts[2] > 0) {
-        k_resample<<<grid(counts[2]), 256, 0, st>>>(src, utts, atiles + counts[0] + counts[1], counts[2], up, down, toff, taps, dst, use_dst_off, 0);
+        k_resample<<<grid(counts[2]), 256, 0, st>>>(src, utts, atiles + counts[0] + counts[1], counts[2], up, down, toff, taps,
+                                                    h->sp_ntaps, dst, use_dst_off);
         h->launches++;
     }
     FE_CUDA(h, cudaGetLastError());
@@ -474,16 +490,20 @@ int fe_configure(fe_handle* h, const fe_config* c) {
     if ((rc = upload(h, h->mel_w, ht.mel_w.data(), ht.mel_w.size() * sizeof(float)))) return rc;
     if (c->feat_type == FE_FEAT_MFCC && (rc = upload(h, h->dct, ht.dctf.data(), ht.dctf.size() * sizeof(float)))) return rc;
     if (c->window && (rc = upload(h, h->window, ht.window.data(), ht.window.size() * sizeof(float)))) return rc;
-    h->sp_up.clear(); h->sp_down.clear(); h->sp_tap_off.clear();
+    h->sp_up.clear(); h->sp_down.clear(); h->sp_tap_off.clear(); h->sp_taps.clear(); h->sp_ntaps = 0;
     if (c->n_speeds > 0) {
         if (!c->speed_up || !c->speed_down || !c->speed_taps) return fail(h, FE_ERR_INVALID, "missing resampler tables");
+        if (c->speed_ntaps < 2 || c->speed_ntaps > 256 || (c->speed_ntaps & 1))
+            return fail(h, FE_ERR_INVALID, "speed_ntaps must be even, 2..256");
+        h->sp_ntaps = c->speed_ntaps;
         int off = 0;
         for (int i = 0; i < c->n_speeds; ++i) {
             if (c->speed_up[i] < 1 || c->speed_down[i] < 1 || c->speed_up[i] > 4096)
                 return fail(h, FE_ERR_INVALID, "bad speed ratio");
             h->sp_up.push_back(c->speed_up[i]); h->sp_down.push_back(c->speed_down[i]); h->sp_tap_off.push_back(off);
-            off += c->speed_up[i] * 32;
+            off += c->speed_up[i] * c->speed_ntaps;
         }
+        h->sp_taps.assign(c->speed_taps, c->speed_taps + off);
         if ((rc = upload(h, h->d_sp_up, h->sp_up.data(), h->sp_up.size() * sizeof(int)))) return rc;
         if ((rc = upload(h, h->d_sp_down, h->sp_down.data(), h->sp_down.size() * sizeof(int)))) return rc;
         if ((rc = upload(h, h->d_sp_tap_off, h->sp_tap_off.data(), h->sp_tap_off.size() * sizeof(int)))) return rc;

@@ -837,25 +837,25 @@ k_cube_local(const TileDesc* __restrict__ tiles, int n_tiles, const float* __res
 }
 
 // ---------------------------------------------------------------------------
-// K0: speed perturbation.  y[j] = sum_t taps[(j*down) % up][t] * x[floor(j*down/up) - 15 + t],
-// x = 0 off the ends, int16 in -> (* gain) -> round-half-even, saturate -> int16 out.
+// K0: speed perturbation.  y[j] = sum_t taps[(j*down) % up][t] * x[floor(j*down/up) - (T/2 - 1) + t],
+// x = 0 off the ends, int16 in -> (* gain) -> round-half-even, saturate -> int16 out.  T = taps per phase.
 // speed_idx < 0: gain only.
 // ---------------------------------------------------------------------------
-constexpr int kK0Outputs = 2880;        // outputs per K0 tile: 32 groups of 9 x up (up = 10) same-phase outputs
+constexpr int kK0Outputs = 2880;        // outputs per K0 tile: 288 groups of UP = 10 consecutive outputs
+constexpr int kK0Taps = 128;            // taps per phase the fast kernels are compiled for (tables.RESAMPLE_TAPS)
 
+// generic kernel: any ratio, any (even) number of taps; also serves gain-only utterances
 __global__ void __launch_bounds__(256)
 k_resample(const short* __restrict__ pcm, const UttDesc* __restrict__ utts,
            const int2* __restrict__ atiles, int n_atiles,
            const int* __restrict__ sp_up, const int* __restrict__ sp_down, const int* __restrict__ sp_tap_off,
-           const float* __restrict__ taps_all, short* __restrict__ dst, int use_dst_off, int skip_fast) {
+           const float* __restrict__ taps_all, int ntaps, short* __restrict__ dst, int use_dst_off) {
     for (int tile = blockIdx.x; tile < n_atiles; tile += gridDim.x) {
         const int2 te = atiles[tile];
         const UttDesc u = utts[te.x];
         const short* x = pcm + u.src_off;
         short* y = dst + (use_dst_off ? u.out_off : u.pcm_off);
         const int j1 = min(te.y + kK0Outputs, u.n_samples);
-        // ratios 10/9 and 10/11 are served by k_resample_fast
-        if (skip_fast && u.speed_idx >= 0 && sp_up[u.speed_idx] == 10 && (sp_down[u.speed_idx] == 9 || sp_down[u.speed_idx] == 11)) continue;
         if (u.speed_idx < 0) {
             for (int j = te.y + threadIdx.x; j < j1; j += blockDim.x) {
                 float v = (float)x[j];
@@ -868,12 +868,12 @@ k_resample(const short* __restrict__ pcm, const UttDesc* __restrict__ utts,
         const float* taps = taps_all + sp_tap_off[u.speed_idx];
         for (int j = te.y + threadIdx.x; j < j1; j += blockDim.x) {
             const long long pos = (long long)j * down;
-            const int base = (int)(pos / up) - 15;
+            const int base = (int)(pos / up) - (ntaps / 2 - 1);
             const int ph = (int)(pos % up);
-            const float* tp = taps + ph * 32;
+            const float* tp = taps + ph * ntaps;
             float acc = 0.f;
 #pragma unroll 8
-            for (int k = 0; k < 32; ++k) {
+            for (int k = 0; k < ntaps; ++k) {
                 int i = base + k;
                 float xv = (i >= 0 && i < u.n_src) ? (float)__ldg(x + i) : 0.f;
                 acc = fmaf(__ldg(tp + k), xv, acc);
@@ -884,22 +884,26 @@ k_resample(const short* __restrict__ pcm, const UttDesc* __restrict__ utts,
     }
 }
 
-// K0, fast path for a compile-time ratio (the reference's speeds 0.9 / 1.1 -> 10/9, 10/11): the tile's input span
-// and the polyphase taps sit in shared memory.  Warp p serves phase p of the tile's 32 groups of R x UP outputs
-// (lane = group): the 32 taps are warp-uniform loads, and a thread computes the R = 9 outputs j, j + UP, ...
-// of its group that share them (input windows shifted by DOWN -> a union of 8 DOWN + 32 samples: 0.36 shared-
-// memory loads per FMA).  The lane stride of the window reads is R x DOWN = 81 / 99 words (odd: bank-conflict free).  Same summation order
-// per output as k_resample (bit-identical results).
-// Staging: the span is fetched as 16-byte vectors (8 int16 samples, at most two vectors per thread), one tile
-// AHEAD of the arithmetic -- the vectors for tile i + 1 are in flight in registers while tile i is computed --
-// so the HBM latency of the descriptor -> sample chain is off the critical path.  Tiles start at multiples of
-// kK0Outputs, i.e. at phase 0 and at a whole number of input samples: all index math is 32-bit, no division.
+// K0, fast path for a compile-time ratio (the reference's speeds 0.9 / 1.1 -> 10/9, 10/11) and T = kK0Taps.
+// A thread computes the UP consecutive outputs j = UP g .. UP g + UP - 1 of its group g: at every instruction all
+// threads of the CTA are at the same (phase, tap), so the tap is a CONSTANT-BANK operand of the FFMA (the polyphase
+// table travels in the kernel parameters: compile-time offset, no register, no load), and one shared-memory load
+// of an input sample feeds ~UP FFMAs (windows of the UP phases overlap almost completely): T + DOWN - 1 loads for
+// UP * T FFMAs = 0.11 loads per FMA.  Lane stride of the window reads is DOWN words (odd: bank-conflict free).
+// Same summation order per output as k_resample and the oracle (t ascending).
+// Staging: the tile's input span is fetched as 16-byte vectors (8 int16 samples, at most two vectors per thread), one
+// tile AHEAD of the arithmetic -- the vectors for tile i + 1 are in flight in registers while tile i is computed.
+// Tiles start at multiples of kK0Outputs, i.e. at phase 0 and at a whole number of input samples: all index math
+// is 32-bit, no division.
 template <int VPT>
 struct K0Stage {
     uint4 v[VPT];       // vector q holds 8 samples: utterance indices [n0 + 8 q THREADS, + 8)
     int n0;
     int n_src;
 };
+
+template <int UP, int T>
+struct K0Taps { float w[UP * T]; };     // [phase][tap]
 
 // float -> int16, round half to even, saturating: one F2I instead of rint + min + max + cast (same result; NaN -> 0)
 __device__ __forceinline__ short f2s16_rn_sat(float a) {
@@ -908,34 +912,31 @@ __device__ __forceinline__ short f2s16_rn_sat(float a) {
     return r;
 }
 
-template <int UP, int DOWN>
-__global__ void __launch_bounds__(UP * 32, 3)
+template <int UP, int DOWN, int T>
+__global__ void __launch_bounds__(kK0Outputs / UP)
 k_resample_fast(const short* __restrict__ pcm, const UttDesc* __restrict__ utts,
                 const int2* __restrict__ atiles, int n_atiles,
-                const int* __restrict__ sp_up, const int* __restrict__ sp_down, const int* __restrict__ sp_tap_off,
-                const float* __restrict__ taps_all, short* __restrict__ dst, int use_dst_off) {
-    constexpr int R = kK0Outputs / (32 * UP), NX = (R - 1) * DOWN + 32;
-    static_assert(R * 32 * UP == kK0Outputs, "tile = 32 groups of R x UP outputs");
-    static_assert(((R * DOWN) & 1) == 1, "odd lane stride");
-    constexpr int SPAN = (kK0Outputs * DOWN + UP - 1) / UP + 34;            // input samples a tile can touch
-    constexpr int NV = (SPAN + 7 + 7) / 8;                                   // 16-byte vectors covering it from an aligned start
-    constexpr int THREADS = UP * 32, VPT = (NV + THREADS - 1) / THREADS;
+                const __grid_constant__ K0Taps<UP, T> W, short* __restrict__ dst, int use_dst_off) {
+    constexpr int THREADS = kK0Outputs / UP;                                 // one group of UP outputs per thread
+    constexpr int HW = T / 2;
     constexpr int TILE_IN = kK0Outputs * DOWN / UP;                           // input samples a tile advances by (tiles start at
     static_assert(TILE_IN * UP == kK0Outputs * DOWN, "tile starts are phase 0");   // multiples of kK0Outputs: 32-bit index math)
-    static_assert(kK0Outputs % 8 == 0, "16-byte aligned output tiles");
+    static_assert(kK0Outputs % 8 == 0 && THREADS * UP == kK0Outputs && (DOWN & 1) == 1, "tile geometry");
+    constexpr int OFF_LAST = ((UP - 1) * DOWN) / UP;                          // window start of the last phase relative to phase 0
+    constexpr int NX = OFF_LAST + T;                                          // input samples one group touches
+    constexpr int SPAN = (THREADS - 1) * DOWN + NX;                           // input samples a tile touches
+    constexpr int NV = (SPAN + 7 + 7) / 8;                                    // 16-byte vectors covering it from an aligned start
+    constexpr int VPT = (NV + THREADS - 1) / THREADS;
     __shared__ __align__(16) float xs[VPT * THREADS * 8];
-    __shared__ float tps[UP * 32];
     __shared__ __align__(16) short ys[kK0Outputs];
     const int tid = threadIdx.x;
-    const int p = tid >> 5, g = tid & 31;
-    int taps_of = -1;                                                        // speed index whose taps are in tps
 
     // issue the staging loads of a tile (nothing is waited for here)
     auto fetch = [&](int tile, K0Stage<VPT>& sg, int2& te, UttDesc& u) {
         if (tile >= n_atiles) return;
         te = atiles[tile];
         u = utts[te.x];
-        const int first = (te.y / kK0Outputs) * TILE_IN - 15;               // first input sample of the tile
+        const int first = (te.y / kK0Outputs) * TILE_IN - (HW - 1);         // first input sample of the tile
         const int a0 = first & ~7;                                           // aligned down (two's complement: also for first < 0)
         sg.n0 = a0 + 8 * tid;
         sg.n_src = u.n_src;
@@ -957,7 +958,7 @@ k_resample_fast(const short* __restrict__ pcm, const UttDesc* __restrict__ utts,
         const UttDesc u = u_n;
         short* y = dst + (use_dst_off ? u.out_off : u.pcm_off) + te.y;
         const int nout = min(kK0Outputs, u.n_samples - te.y);
-        const int first = (te.y / kK0Outputs) * TILE_IN - 15;
+        const int first = (te.y / kK0Outputs) * TILE_IN - (HW - 1);
         const int a0 = first & ~7;
         __syncthreads();                                                     // previous tile's readers of xs / ys are done
 #pragma unroll
@@ -976,38 +977,35 @@ k_resample_fast(const short* __restrict__ pcm, const UttDesc* __restrict__ utts,
 #pragma unroll
                     for (int q = 0; q < 8; ++q) f[q] = (nb + q < sg.n_src) ? f[q] : 0.f;
                 }
+                if (nb < 0) {                                                 // ... or its start (first tile: first < 0)
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) f[q] = (nb + q >= 0) ? f[q] : 0.f;
+                }
                 reinterpret_cast<float4*>(xs)[2 * vi] = make_float4(f[0], f[1], f[2], f[3]);
                 reinterpret_cast<float4*>(xs)[2 * vi + 1] = make_float4(f[4], f[5], f[6], f[7]);
             }
         }
-        if (taps_of != u.speed_idx) {                                        // block-uniform
-            const float* taps = taps_all + sp_tap_off[u.speed_idx];
-            for (int i = tid; i < UP * 32; i += blockDim.x) tps[i] = taps[i];
-            taps_of = u.speed_idx;
-        }
         __syncthreads();
         fetch(tile + gridDim.x, sg, te_n, u_n);                              // next tile's samples fly during the arithmetic
-        const int jl = g * (R * UP) + p;                                     // first of this thread's R outputs (tile-local)
-        const int ph = (p * DOWN) % UP;                                      // phase of output jl: the same for the whole warp
-        const int b0 = g * (R * DOWN) + (p * DOWN) / UP + (first - a0);      // xs index of the first window
-        float acc[R];
+        const float* xw = xs + tid * DOWN + (first - a0);                    // window of phase 0 of this thread's group
+        float acc[UP];
 #pragma unroll
-        for (int m = 0; m < R; ++m) acc[m] = 0.f;
+        for (int p = 0; p < UP; ++p) acc[p] = 0.f;
 #pragma unroll
         for (int k = 0; k < NX; ++k) {
-            const float xv = xs[b0 + k];
+            const float xv = xw[k];
 #pragma unroll
-            for (int m = 0; m < R; ++m) {
-                const int t = k - m * DOWN;                                   // tap index of this sample in window m
-                if (t >= 0 && t < 32) acc[m] = fmaf(tps[ph * 32 + t], xv, acc[m]);
+            for (int p = 0; p < UP; ++p) {
+                const int t = k - (p * DOWN) / UP;                            // tap index of this sample in phase p's window
+                if (t >= 0 && t < T) acc[p] = fmaf(W.w[((p * DOWN) % UP) * T + t], xv, acc[p]);
             }
         }
 #pragma unroll
-        for (int m = 0; m < R; ++m) ys[jl + m * UP] = f2s16_rn_sat(acc[m] * u.gain);     // gain 1 = exact identity
+        for (int p = 0; p < UP; ++p) ys[tid * UP + p] = f2s16_rn_sat(acc[p] * u.gain);     // gain 1 = exact identity
         __syncthreads();
         const int n8 = nout >> 3;                                            // y is 16-byte aligned (offsets % 8 == 0, tiles % 8 == 0)
-        for (int i = tid; i < n8; i += blockDim.x) reinterpret_cast<int4*>(y)[i] = reinterpret_cast<const int4*>(ys)[i];
-        for (int i = (n8 << 3) + tid; i < nout; i += blockDim.x) y[i] = ys[i];
+        for (int i = tid; i < n8; i += THREADS) reinterpret_cast<int4*>(y)[i] = reinterpret_cast<const int4*>(ys)[i];
+        for (int i = (n8 << 3) + tid; i < nout; i += THREADS) y[i] = ys[i];
     }
 }
 

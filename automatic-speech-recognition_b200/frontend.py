@@ -141,6 +141,7 @@ def make_fe_config(c: "FrontendConfig"):
         cfg.speed_up = _ptr(keep["sp_up"], C.c_int32)
         cfg.speed_down = _ptr(keep["sp_down"], C.c_int32)
         cfg.speed_taps = _ptr(keep["sp_taps"], C.c_float)
+        cfg.speed_ntaps = tables.RESAMPLE_TAPS
     return cfg, keep, speed_index
 
 

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define FE_ABI_VERSION 1
+#define FE_ABI_VERSION 2
 
 #define FE_OK 0
 #define FE_ERR_INVALID (-1)      /* bad argument / unsupported configuration */
@@ -73,7 +73,9 @@ typedef struct fe_config {
     int32_t n_speeds;              /* resampler variants (speed perturbation), may be 0 */
     const int32_t* speed_up;       /* [n_speeds] speed = down / up */
     const int32_t* speed_down;     /* [n_speeds] */
-    const float*   speed_taps;     /* concatenated [up_i * 32] polyphase taps */
+    const float*   speed_taps;     /* concatenated [up_i][speed_ntaps] polyphase taps: row p = (j * down) % up of output j,
+                                      column t weighs input floor(j * down / up) - (speed_ntaps / 2 - 1) + t */
+    int32_t speed_ntaps;           /* taps per phase, even, 2..256 (ABI 2; the round-2 filter has 128) */
 } fe_config;
 
 /* Pure host helper: frame-count rule of speechpy.processing.stack_frames with

@@ -103,6 +103,35 @@ def test_golden_vectors(ref, sox, golden):
     np.testing.assert_array_equal(sox.volume_perturb(golden["pcm_0"], 1.23), golden["gain123_pcm_0"])
 
 
+def test_resampler_frequency_response(sox):
+    """the speed-perturbation filter must stand next to SoX `rate -h` (utils/augmentation.py:16-18,28):
+    pass-band flat to +-0.1 dB up to 0.9 x min(Nyquist_in, Nyquist_out), >= 100 dB rejection from that Nyquist upward
+    (no aliasing for speed 1.1, no imaging for speed 0.9).  Response computed from the polyphase taps themselves."""
+    table = {}
+    for speed in (0.9, 1.1):
+        up, down = sox.speed_ratio(speed)
+        taps = sox.polyphase_taps(speed)
+        W = sox.HALF_WIDTH
+        tau = (np.arange(up)[:, None] / up + (W - 1) - np.arange(2 * W)[None, :]).ravel()    # tap positions, input samples
+        h = taps.ravel()
+        nyq = min(1.0, up / down)                                                            # in units of the input Nyquist
+
+        def gain_db(f):                                                                      # f relative to the input Nyquist
+            return 20 * np.log10(np.abs(np.exp(-1j * np.pi * np.outer(f, tau)) @ h) / up + 1e-300)
+        pb = gain_db(np.linspace(0.0, 0.9 * nyq, 500))
+        sb = gain_db(np.concatenate((np.linspace(nyq, 3.0, 3000), np.linspace(3.0, float(up), 1500))))
+        assert np.abs(pb).max() < 0.1, (speed, pb.min(), pb.max())
+        assert sb.max() < -100.0, (speed, sb.max())
+        table[speed] = [round(float(gain_db(np.array([f * nyq]))[0]), 2) for f in (0.5, 0.8, 0.9, 0.95, 1.0, 1.1)]
+    # DESIGN.md quotes this table (dB at 0.5 / 0.8 / 0.9 / 0.95 / 1.0 / 1.1 of the lower Nyquist)
+    assert table[0.9][4] < -100 and table[1.1][4] < -100 and abs(table[0.9][2]) < 0.1 and abs(table[1.1][2]) < 0.1
+    # the polyphase evaluation (upfirdn) and the literal formula agree bit for bit on int16 output
+    rng = np.random.default_rng(3)
+    x = (rng.normal(size=6000) * 6000).astype(np.int16)
+    for speed in (0.9, 1.1, 0.8):
+        assert np.array_equal(sox.speed_perturb(x, speed), sox.speed_perturb_direct(x, speed))
+
+
 def test_resampler_oracle_properties(sox):
     n = 16000
     t = np.arange(n) / 16000.0
@@ -114,7 +143,7 @@ def test_resampler_oracle_properties(sox):
         spec = np.abs(np.fft.rfft(y[2000:2000 + 8192] * np.hanning(8192)))
         peak = np.argmax(spec) * 16000.0 / 8192
         assert abs(peak - 1000 * s) < 4.0                        # pitch scales with speed
-        assert abs(np.abs(y[1000:-1000]).max() - 8000) < 40      # unity passband gain
+        assert abs(np.abs(y[1000:-1000]).max() - 8000) < 8       # unity passband gain (+-0.05 dB ripple)
     dc = np.full(4000, 1000, np.int16)
     assert np.all(np.abs(sox.speed_perturb(dc, 0.9)[100:-100].astype(int) - 1000) <= 1)
     assert sox.volume_perturb(np.array([30000, -30000, 100], np.int16), 1.5).tolist() == [32767, -32768, 150]

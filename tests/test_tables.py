@@ -39,33 +39,34 @@ def test_frontend_config_geometry(pkg):
     assert (c.n_filters, c.out_width) == (80, 80)
 
 
-def test_k0_fast_path_index_math():
-    """The register-tiled resampler (k_resample_fast) replaces the per-output 64-bit `j*down / up`, `% up` of the
-    generic kernel by tile-level constants: tiles start at multiples of 2880 outputs (phase 0, a whole number of
-    input samples), warp p serves phase (p*down) % up, lane g's R=9 outputs j, j+up, ... read windows that start
-    at g*R*down + (p*down)//up + (first - a0) of the staged span.  Check every (tile, warp, lane, m) against the
-    defining formula y[j] = sum_t taps[(j*down) % up][t] * x[floor(j*down/up) - 15 + t]."""
-    K0_OUT, UP, R = 2880, 10, 9
+def test_k0_fast_path_index_math(pkg):
+    """The resampler's fast kernel (k_resample_fast) replaces the per-output 64-bit `j*down / up`, `% up` of the generic
+    kernel by tile-level constants: tiles start at multiples of 2880 outputs (phase 0, a whole number of input
+    samples), thread g owns the UP consecutive outputs j = UP g + p, phase (p*down) % up, whose windows start at
+    g*down + (p*down)//up + (first - a0) of the staged span.  Check every (tile, thread, phase) against the
+    defining formula y[j] = sum_t taps[(j*down) % up][t] * x[floor(j*down/up) - (T/2 - 1) + t]."""
+    K0_OUT, UP, T = 2880, 10, pkg.tables.RESAMPLE_TAPS
+    assert T == 128                                                     # kK0Taps in fe_kernels.cuh
+    HW = T // 2
+    threads = K0_OUT // UP
     for down in (9, 11):
         tile_in = K0_OUT * down // UP
-        assert tile_in * UP == K0_OUT * down and (R * down) % 2 == 1 and R * 32 * UP == K0_OUT
-        span = (K0_OUT * down + UP - 1) // UP + 34
+        assert tile_in * UP == K0_OUT * down and down % 2 == 1
+        nx = ((UP - 1) * down) // UP + T
+        span = (threads - 1) * down + nx
         nv = (span + 14) // 8
-        assert nv <= 2 * UP * 32                                        # at most two staging vectors per thread
+        assert nv <= 2 * threads                                        # at most two staging vectors per thread
         for tile in (0, 1, 7, 12345):
             te_y = tile * K0_OUT
-            first = (te_y // K0_OUT) * tile_in - 15
+            first = (te_y // K0_OUT) * tile_in - (HW - 1)
             a0 = first & ~7
-            assert first == te_y * down // UP - 15 and 0 <= first - a0 < 8 and a0 % 8 == 0
+            assert first == te_y * down // UP - (HW - 1) and 0 <= first - a0 < 8 and a0 % 8 == 0
             hi = 0
-            for p in range(UP):
-                ph = (p * down) % UP
-                for g in range(32):
-                    jl = g * (R * UP) + p
-                    b0 = g * (R * down) + (p * down) // UP + (first - a0)
-                    for m in range(R):
-                        j = te_y + jl + m * UP
-                        assert (j * down) % UP == ph                    # all R outputs of a thread share the warp's phase
-                        assert j * down // UP - 15 - a0 == b0 + m * down    # window m starts m*down further
-                        hi = max(hi, b0 + m * down + 31)
+            for g in range(threads):
+                for p in range(UP):
+                    j = te_y + g * UP + p
+                    assert (j * down) % UP == (p * down) % UP           # the phase is a function of p only
+                    start = g * down + (p * down) // UP + (first - a0)
+                    assert j * down // UP - (HW - 1) - a0 == start
+                    hi = max(hi, start + T - 1)
             assert hi < nv * 8                                          # the staged vectors cover every window
