@@ -4,6 +4,7 @@
 #include <stdint.h>
 #include <string.h>
 #include <stdlib.h>
+#include <math.h>
 #include <string>
 #include <vector>
 #include <algorithm>
@@ -72,6 +73,8 @@ struct fe_handle {
 
     Lane lane[3];
 
+    bool k1t = false;                 // FE_K1T=1: the lane = frame / tensor-memory kernel (fe_k1t.cuh) where it applies; measured
+                                      // slower than K1 (profiles/r02_k1t.md), kept selectable for A/B runs
     int profiling = 0;
     // profiled runs since fe_set_profiling(1): one event set per run (no sync inside the timed region)
     struct ProfSet { cudaEvent_t e[5]; bool k0, k2; };
@@ -211,6 +214,24 @@ int launch_k1(fe_handle* h, cudaStream_t st, const void* pcm, const void* scratc
     int grid = std::min<long long>(n_tiles, (long long)h->num_sms);        // persistent: one 16-warp CTA per SM
     if (grid <= 0) return FE_OK;
     if (!(c.frame_len == 400 && c.hop == 160)) return fail(h, FE_ERR_INVALID, "unsupported frame geometry");
+    if (!in_f32 && c.window == nullptr && h->epi_plan != 0 && h->k1t) {
+        // K1T: lane = frame, exchange in tensor memory (fe_k1t.cuh)
+        K1TParams T;
+        memset(T.epi_w, 0, sizeof(T.epi_w));
+        memcpy(T.epi_w, h->epi_w.data(), sizeof(float) * (size_t)h->epi_w_n);
+        T.pscale = dt.pscale; T.fbank_log = dt.fbank_log; T.dc_elim = dt.dc_elim;
+        const int gt = (int)std::min<long long>((n_tiles + kK1TGroups - 1) / kK1TGroups, (long long)h->num_sms);
+        if (h->epi_plan == 1) {
+            FE_CUDA(h, cudaFuncSetAttribute(k_frames_to_statics_t<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kK1TSmem));
+            k_frames_to_statics_t<1><<<gt, kK1TThreads, kK1TSmem, st>>>((const short*)pcm, (const short*)scratch, tiles, n_tiles, T, statics);
+        } else {
+            FE_CUDA(h, cudaFuncSetAttribute(k_frames_to_statics_t<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kK1TSmem));
+            k_frames_to_statics_t<2><<<gt, kK1TThreads, kK1TSmem, st>>>((const short*)pcm, (const short*)scratch, tiles, n_tiles, T, statics);
+        }
+        h->launches++;
+        FE_CUDA(h, cudaGetLastError());
+        return FE_OK;
+    }
     K1Params P;
     P.dt = dt;
     P.L = k1_smem_layout(c.num_filters, h->mel_groups, h->p_rows, c.feat_dim, h->dct_stride, c.window != nullptr,
@@ -419,6 +440,18 @@ int fe_create(int device, fe_handle** out) {
         if (i == 0) h->lane[i].stream = h->stream;
         else FE_CUDA(nullptr, cudaStreamCreateWithFlags(&h->lane[i].stream, cudaStreamNonBlocking));
         FE_CUDA(nullptr, cudaEventCreateWithFlags(&h->lane[i].done, cudaEventDisableTiming));
+    }
+    h->k1t = getenv("FE_K1T") != nullptr;
+    {   // K1T's twiddles: universal constants, float64 on the host, rounded once (idempotent across handles)
+        std::vector<float2> t256(256), t512(132, make_float2(0.f, 0.f));
+        const double kPi = 3.14159265358979323846;
+        for (int r = 0; r < 16; ++r) for (int j = 0; j < 16; ++j) {
+            const double a = 2.0 * kPi * ((r * j) % 256) / 256.0;
+            t256[r * 16 + j] = make_float2((float)cos(a), (float)-sin(a));
+        }
+        for (int k = 0; k <= 128; ++k) { const double a = 2.0 * kPi * k / 512.0; t512[k] = make_float2((float)cos(a), (float)sin(a)); }
+        FE_CUDA(nullptr, cudaMemcpyToSymbol(c_tw256, t256.data(), sizeof(float2) * 256));
+        FE_CUDA(nullptr, cudaMemcpyToSymbol(c_tw512, t512.data(), sizeof(float2) * 132));
     }
     if (const char* e = getenv("FE_PIPE_CHUNK_MB")) { long long mb = atoll(e); if (mb > 0) h->pipe_chunk_bytes = mb << 20; }
     *out = h;

@@ -30,6 +30,8 @@
 struct float2 { float x, y; };
 struct float4 { float x, y, z, w; };
 struct uint2 { unsigned x, y; };
+struct uint4 { unsigned x, y, z, w; };
+static inline uint4 make_uint4(unsigned a, unsigned b, unsigned c, unsigned d) { uint4 v = {a, b, c, d}; return v; }
 static inline float4 make_float4(float a, float b, float c, float d) { float4 v = {a, b, c, d}; return v; }
 static inline float2 make_float2(float a, float b) { float2 v = {a, b}; return v; }
 #endif
@@ -79,6 +81,17 @@ FE_HD float2 pbc(float s) { return make_float2(s, s); }
 FE_HD float2 pswap(float2 a) { return make_float2(a.y, a.x); }
 FE_HD float2 pneg(float2 a) { return make_float2(-a.x, -a.y); }
 FE_HD float2 pnfma(float2 a, float2 b, float2 c) { return pfma(pneg(a), b, c); }   // c - a*b
+FE_HD float2 pmul_k(float2 a, float k) { return pmul(a, make_float2(k, k)); }
+// scalar twins: the lane = frame kernel (fe_k1t.cuh) runs the same codelets on plain floats -- its twiddles are
+// warp-uniform (constant-bank / uniform-register operands), and a scalar FFMA with such an operand issues every cycle
+FE_HD float padd(float a, float b) { return a + b; }
+FE_HD float psub(float a, float b) { return a - b; }
+FE_HD float pmul(float a, float b) { return a * b; }
+FE_HD float pfma(float a, float b, float c) { return fmaf(a, b, c); }
+FE_HD float pfma_rr(float a, float b, float c) { return fmaf(a, b, c); }
+FE_HD float pfma_k(float a, float k, float c) { return fmaf(a, k, c); }
+FE_HD float pmul_k(float a, float k) { return a * k; }
+FE_HD float pneg(float a) { return -a; }
 
 // ---------------------------------------------------------------------------
 // Shared-memory tables of one CTA
@@ -107,11 +120,12 @@ struct SmemTables {
 // ---------------------------------------------------------------------------
 // radix-4 butterfly and 16-point forward FFT on packed registers
 // ---------------------------------------------------------------------------
-FE_HD void bfly4(float2& r0, float2& i0, float2& r1, float2& i1, float2& r2, float2& i2, float2& r3, float2& i3) {
-    float2 t0r = padd(r0, r2), t0i = padd(i0, i2);
-    float2 t1r = psub(r0, r2), t1i = psub(i0, i2);
-    float2 t2r = padd(r1, r3), t2i = padd(i1, i3);
-    float2 t3r = psub(r1, r3), t3i = psub(i1, i3);
+template <class V>
+FE_HD void bfly4(V& r0, V& i0, V& r1, V& i1, V& r2, V& i2, V& r3, V& i3) {
+    V t0r = padd(r0, r2), t0i = padd(i0, i2);
+    V t1r = psub(r0, r2), t1i = psub(i0, i2);
+    V t2r = padd(r1, r3), t2i = padd(i1, i3);
+    V t3r = psub(r1, r3), t3i = psub(i1, i3);
     r0 = padd(t0r, t2r); i0 = padd(t0i, t2i);
     r2 = psub(t0r, t2r); i2 = psub(t0i, t2i);
     r1 = padd(t1r, t3i); i1 = psub(t1i, t3r);     // t1 - i t3
@@ -119,12 +133,13 @@ FE_HD void bfly4(float2& r0, float2& i0, float2& r1, float2& i1, float2& r2, flo
 }
 
 // bfly4 with a zero fourth input (the zero padding of the frame: rows 13..15 of stage A)
-FE_HD void bfly4_z3(float2& r0, float2& i0, float2& r1, float2& i1, float2& r2, float2& i2, float2& r3, float2& i3) {
-    float2 t0r = padd(r0, r2), t0i = padd(i0, i2);
-    float2 t1r = psub(r0, r2), t1i = psub(i0, i2);
+template <class V>
+FE_HD void bfly4_z3(V& r0, V& i0, V& r1, V& i1, V& r2, V& i2, V& r3, V& i3) {
+    V t0r = padd(r0, r2), t0i = padd(i0, i2);
+    V t1r = psub(r0, r2), t1i = psub(i0, i2);
     r0 = padd(t0r, r1); i0 = padd(t0i, i1);           // t2 = t3 = x1
     r2 = psub(t0r, r1); i2 = psub(t0i, i1);
-    float2 t3r = r1, t3i = i1;
+    V t3r = r1, t3i = i1;
     r1 = padd(t1r, t3i); i1 = psub(t1i, t3r);         // t1 - i t3
     r3 = psub(t1r, t3i); i3 = padd(t1i, t3r);         // t1 + i t3
 }
@@ -133,29 +148,35 @@ FE_HD void bfly4_z3(float2& r0, float2& i0, float2& r1, float2& i1, float2& r2, 
 FE_HD constexpr int pos16(int k) { return (k >> 2) + ((k & 3) << 2); }
 
 // (ar, ai) = (r, i) * (wr + i wi)                       2 FMUL2 + 2 FFMA2
-FE_HD void cmul_c(float2 r, float2 i, float wr, float wi, float2& ar, float2& ai) {
-    ar = pfma_k(i, -wi, pmul(r, pbc(wr)));
-    ai = pfma_k(r, wi, pmul(i, pbc(wr)));
+template <class V>
+FE_HD void cmul_c(V r, V i, float wr, float wi, V& ar, V& ai) {
+    ar = pfma_k(i, -wi, pmul_k(r, wr));
+    ai = pfma_k(r, wi, pmul_k(i, wr));
 }
 // (tr, ti) = (br, bi) + (r, i) * (wr + i wi)            4 FFMA2: the product is never materialised
-FE_HD void cmac_c(float2 r, float2 i, float wr, float wi, float2 br, float2 bi, float2& tr, float2& ti) {
+template <class V>
+FE_HD void cmac_c(V r, V i, float wr, float wi, V br, V bi, V& tr, V& ti) {
     tr = pfma_k(r, wr, pfma_k(i, -wi, br));
     ti = pfma_k(r, wi, pfma_k(i, wr, bi));
 }
 // same with per-half twiddles (packed operands)
-FE_HD void cmul_p(float2 r, float2 i, float2 wr, float2 wi, float2& ar, float2& ai) {
+template <class V>
+FE_HD void cmul_p(V r, V i, V wr, V wi, V& ar, V& ai) {
     ar = pfma_rr(pneg(i), wi, pmul(r, wr));
     ai = pfma_rr(r, wi, pmul(i, wr));
 }
-FE_HD void cmac_p(float2 r, float2 i, float2 wr, float2 wi, float2 br, float2 bi, float2& tr, float2& ti) {
+template <class V>
+FE_HD void cmac_p(V r, V i, V wr, V wi, V br, V bi, V& tr, V& ti) {
     tr = pfma_rr(r, wr, pfma_rr(pneg(i), wi, br));
     ti = pfma_rr(r, wi, pfma_rr(i, wr, bi));
 }
-FE_HD float2 ptwice_minus(float2 a, float2 t) { return pfma_k(a, 2.f, pneg(t)); }     // 2 a - t
+template <class V>
+FE_HD V ptwice_minus(V a, V t) { return pfma_k(a, 2.f, pneg(t)); }     // 2 a - t
 
 // second half of a radix-4 butterfly: (t0, t1, t2, t3) -> outputs
-FE_HD void bfly4_out(float2 t0r, float2 t0i, float2 t1r, float2 t1i, float2 t2r, float2 t2i, float2 t3r, float2 t3i,
-                     float2& r0, float2& i0, float2& r1, float2& i1, float2& r2, float2& i2, float2& r3, float2& i3) {
+template <class V>
+FE_HD void bfly4_out(V t0r, V t0i, V t1r, V t1i, V t2r, V t2i, V t3r, V t3i,
+                     V& r0, V& i0, V& r1, V& i1, V& r2, V& i2, V& r3, V& i3) {
     r0 = padd(t0r, t2r); i0 = padd(t0i, t2i);
     r2 = psub(t0r, t2r); i2 = psub(t0i, t2i);
     r1 = padd(t1r, t3i); i1 = psub(t1i, t3r);     // t1 - i t3
@@ -167,46 +188,47 @@ FE_HD void bfly4_out(float2 t0r, float2 t0i, float2 t1r, float2 t1i, float2 t2r,
 //   x0 + w x2 and x0 - w x2 with w = +-H(1 -+ i) cost 2 adds + 4 FMAs instead of 2 adds + 2 muls + 4 adds,
 //   a = w1 x1 (4 ops), t2 = a + w3 x3 (4 FMAs), t3 = 2 a - t2 (2 FMAs) instead of 4 + 4 + 4.
 // 84 packed operations for the level instead of 96.
-FE_HD void fft16_level2(float2 (&xr)[16], float2 (&xi)[16]) {
+template <class V>
+FE_HD void fft16_level2(V (&xr)[16], V (&xi)[16]) {
     constexpr float C1 = 0.92387953251128674f, S1 = 0.38268343236508977f, H = 0.70710678118654752f;
     bfly4(xr[0], xi[0], xr[1], xi[1], xr[2], xi[2], xr[3], xi[3]);                    // k2 = 0: no twiddles
     {   // k2 = 1: x1 W^1, x2 W^2 = H (1 - i), x3 W^3
-        const float2 s2 = padd(xr[6], xi[6]), d2 = psub(xi[6], xr[6]);
-        const float2 t0r = pfma_k(s2, H, xr[4]), t0i = pfma_k(d2, H, xi[4]);
-        const float2 t1r = pfma_k(s2, -H, xr[4]), t1i = pfma_k(d2, -H, xi[4]);
-        float2 ar, ai, t2r, t2i;
+        const V s2 = padd(xr[6], xi[6]), d2 = psub(xi[6], xr[6]);
+        const V t0r = pfma_k(s2, H, xr[4]), t0i = pfma_k(d2, H, xi[4]);
+        const V t1r = pfma_k(s2, -H, xr[4]), t1i = pfma_k(d2, -H, xi[4]);
+        V ar, ai, t2r, t2i;
         cmul_c(xr[5], xi[5], C1, -S1, ar, ai);
         cmac_c(xr[7], xi[7], S1, -C1, ar, ai, t2r, t2i);
-        const float2 t3r = ptwice_minus(ar, t2r), t3i = ptwice_minus(ai, t2i);
+        const V t3r = ptwice_minus(ar, t2r), t3i = ptwice_minus(ai, t2i);
         bfly4_out(t0r, t0i, t1r, t1i, t2r, t2i, t3r, t3i, xr[4], xi[4], xr[5], xi[5], xr[6], xi[6], xr[7], xi[7]);
     }
     {   // k2 = 2: x1 W^2 = H (s1, d1), x2 W^4 = -i x2, x3 W^6 = H (d3, -s3); the H rides on the output additions
-        const float2 s1 = padd(xr[9], xi[9]), d1 = psub(xi[9], xr[9]);
-        const float2 s3 = padd(xr[11], xi[11]), d3 = psub(xi[11], xr[11]);
-        const float2 t0r = padd(xr[8], xi[10]), t0i = psub(xi[8], xr[10]);
-        const float2 t1r = psub(xr[8], xi[10]), t1i = padd(xi[8], xr[10]);
-        const float2 ur = padd(s1, d3), ui = psub(d1, s3), vr = psub(s1, d3), vi = padd(d1, s3);
+        const V s1 = padd(xr[9], xi[9]), d1 = psub(xi[9], xr[9]);
+        const V s3 = padd(xr[11], xi[11]), d3 = psub(xi[11], xr[11]);
+        const V t0r = padd(xr[8], xi[10]), t0i = psub(xi[8], xr[10]);
+        const V t1r = psub(xr[8], xi[10]), t1i = padd(xi[8], xr[10]);
+        const V ur = padd(s1, d3), ui = psub(d1, s3), vr = psub(s1, d3), vi = padd(d1, s3);
         xr[8] = pfma_k(ur, H, t0r);   xi[8] = pfma_k(ui, H, t0i);
         xr[10] = pfma_k(ur, -H, t0r); xi[10] = pfma_k(ui, -H, t0i);
         xr[9] = pfma_k(vi, H, t1r);   xi[9] = pfma_k(vr, -H, t1i);
         xr[11] = pfma_k(vi, -H, t1r); xi[11] = pfma_k(vr, H, t1i);
     }
     {   // k2 = 3: x1 W^3, x2 W^6 = H (d2, -s2), x3 W^9
-        const float2 s2 = padd(xr[14], xi[14]), d2 = psub(xi[14], xr[14]);
-        const float2 t0r = pfma_k(d2, H, xr[12]), t0i = pfma_k(s2, -H, xi[12]);
-        const float2 t1r = pfma_k(d2, -H, xr[12]), t1i = pfma_k(s2, H, xi[12]);
-        float2 ar, ai, t2r, t2i;
+        const V s2 = padd(xr[14], xi[14]), d2 = psub(xi[14], xr[14]);
+        const V t0r = pfma_k(d2, H, xr[12]), t0i = pfma_k(s2, -H, xi[12]);
+        const V t1r = pfma_k(d2, -H, xr[12]), t1i = pfma_k(s2, H, xi[12]);
+        V ar, ai, t2r, t2i;
         cmul_c(xr[13], xi[13], S1, -C1, ar, ai);
         cmac_c(xr[15], xi[15], -C1, S1, ar, ai, t2r, t2i);
-        const float2 t3r = ptwice_minus(ar, t2r), t3i = ptwice_minus(ai, t2i);
+        const V t3r = ptwice_minus(ar, t2r), t3i = ptwice_minus(ai, t2i);
         bfly4_out(t0r, t0i, t1r, t1i, t2r, t2i, t3r, t3i, xr[12], xi[12], xr[13], xi[13], xr[14], xi[14], xr[15], xi[15]);
     }
 }
 
-// NZ: inputs n >= NZ are known to be zero (12 < NZ <= 16 supported: only the fourth butterfly input can vanish)
-template <int NZ = 16>
-FE_HD void fft16(float2 (&xr)[16], float2 (&xi)[16]) {
-    static_assert(NZ > 12 && NZ <= 16, "fft16: only the last three inputs may be structurally zero");
+// NZ: inputs n >= NZ are known to be zero (12 <= NZ <= 16 supported: only the fourth butterfly input can vanish)
+template <int NZ = 16, class V>
+FE_HD void fft16(V (&xr)[16], V (&xi)[16]) {
+    static_assert(NZ >= 12 && NZ <= 16, "fft16: only the last four inputs may be structurally zero");
 #pragma unroll
     for (int n1 = 0; n1 < 4; ++n1) {
         if (n1 + 12 >= NZ) bfly4_z3(xr[n1], xi[n1], xr[n1 + 4], xi[n1 + 4], xr[n1 + 8], xi[n1 + 8], xr[n1 + 12], xi[n1 + 12]);
@@ -219,18 +241,18 @@ FE_HD void fft16(float2 (&xr)[16], float2 (&xi)[16]) {
 //   a0 = x0 w0 (4 ops, none for n1 = 0), t0 = a0 + x2 w2 (4 FMAs), t1 = 2 a0 - t0 (2), same for (x1, x3):
 //   24 / 28 operations per butterfly instead of 28 / 32 with separate complex multiplies.
 // tw(n) returns (wr, wi) of input n as packed pairs (one twiddle per half).
-template <class TW>
-FE_HD void fft16_twiddled(float2 (&xr)[16], float2 (&xi)[16], TW&& tw) {
+template <class V, class TW>
+FE_HD void fft16_twiddled(V (&xr)[16], V (&xi)[16], TW&& tw) {
 #pragma unroll
     for (int n1 = 0; n1 < 4; ++n1) {
-        float2 a0r = xr[n1], a0i = xi[n1], wr, wi;
+        V a0r = xr[n1], a0i = xi[n1], wr, wi;
         if (n1 > 0) { tw(n1, wr, wi); cmul_p(xr[n1], xi[n1], wr, wi, a0r, a0i); }
-        float2 t0r, t0i, a1r, a1i, t2r, t2i;
+        V t0r, t0i, a1r, a1i, t2r, t2i;
         tw(n1 + 8, wr, wi);  cmac_p(xr[n1 + 8], xi[n1 + 8], wr, wi, a0r, a0i, t0r, t0i);
-        const float2 t1r = ptwice_minus(a0r, t0r), t1i = ptwice_minus(a0i, t0i);
+        const V t1r = ptwice_minus(a0r, t0r), t1i = ptwice_minus(a0i, t0i);
         tw(n1 + 4, wr, wi);  cmul_p(xr[n1 + 4], xi[n1 + 4], wr, wi, a1r, a1i);
         tw(n1 + 12, wr, wi); cmac_p(xr[n1 + 12], xi[n1 + 12], wr, wi, a1r, a1i, t2r, t2i);
-        const float2 t3r = ptwice_minus(a1r, t2r), t3i = ptwice_minus(a1i, t2i);
+        const V t3r = ptwice_minus(a1r, t2r), t3i = ptwice_minus(a1i, t2i);
         bfly4_out(t0r, t0i, t1r, t1i, t2r, t2i, t3r, t3i,
                   xr[n1], xi[n1], xr[n1 + 4], xi[n1 + 4], xr[n1 + 8], xi[n1 + 8], xr[n1 + 12], xi[n1 + 12]);
     }

@@ -8,6 +8,8 @@
 #pragma once
 #include <cuda_runtime.h>
 #include "fe_core.cuh"
+#include "fe_k1t.cuh"
+#include "tmem_ops_gen.h"
 
 namespace fe {
 
@@ -474,6 +476,162 @@ k_frames_to_statics(const void* __restrict__ pcm, const void* __restrict__ scrat
         atomicAdd(&g_k1_prof[14], (unsigned long long)prof[5]);
     }
 #endif
+}
+
+// ---------------------------------------------------------------------------
+// K1T (fe_k1t.cuh): lane = frame, exchange in tensor memory.  One CTA of 8 warps per SM (persistent).  Warps q and
+// q + 4 sit on the same SM sub-partition and own the same 32 tensor-memory lanes: together they are one "lane group"
+// working on one tile (32 consecutive frames of one utterance) at a time -- two warps per scheduler, because a single
+// warp cannot keep the issue port busy (profiles/r02_k1t_summary.md: 45 % issue-active with one).  The group splits
+// the WORK, not the data:
+//     stage A   warp 0: columns 0-3            warp 1: columns 4-15
+//     -- pair barrier: exchange complete; warp 1 re-arms the raw buffer for the group's next tile --
+//     stage B   warp 0: rows (0, 8), 1-4       warp 1: row pairs 5-7
+//     -- pair barrier: power bins complete --
+//     epilogue  warp 0: mel -> log -> DCT      warp 1: already in stage A of the next tile
+// (shares chosen from the measured phase costs so that both warps finish a tile together).  A group needs nobody
+// else: raw rows by per-lane bulk copies into its own shared-memory buffer, exchange in its own TMEM lanes, power
+// bins in its own [bin][lane] buffer, statics straight to HBM (one 128-byte store per coefficient).
+// Serves the configurations with a specialised epilogue plan, int16 PCM and the rectangular window (what the
+// reference runs); everything else stays on k_frames_to_statics.
+// ---------------------------------------------------------------------------
+constexpr int kK1TGroups = 4;
+constexpr int kK1TThreads = 2 * kK1TGroups * 32;
+constexpr int kK1TRawBytes = 2 * kTRawBytes;                               // one group's raw samples, double-buffered
+constexpr int kK1TPRows = 132;                                             // bins 0 .. 128 + 3 pad rows
+constexpr int kK1TPbufBytes = kK1TPRows * kPStride * 4;                    // one group's power buffer: 19 008 bytes
+constexpr int kK1TOffEnergy = kK1TGroups * (kK1TRawBytes + kK1TPbufBytes);
+constexpr int kK1TOffSs = kK1TOffEnergy + kK1TGroups * kTileFrames * 4;
+constexpr int kK1TOffBar = kK1TOffSs + kK1TGroups * kTileFrames * 4;
+constexpr int kK1TSmem = kK1TOffBar + 128;
+constexpr int kK1TSplitA = 1;            // stage A: warp 0 takes column quads [0, kK1TSplitA), warp 1 the rest
+constexpr int kK1TSplitB = 5;            // stage B: warp 0 takes rows (0, 8) and pairs [1, kK1TSplitB), warp 1 the rest
+
+__constant__ float2 c_tw256[256];        // W_256^(j r) = (cos, -sin)(2 pi j r / 256) at [r * 16 + j]
+__constant__ float2 c_tw512[132];        // (cos, sin)(2 pi k / 512), k = 0 .. 128
+
+struct K1TParams {
+    float epi_w[kEpiWCap];               // mel CSR weights (pre-scaled) + folded DCT rows: constant-bank operands
+    float pscale;
+    int fbank_log, dc_elim;
+};
+
+struct TmemExchange {
+    uint32_t base;                       // tensor-memory address of this group's column 0 (lane field = 32 (warp % 4))
+    __device__ __forceinline__ void st2(int col, float a, float b) const {
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" :: "r"(base + (uint32_t)col), "f"(a), "f"(b) : "memory");
+    }
+    __device__ __forceinline__ void ld32(int col, float* v) const { tmem_ld32(base + (uint32_t)col, v); }
+    __device__ __forceinline__ void wait_ld() const { tmem_wait_ld(); }
+    __device__ __forceinline__ void wait_st() const { tmem_wait_st(); }
+};
+
+// the two warps of a lane group meet on a hardware named barrier (ids 1 .. 4); tensor-memory traffic is ordered
+// across it by the tcgen05 fences
+__device__ __forceinline__ void k1t_pair_sync(int group) {
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    asm volatile("bar.sync %0, 64;" :: "r"(1 + group) : "memory");
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+
+#ifdef FE_K1_PROF
+#define FE_TPROF_DECL long long prof[8] = {0}, tick = clock64()
+#define FE_TTICK(i) do { const long long now__ = clock64(); prof[i] += now__ - tick; tick = now__; } while (0)
+#else
+#define FE_TPROF_DECL
+#define FE_TTICK(i) do { } while (0)
+#endif
+
+template <int EPI>
+__global__ void __launch_bounds__(kK1TThreads, 1)
+k_frames_to_statics_t(const short* __restrict__ pcm, const short* __restrict__ scratch,
+                      const TileDesc* __restrict__ tiles, int n_tiles,
+                      const __grid_constant__ K1TParams P, float* __restrict__ statics) {
+    extern __shared__ __align__(16) unsigned char smem_t[];
+    __shared__ uint32_t s_tmem_base;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int group = warp & 3, half = warp >> 2;
+    unsigned char* raw_w = smem_t + group * kK1TRawBytes;
+    float* pbuf_w = reinterpret_cast<float*>(smem_t + kK1TGroups * kK1TRawBytes + group * kK1TPbufBytes);
+    float* energy_w = reinterpret_cast<float*>(smem_t + kK1TOffEnergy) + group * kTileFrames;
+    float* ss_w = reinterpret_cast<float*>(smem_t + kK1TOffSs) + group * kTileFrames;
+    const uint32_t bar = smem_u32(smem_t + kK1TOffBar) + 16 * group;      // two mbarriers per group (raw double buffer)
+
+    for (int i = tid; i < kK1TOffBar / 4; i += kK1TThreads) reinterpret_cast<uint32_t*>(smem_t)[i] = 0u;   // partial tiles read stale rows / bins
+    if (half == 0 && lane == 0) { mbar_init(bar, 1); mbar_init(bar + 8, 1); }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&s_tmem_base)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const TmemExchange ex{s_tmem_base + ((uint32_t)(group * 32) << 16)};
+    const TTwiddles tw{c_tw256, c_tw512};
+    float* pcol = pbuf_w + lane;
+
+    const int stride = gridDim.x * kK1TGroups;
+    int t = blockIdx.x * kK1TGroups + group;
+    // raw samples of a tile: ONE bulk copy (the tile's frames overlap: (n - 1) * 160 + 400 samples), issued by lane 0
+    // of warp 1 one tile ahead into the other buffer
+    auto fetch = [&](int tile, int buf) {
+        if (tile >= n_tiles || lane != 0) return;
+        const TileDesc* td = tiles + tile;
+        const long long off = td->pcm_off;
+        const int2 ns = *reinterpret_cast<const int2*>(&td->n_frames);        // n_frames, src_sel
+        const uint32_t bytes = (uint32_t)((ns.x - 1) * 160 + 400) * 2u;
+        mbar_expect_tx(bar + 8 * buf, bytes);
+        bulk_g2s(smem_u32(raw_w + buf * kTRawBytes), (ns.y ? scratch : pcm) + off, bytes, bar + 8 * buf);
+    };
+    if (half == 1) { fetch(t, 0); fetch(t + stride, 1); }
+    uint32_t phase = 0;          // bit b = parity to wait for on buffer b
+    int buf = 0;
+    FE_TPROF_DECL;
+    for (; t < n_tiles; t += stride) {
+        float* out_t = statics + tiles[t].stat_off;
+        FE_TTICK(7);
+        mbar_wait<32>(bar + 8 * buf, (phase >> buf) & 1u);
+        phase ^= 1u << buf;
+        FE_TTICK(0);
+        const uint4* raw4 = reinterpret_cast<const uint4*>(raw_w + buf * kTRawBytes) + lane * kTFrameVecs;
+        const float ss = half == 0 ? k1t_stage_a(raw4, ex, 0, kK1TSplitA) : k1t_stage_a(raw4, ex, kK1TSplitA, 4);
+        if (half == 1) ss_w[lane] = ss;
+        ex.wait_st();
+        FE_TTICK(1);
+        k1t_pair_sync(group);                                   // exchange complete, this buffer's samples consumed
+        FE_TTICK(2);
+        if (half == 1) {
+            fetch(t + 2 * stride, buf);                         // refill it for the tile after the next one
+#pragma unroll 1
+            for (int r = kK1TSplitB; r < 8; ++r) k1t_row_pair(ex, r, tw, pcol);
+            FE_TTICK(4);
+            k1t_pair_sync(group);                               // power bins complete
+            FE_TTICK(5);
+        } else {
+            float x0, x256;
+            k1t_rows_0_8(ex, tw, pcol, x0, x256);
+            FE_TTICK(3);
+#pragma unroll 1
+            for (int r = 1; r < kK1TSplitB; ++r) k1t_row_pair(ex, r, tw, pcol);
+            energy_w[lane] = frame_energy(ss + ss_w[lane], x0, x256, P.pscale);
+            FE_TTICK(4);
+            k1t_pair_sync(group);
+            FE_TTICK(5);
+            // mel -> log -> DCT for this lane's frame (compile-time filterbank plan, weights in the constant bank)
+            if (EPI == 1) epi_tile_spec<PlanMfcc40, 13, true, true>(pbuf_w, energy_w, out_t, P.epi_w, P.dc_elim != 0, lane);
+            else if (P.fbank_log) epi_tile_spec<PlanFbank80, 80, false, true>(pbuf_w, energy_w, out_t, P.epi_w, false, lane);
+            else epi_tile_spec<PlanFbank80, 80, false, false>(pbuf_w, energy_w, out_t, P.epi_w, false, lane);
+            FE_TTICK(6);
+        }
+        buf ^= 1;
+    }
+#ifdef FE_K1_PROF
+    if (lane == 0) for (int i = 0; i < 8; ++i) atomicAdd(&g_k1_prof[8 * half + i], (unsigned long long)prof[i]);
+#endif
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(s_tmem_base), "r"(512) : "memory");
 }
 
 // ---------------------------------------------------------------------------

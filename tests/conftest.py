@@ -77,22 +77,25 @@ def host_sim(pkg):
     import ctypes
     src = os.path.join(ROOT, "tests", "host_sim", "host_sim.cpp")
     so = os.path.join(ROOT, "tests", "host_sim", "libhost_sim.so")
-    deps = [src] + [os.path.join(ROOT, PKG, "csrc", f) for f in ("fe_core.cuh", "fe_tables.h")]
+    deps = [src] + [os.path.join(ROOT, PKG, "csrc", f) for f in ("fe_core.cuh", "fe_tables.h", "fe_k1t.cuh")]
     if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
         subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", so, src], check=True)
     lib = ctypes.CDLL(so)
     _lib = importlib.import_module(PKG + "._lib")
     lib.sim_statics.restype = ctypes.c_int
     lib.sim_statics.argtypes = [ctypes.POINTER(_lib.FeConfig), ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
+    lib.sim_statics_t.restype = ctypes.c_int
+    lib.sim_statics_t.argtypes = lib.sim_statics.argtypes
     fr = importlib.import_module(PKG + ".frontend")
 
-    def run(pcm, **cfg_kw):
+    def run(pcm, kernel="k1", **cfg_kw):
         c = fr.FrontendConfig(**cfg_kw)
         cfg, keep, _ = fr.make_fe_config(c)
         pcm = np.ascontiguousarray(pcm)
         L = max((len(pcm) - c.frame_len) // c.hop, 0) if len(pcm) >= c.frame_len else 0
         out = np.zeros((L, c.feat_dim), np.float32)
-        rc = lib.sim_statics(ctypes.byref(cfg), pcm.ctypes.data, len(pcm), out.ctypes.data)
+        fn = lib.sim_statics_t if kernel == "k1t" else lib.sim_statics
+        rc = fn(ctypes.byref(cfg), pcm.ctypes.data, len(pcm), out.ctypes.data)
         assert rc == L, (rc, L)
         return out
     return run

@@ -8,7 +8,9 @@
 #include <cstring>
 #include <cstdint>
 #include <cstdlib>
+#include <cmath>
 #include "../../automatic-speech-recognition_b200/csrc/fe_tables.h"
+#include "../../automatic-speech-recognition_b200/csrc/fe_k1t.cuh"
 
 using namespace fe;
 
@@ -88,6 +90,60 @@ int run(const fe_config& c, const void* pcm, int n_samples, float* statics) {
     return L;
 }
 }  // namespace
+
+// ---- K1T (lane = frame, exchange in tensor memory): the per-lane phases with the exchange as a plain array ----
+namespace {
+struct HostExchange {
+    float m[512];
+    bool written[512];
+    HostExchange() { for (int i = 0; i < 512; ++i) { m[i] = 1e30f; written[i] = false; } }
+    void st2(int col, float a, float b) { m[col] = a; m[col + 1] = b; written[col] = written[col + 1] = true; }
+    void ld32(int col, float* v) { for (int i = 0; i < 32; ++i) v[i] = written[col + i] ? m[col + i] : NAN; }
+    void wait_ld() {}
+    void wait_st() {}
+};
+
+int run_t(const fe_config& c, const short* pcm, int n_samples, float* statics) {
+    constexpr int FL = 400, HOP = 160;
+    if (c.frame_len != FL || c.hop != HOP || c.window || c.pcm_dtype != FE_PCM_INT16) return -1;
+    const int L = n_samples < FL ? 0 : (n_samples - FL) / HOP;
+    HostTables ht; build_host_tables(c, ht);
+    SmemTables tb; fill_tables(c, ht, false, tb);
+    if (!ht.ok || tb.full_spectrum) return -2;
+    std::vector<float2> t256(256), t512(129);
+    for (int r = 0; r < 16; ++r) for (int j = 0; j < 16; ++j) {
+        const double a = 2.0 * M_PI * ((r * j) % 256) / 256.0;
+        t256[r * 16 + j] = make_float2((float)cos(a), (float)-sin(a));
+    }
+    for (int k = 0; k <= 128; ++k) { const double a = 2.0 * M_PI * k / 512.0; t512[k] = make_float2((float)cos(a), (float)sin(a)); }
+    TTwiddles tw{t256.data(), t512.data()};
+    const int D = c.feat_dim;
+    std::vector<float> pbuf((size_t)ht.p_rows * kPStride, 0.f), lm((size_t)(c.num_filters + 4) * 32, 0.f), out_t((size_t)D * 32), energy(32, 1.f);
+    alignas(16) uint32_t raw[204];
+    for (int t0 = 0; t0 < L; t0 += kTileFrames) {
+        const int ntile = (L - t0) < kTileFrames ? (L - t0) : kTileFrames;
+        for (int r = 0; r < ht.p_rows - 3; ++r) for (int f = 0; f < 32; ++f) pbuf[(size_t)r * kPStride + f] = 1e30f;   // poison
+        for (int lane = 0; lane < ntile; ++lane) {
+            memset(raw, 0x7f, sizeof(raw));
+            memcpy(raw, pcm + (size_t)(t0 + lane) * HOP, FL * 2);
+            HostExchange ex;
+            energy[lane] = k1t_frame(reinterpret_cast<const uint4*>(raw), ex, tw, pbuf.data() + lane, tb.pscale);
+        }
+        for (int warp = 0; warp < kEpiWarps; ++warp)
+            for (int lane = 0; lane < ntile; ++lane) epi_mel(pbuf.data(), tb.is_mfcc ? lm.data() : out_t.data(), tb, ht.epi_off[warp], ht.epi_cnt[warp], lane);
+        if (tb.is_mfcc)
+            for (int warp = 0; warp < kEpiWarps; ++warp)
+                for (int lane = 0; lane < ntile; ++lane) epi_dct(lm.data(), energy.data(), out_t.data(), tb, warp, lane);
+        for (int f = 0; f < ntile; ++f) for (int m = 0; m < D; ++m) statics[(long long)(t0 + f) * D + m] = out_t[(size_t)m * 32 + f];
+    }
+    return L;
+}
+}  // namespace
+
+// statics (L, D) of one utterance through the simulated K1T (int16 PCM, rectangular window); returns L or < 0
+extern "C" int sim_statics_t(const fe_config* c, const void* pcm, int n_samples, float* statics) {
+    return run_t(*c, static_cast<const short*>(pcm), n_samples, statics);
+}
 
 // statics (L, D) of one utterance through the simulated K1; returns L or < 0
 extern "C" int sim_statics(const fe_config* c, const void* pcm, int n_samples, float* statics) {

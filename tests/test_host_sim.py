@@ -51,3 +51,21 @@ def test_digital_silence_hits_eps_exactly(host_sim, ref):
     got = host_sim(z)
     want = ref.mfcc(ref.pcm_to_float(z), 16000, 0.025, 0.010, 13)
     assert np.abs(got - want).max() < 1e-5       # log(2.22e-16) on c0, ~0 elsewhere
+
+
+def test_k1t_lane_per_frame_dataflow(host_sim, ref, utts):
+    """fe_k1t.cuh (lane = frame, exchange in tensor memory) replayed with the exchange as an array: reads of
+    unwritten exchange words come back NaN, so a wrong column / row index cannot hide."""
+    for u in utts:
+        want = ref.mfcc(ref.pcm_to_float(u), 16000, 0.025, 0.010, 13)
+        got = host_sim(u, kernel="k1t")
+        assert np.isfinite(got).all()
+        assert np.abs(got - want).max() < 2e-5
+        assert np.abs(got - host_sim(u)).max() < 2e-5                 # and it agrees with the K1 dataflow
+    for u in utts[:2]:
+        want, _ = ref.mfe(ref.pcm_to_float(u), 16000, 0.025, 0.010, 80)
+        got = host_sim(u, kernel="k1t", feat_type="fbank", feat_dim=80)
+        assert np.max(np.abs(got - want) / np.abs(want)) < 1e-4
+    z = np.zeros(3000, np.int16)
+    want = ref.mfcc(ref.pcm_to_float(z), 16000, 0.025, 0.010, 13)
+    assert np.abs(host_sim(z, kernel="k1t") - want).max() < 1e-5       # digital silence: exact eps path
