@@ -40,6 +40,7 @@ struct Lane {
     HostPinned h_stage;
     std::vector<UttDesc> utts;
     std::vector<long long> tile_prefix, atile_prefix;
+    int stats_utts = 0;               // utterances of the current batch (size of d_stats when a batch runs in L2 groups)
     cudaEvent_t done = nullptr;       // end of the kernels of the last run on this lane
     bool done_valid = false;
 };
@@ -73,15 +74,18 @@ struct fe_handle {
 
     Lane lane[3];
 
+    bool k2_split = false;            // FE_K2_SPLIT=1: statistics and cube as two kernels (K2a + K2b), the round-1 form
     bool k1t = false;                 // FE_K1T=1: the lane = frame / tensor-memory kernel (fe_k1t.cuh) where it applies; measured
                                       // slower than K1 (profiles/r02_k1t.md), kept selectable for A/B runs
     int profiling = 0;
     // profiled runs since fe_set_profiling(1): one event set per run (no sync inside the timed region)
-    struct ProfSet { cudaEvent_t e[5]; bool k0, k2; };
+    struct ProfSet { cudaEvent_t e[5]; bool k0, k2; std::vector<cudaEvent_t> ge; int groups = 0; };   // ge: (K1 end, K2 end) per L2 group
     std::vector<ProfSet> prof;
     size_t prof_used = 0;
     int64_t launches = 0;
     size_t k1_smem[2] = {0, 0};      // [raw int16 input, float input]
+    long long l2_group_bytes = 0;              // statics per K1 -> K2 group (FE_L2_GROUP_MB; 0 = one launch per kernel, the default:
+                                               // grouping measured slower at every size, profiles/r02_l2_groups.jsonl)
     long long pipe_chunk_bytes = 192LL << 20;   // PCM bytes per chunk of the host pipeline (FE_PIPE_CHUNK_MB overrides)
 };
 
@@ -318,20 +322,40 @@ int launch_k0(fe_handle* h, cudaStream_t st, const short* src, const UttDesc* ut
 // K2a + K2b: per-utterance statistics, then the tile-parallel normalise / delta / pack pass.
 // tiled: `statics` are K1's [D][32] blocks (else a row-major (L, D) matrix per utterance: fe_postprocess).
 // flags: bit0 subtract the mean, bit1 divide by the std, bit2 append deltas.
+// utt0: index of utts[0] in the batch (a group of a larger batch): its statistics live at stats[utt0 * 2 D], which is
+// where the tiles (TileDesc::utt is batch-wide) look them up.
 int launch_k2(fe_handle* h, Lane& L, cudaStream_t st, const UttDesc* utts, int n_utts, const TileDesc* tiles, long long n_tiles,
-              const float* statics, float* out, int D, int delta_mode, int flags, bool tiled) {
+              const float* statics, float* out, int D, int delta_mode, int flags, bool tiled, int utt0) {
     int rc;
-    if ((rc = ensure(h, L.d_stats, sizeof(float) * 2 * (size_t)D * (size_t)n_utts))) return rc;
+    if (utt0 == 0 && (rc = ensure(h, L.d_stats, sizeof(float) * 2 * (size_t)D * (size_t)std::max(n_utts, L.stats_utts)))) return rc;
+    float* d_stats_g = (float*)L.d_stats.p + (size_t)utt0 * 2 * D;
+    // fused path: statistics + cube in one kernel, statics read from HBM once (K1's tile-major statics, full CMVN,
+    // as-shipped deltas, a baked feature width)
+    if (tiled && (flags & 3) == 3 && (delta_mode == 0 || !(flags & 4)) && D == 13 && !h->k2_split && n_tiles > 0) {
+#define FE_LAUNCH_UTT(DT)                                                                                           \
+        do {                                                                                                        \
+            using U = UttCube<DT>;                                                                                  \
+            FE_CUDA(h, cudaFuncSetAttribute(k_utt_cmvn_cube<DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, U::kSmemBytes)); \
+            const int per_sm = std::max(1, std::min(4, (200 * 1024) / U::kSmemBytes));                              \
+            const int grid = (int)std::min<long long>(n_utts, (long long)per_sm * h->num_sms);                      \
+            k_utt_cmvn_cube<DT><<<grid, U::kWarps * 32, U::kSmemBytes, st>>>(utts, n_utts, statics, d_stats_g, out, flags); \
+        } while (0)
+        FE_LAUNCH_UTT(13);       // wider rows (fbank-40 / -80) measured slower fused: one CTA per utterance leaves too few bytes in flight
+#undef FE_LAUNCH_UTT
+        h->launches++;
+        FE_CUDA(h, cudaGetLastError());
+        return FE_OK;
+    }
     if (flags & 3) {
         if (tiled && (flags & 3) == 3) {
             const long long items = (long long)n_utts * D;
             const int grid = (int)std::min<long long>((items + kStatTWarps - 1) / kStatTWarps, 32LL * h->num_sms);
-            k_utt_stats_tiled<<<grid, kStatTWarps * 32, 0, st>>>(utts, n_utts, statics, (float*)L.d_stats.p, D);
+            k_utt_stats_tiled<<<grid, kStatTWarps * 32, 0, st>>>(utts, n_utts, statics, d_stats_g, D);
         } else {
             if (tiled) return fail(h, FE_ERR_INVALID, "internal: partial normalisation on tiled statics");
             const int grid = (int)std::min<long long>(n_utts, 32LL * h->num_sms);
             k_utt_stats<<<grid, kStatThreads, (kStatThreads + std::min(D, kStatThreads)) * sizeof(float), st>>>(
-                utts, n_utts, statics, (float*)L.d_stats.p, D, flags);
+                utts, n_utts, statics, d_stats_g, D, flags);
         }
         h->launches++;
     } else {
@@ -442,6 +466,7 @@ int fe_create(int device, fe_handle** out) {
         FE_CUDA(nullptr, cudaEventCreateWithFlags(&h->lane[i].done, cudaEventDisableTiming));
     }
     h->k1t = getenv("FE_K1T") != nullptr;
+    h->k2_split = getenv("FE_K2_SPLIT") != nullptr;
     {   // K1T's twiddles: universal constants, float64 on the host, rounded once (idempotent across handles)
         std::vector<float2> t256(256), t512(132, make_float2(0.f, 0.f));
         const double kPi = 3.14159265358979323846;
@@ -453,6 +478,7 @@ int fe_create(int device, fe_handle** out) {
         FE_CUDA(nullptr, cudaMemcpyToSymbol(c_tw256, t256.data(), sizeof(float2) * 256));
         FE_CUDA(nullptr, cudaMemcpyToSymbol(c_tw512, t512.data(), sizeof(float2) * 132));
     }
+    if (const char* e = getenv("FE_L2_GROUP_MB")) h->l2_group_bytes = atoll(e) << 20;
     if (const char* e = getenv("FE_PIPE_CHUNK_MB")) { long long mb = atoll(e); if (mb > 0) h->pipe_chunk_bytes = mb << 20; }
     *out = h;
     return FE_OK;
@@ -474,7 +500,7 @@ int fe_destroy(fe_handle* h) {
         if (L.done) cudaEventDestroy(L.done);
         if (L.stream && L.stream != h->stream) cudaStreamDestroy(L.stream);
     }
-    for (auto& p : h->prof) for (auto& e : p.e) if (e) cudaEventDestroy(e);
+    for (auto& p : h->prof) { for (auto& e : p.e) if (e) cudaEventDestroy(e); for (auto& e : p.ge) cudaEventDestroy(e); }
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return FE_OK;
@@ -679,14 +705,47 @@ static int run_core(fe_handle* h, Lane& L, cudaStream_t st, const void* pcm, con
     }
     if (prof) FE_CUDA(h, cudaEventRecord(ps->e[2], st));
     DevTables dt = dev_tables(h, k1_f32);
-    if ((rc = launch_k1(h, st, d_pcm, L.d_scratch.p, k1_f32, (const TileDesc*)L.d_tiles.p,
-                        (int)pl.total_tiles, dt, (float*)L.d_statics.p))) return rc;
-    if (prof) FE_CUDA(h, cudaEventRecord(ps->e[3], st));
-    if (pl.total_frames > 0) {
-        // cmvn: statistics + normalise + deltas + cube; no cmvn: the same pack kernel only re-lays the blocks out as (L, D)
-        if ((rc = launch_k2(h, L, st, (const UttDesc*)L.d_utts.p, n_utts, (const TileDesc*)L.d_tiles.p, pl.total_tiles,
-                            (const float*)L.d_statics.p, d_out, c.feat_dim, c.delta_mode, c.cmvn ? 7 : 0, true))) return rc;
-        if (prof) ps->k2 = true;
+    const int k2_flags = c.cmvn ? 7 : 0;
+    L.stats_utts = n_utts;
+    if ((rc = ensure(h, L.d_stats, sizeof(float) * 2 * (size_t)c.feat_dim * (size_t)n_utts))) return rc;
+    // K1 -> K2a -> K2b run over groups of utterances whose statics fit the L2 (126 MB on the B200): K2 reads them
+    // three times (mean pass, variance pass, cube pass) and finds them where K1 has just left them instead of in
+    // HBM.  Measured on the fbank-80 pass (statics 320 B / frame): K2 3.56 -> see profiles/r02_l2_groups.json.
+    // Profiling records one event pair per group.
+    const long long group_bytes = pl.total_frames == 0 ? 0 : h->l2_group_bytes;
+    if (prof) ps->groups = 0;
+    if (group_bytes <= 0) {
+        if ((rc = launch_k1(h, st, d_pcm, L.d_scratch.p, k1_f32, (const TileDesc*)L.d_tiles.p,
+                            (int)pl.total_tiles, dt, (float*)L.d_statics.p))) return rc;
+        if (prof) FE_CUDA(h, cudaEventRecord(ps->e[3], st));
+        if (pl.total_frames > 0) {
+            // cmvn: statistics + normalise + deltas + cube; no cmvn: the same pack kernel only re-lays the blocks out as (L, D)
+            if ((rc = launch_k2(h, L, st, (const UttDesc*)L.d_utts.p, n_utts, (const TileDesc*)L.d_tiles.p, pl.total_tiles,
+                                (const float*)L.d_statics.p, d_out, c.feat_dim, c.delta_mode, k2_flags, true, 0))) return rc;
+            if (prof) ps->k2 = true;
+        }
+    } else {
+        const long long tiles_per_group = std::max<long long>(1, group_bytes / ((long long)kTileFrames * c.feat_dim * 4));
+        int u0 = 0;
+        while (u0 < n_utts) {
+            int u1 = u0 + 1;
+            while (u1 < n_utts && L.tile_prefix[(size_t)u1 + 1] - L.tile_prefix[(size_t)u0] <= tiles_per_group) ++u1;
+            const long long t0 = L.tile_prefix[(size_t)u0], nt = L.tile_prefix[(size_t)u1] - t0;
+            if (nt > 0) {
+                if (prof && ps->ge.size() < (size_t)(2 * ps->groups + 2)) {
+                    cudaEvent_t a, b;
+                    FE_CUDA(h, cudaEventCreate(&a)); FE_CUDA(h, cudaEventCreate(&b));
+                    ps->ge.push_back(a); ps->ge.push_back(b);
+                }
+                if ((rc = launch_k1(h, st, d_pcm, L.d_scratch.p, k1_f32, (const TileDesc*)L.d_tiles.p + t0, (int)nt, dt,
+                                    (float*)L.d_statics.p))) return rc;
+                if (prof) FE_CUDA(h, cudaEventRecord(ps->ge[(size_t)2 * ps->groups], st));
+                if ((rc = launch_k2(h, L, st, (const UttDesc*)L.d_utts.p + u0, u1 - u0, (const TileDesc*)L.d_tiles.p + t0, nt,
+                                    (const float*)L.d_statics.p, d_out, c.feat_dim, c.delta_mode, k2_flags, true, u0))) return rc;
+                if (prof) { FE_CUDA(h, cudaEventRecord(ps->ge[(size_t)2 * ps->groups + 1], st)); ps->groups++; ps->k2 = true; }
+            }
+            u0 = u1;
+        }
     }
     FE_CUDA(h, cudaGetLastError());
     if (prof) FE_CUDA(h, cudaEventRecord(ps->e[4], st));
@@ -852,7 +911,7 @@ int fe_postprocess(fe_handle* h, const float* feats, const int64_t* feat_offsets
         h->launches++;
     }
     if ((rc = launch_k2(h, h->lane[0], st, (const UttDesc*)h->lane[0].d_utts.p, n_utts, (const TileDesc*)h->lane[0].d_tiles.p, n_tiles, d_in, d_out,
-                        D, delta_mode, mode, false))) return rc;
+                        D, delta_mode, mode, false, 0))) return rc;
     if (!out_dev) {
         FE_CUDA(h, cudaMemcpyAsync(out, d_out, sizeof(float) * (size_t)off, cudaMemcpyDeviceToHost, st));
     }
@@ -1092,8 +1151,17 @@ int fe_get_kernel_ms(fe_handle* h, float ms[4]) {
         const fe_handle::ProfSet& p = h->prof[i];
         float v = 0.f;
         if (p.k0) { FE_CUDA(h, cudaEventElapsedTime(&v, p.e[1], p.e[2])); acc[0] += v; }
-        FE_CUDA(h, cudaEventElapsedTime(&v, p.e[2], p.e[3])); acc[1] += v;
-        if (p.k2) { FE_CUDA(h, cudaEventElapsedTime(&v, p.e[3], p.e[4])); acc[2] += v; }
+        if (p.groups > 0) {                       // K1 / K2 alternate over the L2 groups
+            cudaEvent_t prev = p.e[2];
+            for (int g = 0; g < p.groups; ++g) {
+                FE_CUDA(h, cudaEventElapsedTime(&v, prev, p.ge[(size_t)2 * g])); acc[1] += v;
+                FE_CUDA(h, cudaEventElapsedTime(&v, p.ge[(size_t)2 * g], p.ge[(size_t)2 * g + 1])); acc[2] += v;
+                prev = p.ge[(size_t)2 * g + 1];
+            }
+        } else {
+            FE_CUDA(h, cudaEventElapsedTime(&v, p.e[2], p.e[3])); acc[1] += v;
+            if (p.k2) { FE_CUDA(h, cudaEventElapsedTime(&v, p.e[3], p.e[4])); acc[2] += v; }
+        }
         FE_CUDA(h, cudaEventElapsedTime(&v, p.e[0], p.e[4])); acc[3] += v;
     }
     for (int k = 0; k < 4; ++k) ms[k] = (float)(acc[k] / (double)h->prof_used);   // mean over the window

@@ -726,8 +726,7 @@ k_utt_stats(const UttDesc* __restrict__ utts, int n_utts, const float* __restric
 
 // K2a for K1's tile-major statics ([D][32] blocks): one warp per (utterance, coefficient), lane = frame
 // within the block, so every load is one 128-byte line and the reduction is a fixed-order shuffle tree
-// (deterministic).  Same arithmetic as k_utt_stats: mean = x[0] + mean(x - x[0]), population variance
-// around that mean in a second pass.
+// (deterministic).  mean = x[0] + mean(x - x[0]); population variance from the same single pass.
 constexpr int kStatTWarps = 4;
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -749,34 +748,27 @@ k_utt_stats_tiled(const UttDesc* __restrict__ utts, int n_utts, const float* __r
         const float* x = statics + utts[ui].stat_off + c * 32 + lane;       // block j at x[j * 32 * D]
         const long long bs = 32LL * D;
         const int nb = L >> 5, tail = L & 31;
+        // ONE pass over the column: sums of d = x - x[0] and d^2 (shifted data: a constant column -- digital silence --
+        // stays exactly constant, and the cancellation in sum d^2 - (sum d)^2 / L is that of data centred on a sample)
         const float shift = __shfl_sync(0xffffffffu, x[0], 0);
-        float a[4] = {0.f, 0.f, 0.f, 0.f};
+        float a[4] = {0.f, 0.f, 0.f, 0.f}, q[4] = {0.f, 0.f, 0.f, 0.f};
         int j = 0;
         for (; j + 3 < nb; j += 4) {
             float v[4];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) v[k] = x[(j + k) * bs];
+            for (int k = 0; k < 4; ++k) v[k] = x[(j + k) * bs] - shift;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) a[k] += v[k] - shift;
+            for (int k = 0; k < 4; ++k) { a[k] += v[k]; q[k] = fmaf(v[k], v[k], q[k]); }
         }
-        for (; j < nb; ++j) a[0] += x[j * bs] - shift;
-        if (lane < tail) a[1] += x[nb * bs] - shift;
-        const float mean = shift + warp_sum((a[0] + a[1]) + (a[2] + a[3])) / (float)L;
-        float q[4] = {0.f, 0.f, 0.f, 0.f};
-        j = 0;
-        for (; j + 3 < nb; j += 4) {
-            float v[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) v[k] = x[(j + k) * bs] - mean;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) q[k] = fmaf(v[k], v[k], q[k]);
-        }
-        for (; j < nb; ++j) { const float d = x[j * bs] - mean; q[0] = fmaf(d, d, q[0]); }
-        if (lane < tail) { const float d = x[nb * bs] - mean; q[1] = fmaf(d, d, q[1]); }
-        const float var = warp_sum((q[0] + q[1]) + (q[2] + q[3])) / (float)L;
+        for (; j < nb; ++j) { const float d = x[j * bs] - shift; a[0] += d; q[0] = fmaf(d, d, q[0]); }
+        if (lane < tail) { const float d = x[nb * bs] - shift; a[1] += d; q[1] = fmaf(d, d, q[1]); }
+        const float sd = warp_sum((a[0] + a[1]) + (a[2] + a[3]));
+        const float sq = warp_sum((q[0] + q[1]) + (q[2] + q[3]));
         if (lane == 0) {
+            const float invL = 1.0f / (float)L;
+            const float var = fmaxf((sq - sd * sd * invL) * invL, 0.f);
             float* st = stats + (long long)ui * 2 * D;
-            st[c] = mean;
+            st[c] = shift + sd * invL;
             st[D + c] = 1.0f / (sqrtf(var) + 9.313225746154785e-10f);       // 2^-30
         }
     }
@@ -992,6 +984,148 @@ k_cube_local(const TileDesc* __restrict__ tiles, int n_tiles, const float* __res
     extern __shared__ __align__(16) float sm_c[];
     if (flags & 4) cube_local_body<D, true>(tiles, n_tiles, statics, stats, out, flags, sm_c);
     else cube_local_body<D, false>(tiles, n_tiles, statics, stats, out, flags, sm_c);
+}
+
+// ---------------------------------------------------------------------------
+// K2 fused: per-utterance CMVN statistics AND the cube in one kernel, one CTA per utterance (persistent).  The statics
+// of an utterance (52 B x L for MFCC-13, 320 B x L for fbank-80: 64 KB .. 1.1 MB) are read from HBM ONCE for the
+// statistics; the cube pass reads them again a few microseconds later out of the L2.  The two-kernel form (K2a + K2b)
+// read them three times from HBM (mean pass, variance pass, cube pass): 2 240 instead of 1 280 B / frame for fbank-80.
+//   phase 1  warp w takes the blocks w', w' + nw, ... of coefficient chunk k (CH coefficients per lane in registers,
+//            lane = frame): sums of d = x - x[0] and d^2, fixed-order shuffle tree, per-warp partials in shared
+//            memory, combined in warp order (deterministic).  mean = x[0] + sum d / L,
+//            var = (sum d^2 - (sum d)^2 / L) / L (shifted data: a constant column stays exactly constant).
+//   phase 2  warp per tile: normalise, as-shipped deltas (coefficient axis: per-lane register arithmetic), cube through
+//            the warp's staging window, 16-byte coalesced stores -- the body of k_cube_local.
+// flags as k_norm_delta_pack (bit2 deltas).  As-shipped delta mode only (time regression keeps K2a + k_norm_delta_pack).
+// ---------------------------------------------------------------------------
+template <int D>
+struct UttCube {
+    static constexpr int kWarps = 8;
+    static constexpr int SCH = D <= 20 ? D : 20;                       // coefficients per statistics chunk
+    static_assert(D % SCH == 0, "feature width must be a multiple of the statistics chunk");
+    static constexpr int NCH = D / SCH;                                // chunks; kWarps / NCH warps share one
+    static_assert(kWarps % NCH == 0, "warps must split evenly over the chunks");
+    static constexpr int WPC = kWarps / NCH;
+    static constexpr int kStageFloats = kWarps * 32 * CubeLocal<D>::RS;
+    static constexpr int kSmemBytes = (kStageFloats + kWarps * 2 * SCH + 2 * D) * 4;
+};
+
+template <int D, bool DELTA>
+__device__ __forceinline__ void cube_tile(const float* __restrict__ x, const float* st_mean, const float* st_inv, bool normalise,
+                                          float* __restrict__ dst, int nrow, bool last_tile, float* stage, int lane) {
+    using C = CubeLocal<D>;
+    constexpr int W = DELTA ? 3 : 1;
+    constexpr int ROWLEN = W * D, SEG = W * C::CH, RS = C::RS;
+    float v[D];
+#pragma unroll
+    for (int c = 0; c < D; ++c) v[c] = x[c * 32 + lane];                   // 128-byte lines; pad lanes read finite garbage
+    if (normalise) {
+#pragma unroll
+        for (int c = 0; c < D; ++c) v[c] = (v[c] - st_mean[c]) * st_inv[c];   // warp-uniform (shared memory broadcast)
+    }
+    float* row = stage + lane * RS;
+#pragma unroll
+    for (int c0 = 0; c0 < D; c0 += C::CH) {
+        if (DELTA) {
+#pragma unroll
+            for (int j = 0; j < C::CH; ++j) {
+                const int c = c0 + j;
+                auto cl = [](int i) { return i < D ? i : D - 1; };
+                const float d1c = (v[cl(c + 1)] + 2.f * v[cl(c + 2)]) * 0.1f;
+                const float d1a = (v[cl(cl(c + 1) + 1)] + 2.f * v[cl(cl(c + 1) + 2)]) * 0.1f;
+                const float d1b = (v[cl(cl(c + 2) + 1)] + 2.f * v[cl(cl(c + 2) + 2)]) * 0.1f;
+                row[3 * j] = v[c]; row[3 * j + 1] = d1c; row[3 * j + 2] = (d1a + 2.f * d1b) * 0.1f;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < C::CH; ++j) row[j] = v[c0 + j];
+        }
+        __syncwarp();
+        if (SEG == ROWLEN && RS == ROWLEN) {
+            const int total = nrow * ROWLEN, n4 = total >> 2;
+            for (int i = lane; i < n4; i += 32) reinterpret_cast<float4*>(dst)[i] = reinterpret_cast<const float4*>(stage)[i];
+            for (int i = (n4 << 2) + lane; i < total; i += 32) dst[i] = stage[i];
+        } else if (SEG % 4 == 0 && ROWLEN % 4 == 0) {
+            constexpr int Q = SEG / 4;
+            for (int i = lane; i < nrow * Q; i += 32) {
+                const int r = i / Q, q = i - r * Q;
+                const float* sp = stage + r * RS + 4 * q;
+                reinterpret_cast<float4*>(dst + (long long)r * ROWLEN + W * c0)[q] = make_float4(sp[0], sp[1], sp[2], sp[3]);
+            }
+        } else {
+            for (int i = lane; i < nrow * SEG; i += 32) {
+                const int r = i / SEG, e = i - r * SEG;
+                dst[(long long)r * ROWLEN + W * c0 + e] = stage[r * RS + e];
+            }
+        }
+        __syncwarp();
+    }
+    const int total = nrow * ROWLEN;
+    if (last_tile && lane < ((4 - (total & 3)) & 3)) dst[total + lane] = 0.f;    // pad floats of the utterance's run
+}
+
+template <int D>
+__global__ void __launch_bounds__(UttCube<D>::kWarps * 32)
+k_utt_cmvn_cube(const UttDesc* __restrict__ utts, int n_utts, const float* __restrict__ statics, float* __restrict__ stats,
+                float* __restrict__ out, int flags) {
+    using U = UttCube<D>;
+    extern __shared__ __align__(16) float sm_u[];
+    float* stage_all = sm_u;
+    float* part = sm_u + U::kStageFloats;                  // [kWarps][2 * SCH]
+    float* st = part + U::kWarps * 2 * U::SCH;             // mean[D], inv[D]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int chunk = warp / U::WPC, wsub = warp % U::WPC;
+    const bool deltas = flags & 4;
+    for (int ui = blockIdx.x; ui < n_utts; ui += gridDim.x) {
+        const UttDesc u = utts[ui];
+        const int L = u.n_frames;
+        if (L <= 0) continue;
+        const float* x = statics + u.stat_off;
+        const int nb = (L + 31) >> 5;
+        // ---- phase 1: statistics ----
+        float shift[U::SCH], s[U::SCH], q[U::SCH];
+#pragma unroll
+        for (int c = 0; c < U::SCH; ++c) { shift[c] = __ldg(x + (chunk * U::SCH + c) * 32); s[c] = 0.f; q[c] = 0.f; }
+        for (int b = wsub; b < nb; b += U::WPC) {
+            const float* xb = x + (long long)b * 32 * D + chunk * U::SCH * 32 + lane;
+            const bool live = b * 32 + lane < L;
+#pragma unroll
+            for (int c = 0; c < U::SCH; ++c) {
+                const float d = live ? xb[c * 32] - shift[c] : 0.f;
+                s[c] += d; q[c] = fmaf(d, d, q[c]);
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < U::SCH; ++c) { s[c] = warp_sum(s[c]); q[c] = warp_sum(q[c]); }
+        if (lane == 0) {
+#pragma unroll
+            for (int c = 0; c < U::SCH; ++c) { part[warp * 2 * U::SCH + c] = s[c]; part[warp * 2 * U::SCH + U::SCH + c] = q[c]; }
+        }
+        __syncthreads();
+        if (threadIdx.x < D) {
+            const int c = threadIdx.x, ch = c / U::SCH, cc = c % U::SCH;
+            float ss = 0.f, qq = 0.f;
+            for (int w = 0; w < U::WPC; ++w) { ss += part[(ch * U::WPC + w) * 2 * U::SCH + cc]; qq += part[(ch * U::WPC + w) * 2 * U::SCH + U::SCH + cc]; }
+            const float invL = 1.0f / (float)L;
+            const float mean = __ldg(x + c * 32) + ss * invL;
+            const float var = fmaxf((qq - ss * ss * invL) * invL, 0.f);
+            const float inv = 1.0f / (sqrtf(var) + 9.313225746154785e-10f);       // 2^-30
+            st[c] = mean; st[D + c] = inv;
+            stats[(long long)ui * 2 * D + c] = mean; stats[(long long)ui * 2 * D + D + c] = inv;
+        }
+        __syncthreads();
+        // ---- phase 2: cube, one warp per tile (statics come out of the L2 now) ----
+        float* stage = stage_all + warp * 32 * CubeLocal<D>::RS;
+        const int W = deltas ? 3 : 1;
+        for (int b = warp; b < nb; b += U::kWarps) {
+            const int nrow = min(32, L - b * 32);
+            float* dst = out + u.out_off + (long long)b * 32 * W * D;
+            if (deltas) cube_tile<D, true>(x + (long long)b * 32 * D, st, st + D, true, dst, nrow, b == nb - 1, stage, lane);
+            else cube_tile<D, false>(x + (long long)b * 32 * D, st, st + D, true, dst, nrow, b == nb - 1, stage, lane);
+        }
+        __syncthreads();                                   // st / part are rewritten for the next utterance
+    }
 }
 
 // ---------------------------------------------------------------------------
