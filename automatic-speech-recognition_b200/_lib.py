@@ -64,6 +64,7 @@ SYMBOLS = {
     "fe_sync": (C.c_int, [C.c_void_p]),
     "fe_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
     "fe_measure_fp32_peak": (C.c_int, [C.c_void_p, _f32p]),
+    "fe_measure_fp32_peaks": (C.c_int, [C.c_void_p, _f32p]),
     "fe_get_kernel_ms": (C.c_int, [C.c_void_p, _f32p]),
     "fe_launch_count": (C.c_int64, [C.c_void_p]),
     "fe_debug_counters": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),

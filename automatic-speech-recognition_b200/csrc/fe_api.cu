@@ -218,7 +218,7 @@ int launch_k1(fe_handle* h, cudaStream_t st, const void* pcm, const void* scratc
     int grid = std::min<long long>(n_tiles, (long long)h->num_sms);        // persistent: one 16-warp CTA per SM
     if (grid <= 0) return FE_OK;
     if (!(c.frame_len == 400 && c.hop == 160)) return fail(h, FE_ERR_INVALID, "unsupported frame geometry");
-    if (!in_f32 && c.window == nullptr && h->epi_plan != 0 && h->k1t) {
+    if (!in_f32 && c.window == nullptr && (h->epi_plan == 1 || h->epi_plan == 2) && h->k1t) {
         // K1T: lane = frame, exchange in tensor memory (fe_k1t.cuh)
         K1TParams T;
         memset(T.epi_w, 0, sizeof(T.epi_w));
@@ -255,6 +255,8 @@ int launch_k1(fe_handle* h, cudaStream_t st, const void* pcm, const void* scratc
     do {                                                                                                   \
         if (h->epi_plan == 1) FE_LAUNCH_K1E(F32, WIN, 1);                                                  \
         else if (h->epi_plan == 2) FE_LAUNCH_K1E(F32, WIN, 2);                                             \
+        else if (h->epi_plan == 3) FE_LAUNCH_K1E(F32, WIN, 3);                                             \
+        else if (h->epi_plan == 4) FE_LAUNCH_K1E(F32, WIN, 4);                                             \
         else FE_LAUNCH_K1E(F32, WIN, 0);                                                                   \
     } while (0)
     if (!in_f32 && !win) FE_LAUNCH_K1(0, 0);
@@ -362,7 +364,7 @@ int launch_k2(fe_handle* h, Lane& L, cudaStream_t st, const UttDesc* utts, int n
         flags |= 8;              // no statistics: mean 0, scale 1 inside the pack kernel
     }
     // fast path: K1's tile-major statics with the as-shipped (per-frame) deltas -- one warp per tile, no CTA barrier
-    const bool local = tiled && (delta_mode == 0 || !(flags & 4)) && (D == 13 || D == 40 || D == 80);
+    const bool local = tiled && (delta_mode == 0 || !(flags & 4)) && (D == 13 || D == 39 || D == 40 || D == 80);
     if (n_tiles > 0 && local) {
 #define FE_LAUNCH_CUBE(DT)                                                                                          \
         do {                                                                                                        \
@@ -374,6 +376,7 @@ int launch_k2(fe_handle* h, Lane& L, cudaStream_t st, const UttDesc* utts, int n
                 (const float*)L.d_stats.p, out, flags);                                                             \
         } while (0)
         if (D == 13) FE_LAUNCH_CUBE(13);
+        else if (D == 39) FE_LAUNCH_CUBE(39);
         else if (D == 40) FE_LAUNCH_CUBE(40);
         else FE_LAUNCH_CUBE(80);
 #undef FE_LAUNCH_CUBE
@@ -1108,29 +1111,44 @@ int fe_sync(fe_handle* h) {
     return FE_OK;
 }
 
-int fe_measure_fp32_peak(fe_handle* h, float* tflops) {
+int fe_measure_fp32_peaks(fe_handle* h, float tflops[4]) {
     if (!h || !tflops) return FE_ERR_INVALID;
     FE_CUDA(h, cudaSetDevice(h->device));
-    const int grid = h->num_sms * 8, block = 256, iters = 20000;
+    const int grid = h->num_sms * 8, block = 256, iters = 2500;
     int rc;
     if ((rc = ensure(h, h->lane[0].d_out, sizeof(float) * (size_t)grid * block))) return rc;
     cudaEvent_t e0, e1;
     FE_CUDA(h, cudaEventCreate(&e0)); FE_CUDA(h, cudaEventCreate(&e1));
-    float best = 0.f;
-    k_fp32_peak<<<grid, block, 0, h->stream>>>((float*)h->lane[0].d_out.p, 200);
-    for (int rep = 0; rep < 3; ++rep) {
-        FE_CUDA(h, cudaEventRecord(e0, h->stream));
-        k_fp32_peak<<<grid, block, 0, h->stream>>>((float*)h->lane[0].d_out.p, iters);
-        FE_CUDA(h, cudaEventRecord(e1, h->stream));
-        FE_CUDA(h, cudaEventSynchronize(e1));
-        float ms = 0.f;
-        FE_CUDA(h, cudaEventElapsedTime(&ms, e0, e1));
-        const double flops = (double)grid * block * iters * 8.0 * 2.0 * 2.0;     // 8 FFMA2 = 16 FMA = 32 FLOP
-        best = std::max(best, (float)(flops / (ms * 1e-3) / 1e12));
+    float* o = (float*)h->lane[0].d_out.p;
+    for (int mode = 0; mode < 4; ++mode) {
+        float best = 0.f;
+        for (int rep = 0; rep < 4; ++rep) {                                      // rep 0 = warm-up
+            FE_CUDA(h, cudaEventRecord(e0, h->stream));
+            if (mode == 0) k_fp32_peak<0><<<grid, block, 0, h->stream>>>(o, iters, 1.0001f, 0.5f);
+            else if (mode == 1) k_fp32_peak<1><<<grid, block, 0, h->stream>>>(o, iters, 1.0001f, 0.5f);
+            else if (mode == 2) k_fp32_peak<2><<<grid, block, 0, h->stream>>>(o, iters, 1.0001f, 0.5f);
+            else k_fp32_peak<3><<<grid, block, 0, h->stream>>>(o, iters, 1.0001f, 0.5f);
+            FE_CUDA(h, cudaEventRecord(e1, h->stream));
+            FE_CUDA(h, cudaEventSynchronize(e1));
+            float ms = 0.f;
+            FE_CUDA(h, cudaEventElapsedTime(&ms, e0, e1));
+            const double flops = (double)grid * block * iters * 8.0 * 8.0 * 2.0 * 2.0;   // 64 FMA pairs per iteration
+            if (rep > 0) best = std::max(best, (float)(flops / (ms * 1e-3) / 1e12));
+        }
+        tflops[mode] = best;
+        h->launches += 4;
     }
-    h->launches += 4;
     cudaEventDestroy(e0); cudaEventDestroy(e1);
-    *tflops = best;
+    FE_CUDA(h, cudaGetLastError());
+    return FE_OK;
+}
+
+int fe_measure_fp32_peak(fe_handle* h, float* tflops) {
+    if (!tflops) return FE_ERR_INVALID;
+    float v[4];
+    const int rc = fe_measure_fp32_peaks(h, v);
+    if (rc) return rc;
+    *tflops = std::max(std::max(v[0], v[1]), std::max(v[2], v[3]));
     return FE_OK;
 }
 

@@ -199,7 +199,7 @@ __device__ __forceinline__ void full_wait(int slot) {
 }
 
 // everything K1 needs besides the data pointers; lives in the constant bank
-constexpr int kEpiWCap = 512;            // floats of specialised-epilogue weights carried in the kernel parameters
+constexpr int kEpiWCap = 1024;           // floats of specialised-epilogue weights carried in the kernel parameters
 
 struct K1Params {
     DevTables dt;
@@ -237,7 +237,8 @@ __device__ unsigned long long g_k1_prof[16];
 // The latency-bound, LSU-heavy epilogue so runs in the issue slots the FP32-bound FFT warps leave idle.
 // ---------------------------------------------------------------------------
 // EPI: 0 = generic epilogue (run-time mel plan, the 4 consumer warps share every tile),
-//      1 / 2 = specialised for PlanMfcc40 (13 cepstra) / PlanFbank80: consumer warp w takes tiles w, w + 4, ... whole.
+//      1 / 2 / 3 / 4 = specialised for the reference's filterbanks: 40 filters -> 13 cepstra, fbank-80, 40 filters -> 39
+//      cepstra (run.sh's default feat_dim), fbank-40: consumer warp w takes tiles w, w + 4, ... whole.
 template <int FRAME_LEN, int HOP, int IN_F32, int HAS_WINDOW, int EPI>
 __global__ void __launch_bounds__(kK1Threads, 1)
 k_frames_to_statics(const void* __restrict__ pcm, const void* __restrict__ scratch,
@@ -309,9 +310,13 @@ k_frames_to_statics(const void* __restrict__ pcm, const void* __restrict__ scrat
                 const float* pb = s_pbuf + slot * L.pbuf_floats;
                 full_wait<kFullThreads>(slot);
                 if (!(P.dbg & 1)) {
-                    if (EPI == 1) epi_tile_spec<PlanMfcc40, 13, true, true>(pb, s_energy + slot * kTileFrames, out_t, P.epi_w, tb.dc_elim, lane);
-                    else if (tb.fbank_log) epi_tile_spec<PlanFbank80, 80, false, true>(pb, s_energy + slot * kTileFrames, out_t, P.epi_w, false, lane);
-                    else epi_tile_spec<PlanFbank80, 80, false, false>(pb, s_energy + slot * kTileFrames, out_t, P.epi_w, false, lane);
+                    const float* en = s_energy + slot * kTileFrames;
+                    if (EPI == 1) epi_tile_spec<PlanMfcc40, 13, true, true>(pb, en, out_t, P.epi_w, tb.dc_elim, lane);
+                    else if (EPI == 3) epi_tile_spec<PlanMfcc40, 39, true, true>(pb, en, out_t, P.epi_w, tb.dc_elim, lane);
+                    else if (EPI == 2 && tb.fbank_log) epi_tile_spec<PlanFbank80, 80, false, true>(pb, en, out_t, P.epi_w, false, lane);
+                    else if (EPI == 2) epi_tile_spec<PlanFbank80, 80, false, false>(pb, en, out_t, P.epi_w, false, lane);
+                    else if (tb.fbank_log) epi_tile_spec<PlanMfcc40, 40, false, true>(pb, en, out_t, P.epi_w, false, lane);
+                    else epi_tile_spec<PlanMfcc40, 40, false, false>(pb, en, out_t, P.epi_w, false, lane);
                 } else {
                     out_t[lane] = pb[(5 + (lane & 7)) * kPStride + lane] + s_energy[slot * kTileFrames + lane];
                 }
@@ -900,7 +905,7 @@ k_norm_delta_pack(const TileDesc* __restrict__ tiles, int n_tiles, const float* 
 // ---------------------------------------------------------------------------
 template <int D>
 struct CubeLocal {
-    static constexpr int CH = D <= 16 ? D : (D % 20 == 0 && D <= 40 ? 20 : 16);    // coefficients staged per round
+    static constexpr int CH = D <= 16 ? D : (D == 39 ? 13 : (D % 20 == 0 && D <= 40 ? 20 : 16));    // coefficients staged per round
     static_assert(D % CH == 0, "feature width must be a multiple of the staging chunk");
     static constexpr int RS = (3 * CH) | 1;                              // staging row stride (odd: no bank conflicts)
     static constexpr int kWarps = 8;
@@ -1386,15 +1391,35 @@ k_pad_slots(const float* __restrict__ src, const PadSlot* __restrict__ slots, in
     }
 }
 
-// FP32 roofline denominator measured on the spot: independent packed FFMA2 chains, no memory.
-__global__ void __launch_bounds__(256) k_fp32_peak(float* __restrict__ out, int iters) {
-    float2 x[8];
+// FP32 roofline denominator measured on the spot, no memory traffic.  Four instruction forms (VERDICT r1 item 3 asked
+// for a cross-check of the packed probe): what the FP32 pipe sustains depends on where the operands come from -- the
+// register file delivers about two operand words per lane and cycle (tools/ubench_issue2.cu):
+//   MODE 0  scalar FFMA, warp-uniform multiplier and addend (the form that reaches the nominal 128 FMA / clk / SM)
+//   MODE 1  scalar FFMA, three distinct register operands
+//   MODE 2  packed FFMA2, uniform multiplier and addend (the round-1 probe)
+//   MODE 3  packed FFMA2, three distinct register pairs
+// 8 independent chains per thread, body unrolled 8x (loop overhead < 2 %).
+template <int MODE>
+__global__ void __launch_bounds__(256) k_fp32_peak(float* __restrict__ out, int iters, float ua, float ub) {
+    float2 x[8], a[8], b[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) x[i] = make_float2(threadIdx.x * 1e-3f + i, threadIdx.x * 2e-3f - i);
-    const float2 a = make_float2(1.0001f, 0.9999f), b = make_float2(0.5f, 0.25f);
+    for (int i = 0; i < 8; ++i) {
+        x[i] = make_float2(threadIdx.x * 1e-3f + i, threadIdx.x * 2e-3f - i);
+        a[i] = make_float2(ua + i * 1e-7f + threadIdx.x * 1e-9f, ua * 0.999f + threadIdx.x * 1e-9f);
+        b[i] = make_float2(ub + threadIdx.x * 1e-6f, ub * 0.5f + i);
+    }
+    const float2 u2a = make_float2(ua, ua), u2b = make_float2(ub, ub);
     for (int it = 0; it < iters; ++it) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) x[i] = __ffma2_rn(x[i], a, b);
+        for (int u = 0; u < 8; ++u) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                if (MODE == 0) { x[i].x = fmaf(x[i].x, ua, ub); x[i].y = fmaf(x[i].y, ua, ub); }
+                if (MODE == 1) { x[i].x = fmaf(x[i].x, a[i].x, b[i].x); x[i].y = fmaf(x[i].y, a[i].y, b[i].y); }
+                if (MODE == 2) x[i] = __ffma2_rn(x[i], u2a, u2b);
+                if (MODE == 3) x[i] = __ffma2_rn(x[i], a[i], b[i]);
+            }
+        }
     }
     float s = 0.f;
 #pragma unroll

@@ -20,7 +20,7 @@ struct HostTables {
     int mel_groups = 0, nh = 0, dct_stride = 0;
     int p_rows = 0;                 // rows of the power buffer: 129 (bins 0..128) or 257, + 3 zero pad rows
     bool ok = true;                 // false: a run does not fit the descriptor fields
-    int epi_plan = 0;               // 0 generic epilogue, 1 PlanMfcc40 (D = 13), 2 PlanFbank80 (specialised kernels)
+    int epi_plan = 0;               // 0 generic epilogue; specialised: 1 mfcc 40 -> 13, 2 fbank-80, 3 mfcc 40 -> 39, 4 fbank-40
     std::vector<float> epi_w;       // [2][epi_w_n] specialised epilogue's weights: mel CSR (pre-scaled) + folded DCT rows
     int epi_w_n = 0;
 };
@@ -102,10 +102,14 @@ inline void build_host_tables(const fe_config& c, HostTables& t) {
     }
     // specialised epilogue: only when the caller's filterbank has exactly a baked structure
     t.epi_plan = 0; t.epi_w.clear(); t.epi_w_n = 0;
-    if (c.feat_type == FE_FEAT_MFCC && c.feat_dim == 13 && plan_matches<PlanMfcc40>(c.fb_row_start, c.fb_first_bin, nf)) t.epi_plan = 1;
+    const bool is40 = plan_matches<PlanMfcc40>(c.fb_row_start, c.fb_first_bin, nf);
+    if (c.feat_type == FE_FEAT_MFCC && c.feat_dim == 13 && is40) t.epi_plan = 1;
     if (c.feat_type == FE_FEAT_FBANK && plan_matches<PlanFbank80>(c.fb_row_start, c.fb_first_bin, nf)) t.epi_plan = 2;
+    if (c.feat_type == FE_FEAT_MFCC && c.feat_dim == 39 && is40) t.epi_plan = 3;       // run.sh:41-50 default feat_dim
+    if (c.feat_type == FE_FEAT_FBANK && is40) t.epi_plan = 4;
     if (t.epi_plan) {
-        const int nnz = c.fb_nnz, nd = t.epi_plan == 1 ? c.feat_dim * t.nh : 0;
+        const bool mfcc = c.feat_type == FE_FEAT_MFCC;
+        const int nnz = c.fb_nnz, nd = mfcc ? c.feat_dim * t.nh : 0;
         t.epi_w_n = nnz + nd;
         t.epi_w.assign((size_t)2 * t.epi_w_n, 0.f);
         for (int i = 0; i < nnz; ++i) {
@@ -113,7 +117,7 @@ inline void build_host_tables(const fe_config& c, HostTables& t) {
             t.epi_w[i] = v * (1.0f / 1073741824.0f);
             t.epi_w[(size_t)t.epi_w_n + i] = v;
         }
-        for (int k = 0; k < (t.epi_plan == 1 ? c.feat_dim : 0); ++k)
+        for (int k = 0; k < (mfcc ? c.feat_dim : 0); ++k)
             for (int m = 0; m < t.nh; ++m)
                 t.epi_w[nnz + k * t.nh + m] = t.epi_w[(size_t)t.epi_w_n + nnz + k * t.nh + m] = c.dct[k * nf + m];
     }

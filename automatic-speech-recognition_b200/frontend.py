@@ -419,10 +419,18 @@ class Frontend:
         return {"resample": ms[0], "frames_to_statics": ms[1], "cmvn_delta_pack": ms[2], "device_pass": ms[3]}
 
     def measure_fp32_peak(self):
-        """TFLOP/s sustained by packed FFMA2 chains on this GPU (roofline denominator)."""
+        """Best FP32 TFLOP/s any of the four FMA probes sustains on this GPU (roofline denominator)."""
         v = C.c_float()
         self._check(self._lib.fe_measure_fp32_peak(self._h, C.byref(v)), "fe_measure_fp32_peak")
         return float(v.value)
+
+    def measure_fp32_peaks(self):
+        """The four probes behind ``measure_fp32_peak`` (TFLOP/s each), keyed by instruction form."""
+        v = (C.c_float * 4)()
+        self._check(self._lib.fe_measure_fp32_peaks(self._h, v), "fe_measure_fp32_peaks")
+        names = ("ffma_scalar_uniform_operands", "ffma_scalar_register_operands", "ffma2_packed_uniform_operands",
+                 "ffma2_packed_register_operands")
+        return {n: float(x) for n, x in zip(names, v)}
 
     def debug_counters(self):
         """K1 per-phase clock64 totals (needs FE_K1_DBG=8); profiling aid, see tools/k1_phases.py."""

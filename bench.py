@@ -33,13 +33,36 @@ FLOP_PER_FRAME_ALL = 14440       # + CMVN 78 + deltas 78
 BYTES_PER_FRAME_ALL = 476        # 320 B int16 in + 156 B cube out
 
 
+# BASELINE.json configs[]: what one bench line can time.  flop / bytes per frame: SURVEY.md 8d (algorithmic).
+WORKLOADS = {
+    "configs4": dict(metric=METRIC, hours=125.0, cfg={}, planes=39, shape=(13, 3), flop_k1=FLOP_PER_FRAME_K1, flop_all=FLOP_PER_FRAME_ALL,
+                     bytes_k1=372, bytes_all=BYTES_PER_FRAME_ALL, speeds=None, oracle=dict(feat_dim=13, feat_type="mfcc"),
+                     text="BASELINE configs[4]: 1000-hour LibriSpeech-length corpus, MFCC-39 (13+d+dd) + per-utterance CMVN, "
+                          "sharded 8 ways -> %.0f audio-h per GPU (weak scaling; N=8 is the whole corpus)"),
+    "configs1": dict(metric="audio-hours/sec fbank-80+CMVN", hours=30.0, cfg=dict(feat_type="fbank", feat_dim=80), planes=240, shape=(80, 3),
+                     flop_k1=11520 + 1284 + 368, flop_all=11520 + 1284 + 368 + 960, bytes_k1=320 + 320, bytes_all=320 + 960, speeds=None,
+                     oracle=dict(feat_dim=80, feat_type="fbank"),
+                     text="BASELINE configs[1]: 80 mel energies (linear, as speechpy.mfe ships them) + CMVN on a LibriSpeech-length "
+                          "distribution, %.0f audio-h per GPU"),
+    "configs2": dict(metric="audio-hours/sec MFCC-39+CMVN with speed perturbation 0.9/1.0/1.1", hours=30.0, cfg={}, planes=39, shape=(13, 3),
+                     flop_k1=FLOP_PER_FRAME_K1, flop_all=FLOP_PER_FRAME_ALL, bytes_k1=372, bytes_all=BYTES_PER_FRAME_ALL,
+                     speeds=(0.9, 1.0, 1.1), oracle=dict(feat_dim=13, feat_type="mfcc"),
+                     text="BASELINE configs[2]: MFCC-39 + CMVN with the speed perturbation of utils/augmentation.py in front "
+                          "(speeds 0.9 / 1.0 / 1.1 cycling over the utterances), %.0f audio-h of input per GPU"),
+}
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--hours-per-gpu", type=float, default=125.0)
+    ap.add_argument("--hours-per-gpu", type=float, default=None, help="default: 125 (configs4), 30 (configs1 / configs2)")
+    ap.add_argument("--config", default="configs4", choices=sorted(WORKLOADS),
+                    help="BASELINE.json configs[] entry; the driver's default run is configs4 (the headline metric)")
+    ap.add_argument("--files-hours", type=float, default=6.0,
+                    help="audio-hours of FLAC files per rank for the e2e_files leg (process_audios on paths); 0 = skip")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--cpu-sample-hours", type=float, default=None, help="audio-hours the CPU baseline times")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -86,7 +109,11 @@ _CHK = {}
 def _chk_worker(k):
     """Checker only (never timed, never shipped): oracle features of one picked utterance vs the kernels' cube."""
     from oracle import speechpy_ref as ref
-    want = ref.features_one(_CHK["pcm"][k]).astype(np.float64)
+    pcm = _CHK["pcm"][k]
+    if _CHK.get("speed") is not None and _CHK["speed"][k] != 1.0:
+        from oracle import sox_ref
+        pcm = sox_ref.speed_perturb(pcm, float(_CHK["speed"][k]))
+    want = ref.features_one(pcm, **_CHK.get("kw", {})).astype(np.float64)
     err = np.abs(_CHK["cube"][k].astype(np.float64) - want)
     return float(err.max()) if err.size else 0.0, int(((err > 1e-3) & (err > 1e-4 * np.abs(want))).sum())
 
@@ -222,6 +249,57 @@ def emit(line):
     print(json.dumps(line), flush=True)
 
 
+def _gen_speechlike(i):
+    synth = importlib.import_module(PKG + ".synth")
+    return synth.utterance(int(_CHK["lens"][i]), np.random.default_rng([_CHK["seed"], i]))
+
+
+def files_leg(pkg, hours, rank, local, world, dist, torch):
+    """e2e_files: FLAC files on disk (page cache) -> process_audios(paths, args) -> object array of cubes, per rank.
+    Speech-like synthetic utterances (they compress like speech, ~0.55 of the PCM), written once with the package's
+    own FLAC encoder, read back through the path the reference's caller uses.  Timed: 1 warm-up + 2 passes."""
+    import multiprocessing as mp
+    import shutil
+    import tempfile
+    lens = shard_lengths(hours, 777 + rank)
+    _CHK.update(lens=lens, seed=4242 + rank)
+    procs = max(1, (os.cpu_count() or 1) // max(int(os.environ.get("LOCAL_WORLD_SIZE", world)), 1))
+    with mp.get_context("fork").Pool(procs) as pool:
+        pcm = pool.map(_gen_speechlike, range(len(lens)), chunksize=8)
+    d = tempfile.mkdtemp(prefix="asr_b200_bench_r%d_" % rank)
+    try:
+        paths = [os.path.join(d, "%06d.flac" % i) for i in range(len(pcm))]
+        packed, off, ln = pkg.pack_pcm(pcm)
+        pkg.audio_io.write_audio_batch(paths, packed, off, ln)
+        del packed
+        nbytes = sum(os.path.getsize(p) for p in paths)
+        hours = float(sum(len(p) for p in pcm)) / FS / 3600.0
+        args = ref_args()
+        feats, featlen = pkg.process_audios(paths, args, device=local)                 # warm: page cache, staging buffers
+        assert featlen == [int((len(p) - 400) // 160) for p in pcm]
+        out_bytes = int(sum(f.nbytes for f in feats))
+        if dist is not None:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(2):
+            feats, featlen = pkg.process_audios(paths, args, device=local)
+        dt = (time.perf_counter() - t0) / 2
+        td = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        th = torch.tensor([hours, float(nbytes), float(out_bytes)], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(td, op=dist.ReduceOp.MAX)
+            dist.all_reduce(th, op=dist.ReduceOp.SUM)
+        return {"value": float(th[0]) / float(td[0]), "unit": UNIT, "ms_per_step": float(td[0]) * 1e3,
+                "files": int(len(paths)) * world, "audio_hours": float(th[0]), "file_bytes_read_per_step": int(th[1]),
+                "h2d_bytes_per_step": int(th[1]), "d2h_bytes_per_step": int(th[2]),
+                "api": "process_audios(list of .flac paths, args) -> (object ndarray of (L, 13, 3) float32, featlen): "
+                       "file bytes uploaded compressed, FLAC decoded on the GPU (fe_decode_flac), fe_run, cubes to host",
+                "data": "speech-like synthetic utterances (synth.utterance), FLAC-compressed to %.2f of the PCM, page cache" %
+                        (float(th[1]) / (float(th[0]) * 3600 * FS * 2))}
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
+
+
 def main():
     a = parse()
     _guard_stdout()
@@ -241,6 +319,9 @@ def main():
     pkg = importlib.import_module(PKG)
     importlib.import_module(PKG + ".build").build_library()
 
+    W = WORKLOADS[a.config]
+    if a.hours_per_gpu is None:
+        a.hours_per_gpu = W["hours"]
     # ---- this rank's shard, generated on the device (seeded) ----
     lens = shard_lengths(a.hours_per_gpu, 5678 + rank)
     pad = (lens + 7) // 8 * 8
@@ -254,9 +335,11 @@ def main():
     for s in range(0, total, CH):
         e = min(total, s + CH)
         d_pcm[s:e] = (torch.randn(e - s, device="cuda", generator=g) * 3000.0).clamp_(-32768, 32767).to(torch.int16)
-    cfg = pkg.FrontendConfig()                      # mfcc, D=13, cmvn, as-shipped deltas: MFCC-39 cube
+    cfg = pkg.FrontendConfig(**W["cfg"])            # default: mfcc, D=13, cmvn, as-shipped deltas: MFCC-39 cube
     fe = pkg.Frontend(cfg, device=local)
-    out_off, nfr = fe.plan(lens)
+    speeds = None if W["speeds"] is None else [W["speeds"][i % len(W["speeds"])] for i in range(len(lens))]
+    speed_idx = fe.speed_indices(speeds)
+    out_off, nfr = fe.plan(lens, speed_idx)
     frames = int(nfr.sum())
     d_out = torch.empty(int(out_off[-1]), dtype=torch.float32, device="cuda")
     # an explicit (non-default) stream: the kernels, the timing events and the library's own
@@ -268,15 +351,15 @@ def main():
     assert stream != 0
 
     def step():
-        fe.run_packed(d_pcm, off, lens, out=d_out, stream=stream)
+        fe.run_packed(d_pcm, off, lens, speed_idx=speed_idx, out=d_out, stream=stream)
 
-    fp32_peak = fe.measure_fp32_peak()
+    peak_variants = fe.measure_fp32_peaks()
+    fp32_peak = max(peak_variants.values())
     for _ in range(max(a.warmup, 3)):
         step()
     torch.cuda.synchronize()
 
-    # ---- timed region: device-resident ----
-    fe.set_profiling(True)
+    # ---- timed region: device-resident (no per-kernel events inside: they come from a second, profiled pass) ----
     sampler = ClockSampler(local)
     sampler.start()
     if world > 1:
@@ -291,13 +374,19 @@ def main():
     ev[1].record()
     torch.cuda.synchronize()
     launches = fe.launch_count() - l0
-    km = fe.kernel_ms()                               # mean over the timed steps, events on the launching stream
+    ms_total = ev[0].elapsed_time(ev[1])
+    # the same K steps once more with the library's per-kernel events (on the launching stream) for the roofline
+    fe.set_profiling(True)
+    for _ in range(a.steps):
+        step()
+    torch.cuda.synchronize()
+    km = fe.kernel_ms()                               # mean over those steps
     k1_ms.append(km["frames_to_statics"]); k2_ms.append(km["cmvn_delta_pack"])
+    k0_ms = float(km["resample"])
     if world > 1:
         dist.barrier()
     sampler.stop_flag.set()
     sampler.join(timeout=3)
-    ms_total = ev[0].elapsed_time(ev[1])
     t = torch.tensor([ms_total, hours, float(frames)], dtype=torch.float64, device="cuda")
     if world > 1:
         tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -338,7 +427,7 @@ def main():
         h_pcm_t.copy_(d_pcm[:tot_e])
         h_out_t = torch.empty(out_e, dtype=torch.float32).pin_memory()
         h_pcm, h_out = h_pcm_t.numpy(), h_out_t.numpy()
-        fe.run_packed(h_pcm, off[:n_e2e], lens[:n_e2e], out=h_out)      # warm (device staging buffers)
+        fe.run_packed(h_pcm, off[:n_e2e], lens[:n_e2e], speed_idx=None if speed_idx is None else speed_idx[:n_e2e], out=h_out)      # warm (device staging buffers)
     except Exception as ex:                                             # e.g. not enough pinnable host memory
         ok, err = 0.0, str(ex)[:200]
     if all_min(ok) < 1.0:
@@ -349,7 +438,7 @@ def main():
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         for _ in range(a.e2e_steps):
-            fe.run_packed(h_pcm, off[:n_e2e], lens[:n_e2e], out=h_out)  # synchronous for host outputs
+            fe.run_packed(h_pcm, off[:n_e2e], lens[:n_e2e], speed_idx=None if speed_idx is None else speed_idx[:n_e2e], out=h_out)  # synchronous for host outputs
         torch.cuda.synchronize()
         dt = (time.perf_counter() - t0) / a.e2e_steps
         td = torch.tensor([dt], dtype=torch.float64, device="cuda")
@@ -365,6 +454,16 @@ def main():
         k = min(64, n_e2e)
         chk = float(np.abs(h_out[:int(out_off[k])] - d_out[:int(out_off[k])].cpu().numpy()).max())
 
+    # ---- end to end through the reference's real entry point: process_audios(list of FLAC paths, args) ----
+    # (preprocess.py:50-69 takes file paths; files sit in the page cache, as LibriSpeech does on the second pass)
+    e2e_files = None
+    if a.files_hours > 0 and a.config == "configs4":
+        h_pcm_t = h_out_t = h_pcm = h_out = None        # release the pinned 21 GB before the file leg
+        try:
+            e2e_files = files_leg(pkg, a.files_hours, rank, local, world, dist if world > 1 else None, torch)
+        except Exception as ex:
+            e2e_files = {"value": None, "unit": UNIT, "error": str(ex)[:200]}
+
     if rank != 0:
         if world > 1:
             dist.barrier(); dist.destroy_process_group()
@@ -376,12 +475,17 @@ def main():
         import multiprocessing as mp
         pick = np.unique(np.linspace(0, len(lens) - 1, 256).astype(np.int64))
         _CHK["pcm"] = [d_pcm[int(off[i]):int(off[i]) + int(lens[i])].cpu().numpy() for i in pick]
-        _CHK["cube"] = [d_out[int(out_off[i]):int(out_off[i]) + int(nfr[i]) * 39].cpu().numpy().reshape(int(nfr[i]), 13, 3) for i in pick]
+        _CHK["cube"] = [d_out[int(out_off[i]):int(out_off[i]) + int(nfr[i]) * W["planes"]].cpu().numpy().reshape((int(nfr[i]),) + W["shape"]) for i in pick]
+        _CHK["kw"] = W["oracle"]
+        _CHK["speed"] = None if speeds is None else [speeds[i] for i in pick]
         with mp.get_context("fork").Pool(min(os.cpu_count() or 1, 32)) as pool:
             rows = np.array(pool.map(_chk_worker, range(len(pick))))
         parity = {"utterances": int(len(pick)), "spread": "np.linspace over the %d utterances of the rank-0 shard" % len(lens),
                   "max_abs_err_vs_oracle": float(rows[:, 0].max()), "elements_out_of_tolerance": int(rows[:, 1].sum()),
                   "tolerance": "abs <= 1e-3 OR abs <= 1e-4 |ref| (north_star)", "host_vs_device_max_abs": chk}
+        if speeds is not None:
+            parity["note"] = ("the resampler re-quantises to int16: FP32 vs FP64 accumulation differs by 1 LSB on ~0.05 % of the samples, "
+                              "which the log amplifies in low-energy mel bands (tests/test_gpu_fullsize_parity.py separates the two stages)")
     except Exception as ex:
         parity = {"error": str(ex)[:200]}
 
@@ -409,6 +513,15 @@ def main():
             dt1 = time.perf_counter() - t1
             h1 = sum(len(p) for p in one) / FS / 3600.0
             cpu["single_process"] = {"value": h1 / dt1, "unit": UNIT, "sample": "%d utterances (%.3f audio-h), %.1f s, 1 BLAS thread" % (len(one), h1, dt1)}
+            # the same process with BLAS threads left at the library's default (what `python3 preprocess.py` gets)
+            from oracle import speechpy_ref as _ref
+            t1 = time.perf_counter()
+            for p_ in one:
+                _ref.features_one(p_)
+            dt2 = time.perf_counter() - t1
+            cpu["single_process_blas_unpinned"] = {"value": h1 / dt2, "unit": UNIT, "sample": "same %d utterances, %.1f s, BLAS threads at default" % (len(one), dt2)}
+            cpu["note"] = ("the %d-process figure is %.1fx one process: the numpy port is memory-bound (index gathers, (L, 400) float64 "
+                           "temporaries), not core-bound" % (cores, v / (h1 / dt1)))
         except Exception as ex:
             cpu["single_process"] = {"error": str(ex)[:120]}
 
@@ -419,38 +532,43 @@ def main():
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     k1 = float(np.mean(k1_ms)) * 1e-3
-    traffic = None
+    traffic, traffic_source = None, None
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "k1_traffic.json")))
-        traffic = float(tj["dram_bytes_per_frame"]) * frames
+        if a.config == "configs4":
+            traffic = float(tj["dram_bytes_per_frame"]) * frames
+            traffic_source = "replayed: dram__bytes_read.sum + dram__bytes_write.sum per frame of the ncu capture %s x frames of this launch" % tj.get("capture", "")
     except Exception:
         pass
-    ach = frames * FLOP_PER_FRAME_K1 / k1 / 1e12
+    ach = frames * W["flop_k1"] / k1 / 1e12
+    nominal = 148 * 128 * 2 * 1.965e9 / 1e12
     roofline = {
         "kernel": "k_frames_to_statics", "bound": "fp32", "achieved": ach, "peak": fp32_peak, "unit": "TFLOP/s",
-        "frac": ach / fp32_peak, "traffic": traffic,
-        "peak_source": "measured live: packed FFMA2 chains (fe_measure_fp32_peak); nominal 148 SM x 128 lanes x 2 x 1.965 GHz = 74.5",
-        "frac_of_nominal": ach / 74.5,
-        "algorithmic_flop_per_frame": FLOP_PER_FRAME_K1, "frames_per_launch": frames, "launch_ms": k1 * 1e3,
-        "hbm": {"achieved_gbs": frames * (320 + 52) / k1 / 1e9, "peak_gbs": hbm_peak,
+        "frac": ach / fp32_peak, "traffic": traffic, "traffic_source": traffic_source,
+        "peak_source": "measured live, best of four FMA probes (fe_measure_fp32_peaks): what the FP32 pipe sustains depends on the operand "
+                       "source -- scalar FFMA with a warp-uniform operand reaches the nominal rate, three register operands do not "
+                       "(register-file read bandwidth, tools/ubench_issue2.cu); nominal 148 SM x 128 lanes x 2 x 1.965 GHz = %.1f" % nominal,
+        "peak_variants": peak_variants, "peak_nominal": nominal, "frac_of_nominal": ach / nominal,
+        "algorithmic_flop_per_frame": W["flop_k1"], "frames_per_launch": frames, "launch_ms": k1 * 1e3,
+        "launch_ms_source": "CUDA events on the launching stream around every K1 launch, mean over %d steps run right after the timed region" % a.steps,
+        "hbm": {"achieved_gbs": frames * W["bytes_k1"] / k1 / 1e9, "peak_gbs": hbm_peak,
                 "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650 (B200_PROFILING.md)",
-                "algorithmic_bytes_per_frame": 372},
-        "whole_pass": {"flop_per_frame": FLOP_PER_FRAME_ALL, "bytes_per_frame": BYTES_PER_FRAME_ALL,
-                       "achieved_tflops": frames_all * FLOP_PER_FRAME_ALL / (ms_per_step * 1e-3) / 1e12 / world,
-                       "achieved_gbs": frames_all * BYTES_PER_FRAME_ALL / (ms_per_step * 1e-3) / 1e9 / world},
-        "cmvn_delta_pack_ms": float(np.mean(k2_ms)),
+                "algorithmic_bytes_per_frame": W["bytes_k1"]},
+        "whole_pass": {"flop_per_frame": W["flop_all"], "bytes_per_frame": W["bytes_all"],
+                       "achieved_tflops": frames_all * W["flop_all"] / (ms_per_step * 1e-3) / 1e12 / world,
+                       "achieved_gbs": frames_all * W["bytes_all"] / (ms_per_step * 1e-3) / 1e9 / world},
+        "cmvn_delta_pack_ms": float(np.mean(k2_ms)), "resample_ms": k0_ms,
     }
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
+        "metric": W["metric"], "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "BASELINE configs[4]: 1000-hour LibriSpeech-length corpus, MFCC-39 (13+d+dd) + per-utterance "
-                               "CMVN, sharded 8 ways -> %.0f audio-h per GPU (weak scaling; N=8 is the whole corpus)" % a.hours_per_gpu,
+        "config": {"workload": W["text"] % a.hours_per_gpu,
                    "audio_hours_per_gpu": hours, "utterances_per_gpu": int(len(lens)), "frames_per_gpu": frames,
                    "pcm": "int16 16 kHz, seeded on-device Gaussian noise (broadband), clip(N(12.3,3.8^2),2,35) s",
                    "l2": "inputs (%.1f GB/GPU) far larger than the 126 MB L2; no flush needed" % (total * 2 / 1e9),
                    "sharding": "utterances, no collective (per-utterance CMVN)"},
-        "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+        "e2e": e2e, "e2e_files": e2e_files, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
         "clocks": sampler.summary(), "parity_check": parity,
     }
     emit(line)

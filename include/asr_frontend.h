@@ -185,9 +185,12 @@ int fe_sync(fe_handle* h);
  * runs since fe_set_profiling(h, 1) was last called.
  *   ms[0] resample  ms[1] frames->statics  ms[2] cmvn+delta+pack  ms[3] whole device pass */
 int fe_set_profiling(fe_handle* h, int on);
-/* FP32 CUDA-core peak of this GPU as sustained by independent packed FFMA2 chains (TFLOP/s); the
- * measured denominator of the kernels' FP32 roofline. */
+/* FP32 CUDA-core peak of this GPU (TFLOP/s), the measured denominator of the kernels' FP32 roofline: the best of four
+ * independent-chain probes -- [0] scalar FFMA with warp-uniform multiplier / addend, [1] scalar FFMA with three
+ * register operands, [2] packed FFMA2 with uniform operands, [3] packed FFMA2 with three register pairs.
+ * fe_measure_fp32_peaks returns all four (what the pipe sustains depends on where the operands come from). */
 int fe_measure_fp32_peak(fe_handle* h, float* tflops);
+int fe_measure_fp32_peaks(fe_handle* h, float tflops[4]);
 int fe_get_kernel_ms(fe_handle* h, float ms[4]);
 int64_t fe_launch_count(fe_handle* h);       /* kernels launched since fe_create */
 /* profiling aid: with FE_K1_DBG=8 in the environment K1 accumulates clock64 totals per phase

@@ -32,6 +32,11 @@ run("configs[1] fbank-80 (linear, as shipped) + cmvn", pkg.FrontendConfig(feat_t
 run("configs[1] fbank-80 log + cmvn", pkg.FrontendConfig(feat_type="fbank", feat_dim=80, fbank_log=True))
 sp = np.array([(-1, 0, 1)[i % 3] for i in range(len(lens))], np.int32)
 run("configs[2] mfcc-39 + speed 0.9/1.0/1.1", pkg.FrontendConfig(), sp)
+run("mfcc 40 filters -> 39 cepstra (run.sh default feat_dim), specialised plan", pkg.FrontendConfig(feat_dim=39))
+run("fbank-40 + cmvn, specialised plan", pkg.FrontendConfig(feat_type="fbank", feat_dim=40))
+run("mfcc-39, Hamming window (window switch), specialised plan", pkg.FrontendConfig(window=np.hamming(400)))
 os.environ["FE_K1_GENERIC"] = "1"
 run("mfcc-39, generic (run-time plan) epilogue", pkg.FrontendConfig())
+run("mfcc 40 -> 39, generic epilogue", pkg.FrontendConfig(feat_dim=39))
+run("fbank-40, generic epilogue", pkg.FrontendConfig(feat_type="fbank", feat_dim=40))
 print(json.dumps({"audio_hours": h, "results": res}, indent=1))
