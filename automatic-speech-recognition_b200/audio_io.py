@@ -184,6 +184,10 @@ def load_flac_batch(paths, n_threads=0, out=None):
     sizes = sizes[:n]
     if np.any(sizes >= 2 ** 31):
         raise AudioFormatError("file larger than 2 GB")
+    if np.any(sizes >= 2 ** 28):
+        # the device decoder addresses bits with 32-bit integers: files of 256 MB or more go to the host decoder
+        raise UnsupportedStreamError("%s: file of %d MB; the device decoder takes files below 256 MB; use read_audio_batch"
+                                     % (paths[int(np.argmax(sizes))], int(sizes.max()) >> 20))
     offsets = np.zeros(n, dtype=np.int64)
     if n > 1:
         np.cumsum((sizes[:-1] + 15) // 16 * 16, out=offsets[1:])

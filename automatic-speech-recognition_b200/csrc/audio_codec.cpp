@@ -1002,6 +1002,11 @@ int aio_flac_layout(const uint8_t* data, int64_t n_bytes, aio_flac_layout_t* out
     out->first_frame = (int32_t)si.first_frame;
     out->min_block = si.min_block;
     out->max_block = si.max_block;
+    // a stream may declare min == max block size and still use the variable-blocking frame headers (sync 0xFFF9: the
+    // header then numbers samples, not frames): report it as not fixed-block so that the device decoder declines it
+    if (si.first_frame + 2 <= n_bytes && data[si.first_frame] == 0xFF && (data[si.first_frame + 1] & 0xFE) == 0xF8 &&
+        (data[si.first_frame + 1] & 1))
+        out->min_block = 0;
     out->sample_rate = si.sample_rate;
     out->channels = si.channels;
     out->bits_per_sample = si.bps;

@@ -191,6 +191,14 @@ class Frontend:
         raw = (C.c_uint8 * (int(max(n, 1)) * dt.itemsize)).from_address(ptr.value)
         return np.frombuffer(raw, dtype=dt, count=int(max(n, 1)))
 
+    def free_pinned(self, arrays):
+        """Release page-locked arrays obtained from ``pinned`` (a staging buffer that has been replaced by a larger one)."""
+        for a in arrays:
+            ptr = a.__array_interface__["data"][0]
+            if ptr in self._pinned_ptrs:
+                self._pinned_ptrs.remove(ptr)
+                self._check(self._lib.fe_host_free(self._h, C.c_void_p(ptr)), "fe_host_free")
+
     # -- lifecycle ---------------------------------------------------------
     def close(self):
         if getattr(self, "_h", None) is not None and self._h.value:

@@ -55,7 +55,14 @@ def to_object_array(cubes):
 
 def process_pcm(pcm_list, args, fs=16000, device=0, speeds=None, gains=None, **switches):
     """In-memory variant of process_audios: list of int16 (or float) arrays in."""
-    pcm_dtype = "int16" if all(np.asarray(p).dtype == np.int16 for p in pcm_list) else "float32"
+    dts = {np.asarray(p).dtype for p in pcm_list}
+    bad = [d for d in dts if d != np.int16 and not np.issubdtype(d, np.floating)]
+    if bad:
+        raise TypeError("PCM must be int16 (sample counts) or floating point in [-1, 1): got %s" % sorted(str(d) for d in bad))
+    pcm_dtype = "int16" if dts <= {np.dtype(np.int16)} else "float32"
+    if pcm_dtype == "float32" and np.dtype(np.int16) in dts:
+        # a mixed list: int16 utterances join the float path at the scale soundfile gives them (x / 32768)
+        pcm_list = [np.asarray(p, dtype=np.float32) / np.float32(32768.0) if np.asarray(p).dtype == np.int16 else p for p in pcm_list]
     cfg = FrontendConfig.from_args(args, sample_rate=fs, pcm_dtype=pcm_dtype, **switches)
     fe = get_frontend(cfg, device)
     for p in pcm_list:
@@ -107,6 +114,8 @@ def _process_flac_on_device(audio_path, args, device, n_threads, switches, speed
     need = max(sum(sizes[lo:hi]) + 16 * (hi - lo) for lo, hi in ranges) + 64
     stage = getattr(fe0, "_flac_stage", None)
     if stage is None or stage[0].size < need:
+        if stage is not None:
+            fe0.free_pinned(stage)
         stage = fe0._flac_stage = [fe0.pinned(need + need // 4), fe0.pinned(need + need // 4)]
     trace = {"wait_files": 0.0, "decode": 0.0, "features": 0.0, "views": 0.0} if os.environ.get("FE_TRACE_INGEST") else None
     cubes, featlen = [], []
@@ -151,6 +160,8 @@ def _process_flac_on_device(audio_path, args, device, n_threads, switches, speed
                 for fs_ in copies:                                            # old buffers may still be read by the copy threads
                     for f in fs_:
                         f.result()
+                if bounce is not None:
+                    fe.free_pinned(bounce)
                 bounce = fe._out_stage = [fe.pinned(n_out + n_out // 4, np.float32), fe.pinned(n_out + n_out // 4, np.float32)]
             if b >= 2:
                 for f in copies[b - 2]:                                       # the bounce buffer of batch b - 2 is free again
@@ -202,7 +213,7 @@ def process_audios(audio_path, args, device=0, n_threads=0, device_decode=None, 
         try:
             logging.info("process_audios: %d FLAC files, decoding on the GPU", len(audio_path))
             return _process_flac_on_device(audio_path, args, device, n_threads, switches, speed, gain)
-        except audio_io.UnsupportedStreamError as e:
+        except (audio_io.UnsupportedStreamError, ImportError) as e:      # ImportError: no torch for the device PCM buffer
             logging.info("process_audios: host FLAC decoder instead (%s)", e)
     if not exts <= {".flac", ".wav"}:
         pcm_list, fs_seen = [], None
@@ -221,6 +232,12 @@ def process_audios(audio_path, args, device=0, n_threads=0, device_decode=None, 
     fs = infos[0]["sample_rate"]
     cfg = FrontendConfig.from_args(args, sample_rate=fs, pcm_dtype="int16", **switches)
     fe = get_frontend(cfg, device)
+    if any(inf["n_samples"] < 0 for inf in infos):
+        # a stream whose STREAMINFO carries no total sample count (valid FLAC, what a piping encoder writes) cannot be
+        # planned into the packed batch: decode file by file, like the reference's sf.read, then the in-memory path
+        pcm_list = [audio_io.read_audio(p)[0] for p in audio_path]
+        return process_pcm(pcm_list, args, fs=fs, device=device, speeds=_uniform(speed, len(pcm_list)),
+                           gains=_uniform(gain, len(pcm_list)), **switches)
     for p, inf in zip(audio_path, infos):
         if inf["channels"] != 1:
             raise ValueError("%s: mono audio expected" % p)

@@ -58,6 +58,53 @@ def merge_shards(parts, shard_results, n_total):
     return out
 
 
+def _gather_cubes(feats, dist, rank, world, gather_to):
+    """Hand every rank's cubes to rank ``gather_to`` WITHOUT pickling them through the process group: a rank writes its
+    shard as one flat float32 file in shared memory (/dev/shm; one node, as the whole path is), only the file name and the
+    shapes (a few ints per utterance) go through ``gather_object``; the receiver maps the files and returns views --
+    one copy on the sending side, none on the receiving side.  Returns the per-rank lists of cubes on ``gather_to``."""
+    import os
+    import tempfile
+    import uuid
+    tag = [uuid.uuid4().hex if rank == gather_to else None]
+    dist.broadcast_object_list(tag, src=gather_to)
+    shm = "/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else tempfile.gettempdir()
+    shapes = [tuple(f.shape) for f in feats]
+    sizes = [int(np.prod(sh)) for sh in shapes]
+    total = int(sum(sizes))
+    path = None
+    if rank != gather_to and total > 0:
+        path = os.path.join(shm, "asr_b200_%s_%d.f32" % (tag[0], rank))
+        mm = np.memmap(path, dtype=np.float32, mode="w+", shape=(total,))
+        o = 0
+        for f, n in zip(feats, sizes):
+            mm[o:o + n] = np.asarray(f, dtype=np.float32).reshape(-1)
+            o += n
+        mm.flush()
+        del mm
+    gathered = [None] * world if rank == gather_to else None
+    dist.gather_object((path, shapes), gathered, dst=gather_to)
+    if rank != gather_to:
+        return None
+    out = []
+    for r, (pth, shp) in enumerate(gathered):
+        if r == gather_to:
+            out.append(list(feats))
+            continue
+        if pth is None:
+            out.append([np.empty(sh, np.float32) for sh in shp])
+            continue
+        flat = np.asarray(np.memmap(pth, dtype=np.float32, mode="r+"))
+        os.unlink(pth)                                   # the mapping keeps the pages alive for as long as the views live
+        cubes, o = [], 0
+        for sh in shp:
+            n = int(np.prod(sh))
+            cubes.append(flat[o:o + n].reshape(sh))
+            o += n
+        out.append(cubes)
+    return out
+
+
 def process_pcm_sharded(pcm_list, args, fs=16000, gather_to=0, extract_fn=None, **switches):
     """Every rank calls this with the SAME ``pcm_list``; each extracts its LPT shard on
     its own GPU (LOCAL_RANK) and rank ``gather_to`` gets the re-assembled
@@ -85,8 +132,7 @@ def process_pcm_sharded(pcm_list, args, fs=16000, gather_to=0, extract_fn=None, 
     feats, _ = extract(mine, args, fs=fs, device=device, **switches) if mine else (to_object_array([]), [])
     if world == 1:
         return feats, [len(f) for f in feats]
-    gathered = [None] * world if rank == gather_to else None
-    dist.gather_object(list(feats), gathered, dst=gather_to)
+    gathered = _gather_cubes(feats, dist, rank, world, gather_to)
     if rank != gather_to:
         return None, None
     merged = merge_shards(parts, gathered, len(pcm_list))
@@ -122,8 +168,7 @@ def process_audios_sharded(audio_path, args, gather_to=0, process_fn=None, lengt
     parts = lpt_partition(frame_counts(lengths) + 1, world)
     mine = [audio_path[int(i)] for i in parts[rank]]
     feats, _ = fn(mine, args, device=device, **kw) if mine else (to_object_array([]), [])
-    gathered = [None] * world if rank == gather_to else None
-    dist.gather_object(list(feats), gathered, dst=gather_to)
+    gathered = _gather_cubes(feats, dist, rank, world, gather_to)
     if rank != gather_to:
         return None, None
     merged = merge_shards(parts, gathered, len(audio_path))

@@ -70,7 +70,7 @@ int aio_decode_files(const char* const* paths, int32_t n, int32_t n_threads, int
 typedef struct aio_flac_layout_t {
     int64_t n_samples;         /* per channel (0 if unknown) */
     int32_t first_frame;       /* byte offset of the first audio frame */
-    int32_t min_block, max_block;
+    int32_t min_block, max_block;   /* STREAMINFO values; min_block = 0 when the first frame uses variable blocking (0xFFF9) */
     int32_t sample_rate, channels, bits_per_sample;
 } aio_flac_layout_t;
 int aio_flac_layout(const uint8_t* data, int64_t n_bytes, aio_flac_layout_t* out);

@@ -14,7 +14,7 @@ import sys
 import numpy as np
 import pytest
 
-from conftest import ROOT, PKG
+from conftest import ROOT, PKG, make_args
 
 FLAC_DIR = os.path.join(ROOT, "tests", "golden", "flac")
 
@@ -197,3 +197,31 @@ def test_flac_round_trip_property(pkg):
         assert fs2 == fs and back.dtype == np.int16 and np.array_equal(back, x)
         assert len(data) <= 2 * x.size + 64 + 24 * (x.size // 4096 + 1)          # never worse than verbatim + framing
     check()
+
+
+def test_advice_r1_stream_without_sample_count_and_variable_blocking_flag(pkg, tmp_path):
+    """a FLAC stream whose STREAMINFO has no total-sample count must still decode on the host path, and a
+    stream that sets the variable-blocking bit (0xFFF9) is reported as not fixed-block (the device decoder declines it)."""
+    x = pkg.synth.corpus(1, 0.5, 0.6, seed=3)[0]
+    data = bytearray(pkg.audio_io.encode_flac(x))
+    lay = pkg.audio_io.flac_layout(bytes(data))
+    assert lay["min_block"] == lay["max_block"] > 0 and lay["n_samples"] == len(x)
+    ff = lay["first_frame"]
+    assert data[ff] == 0xFF and data[ff + 1] == 0xF8
+    flagged = bytearray(data); flagged[ff + 1] = 0xF9
+    assert pkg.audio_io.flac_layout(bytes(flagged))["min_block"] == 0
+    # clear the 36-bit total-sample field of STREAMINFO (bytes 4+4+13 .. : low nibble of byte 21, bytes 22..25)
+    nosize = bytearray(data)
+    nosize[21] &= 0xF0
+    nosize[22:26] = b"\x00\x00\x00\x00"
+    p = str(tmp_path / "nosize.flac")
+    open(p, "wb").write(bytes(nosize))
+    assert pkg.audio_io.probe(p)["n_samples"] <= 0
+    y, fs = pkg.audio_io.read_audio(p, check_md5=False)
+    assert fs == 16000 and np.array_equal(y, x)
+
+
+def test_advice_r1_process_pcm_rejects_unscaled_integer_dtypes(pkg):
+    pre = importlib.import_module(PKG + ".preprocess")
+    with pytest.raises(TypeError, match="int16"):
+        pre.process_pcm([np.zeros(1000, np.int32)], make_args())
