@@ -449,6 +449,10 @@ def main():
         e2e = {"value": float(th[0]) / float(td[0]), "unit": UNIT, "h2d_bytes_per_step": int(tot_e * 2),
                "d2h_bytes_per_step": out_e * 4, "ms_per_step": float(td[0]) * 1e3,
                "api": "Frontend.run_packed(host ndarray) -> fe_run (C-ABI), pinned host buffers",
+               "host_gbs_per_rank": (tot_e * 2 + out_e * 4) / float(td[0]) / 1e9,
+               "host_gbs_all_ranks": world * (tot_e * 2 + out_e * 4) / float(td[0]) / 1e9,
+               "note": "every rank moves its whole shard between pinned host memory and HBM: PCIe Gen5 x16 at N = 1; at N >= 4 the box's "
+                       "aggregate host-memory / root-complex rate (one NUMA node, all GPUs behind it: nvidia-smi topo) is the ceiling",
                "sample": "whole shard" if n_e2e == n_all else
                          "first %d of %d utterances of every shard (%.1f audio-h per GPU): host memory" % (n_e2e, n_all, hours_e)}
         k = min(64, n_e2e)
