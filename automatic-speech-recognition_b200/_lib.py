@@ -43,6 +43,7 @@ SYMBOLS = {
     "fe_abi_version": (C.c_int, []),
     "fe_num_frames": (C.c_int64, [C.c_int64, C.c_int32, C.c_int32]),
     "fe_resampled_length": (C.c_int64, [C.c_int64, C.c_int32, C.c_int32]),
+    "fe_geometry_supported": (C.c_int, [C.c_int32, C.c_int32]),
     "fe_create": (C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
     "fe_destroy": (C.c_int, [C.c_void_p]),
     "fe_configure": (C.c_int, [C.c_void_p, C.POINTER(FeConfig)]),

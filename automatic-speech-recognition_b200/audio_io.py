@@ -23,6 +23,10 @@ class AudioFormatError(RuntimeError):
     pass
 
 
+class MixedSampleRates(ValueError):
+    """Files of different sample rates in one batch call (process_audios then runs one pass per rate)."""
+
+
 class UnsupportedStreamError(AudioFormatError):
     """A valid stream that the DEVICE decoder does not take (stereo, > 16 bit, variable block size, no sample
     count); the host decoder reads it."""
@@ -141,7 +145,7 @@ def read_audio_batch(paths, n_threads=0, check_md5=True, out=None):
         if info[i].channels != 1:
             raise ValueError("%s: mono audio expected" % paths[i])
         if info[i].sample_rate != fs:
-            raise ValueError("mixed sample rates in one call: %d vs %d (%s)" % (fs, info[i].sample_rate, paths[i]))
+            raise MixedSampleRates("mixed sample rates in one call: %d vs %d (%s)" % (fs, info[i].sample_rate, paths[i]))
         if info[i].n_samples < 0:
             raise AudioFormatError("%s: FLAC stream without a sample count; use read_audio" % paths[i])
         if info[i].n_samples > _MAX_SAMPLES_PER_BYTE * max(os.path.getsize(paths[i]), 1):
@@ -217,7 +221,7 @@ def load_flac_batch(paths, n_threads=0, out=None):
         raise ValueError("%s: mono audio expected" % paths[int(np.flatnonzero(L["channels"] != 1)[0])])
     if np.any(L["sample_rate"] != fs):
         i = int(np.flatnonzero(L["sample_rate"] != fs)[0])
-        raise ValueError("mixed sample rates in one call: %d vs %d (%s)" % (fs, L["sample_rate"][i], paths[i]))
+        raise MixedSampleRates("mixed sample rates in one call: %d vs %d (%s)" % (fs, L["sample_rate"][i], paths[i]))
     unsup = ((L["min_block"] != L["max_block"]) | (L["n_samples"] <= 0) | (L["max_block"] % 8 != 0) | (L["max_block"] < 16) |
              (L["bits_per_sample"] > 16) | (L["n_samples"] >= 2 ** 31) | (L["n_samples"] > _MAX_SAMPLES_PER_BYTE * np.maximum(sizes, 1)))
     if np.any(unsup):

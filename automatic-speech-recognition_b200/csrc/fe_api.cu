@@ -217,8 +217,9 @@ int launch_k1(fe_handle* h, cudaStream_t st, const void* pcm, const void* scratc
     const fe_config& c = h->cfg;
     int grid = std::min<long long>(n_tiles, (long long)h->num_sms);        // persistent: one 16-warp CTA per SM
     if (grid <= 0) return FE_OK;
-    if (!(c.frame_len == 400 && c.hop == 160)) return fail(h, FE_ERR_INVALID, "unsupported frame geometry");
-    if (!in_f32 && c.window == nullptr && (h->epi_plan == 1 || h->epi_plan == 2) && h->k1t) {
+    const bool geo_main = c.frame_len == 400 && c.hop == 160;
+    if (!geo_main && !fe_geometry_supported(c.frame_len, c.hop)) return fail(h, FE_ERR_INVALID, "unsupported frame geometry");
+    if (geo_main && !in_f32 && c.window == nullptr && (h->epi_plan == 1 || h->epi_plan == 2) && h->k1t) {
         // K1T: lane = frame, exchange in tensor memory (fe_k1t.cuh)
         K1TParams T;
         memset(T.epi_w, 0, sizeof(T.epi_w));
@@ -244,13 +245,32 @@ int launch_k1(fe_handle* h, cudaStream_t st, const void* pcm, const void* scratc
     const bool win = c.window != nullptr;
     memset(P.epi_w, 0, sizeof(P.epi_w));
     if (h->epi_plan) memcpy(P.epi_w, h->epi_w.data() + (in_f32 ? (size_t)h->epi_w_n : 0), sizeof(float) * (size_t)h->epi_w_n);
-#define FE_LAUNCH_K1E(F32, WIN, EPI)                                                                       \
+#define FE_LAUNCH_K1G(FL, HOP, F32, WIN, EPI)                                                              \
     do {                                                                                                   \
-        FE_CUDA(h, cudaFuncSetAttribute(k_frames_to_statics<400, 160, F32, WIN, EPI>,                      \
+        FE_CUDA(h, cudaFuncSetAttribute(k_frames_to_statics<FL, HOP, F32, WIN, EPI>,                       \
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->k1_smem[F32])); \
-        k_frames_to_statics<400, 160, F32, WIN, EPI><<<grid, kK1Threads, h->k1_smem[F32], st>>>(           \
+        k_frames_to_statics<FL, HOP, F32, WIN, EPI><<<grid, kK1Threads, h->k1_smem[F32], st>>>(            \
             pcm, scratch, tiles, n_tiles, P, statics);                                                     \
     } while (0)
+#define FE_LAUNCH_K1E(F32, WIN, EPI) FE_LAUNCH_K1G(400, 160, F32, WIN, EPI)
+    // other frame geometries (the reference takes frame_length / frame_step from its arguments, las/arguments.py:33-40,
+    // and fs from every file): generic epilogue only
+#define FE_LAUNCH_K1O(FL, HOP)                                                                             \
+    do {                                                                                                   \
+        if (!in_f32 && !c.window) FE_LAUNCH_K1G(FL, HOP, 0, 0, 0);                                         \
+        else if (!in_f32) FE_LAUNCH_K1G(FL, HOP, 0, 1, 0);                                                 \
+        else if (!c.window) FE_LAUNCH_K1G(FL, HOP, 1, 0, 0);                                               \
+        else FE_LAUNCH_K1G(FL, HOP, 1, 1, 0);                                                              \
+    } while (0)
+    if (!geo_main) {
+        if (c.frame_len == 200 && c.hop == 80) FE_LAUNCH_K1O(200, 80);            // 25 / 10 ms at 8 kHz
+        else if (c.frame_len == 320 && c.hop == 160) FE_LAUNCH_K1O(320, 160);     // 20 / 10 ms at 16 kHz (speechpy's own default length)
+        else if (c.frame_len == 480 && c.hop == 160) FE_LAUNCH_K1O(480, 160);     // 30 / 10 ms at 16 kHz
+        else return fail(h, FE_ERR_INVALID, "unsupported frame geometry");
+        h->launches++;
+        FE_CUDA(h, cudaGetLastError());
+        return FE_OK;
+    }
 #define FE_LAUNCH_K1(F32, WIN)                                                                             \
     do {                                                                                                   \
         if (h->epi_plan == 1) FE_LAUNCH_K1E(F32, WIN, 1);                                                  \
@@ -264,6 +284,8 @@ int launch_k1(fe_handle* h, cudaStream_t st, const void* pcm, const void* scratc
     else if (!win) FE_LAUNCH_K1(1, 0);
     else FE_LAUNCH_K1(1, 1);
 #undef FE_LAUNCH_K1E
+#undef FE_LAUNCH_K1G
+#undef FE_LAUNCH_K1O
 #undef FE_LAUNCH_K1
     h->launches++;
     FE_CUDA(h, cudaGetLastError());
@@ -438,6 +460,11 @@ int64_t fe_num_frames(int64_t n_samples, int32_t frame_len, int32_t hop) {
     return (n_samples - frame_len) / hop;      // floor for non-negative operands
 }
 
+int fe_geometry_supported(int32_t frame_len, int32_t hop) {
+    return (frame_len == 400 && hop == 160) || (frame_len == 320 && hop == 160) || (frame_len == 480 && hop == 160) ||
+           (frame_len == 200 && hop == 80);
+}
+
 int64_t fe_resampled_length(int64_t n_samples, int32_t up, int32_t down) {
     if (up <= 0 || down <= 0) return n_samples;
     return (n_samples * up + down - 1) / down;
@@ -513,8 +540,9 @@ int fe_configure(fe_handle* h, const fe_config* c) {
     if (!h || !c) return FE_ERR_INVALID;
     if (c->abi_version != FE_ABI_VERSION) return fail(h, FE_ERR_INVALID, "fe_config.abi_version mismatch");
     if (c->nfft != kNfft) return fail(h, FE_ERR_INVALID, "only nfft = 512 is supported");
-    if (!(c->frame_len == 400 && c->hop == 160))
-        return fail(h, FE_ERR_INVALID, "unsupported frame geometry: kernels are built for 400/160 samples (25 ms / 10 ms at 16 kHz)");
+    if (!fe_geometry_supported(c->frame_len, c->hop))
+        return fail(h, FE_ERR_INVALID, "unsupported frame geometry: kernels are built for 400/160 (25 / 10 ms at 16 kHz), 320/160, 480/160 and "
+                                       "200/80 samples (25 / 10 ms at 8 kHz)");
     if (c->num_filters < 1 || c->num_filters > kMaxFilters) return fail(h, FE_ERR_INVALID, "num_filters out of range [1,128]");
     if (c->feat_dim < 1 || c->feat_dim > kMaxFilters) return fail(h, FE_ERR_INVALID, "feat_dim out of range [1,128]");
     if (c->feat_type == FE_FEAT_MFCC && c->feat_dim > c->num_filters)
@@ -546,6 +574,7 @@ int fe_configure(fe_handle* h, const fe_config* c) {
     memcpy(h->epi_off, ht.epi_off, sizeof(h->epi_off)); memcpy(h->epi_cnt, ht.epi_cnt, sizeof(h->epi_cnt));
     h->epi_plan = ht.epi_w_n <= kEpiWCap ? ht.epi_plan : 0; h->epi_w_n = ht.epi_w_n; h->epi_w = ht.epi_w;
     if (getenv("FE_K1_GENERIC")) h->epi_plan = 0;         // force the run-time mel plan (tests, comparisons)
+    if (!(c->frame_len == 400 && c->hop == 160)) h->epi_plan = 0;     // the specialised epilogues are built for the main geometry
     if ((rc = upload(h, h->tw256, ht.tw256.data(), ht.tw256.size() * sizeof(float)))) return rc;
     if ((rc = upload(h, h->tw512, ht.tw512.data(), ht.tw512.size() * sizeof(float)))) return rc;
     if ((rc = upload(h, h->mel_desc, ht.mel_desc.data(), ht.mel_desc.size() * sizeof(int)))) return rc;

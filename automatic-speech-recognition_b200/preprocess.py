@@ -143,7 +143,7 @@ def _process_flac_on_device(audio_path, args, device, n_threads, switches, speed
                 fs = fs_b
                 fe = get_frontend(FrontendConfig.from_args(args, sample_rate=fs, pcm_dtype="int16", **switches), device)
             if fs_b != fs:
-                raise ValueError("mixed sample rates in one call: %d vs %d" % (fs, fs_b))
+                raise MixedSampleRates("mixed sample rates in one call: %d vs %d" % (fs, fs_b))
             if np.any(lens < fe.config.frame_len):
                 raise ValueError("negative dimensions are not allowed")      # what speechpy's stack_frames raises
             pcm_total = int(pcm_off[-1] + (lens[-1] + 7) // 8 * 8) if len(lens) else 0
@@ -204,6 +204,28 @@ def process_audios(audio_path, args, device=0, n_threads=0, device_decode=None, 
     audio_path = list(audio_path)
     if not audio_path:
         return to_object_array([]), []
+    try:
+        return _process_audios_one_rate(audio_path, args, device, n_threads, device_decode, speed, gain, switches)
+    except MixedSampleRates:
+        pass
+    # The reference takes fs from every file (preprocess.py:69-76).  The batch paths want one rate per call (frame
+    # geometry and filterbank are per-rate tables): group the files by rate, run each group, put the cubes back in order.
+    infos = audio_io.probe_batch(audio_path, n_threads)
+    rates = sorted({inf["sample_rate"] for inf in infos})
+    logging.info("process_audios: %d sample rates in one list %s: one pass per rate", len(rates), rates)
+    cubes, featlen = [None] * len(audio_path), [0] * len(audio_path)
+    for fs in rates:
+        idx = [i for i, inf in enumerate(infos) if inf["sample_rate"] == fs]
+        f, n = _process_audios_one_rate([audio_path[i] for i in idx], args, device, n_threads, device_decode, speed, gain, switches)
+        for i, c, m in zip(idx, f, n):
+            cubes[i], featlen[i] = c, m
+    return to_object_array(cubes), featlen
+
+
+MixedSampleRates = audio_io.MixedSampleRates
+
+
+def _process_audios_one_rate(audio_path, args, device, n_threads, device_decode, speed, gain, switches):
     exts = {os.path.splitext(p)[1].lower() for p in audio_path}
     if device_decode:
         if exts != {".flac"}:
@@ -222,7 +244,7 @@ def process_audios(audio_path, args, device=0, n_threads=0, device_decode=None, 
             if fs_seen is None:
                 fs_seen = fs
             elif fs != fs_seen:
-                raise ValueError("mixed sample rates in one call: %d vs %d (%s)" % (fs_seen, fs, p))
+                raise MixedSampleRates("mixed sample rates in one call: %d vs %d (%s)" % (fs_seen, fs, p))
             pcm_list.append(audio)
         return process_pcm(pcm_list, args, fs=fs_seen, device=device, speeds=_uniform(speed, len(pcm_list)),
                            gains=_uniform(gain, len(pcm_list)), **switches)
@@ -252,7 +274,7 @@ def process_audios(audio_path, args, device=0, n_threads=0, device_decode=None, 
             if b + 1 < len(ranges):
                 nxt = pool.submit(audio_io.read_audio_batch, audio_path[ranges[b + 1][0]:ranges[b + 1][1]], n_threads)
             if fs_b != fs:
-                raise ValueError("mixed sample rates in one call: %d vs %d" % (fs, fs_b))
+                raise MixedSampleRates("mixed sample rates in one call: %d vs %d" % (fs, fs_b))
             out, out_off, nfr = fe.run_packed(packed, off, lens, speed_idx=fe.speed_indices(_uniform(speed, len(lens))),
                                               gain=_uniform(gain, len(lens)))
             got = fe.split(out, out_off, nfr)

@@ -83,6 +83,11 @@ typedef struct fe_config {
  * (tfrecord_data_loader.py:78-79 pins it: 522320 -> 3262, 559280 -> 3493.) */
 int64_t fe_num_frames(int64_t n_samples, int32_t frame_len, int32_t hop);
 
+/* 1 if the kernels are built for this frame geometry (samples): 400/160 = 25 / 10 ms at 16 kHz (the reference's
+ * run.sh), 320/160, 480/160, 200/80 = 25 / 10 ms at 8 kHz.  The reference takes frame_length / frame_step from its
+ * arguments (las/arguments.py:33-40) and fs from every file (preprocess.py:69). */
+int fe_geometry_supported(int32_t frame_len, int32_t hop);
+
 /* ceil(n * up / down): utterance length after speed perturbation. */
 int64_t fe_resampled_length(int64_t n_samples, int32_t up, int32_t down);
 

@@ -216,8 +216,10 @@ def test_speechpy_shims(pkg, ref, corpus1):
     assert_close(sp.cmvn(want, False), ref.cmvn(want, False), what="cmvn shim (mean only)")
     cube = sp.extract_derivative_feature(ref.cmvn(want, True))
     assert_close(cube, ref.extract_derivative_feature(ref.cmvn(want, True)), what="delta shim")
+    m20 = sp.mfcc(x, 16000)                                            # speechpy's own defaults: 20 ms frames, 10 ms stride
+    assert np.abs(m20 - ref.mfcc(x, 16000)).max() < 1e-4
     with pytest.raises(RuntimeError, match="frame geometry"):
-        sp.mfcc(x, 16000)                                              # speechpy default 20 ms frames: unsupported
+        sp.mfcc(x, 16000, frame_length=0.032)                          # a geometry no kernel is built for fails loudly
 
 
 def test_process_audios_files_and_pickles(pkg, ref, tmp_path, corpus1, args, monkeypatch):
@@ -469,3 +471,43 @@ def test_epoch_augmenter_features(pkg, ref, sox):
     with pytest.raises(ValueError, match="not in FrontendConfig.speeds"):
         aug.EpochAugmenter(fe, speeds=(0.8,))
     fe.close()
+
+
+@pytest.mark.parametrize("fs,fl,fstep,kw", [(16000, 20, 10, dict()), (16000, 30, 10, dict()), (8000, 25, 10, dict()),
+                                           (8000, 25, 10, dict(feat_type="fbank", feat_dim=40)),
+                                           (16000, 20, 10, dict(window="hamming"))])
+def test_other_frame_geometries_and_sample_rates(pkg, ref, fs, fl, fstep, kw):
+    """VERDICT r1 missing 5: the reference takes frame_length / frame_step from its arguments (las/arguments.py:33-40)
+    and fs from every file (preprocess.py:69): 20 / 30 ms frames at 16 kHz, 25 / 10 ms at 8 kHz."""
+    rng = np.random.default_rng(fs + fl)
+    pcm = [pkg.synth.utterance(int(n), rng) for n in (fs * 2 + 37, fs // 2, fs * 3)]
+    kw = dict(kw)
+    sw = {}
+    if kw.pop("window", None):
+        sw["window"] = np.hamming(int(round(fs * fl / 1000.0)))
+    a = make_args(frame_length=fl, frame_step=fstep, **kw)
+    feats, featlen = pkg.process_pcm(pcm, a, fs=fs, **sw)
+    flen, hop = int(round(fs * fl / 1000.0)), int(round(fs * fstep / 1000.0))
+    assert featlen == [(len(p) - flen) // hop for p in pcm]
+    for f, p in zip(feats, pcm):
+        want = ref.features_one(p, fs, fl, fstep, a.feat_dim, a.feat_type, a.cmvn, **sw)
+        assert_close(f, want, what="geometry %d/%d at %d Hz" % (flen, hop, fs))
+    with pytest.raises(RuntimeError, match="frame geometry"):
+        pkg.process_pcm(pcm, make_args(frame_length=32, frame_step=10), fs=fs)
+
+
+def test_mixed_sample_rates_in_one_file_list(pkg, ref, tmp_path, args):
+    """preprocess.py:69 reads fs per file; a list mixing 16 kHz and 8 kHz files is processed rate by rate, order kept."""
+    rng = np.random.default_rng(77)
+    specs = [(16000, 16000 * 2), (8000, 8000 * 3), (16000, 16000 + 123), (8000, 8000 * 2 + 7)]
+    paths, pcm = [], []
+    for i, (fs, n) in enumerate(specs):
+        x = pkg.synth.utterance(n, rng)
+        p = str(tmp_path / ("m%d.flac" % i))
+        pkg.audio_io.write_audio(p, x, fs)
+        paths.append(p); pcm.append((x, fs))
+    feats, featlen = pkg.process_audios(paths, args)
+    for f, n, (x, fs) in zip(feats, featlen, pcm):
+        want = ref.features_one(x, fs)
+        assert n == len(want)
+        assert_close(f, want, what="mixed rates %d" % fs)
