@@ -59,7 +59,7 @@ def test_error_codes(pkg):
     rc = lib.fe_run(h, pcm.ctypes.data, p64(bad_off), p64(lens), 1, None, None, out.ctypes.data, out.size,
                     p64(oo), nf.ctypes.data_as(C.POINTER(C.c_int32)), None)
     assert rc == _lib.FE_ERR_INVALID and b"16 bytes" in lib.fe_last_error(h)
-    cfg.frame_len = 320
+    cfg.frame_len = 352
     assert lib.fe_configure(h, C.byref(cfg)) == _lib.FE_ERR_INVALID    # unsupported geometry fails loudly
     assert lib.fe_destroy(h) == 0
 
