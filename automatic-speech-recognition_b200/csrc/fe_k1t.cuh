@@ -18,10 +18,15 @@
 //     TENSOR MEMORY (tcgen05.st / tcgen05.ld, shape 32x32b: thread i of a warp owns TMEM lane 32 (warp % 4) + i) --
 //     Blackwell's 256 KB of TMEM per SM is exactly 128 lanes x 512 x 32 bit, one frame per lane for 4 warps.  Shared
 //     memory could not hold it (4 warps x 32 frames x 2 KB = 256 KB);
-//   * nothing is exchanged between lanes or warps: no named barriers, no producer / consumer hand-off, no
-//     __syncthreads after the prologue.  A warp = a tile of 32 consecutive frames of one utterance.
+//   * nothing is exchanged between lanes: no shared-memory transposition, no selects, no producer / consumer slots.  A
+//     tile = 32 consecutive frames of one utterance; the kernel (fe_kernels.cuh: k_frames_to_statics_t) lets the two
+//     warps that share a scheduler and its 32 TMEM lanes split a tile's columns / row pairs between them.
 // Shared memory only stages the raw samples (one bulk copy per tile, double-buffered) and the lane's 129 power bins
 // ([bin][lane]).
+//
+// Status: parity-green, SLOWER than K1 (20.6 vs 16.7 ms on the bench shard) -- TMEM holds one frame per lane for four
+// warps per SM, and scalar straight-line code of this size is bound by instruction fetch, not issue
+// (profiles/r02_k1t.md).  Selected with FE_K1T=1 only.
 //
 // The per-lane phases are host/device functions over an exchange accessor, so tests/host_sim replays them on the CPU
 // (exchange = a float[512]) against the float64 oracle before anything runs on a GPU.
