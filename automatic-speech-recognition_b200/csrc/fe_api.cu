@@ -498,14 +498,11 @@ int fe_create(int device, fe_handle** out) {
     h->k1t = getenv("FE_K1T") != nullptr;
     h->k2_split = getenv("FE_K2_SPLIT") != nullptr;
     {   // K1T's twiddles: universal constants, float64 on the host, rounded once (idempotent across handles)
-        std::vector<float2> t256(256), t512(132, make_float2(0.f, 0.f));
-        const double kPi = 3.14159265358979323846;
-        for (int r = 0; r < 16; ++r) for (int j = 0; j < 16; ++j) {
-            const double a = 2.0 * kPi * ((r * j) % 256) / 256.0;
-            t256[r * 16 + j] = make_float2((float)cos(a), (float)-sin(a));
-        }
-        for (int k = 0; k <= 128; ++k) { const double a = 2.0 * kPi * k / 512.0; t512[k] = make_float2((float)cos(a), (float)sin(a)); }
-        FE_CUDA(nullptr, cudaMemcpyToSymbol(c_tw256, t256.data(), sizeof(float2) * 256));
+        std::vector<float4> t256p(128), t512p(64);
+        std::vector<float2> t512(132, make_float2(0.f, 0.f));
+        k1t_build_twiddles(t256p.data(), t512p.data(), t512.data());
+        FE_CUDA(nullptr, cudaMemcpyToSymbol(c_tw256p, t256p.data(), sizeof(float4) * 128));
+        FE_CUDA(nullptr, cudaMemcpyToSymbol(c_tw512p, t512p.data(), sizeof(float4) * 64));
         FE_CUDA(nullptr, cudaMemcpyToSymbol(c_tw512, t512.data(), sizeof(float2) * 132));
     }
     if (const char* e = getenv("FE_L2_GROUP_MB")) h->l2_group_bytes = atoll(e) << 20;

@@ -583,14 +583,14 @@ FE_HD void static_for(F&& f) {
     }
 }
 
-template <class Plan, int M, bool LOG>
+template <class Plan, int M, bool LOG, int PS = kPStride>
 FE_HD float mel_spec(const float* pcol, const float* w) {
     constexpr int b0 = Plan::B0[M], n = Plan::N[M], off = Plan::OFF[M];
     float a0 = 0.f, a1 = 0.f;
     static_for<0, n>([&](auto ii) {
         constexpr int i = decltype(ii)::value;
-        if (i & 1) a1 = fmaf(w[off + i], pcol[(b0 + i) * kPStride], a1);
-        else a0 = fmaf(w[off + i], pcol[(b0 + i) * kPStride], a0);
+        if (i & 1) a1 = fmaf(w[off + i], pcol[(b0 + i) * PS], a1);
+        else a0 = fmaf(w[off + i], pcol[(b0 + i) * PS], a0);
     });
     float v = a0 + a1;
     v = v == 0.f ? kEpsF64 : v;                 // speechpy.functions.zero_handling
@@ -598,13 +598,14 @@ FE_HD float mel_spec(const float* pcol, const float* w) {
     return v;
 }
 
-template <class Plan, int D, bool MFCC, bool LOG>
-FE_HD void epi_tile_spec(const float* pbuf, const float* energies, float* out_t, const float* w, bool dc_elim, int lane) {
+// PS: row stride of the power buffer in floats; `energy`: this lane's (zero-handled) frame energy
+template <class Plan, int D, bool MFCC, bool LOG, int PS = kPStride>
+FE_HD void epi_tile_spec_e(const float* pbuf, float energy, float* out_t, const float* w, bool dc_elim, int lane) {
     const float* pcol = pbuf + lane;
     if constexpr (!MFCC) {
         static_for<0, Plan::NF>([&](auto mi) {
             constexpr int M = decltype(mi)::value;
-            out_t[M * 32 + lane] = mel_spec<Plan, M, LOG>(pcol, w);
+            out_t[M * 32 + lane] = mel_spec<Plan, M, LOG, PS>(pcol, w);
         });
     } else {
         constexpr int NH = Plan::NF / 2;
@@ -612,7 +613,7 @@ FE_HD void epi_tile_spec(const float* pbuf, const float* energies, float* out_t,
         float s[NH], d[NH];                     // folded log-mel: x[n] +- x[NF-1-n]
         static_for<0, NH>([&](auto ni) {
             constexpr int n = decltype(ni)::value;
-            const float lo = mel_spec<Plan, n, LOG>(pcol, w), hi = mel_spec<Plan, Plan::NF - 1 - n, LOG>(pcol, w);
+            const float lo = mel_spec<Plan, n, LOG, PS>(pcol, w), hi = mel_spec<Plan, Plan::NF - 1 - n, LOG, PS>(pcol, w);
             s[n] = lo + hi; d[n] = lo - hi;
         });
         const float* dw = w + Plan::NNZ;
@@ -625,10 +626,14 @@ FE_HD void epi_tile_spec(const float* pbuf, const float* energies, float* out_t,
                 a1 = fmaf(dw[c * NH + n + 1], (c & 1) ? d[n + 1] : s[n + 1], a1);
             }
             float v = a0 + a1;
-            if (c == 0 && dc_elim) v = fe_log(energies[lane]);
+            if (c == 0 && dc_elim) v = fe_log(energy);
             out_t[c * 32 + lane] = v;
         }
     }
+}
+template <class Plan, int D, bool MFCC, bool LOG>
+FE_HD void epi_tile_spec(const float* pbuf, const float* energies, float* out_t, const float* w, bool dc_elim, int lane) {
+    epi_tile_spec_e<Plan, D, MFCC, LOG, kPStride>(pbuf, energies[lane], out_t, w, dc_elim, lane);
 }
 
 // which specialised epilogue (if any) serves a configuration: 0 = generic, 1 = mfcc 40 filters -> 13, 2 = fbank 80

@@ -42,19 +42,31 @@ namespace fe {
 constexpr int kTFrameVecs = 20;
 constexpr int kTRawBytes = ((kTileFrames - 1) * 160 + 400) * 2 + 32;      // 10 752 bytes per buffer
 
-// Twiddles as plain arrays of (re, im): tw256[r * 16 + j] = W_256^(j r) = (cos, -sin)(2 pi j r / 256), r, j in 0..15;
-// tw512[k] = (cos, sin)(2 pi k / 512), k in 0..128.  On the device they sit in constant memory and every index below
-// is warp-uniform.
+// Twiddles.  The two rows of a pair share every instruction of stage B (packed f32x2 halves), so their twiddles are
+// stored as pairs: tw256p[p * 16 + j] = (wr_a, wr_b, wi_a, wi_b) of W_256^(j ra), W_256^(j rb) = (cos, -sin), and
+// tw512p[p * 8 + k2] = (c_a, c_b, s_a, s_b) = (cos, sin)(2 pi k / 512) of the bins k = ra + 16 k2, rb + 16 k2, where pair
+// p = 0 is rows (0, 8) and pair p >= 1 rows (p, 16 - p); tw512[k] (cos, sin), k = 0 .. 128, serves the self-paired
+// rows 0 and 8.  On the device they sit in constant memory; every index is warp-uniform, so an FFMA2 takes its
+// twiddle as a uniform-register PAIR operand (`FFMA2 R, R, UR.F32x2, R`).
 struct TTwiddles {
-    const float2* tw256;
+    const float4* tw256p;
+    const float4* tw512p;
     const float2* tw512;
 };
 
+FE_HD constexpr int k1t_row_a(int p) { return p == 0 ? 0 : p; }
+FE_HD constexpr int k1t_row_b(int p) { return p == 0 ? 8 : 16 - p; }
+
 // ---------------------------------------------------------------------------
+// Exchange layout (512 words per lane): pair p, plane (re / im), column j, slot (row a / row b) at
+//     64 p + 32 plane + 2 j + slot
+// so that stage B reads a pair's plane with ONE 32-column load whose consecutive register pairs are the packed
+// halves (row a, row b) of column j.
+//
 // Stage A: 16 column FFT16s over the rows of z[m] = x[2m] + i x[2m+1], m = j + 16 a (a < 13: 400 samples), from the
-// lane's raw row (int16 pairs = one 32-bit word per complex point).  Column j's output row k1 goes to exchange
-// words 32 k1 + 2 j (+1 for the imaginary part): row-major, so stage B reads a row with one 32-column load.
-// Returns the lane's sum of squares (Parseval frame energy, sample units).
+// lane's raw samples (int16 pairs = one 32-bit word per complex point).  Plain scalar code: no twiddles here, and
+// scalar results can be stored as the (row a, row b) pairs the layout wants (8 pairs x 2 planes x st2 per column).
+// Returns the lane's sum of squares over the columns it processed (Parseval frame energy, sample units).
 // ---------------------------------------------------------------------------
 template <class EX>
 FE_HD float k1t_stage_a(const uint4* raw4, EX& ex, int q_begin = 0, int q_end = 4) {
@@ -89,7 +101,11 @@ FE_HD float k1t_stage_a(const uint4* raw4, EX& ex, int q_begin = 0, int q_end = 
             fft16<13>(re, im);
             const int j = 4 * q + c;
 #pragma unroll
-            for (int k1 = 0; k1 < 16; ++k1) ex.st2(32 * k1 + 2 * j, re[pos16(k1)], im[pos16(k1)]);
+            for (int p = 0; p < 8; ++p) {
+                const int sa = pos16(k1t_row_a(p)), sb = pos16(k1t_row_b(p));
+                ex.st2(64 * p + 2 * j, re[sa], re[sb]);
+                ex.st2(64 * p + 32 + 2 * j, im[sa], im[sb]);
+            }
         }
     }
     return (ss0 + ss1) + (ss2 + ss3);
@@ -105,75 +121,98 @@ FE_HD float k1t_bin_power(float ar, float ai, float pr, float pi, float c, float
 }
 
 // ---------------------------------------------------------------------------
-// Stage B + real-FFT split for the row pair (r, 16 - r), r = 1 .. 7: two twiddled FFT16s over the columns, then the
-// 16 bins r + 16 k2 and 16 - r + 16 k2 (k2 < 8) -- Z[k] and Z[256 - k] sit in the two rows of the pair.
-// pcol: this lane's column of the power buffer (bin k at pcol[k * kPStride]).
+// Stage B + real-FFT split of pair p: ONE packed twiddled FFT16 over the columns (halves = the pair's two rows), then
+//   p >= 1: the 16 bins p + 16 k2 and 16 - p + 16 k2 (k2 < 8): Z[k] and Z[256 - k] are the two halves of slots k2 and
+//           15 - k2, so the partner is a half-swapped operand (as in K1's post-pass);
+//   p == 0: rows 0 and 8 are their own partners (index (16 - k2) & 15 of row 0, 15 - k2 of row 8): 17 bins in scalar
+//           code, plus X[0] and X[256] for the Parseval frame energy.
+// pcol: this lane's column of the power buffer (bin k at pcol[k * PS]).
 // ---------------------------------------------------------------------------
-template <class EX>
-FE_HD void k1t_row_pair(EX& ex, int r, const TTwiddles& tw, float* pcol) {
-    const int s = 16 - r;
+template <int PS = kPStride, class EX>
+FE_HD void k1t_pair(EX& ex, int p, const TTwiddles& tw, float* pcol, float& x0, float& x256) {
     float va[32], vb[32];
-    ex.ld32(32 * r, va);
-    ex.ld32(32 * s, vb);
+    ex.ld32(64 * p, va);
+    ex.ld32(64 * p + 32, vb);
     ex.wait_ld();
-    float ar[16], ai[16], br[16], bi[16];
+    float2 zr[16], zi[16];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) { ar[j] = va[2 * j]; ai[j] = va[2 * j + 1]; br[j] = vb[2 * j]; bi[j] = vb[2 * j + 1]; }
-    const float2* ta = tw.tw256 + r * 16;
-    const float2* tb = tw.tw256 + s * 16;
-    fft16_twiddled(ar, ai, [&](int j, float& wr, float& wi) { const float2 w = ta[j]; wr = w.x; wi = w.y; });
-    fft16_twiddled(br, bi, [&](int j, float& wr, float& wi) { const float2 w = tb[j]; wr = w.x; wi = w.y; });
+    for (int j = 0; j < 16; ++j) { zr[j] = make_float2(va[2 * j], va[2 * j + 1]); zi[j] = make_float2(vb[2 * j], vb[2 * j + 1]); }
+    const float4* t256 = tw.tw256p + p * 16;
+    fft16_twiddled(zr, zi, [&](int j, float2& wr, float2& wi) {
+        const float4 w = t256[j];
+        wr = make_float2(w.x, w.y); wi = make_float2(w.z, w.w);
+    });
+    if (p == 0) {
+#pragma unroll
+        for (int k2 = 0; k2 <= 8; ++k2) {
+            const int sa = pos16(k2), sp = pos16((16 - k2) & 15);
+            const float2 w = tw.tw512[16 * k2];
+            pcol[(16 * k2) * PS] = k1t_bin_power(zr[sa].x, zi[sa].x, zr[sp].x, zi[sp].x, w.x, w.y);
+        }
+#pragma unroll
+        for (int k2 = 0; k2 < 8; ++k2) {
+            const int sa = pos16(k2), sp = pos16(15 - k2);
+            const float2 w = tw.tw512[8 + 16 * k2];
+            pcol[(8 + 16 * k2) * PS] = k1t_bin_power(zr[sa].y, zi[sa].y, zr[sp].y, zi[sp].y, w.x, w.y);
+        }
+        x0 = zr[0].x + zi[0].x;           // X[0]   = Re Z[0] + Im Z[0]
+        x256 = zr[0].x - zi[0].x;         // X[256] = Re Z[0] - Im Z[0]
+        return;
+    }
+    const float4* t512 = tw.tw512p + p * 8;
+    float* pa = pcol + p * PS;
+    float* pb = pcol + (16 - p) * PS;
 #pragma unroll
     for (int k2 = 0; k2 < 8; ++k2) {
         const int sa = pos16(k2), sp = pos16(15 - k2);
-        const float2 wa = tw.tw512[r + 16 * k2], wb = tw.tw512[s + 16 * k2];
-        pcol[(r + 16 * k2) * kPStride] = k1t_bin_power(ar[sa], ai[sa], br[sp], bi[sp], wa.x, wa.y);
-        pcol[(s + 16 * k2) * kPStride] = k1t_bin_power(br[sa], bi[sa], ar[sp], ai[sp], wb.x, wb.y);
+        const float2 ar = zr[sa], ai = zi[sa], pr = pswap(zr[sp]), pi = pswap(zi[sp]);
+        const float4 w = t512[k2];
+        const float2 c = make_float2(w.x, w.y), s = make_float2(w.z, w.w);
+        const float2 er = padd(ar, pr), ei = psub(ai, pi);          // 2E  (B = conj(partner))
+        const float2 orr = psub(ar, pr), oi = padd(ai, pi);         // 2O
+        const float2 xr = pfma_rr(pneg(s), orr, pfma_rr(c, oi, er));
+        const float2 xi = pfma_rr(pneg(s), oi, pfma_rr(pneg(c), orr, ei));
+        const float2 plo = pfma_rr(xi, xi, pmul(xr, xr));
+        pa[16 * k2 * PS] = plo.x;
+        pb[16 * k2 * PS] = plo.y;
     }
 }
 
-// Rows 0 and 8 are their own partners: bins 16 k2 (k2 = 0 .. 8, partner index (16 - k2) & 15 of row 0) and
-// 8 + 16 k2 (k2 < 8, partner index 15 - k2 of row 8).  Also X[0] and X[256] for the Parseval frame energy.
-template <class EX>
-FE_HD void k1t_rows_0_8(EX& ex, const TTwiddles& tw, float* pcol, float& x0, float& x256) {
-    float va[32], vb[32];
-    ex.ld32(0, va);
-    ex.ld32(32 * 8, vb);
-    ex.wait_ld();
-    float ar[16], ai[16], br[16], bi[16];
-#pragma unroll
-    for (int j = 0; j < 16; ++j) { ar[j] = va[2 * j]; ai[j] = va[2 * j + 1]; br[j] = vb[2 * j]; bi[j] = vb[2 * j + 1]; }
-    fft16(ar, ai);                                              // row 0: W_256^0 = 1
-    const float2* tb = tw.tw256 + 8 * 16;
-    fft16_twiddled(br, bi, [&](int j, float& wr, float& wi) { const float2 w = tb[j]; wr = w.x; wi = w.y; });
-#pragma unroll
-    for (int k2 = 0; k2 <= 8; ++k2) {
-        const int sa = pos16(k2), sp = pos16((16 - k2) & 15);
-        const float2 w = tw.tw512[16 * k2];
-        pcol[(16 * k2) * kPStride] = k1t_bin_power(ar[sa], ai[sa], ar[sp], ai[sp], w.x, w.y);
-    }
-#pragma unroll
-    for (int k2 = 0; k2 < 8; ++k2) {
-        const int sa = pos16(k2), sp = pos16(15 - k2);
-        const float2 w = tw.tw512[8 + 16 * k2];
-        pcol[(8 + 16 * k2) * kPStride] = k1t_bin_power(br[sa], bi[sa], br[sp], bi[sp], w.x, w.y);
-    }
-    x0 = ar[0] + ai[0];           // X[0]   = Re Z[0] + Im Z[0]
-    x256 = ar[0] - ai[0];         // X[256] = Re Z[0] - Im Z[0]
-}
-
-// the whole frame: raw row -> exchange -> power column; returns the frame energy (zero-handled)
+// the whole frame (host replay; the kernel splits the same phases over two warps): raw samples -> exchange -> power
+// column; returns the frame energy (zero-handled)
 template <class EX>
 FE_HD float k1t_frame(const uint4* raw4, EX& ex, const TTwiddles& tw, float* pcol, float pscale) {
     const float ss = k1t_stage_a(raw4, ex);
     ex.wait_st();
-    float x0, x256;
-    k1t_rows_0_8(ex, tw, pcol, x0, x256);
+    float x0 = 0.f, x256 = 0.f, d0, d1;
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
 #endif
-    for (int r = 1; r < 8; ++r) k1t_row_pair(ex, r, tw, pcol);
+    for (int p = 0; p < 8; ++p) {
+        if (p == 0) k1t_pair(ex, p, tw, pcol, x0, x256);
+        else k1t_pair(ex, p, tw, pcol, d0, d1);
+    }
     return frame_energy(ss, x0, x256, pscale);
+}
+
+// host-side construction of the packed twiddle tables (float64, rounded once)
+template <class F4, class F2>
+inline void k1t_build_twiddles(F4* tw256p /* [128] */, F4* tw512p /* [64] */, F2* tw512 /* [129] */) {
+    const double kPi = 3.14159265358979323846;
+    for (int p = 0; p < 8; ++p) {
+        const int ra = k1t_row_a(p), rb = k1t_row_b(p);
+        for (int j = 0; j < 16; ++j) {
+            const double aa = 2.0 * kPi * ((ra * j) % 256) / 256.0, ab = 2.0 * kPi * ((rb * j) % 256) / 256.0;
+            tw256p[p * 16 + j].x = (float)cos(aa); tw256p[p * 16 + j].y = (float)cos(ab);
+            tw256p[p * 16 + j].z = (float)-sin(aa); tw256p[p * 16 + j].w = (float)-sin(ab);
+        }
+        for (int k2 = 0; k2 < 8; ++k2) {
+            const double aa = 2.0 * kPi * (ra + 16 * k2) / 512.0, ab = 2.0 * kPi * (rb + 16 * k2) / 512.0;
+            tw512p[p * 8 + k2].x = (float)cos(aa); tw512p[p * 8 + k2].y = (float)cos(ab);
+            tw512p[p * 8 + k2].z = (float)sin(aa); tw512p[p * 8 + k2].w = (float)sin(ab);
+        }
+    }
+    for (int k = 0; k <= 128; ++k) { const double a = 2.0 * kPi * k / 512.0; tw512[k].x = (float)cos(a); tw512[k].y = (float)sin(a); }
 }
 
 }  // namespace fe

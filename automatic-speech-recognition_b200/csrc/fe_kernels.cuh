@@ -510,10 +510,11 @@ constexpr int kK1TOffSs = kK1TOffEnergy + kK1TGroups * kTileFrames * 4;
 constexpr int kK1TOffBar = kK1TOffSs + kK1TGroups * kTileFrames * 4;
 constexpr int kK1TSmem = kK1TOffBar + 128;
 constexpr int kK1TSplitA = 1;            // stage A: warp 0 takes column quads [0, kK1TSplitA), warp 1 the rest
-constexpr int kK1TSplitB = 5;            // stage B: warp 0 takes rows (0, 8) and pairs [1, kK1TSplitB), warp 1 the rest
+constexpr unsigned kK1TPairs0 = 0xD5u;   // stage B: warp 0 takes the row pairs whose bit is set (0, 2, 4, 6, 7), warp 1 the rest (1, 3, 5)
 
-__constant__ float2 c_tw256[256];        // W_256^(j r) = (cos, -sin)(2 pi j r / 256) at [r * 16 + j]
-__constant__ float2 c_tw512[132];        // (cos, sin)(2 pi k / 512), k = 0 .. 128
+__constant__ float4 c_tw256p[128];       // packed stage-B twiddles of the 8 row pairs (fe_k1t.cuh: TTwiddles)
+__constant__ float4 c_tw512p[64];        // packed real-FFT-split twiddles of pairs 1 .. 7
+__constant__ float2 c_tw512[132];        // (cos, sin)(2 pi k / 512), k = 0 .. 128 (rows 0 and 8)
 
 struct K1TParams {
     float epi_w[kEpiWCap];               // mel CSR weights (pre-scaled) + folded DCT rows: constant-bank operands
@@ -573,7 +574,7 @@ k_frames_to_statics_t(const short* __restrict__ pcm, const short* __restrict__ s
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const TmemExchange ex{s_tmem_base + ((uint32_t)(group * 32) << 16)};
-    const TTwiddles tw{c_tw256, c_tw512};
+    const TTwiddles tw{c_tw256p, c_tw512p, c_tw512};
     float* pcol = pbuf_w + lane;
 
     const int stride = gridDim.x * kK1TGroups;
@@ -600,29 +601,29 @@ k_frames_to_statics_t(const short* __restrict__ pcm, const short* __restrict__ s
         phase ^= 1u << buf;
         FE_TTICK(0);
         const uint4* raw4 = reinterpret_cast<const uint4*>(raw_w + buf * kTRawBytes) + lane * kTFrameVecs;
-        const float ss = half == 0 ? k1t_stage_a(raw4, ex, 0, kK1TSplitA) : k1t_stage_a(raw4, ex, kK1TSplitA, 4);
+        const float ss = k1t_stage_a(raw4, ex, half == 0 ? 0 : kK1TSplitA, half == 0 ? kK1TSplitA : 4);
         if (half == 1) ss_w[lane] = ss;
         ex.wait_st();
         FE_TTICK(1);
         k1t_pair_sync(group);                                   // exchange complete, this buffer's samples consumed
         FE_TTICK(2);
-        if (half == 1) {
-            fetch(t + 2 * stride, buf);                         // refill it for the tile after the next one
+        // the row-pair loop is the same for both warps (p is a uniform loop counter: the twiddles arrive through uniform
+        // loads and are uniform-register operands of the packed FMAs); a warp skips the pairs of the other one
+        const unsigned mine = half == 0 ? kK1TPairs0 : (~kK1TPairs0 & 0xffu);
+        float x0 = 0.f, x256 = 0.f;
+        if (half == 1) fetch(t + 2 * stride, buf);              // refill the drained buffer for the tile after the next one
 #pragma unroll 1
-            for (int r = kK1TSplitB; r < 8; ++r) k1t_row_pair(ex, r, tw, pcol);
-            FE_TTICK(4);
-            k1t_pair_sync(group);                               // power bins complete
-            FE_TTICK(5);
-        } else {
-            float x0, x256;
-            k1t_rows_0_8(ex, tw, pcol, x0, x256);
-            FE_TTICK(3);
-#pragma unroll 1
-            for (int r = 1; r < kK1TSplitB; ++r) k1t_row_pair(ex, r, tw, pcol);
-            energy_w[lane] = frame_energy(ss + ss_w[lane], x0, x256, P.pscale);
-            FE_TTICK(4);
-            k1t_pair_sync(group);
-            FE_TTICK(5);
+        for (int p = 0; p < 8; ++p) {
+            if (!((mine >> p) & 1u)) continue;
+            float d0, d1;
+            k1t_pair(ex, p, tw, pcol, d0, d1);
+            if (p == 0) { x0 = d0; x256 = d1; }
+        }
+        if (half == 0) energy_w[lane] = frame_energy(ss + ss_w[lane], x0, x256, P.pscale);
+        FE_TTICK(4);
+        k1t_pair_sync(group);                                   // power bins complete
+        FE_TTICK(5);
+        if (half == 0) {
             // mel -> log -> DCT for this lane's frame (compile-time filterbank plan, weights in the constant bank)
             if (EPI == 1) epi_tile_spec<PlanMfcc40, 13, true, true>(pbuf_w, energy_w, out_t, P.epi_w, P.dc_elim != 0, lane);
             else if (P.fbank_log) epi_tile_spec<PlanFbank80, 80, false, true>(pbuf_w, energy_w, out_t, P.epi_w, false, lane);

@@ -110,13 +110,10 @@ int run_t(const fe_config& c, const short* pcm, int n_samples, float* statics) {
     HostTables ht; build_host_tables(c, ht);
     SmemTables tb; fill_tables(c, ht, false, tb);
     if (!ht.ok || tb.full_spectrum) return -2;
-    std::vector<float2> t256(256), t512(129);
-    for (int r = 0; r < 16; ++r) for (int j = 0; j < 16; ++j) {
-        const double a = 2.0 * M_PI * ((r * j) % 256) / 256.0;
-        t256[r * 16 + j] = make_float2((float)cos(a), (float)-sin(a));
-    }
-    for (int k = 0; k <= 128; ++k) { const double a = 2.0 * M_PI * k / 512.0; t512[k] = make_float2((float)cos(a), (float)sin(a)); }
-    TTwiddles tw{t256.data(), t512.data()};
+    std::vector<float4> t256p(128), t512p(64);
+    std::vector<float2> t512(129);
+    k1t_build_twiddles(t256p.data(), t512p.data(), t512.data());
+    TTwiddles tw{t256p.data(), t512p.data(), t512.data()};
     const int D = c.feat_dim;
     std::vector<float> pbuf((size_t)ht.p_rows * kPStride, 0.f), lm((size_t)(c.num_filters + 4) * 32, 0.f), out_t((size_t)D * 32), energy(32, 1.f);
     alignas(16) uint32_t raw[204];
