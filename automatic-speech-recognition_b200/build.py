@@ -8,7 +8,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB_NAME = "libasr_frontend.so"
 LIB_PATH = os.path.join(HERE, LIB_NAME)
 SOURCES = ["fe_api.cu", "audio_codec.cpp", "record_io.cpp"]
-HEADERS = ["fe_core.cuh", "fe_kernels.cuh", "flac_gpu.cuh", "fe_tables.h", "fe_plans_gen.h", os.path.join("..", "..", "include", "asr_frontend.h"),
+HEADERS = ["fe_core.cuh", "fe_kernels.cuh", "fe_k1t.cuh", "tmem_ops_gen.h", "flac_gpu.cuh", "fe_tables.h", "fe_plans_gen.h", os.path.join("..", "..", "include", "asr_frontend.h"),
            os.path.join("..", "..", "include", "asr_audio_io.h"), os.path.join("..", "..", "include", "asr_record_io.h")]
 
 NVCC_FLAGS = [

@@ -641,6 +641,172 @@ k_frames_to_statics_t(const short* __restrict__ pcm, const short* __restrict__ s
 }
 
 // ---------------------------------------------------------------------------
+// K1U: K1T's lane = frame phases on 16 FFT warps + 4 epilogue warps per SM, written so that ptxas keeps every
+// warp-uniform quantity in the UNIFORM datapath.
+//
+// Lane group g (= SM sub-partition g = tensor-memory lanes 32 g .. 32 g + 31) owns one tile at a time; its FOUR FFT
+// warps (g, g + 4, g + 8, g + 12) split the tile's work evenly -- stage A: one column quad each, stage B: two row pairs
+// each -- and warp 16 + g runs the mel -> log -> DCT epilogue of tile i while the FFT warps are already in tile i + 1
+// (power bins double-buffered).  Five resident warps per scheduler instead of K1T's two.
+//     FFT warps:  wait raw[b] -> stage A (quad s) -> group barrier -> refill raw[b] (tile i + 2) -> wait pbuf[b] empty
+//                 -> stage B (pairs 2 s, 2 s + 1) -> arrive "pbuf[b] full" -> group barrier (exchange drained)
+//     epilogue:   wait "pbuf[b] full" -> energy, mel, log, DCT -> statics -> arrive "pbuf[b] empty"
+//
+// What ptxas needs for uniform-register operands (measured on small probes, _scratch notes in profiles/r02_k1u.md):
+//   * a value derived from threadIdx is never uniform to it; loop counters with constant or kernel-parameter bounds
+//     are.  So the roles are entered through `for (ug) for (us) if (vote(ug == group && us == sub))`: inside, (ug, us)
+//     are uniform loop counters and the tile index, buffer addresses, tensor-memory addresses, barrier ids and twiddle
+//     indices derived from them are uniform-register arithmetic;
+//   * a branch or loop exit whose predicate is not provably uniform makes everything it encloses "divergent" as soon as
+//     it contains an `.aligned` instruction (tcgen05.ld / .st) or a loop: role tests and mbarrier spins therefore go
+//     through `vote.all`, which yields a uniform predicate.
+// With that, stage B's twiddles are `FFMA2 R, R, UR.F32x2, R` (2 issue cycles instead of 3 with three register pairs)
+// and tcgen05 addresses need no per-instruction R2UR.
+// ---------------------------------------------------------------------------
+constexpr int kUGroups = 4;
+constexpr int kUSub = 4;
+constexpr int kUFftWarps = kUGroups * kUSub;
+constexpr int kUThreads = (kUFftWarps + kUGroups) * 32;                    // 640
+constexpr int kUPS = 32;                                                   // power-buffer row stride: [bin][lane]
+constexpr int kUPRows = 132;
+constexpr int kUPbufBytes = kUPRows * kUPS * 4;                            // 16 896
+constexpr int kUOffPbuf = kUGroups * 2 * kTRawBytes;                       // raw samples: [group][2][kTRawBytes]
+constexpr int kUOffSs = kUOffPbuf + kUGroups * 2 * kUPbufBytes;            // power bins:  [group][2][rows][32]
+constexpr int kUOffX = kUOffSs + kUGroups * 2 * kUSub * 32 * 4;            // sum of squares per quad: [group][2][sub][32]
+constexpr int kUOffBar = kUOffX + kUGroups * 2 * 2 * 32 * 4;               // X[0], X[256]: [group][2][2][32]
+constexpr int kUSmem = kUOffBar + 128;                                     // mbarriers: raw full [g][2], pbuf empty [g][2]
+constexpr int kUFftRegs = 104, kUEpiRegs = 64;                             // 16 x 32 x 104 + 4 x 32 x 64 = 640 x 96
+static_assert(kUSmem <= 232448 - 16, "K1U shared memory");
+
+__device__ __forceinline__ void mbar_wait_vote(uint32_t bar, uint32_t parity) {       // uniform loop exit
+    while (!__all_sync(0xffffffffu, mbar_try(bar, parity))) __nanosleep(20);
+}
+__device__ __forceinline__ void ubar_sync(int id, int threads) {
+    asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(threads) : "memory");
+}
+__device__ __forceinline__ void ubar_arrive(int id, int threads) {
+    asm volatile("bar.arrive %0, %1;" :: "r"(id), "r"(threads) : "memory");
+}
+// the four FFT warps of a lane group meet on named barrier 1 + g; tensor-memory traffic is ordered across it by the fences
+__device__ __forceinline__ void k1u_group_sync(int g) {
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    ubar_sync(1 + g, kUSub * 32);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+
+template <int EPI>
+__global__ void __launch_bounds__(kUThreads, 1)
+k_frames_to_statics_u(const short* __restrict__ pcm, const short* __restrict__ scratch,
+                      const TileDesc* __restrict__ tiles, int n_tiles,
+                      const __grid_constant__ K1TParams P, float* __restrict__ statics) {
+    extern __shared__ __align__(16) unsigned char smem_u[];
+    __shared__ uint32_t s_tmem_base;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int group = warp & 3, sub = warp >> 2;                 // sub == kUSub: the group's epilogue warp
+    const uint32_t bar0 = smem_u32(smem_u + kUOffBar);
+
+    for (int i = tid; i < kUOffBar / 4; i += kUThreads) reinterpret_cast<uint32_t*>(smem_u)[i] = 0u;   // partial tiles read stale rows / bins
+    if (tid == 0) for (int i = 0; i < 16; ++i) mbar_init(bar0 + 8 * i, 1);
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&s_tmem_base)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (s_tmem_base != 0u) __trap();                             // all 512 columns are ours: the allocation starts at 0
+    const int tile_stride = gridDim.x * kUGroups;
+    const int n_iter = (n_tiles + tile_stride - 1) / tile_stride;
+
+    if (__all_sync(0xffffffffu, sub < kUSub)) {
+        // =============================== FFT warps ===============================
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" :: "n"(kUFftRegs));
+        const TTwiddles tw{c_tw256p, c_tw512p, c_tw512};
+#pragma unroll 1
+        for (int ug = 0; ug < kUGroups; ++ug) {
+#pragma unroll 1
+        for (int us = 0; us < kUSub; ++us) {
+        if (!__all_sync(0xffffffffu, ug == group && us == sub)) continue;
+        const TmemExchange ex{(uint32_t)(ug * 32) << 16};
+        unsigned char* raw_g = smem_u + ug * (2 * kTRawBytes);
+        float* pbuf_g = reinterpret_cast<float*>(smem_u + kUOffPbuf + ug * (2 * kUPbufBytes));
+        float* ss_g = reinterpret_cast<float*>(smem_u + kUOffSs) + ug * (2 * kUSub * 32);
+        float* x_g = reinterpret_cast<float*>(smem_u + kUOffX) + ug * (2 * 2 * 32);
+        const uint32_t bar_raw = bar0 + 16 * ug, bar_empty = bar0 + 64 + 16 * ug;
+        // raw samples of a tile: ONE bulk copy (its frames overlap: (n - 1) * 160 + 400 samples) by lane 0 of sub-warp 3
+        auto fetch = [&](int it, int b) {
+            const int tile = (blockIdx.x + it * gridDim.x) * kUGroups + ug;
+            if (tile >= n_tiles || lane != 0) return;
+            const TileDesc* td = tiles + tile;
+            const long long off = td->pcm_off;
+            const int2 ns = *reinterpret_cast<const int2*>(&td->n_frames);        // n_frames, src_sel
+            const uint32_t bytes = (uint32_t)((ns.x - 1) * 160 + 400) * 2u;
+            mbar_expect_tx(bar_raw + 8 * b, bytes);
+            bulk_g2s(smem_u32(raw_g + b * kTRawBytes), (ns.y ? scratch : pcm) + off, bytes, bar_raw + 8 * b);
+        };
+        if (us == kUSub - 1) { fetch(0, 0); fetch(1, 1); }
+#pragma unroll 1
+        for (int it = 0; it < n_iter; ++it) {
+            const int t = (blockIdx.x + it * gridDim.x) * kUGroups + ug;
+            if (t >= n_tiles) break;
+            const int b = it & 1;
+            const uint32_t par = (uint32_t)(it >> 1) & 1u;
+            mbar_wait_vote(bar_raw + 8 * b, par);
+            const uint4* raw4 = reinterpret_cast<const uint4*>(raw_g + b * kTRawBytes) + lane * kTFrameVecs;
+            const float ss = k1t_stage_a(raw4, ex, us, us + 1);
+            ex.wait_st();
+            k1u_group_sync(ug);                                      // exchange complete, this buffer's samples consumed
+            if (us == kUSub - 1) fetch(it + 2, b);                  // refill it for the tile after the next one
+            if (it >= 2) mbar_wait_vote(bar_empty + 8 * b, par ^ 1u);   // the epilogue of tile it - 2 has drained pbuf[b]
+            ss_g[(b * kUSub + us) * 32 + lane] = ss;
+            float* pcol = pbuf_g + b * (kUPRows * kUPS) + lane;
+#pragma unroll 1
+            for (int pp = 0; pp < 2; ++pp) {
+                float x0, x256;
+                k1t_pair<kUPS>(ex, 2 * us + pp, tw, pcol, x0, x256);
+                if (us == 0 && pp == 0) { x_g[(b * 2 + 0) * 32 + lane] = x0; x_g[(b * 2 + 1) * 32 + lane] = x256; }
+            }
+            ubar_arrive(5 + 2 * ug + b, 160);                       // power bins of this tile complete
+            k1u_group_sync(ug);                                      // exchange drained
+        }
+        }}
+    } else {
+        // ============================= epilogue warps =============================
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" :: "n"(kUEpiRegs));
+#pragma unroll 1
+        for (int ug = 0; ug < kUGroups; ++ug) {
+        if (!__all_sync(0xffffffffu, ug == group)) continue;
+        const float* pbuf_g = reinterpret_cast<const float*>(smem_u + kUOffPbuf + ug * (2 * kUPbufBytes));
+        const float* ss_g = reinterpret_cast<const float*>(smem_u + kUOffSs) + ug * (2 * kUSub * 32);
+        const float* x_g = reinterpret_cast<const float*>(smem_u + kUOffX) + ug * (2 * 2 * 32);
+        const uint32_t bar_empty = bar0 + 64 + 16 * ug;
+#pragma unroll 1
+        for (int it = 0; it < n_iter; ++it) {
+            const int t = (blockIdx.x + it * gridDim.x) * kUGroups + ug;
+            if (t >= n_tiles) break;
+            const int b = it & 1;
+            float* out_t = statics + tiles[t].stat_off;
+            ubar_sync(5 + 2 * ug + b, 160);
+            const float* ssb = ss_g + b * kUSub * 32 + lane;
+            const float ss = (ssb[0] + ssb[32]) + (ssb[64] + ssb[96]);
+            const float energy = frame_energy(ss, x_g[(b * 2 + 0) * 32 + lane], x_g[(b * 2 + 1) * 32 + lane], P.pscale);
+            const float* pb = pbuf_g + b * (kUPRows * kUPS);
+            // mel -> log -> DCT for this lane's frame (compile-time filterbank plan, weights in the constant bank)
+            if (EPI == 1) epi_tile_spec_e<PlanMfcc40, 13, true, true, kUPS>(pb, energy, out_t, P.epi_w, P.dc_elim != 0, lane);
+            else if (P.fbank_log) epi_tile_spec_e<PlanFbank80, 80, false, true, kUPS>(pb, energy, out_t, P.epi_w, false, lane);
+            else epi_tile_spec_e<PlanFbank80, 80, false, false, kUPS>(pb, energy, out_t, P.epi_w, false, lane);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_empty + 8 * b);
+        }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(s_tmem_base), "r"(512) : "memory");
+}
+
+// ---------------------------------------------------------------------------
 // K2a k_utt_stats: per-utterance mean and 1 / (population std + 2^-30) of every statics column
 // (speechpy.processing.cmvn, preprocess.py:85).  One 128-thread CTA per utterance (grid-stride),
 // two passes, fixed-order block reductions (deterministic).  mean = x[0] + mean(x - x[0]): the

@@ -135,16 +135,18 @@ def test_maximum_length_matches_reference_comment(pkg, ref, args):
     assert_close(feats[0], ref.features_one(p), what="35 s utterance")
 
 
-def test_k1t_tensor_memory_kernel(pkg, ref, corpus1, args, monkeypatch):
-    """FE_K1T=1 selects the lane = frame kernel whose FFT exchange lives in tensor memory (fe_k1t.cuh): same features
-    as the default kernel to FP32 round-off, same parity against the oracle, for both specialised plans."""
+@pytest.mark.parametrize("variant", ["1", "2"])
+def test_k1t_tensor_memory_kernel(pkg, ref, corpus1, args, monkeypatch, variant):
+    """FE_K1T=1 / 2 select the lane = frame kernels whose FFT exchange lives in tensor memory (fe_k1t.cuh; 2 = K1U,
+    16 FFT + 4 epilogue warps): same features as the default kernel to FP32 round-off, same parity against the oracle,
+    for both specialised plans."""
     fr = importlib.import_module(PKG + ".frontend")
     for kw, a in ((dict(), args), (dict(feat_type="fbank", feat_dim=80), make_args(feat_type="fbank", feat_dim=80))):
         monkeypatch.delenv("FE_K1T", raising=False)
         fe0 = fr.Frontend(fr.FrontendConfig(**kw))
         base = fe0.extract(corpus1[:12])
         fe0.close()
-        monkeypatch.setenv("FE_K1T", "1")
+        monkeypatch.setenv("FE_K1T", variant)
         fe1 = fr.Frontend(fr.FrontendConfig(**kw))
         got = fe1.extract(corpus1[:12])
         again = fe1.extract(corpus1[:12])
