@@ -599,13 +599,14 @@ FE_HD float mel_spec(const float* pcol, const float* w) {
 }
 
 // PS: row stride of the power buffer in floats; `energy`: this lane's (zero-handled) frame energy
+// `lane` selects the column of the power buffer, `frame` the position inside the tile's [D][32] statics block
 template <class Plan, int D, bool MFCC, bool LOG, int PS = kPStride>
-FE_HD void epi_tile_spec_e(const float* pbuf, float energy, float* out_t, const float* w, bool dc_elim, int lane) {
+FE_HD void epi_tile_spec_e(const float* pbuf, float energy, float* out_t, const float* w, bool dc_elim, int lane, int frame) {
     const float* pcol = pbuf + lane;
     if constexpr (!MFCC) {
         static_for<0, Plan::NF>([&](auto mi) {
             constexpr int M = decltype(mi)::value;
-            out_t[M * 32 + lane] = mel_spec<Plan, M, LOG, PS>(pcol, w);
+            out_t[M * 32 + frame] = mel_spec<Plan, M, LOG, PS>(pcol, w);
         });
     } else {
         constexpr int NH = Plan::NF / 2;
@@ -627,13 +628,13 @@ FE_HD void epi_tile_spec_e(const float* pbuf, float energy, float* out_t, const 
             }
             float v = a0 + a1;
             if (c == 0 && dc_elim) v = fe_log(energy);
-            out_t[c * 32 + lane] = v;
+            out_t[c * 32 + frame] = v;
         }
     }
 }
 template <class Plan, int D, bool MFCC, bool LOG>
 FE_HD void epi_tile_spec(const float* pbuf, const float* energies, float* out_t, const float* w, bool dc_elim, int lane) {
-    epi_tile_spec_e<Plan, D, MFCC, LOG, kPStride>(pbuf, energies[lane], out_t, w, dc_elim, lane);
+    epi_tile_spec_e<Plan, D, MFCC, LOG, kPStride>(pbuf, energies[lane], out_t, w, dc_elim, lane, lane);
 }
 
 // which specialised epilogue (if any) serves a configuration: 0 = generic, 1 = mfcc 40 filters -> 13, 2 = fbank 80

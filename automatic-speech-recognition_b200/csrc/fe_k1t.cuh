@@ -39,7 +39,10 @@ namespace fe {
 // = 320 bytes = 20 sixteen-byte vectors after frame f - 1.  The 16-byte loads of 8 neighbouring lanes then hit only
 // two bank groups (4-way conflict): 16 instead of 4 wavefronts per load, 832 per tile -- the LSU is far from
 // saturated (28 %), whereas 32 per-frame copies into padded rows cost the issuing warp > 1 000 cycles per tile.
-constexpr int kTFrameVecs = 20;
+#ifndef FE_TFRAMEVECS
+#define FE_TFRAMEVECS 20           // 21: timing experiment only (conflict-free lane stride, wrong samples)
+#endif
+constexpr int kTFrameVecs = FE_TFRAMEVECS;
 constexpr int kTRawBytes = ((kTileFrames - 1) * 160 + 400) * 2 + 32;      // 10 752 bytes per buffer
 
 // Twiddles.  The two rows of a pair share every instruction of stage B (packed f32x2 halves), so their twiddles are
@@ -87,8 +90,12 @@ FE_HD float k1t_stage_a(const uint4* raw4, EX& ex, int q_begin = 0, int q_end = 
             for (int a = 0; a < 16; ++a) {
                 if (a < 13) {
                     const uint32_t u = c == 0 ? w[a].x : (c == 1 ? w[a].y : (c == 2 ? w[a].z : w[a].w));
+#if defined(__CUDA_ARCH__) && defined(FE_K1T_ASM_CVT)
+                    asm("{\n\t.reg .b16 lo, hi;\n\tmov.b32 {lo, hi}, %2;\n\tcvt.rn.f32.s16 %0, lo;\n\tcvt.rn.f32.s16 %1, hi;\n\t}" : "=f"(re[a]), "=f"(im[a]) : "r"(u));
+#else
                     re[a] = (float)(short)(u & 0xffffu);
                     im[a] = (float)((int)u >> 16);
+#endif
                 } else {
                     re[a] = 0.f; im[a] = 0.f;
                 }
@@ -128,12 +135,16 @@ FE_HD float k1t_bin_power(float ar, float ai, float pr, float pi, float c, float
 //           code, plus X[0] and X[256] for the Parseval frame energy.
 // pcol: this lane's column of the power buffer (bin k at pcol[k * PS]).
 // ---------------------------------------------------------------------------
-template <int PS = kPStride, class EX>
-FE_HD void k1t_pair(EX& ex, int p, const TTwiddles& tw, float* pcol, float& x0, float& x256) {
+// after_loads(): called once the pair's exchange values are in registers (the kernel signals "exchange drained" there).
+struct K1TNoop { FE_HD void operator()() const {} };
+// BIN_LO .. BIN_HI: the bins the caller's power buffer has rows for (others are computed but not stored)
+template <int PS = kPStride, int BIN_LO = 0, int BIN_HI = 128, class EX, class AL = K1TNoop>
+FE_HD void k1t_pair(EX& ex, int p, const TTwiddles& tw, float* pcol, float& x0, float& x256, AL&& after_loads = AL()) {
     float va[32], vb[32];
     ex.ld32(64 * p, va);
     ex.ld32(64 * p + 32, vb);
     ex.wait_ld();
+    after_loads();
     float2 zr[16], zi[16];
 #pragma unroll
     for (int j = 0; j < 16; ++j) { zr[j] = make_float2(va[2 * j], va[2 * j + 1]); zi[j] = make_float2(vb[2 * j], vb[2 * j + 1]); }
@@ -147,7 +158,8 @@ FE_HD void k1t_pair(EX& ex, int p, const TTwiddles& tw, float* pcol, float& x0, 
         for (int k2 = 0; k2 <= 8; ++k2) {
             const int sa = pos16(k2), sp = pos16((16 - k2) & 15);
             const float2 w = tw.tw512[16 * k2];
-            pcol[(16 * k2) * PS] = k1t_bin_power(zr[sa].x, zi[sa].x, zr[sp].x, zi[sp].x, w.x, w.y);
+            if (16 * k2 >= BIN_LO && 16 * k2 <= BIN_HI)
+                pcol[(16 * k2) * PS] = k1t_bin_power(zr[sa].x, zi[sa].x, zr[sp].x, zi[sp].x, w.x, w.y);
         }
 #pragma unroll
         for (int k2 = 0; k2 < 8; ++k2) {
@@ -173,8 +185,8 @@ FE_HD void k1t_pair(EX& ex, int p, const TTwiddles& tw, float* pcol, float& x0, 
         const float2 xr = pfma_rr(pneg(s), orr, pfma_rr(c, oi, er));
         const float2 xi = pfma_rr(pneg(s), oi, pfma_rr(pneg(c), orr, ei));
         const float2 plo = pfma_rr(xi, xi, pmul(xr, xr));
-        pa[16 * k2 * PS] = plo.x;
-        pb[16 * k2 * PS] = plo.y;
+        if (BIN_LO <= 1 || k2 > 0 || p >= BIN_LO) pa[16 * k2 * PS] = plo.x;      // bin p + 16 k2
+        pb[16 * k2 * PS] = plo.y;                                                 // bin 16 - p + 16 k2 (9 .. 127)
     }
 }
 

@@ -648,8 +648,9 @@ k_frames_to_statics_t(const short* __restrict__ pcm, const short* __restrict__ s
 // warps (g, g + 4, g + 8, g + 12) split the tile's work evenly -- stage A: one column quad each, stage B: two row pairs
 // each -- and warp 16 + g runs the mel -> log -> DCT epilogue of tile i while the FFT warps are already in tile i + 1
 // (power bins double-buffered).  Five resident warps per scheduler instead of K1T's two.
-//     FFT warps:  wait raw[b] -> stage A (quad s) -> group barrier -> refill raw[b] (tile i + 2) -> wait pbuf[b] empty
-//                 -> stage B (pairs 2 s, 2 s + 1) -> arrive "pbuf[b] full" -> group barrier (exchange drained)
+//     FFT warps:  wait raw[b], "exchange drained" -> stage A (quad s) -> group barrier -> refill raw[b] (tile i + 2)
+//                 -> wait pbuf[b] empty -> stage B (pairs 2 s, 2 s + 1; arrive "exchange drained" after the last load)
+//                 -> arrive "pbuf[b] full"
 //     epilogue:   wait "pbuf[b] full" -> energy, mel, log, DCT -> statics -> arrive "pbuf[b] empty"
 //
 // What ptxas needs for uniform-register operands (measured on small probes, _scratch notes in profiles/r02_k1u.md):
@@ -668,15 +669,29 @@ constexpr int kUSub = 4;
 constexpr int kUFftWarps = kUGroups * kUSub;
 constexpr int kUThreads = (kUFftWarps + kUGroups) * 32;                    // 640
 constexpr int kUPS = 32;                                                   // power-buffer row stride: [bin][lane]
-constexpr int kUPRows = 132;
-constexpr int kUPbufBytes = kUPRows * kUPS * 4;                            // 16 896
-constexpr int kUOffPbuf = kUGroups * 2 * kTRawBytes;                       // raw samples: [group][2][kTRawBytes]
-constexpr int kUOffSs = kUOffPbuf + kUGroups * 2 * kUPbufBytes;            // power bins:  [group][2][rows][32]
-constexpr int kUOffX = kUOffSs + kUGroups * 2 * kUSub * 32 * 4;            // sum of squares per quad: [group][2][sub][32]
-constexpr int kUOffBar = kUOffX + kUGroups * 2 * 2 * 32 * 4;               // X[0], X[256]: [group][2][2][32]
-constexpr int kUSmem = kUOffBar + 128;                                     // mbarriers: raw full [g][2], pbuf empty [g][2]
+constexpr int kUPBin0 = 5, kUPRows = 123;                                  // bins 5 .. 127: all the reference's filterbanks touch (fe_plans_gen.h)
+constexpr int kUPbufBytes = kUPRows * kUPS * 4;                            // 15 744
+// Raw samples of a tile: FOUR chunks of 8 frames each (190 sixteen-byte vectors: 7 * 160 + 400 samples), chunk c at
+// vector 191 c of the buffer, and lane 8 i + j works on frame 8 (j & 3) + 2 i + (j >> 2).  The 16-byte loads of a
+// quarter warp (fixed i) then fall into the 8 different bank groups (191 c + 20 t + w = -(j & 3) + 4 (j >> 2) + w mod 8):
+// conflict-free, where one contiguous copy (lane stride 20 vectors) costs 4 wavefronts per quarter warp.
+constexpr int kUChunkVecs = 191;
+constexpr int kURawBytes = 4 * kUChunkVecs * 16;                           // 12 224 per buffer
+#ifndef FE_K1U_RAW_BUFS
+#define FE_K1U_RAW_BUFS 2          // raw buffers per group (copies issued this many tiles ahead)
+#endif
+#ifndef FE_K1U_PBUF_BUFS
+#define FE_K1U_PBUF_BUFS 2         // power buffers per group (2: the epilogue of tile i may still run during stage B of i + 1)
+#endif
+constexpr int kURawBufs = FE_K1U_RAW_BUFS, kUPbufBufs = FE_K1U_PBUF_BUFS;
+constexpr int kUOffPbuf = kUGroups * kURawBufs * kURawBytes;               // raw samples: [group][raw buf][4 chunks]
+constexpr int kUOffSs = kUOffPbuf + kUGroups * kUPbufBufs * kUPbufBytes;   // power bins:  [group][pbuf][rows][32]
+constexpr int kUOffX = kUOffSs + kUGroups * kUPbufBufs * kUSub * 32 * 4;   // sum of squares per quad: [group][pbuf][sub][32]
+constexpr int kUOffBar = kUOffX + kUGroups * kUPbufBufs * 2 * 32 * 4;      // X[0], X[256]: [group][pbuf][2][32]
+constexpr int kUSmem = kUOffBar + 192;                                     // mbarriers: raw full [g][2], pbuf empty [g][2], exchange drained [g]
 constexpr int kUFftRegs = 104, kUEpiRegs = 64;                             // 16 x 32 x 104 + 4 x 32 x 64 = 640 x 96
 static_assert(kUSmem <= 232448 - 16, "K1U shared memory");
+static_assert(kURawBufs >= 1 && kURawBufs <= 2 && kUPbufBufs >= 1 && kUPbufBufs <= 2, "K1U buffer counts");
 
 __device__ __forceinline__ void mbar_wait_vote(uint32_t bar, uint32_t parity) {       // uniform loop exit
     while (!__all_sync(0xffffffffu, mbar_try(bar, parity))) __nanosleep(20);
@@ -693,6 +708,8 @@ __device__ __forceinline__ void k1u_group_sync(int g) {
     ubar_sync(1 + g, kUSub * 32);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 }
+// lane 8 i + j of a K1U warp owns this frame of the tile (see the raw layout above)
+__device__ __forceinline__ int k1u_frame_of_lane(int lane) { return 8 * (lane & 3) + 2 * (lane >> 3) + ((lane >> 2) & 1); }
 
 template <int EPI>
 __global__ void __launch_bounds__(kUThreads, 1)
@@ -706,7 +723,10 @@ k_frames_to_statics_u(const short* __restrict__ pcm, const short* __restrict__ s
     const uint32_t bar0 = smem_u32(smem_u + kUOffBar);
 
     for (int i = tid; i < kUOffBar / 4; i += kUThreads) reinterpret_cast<uint32_t*>(smem_u)[i] = 0u;   // partial tiles read stale rows / bins
-    if (tid == 0) for (int i = 0; i < 16; ++i) mbar_init(bar0 + 8 * i, 1);
+    if (tid == 0) {
+        for (int i = 0; i < 2 * kUGroups; ++i) { mbar_init(bar0 + 8 * i, 1); mbar_init(bar0 + 64 + 8 * i, 1); }
+        for (int i = 0; i < kUGroups; ++i) mbar_init(bar0 + 128 + 8 * i, kUSub);
+    }
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&s_tmem_base)), "r"(512) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -718,6 +738,7 @@ k_frames_to_statics_u(const short* __restrict__ pcm, const short* __restrict__ s
     if (s_tmem_base != 0u) __trap();                             // all 512 columns are ours: the allocation starts at 0
     const int tile_stride = gridDim.x * kUGroups;
     const int n_iter = (n_tiles + tile_stride - 1) / tile_stride;
+    const int frame = k1u_frame_of_lane(lane);
 
     if (__all_sync(0xffffffffu, sub < kUSub)) {
         // =============================== FFT warps ===============================
@@ -729,46 +750,67 @@ k_frames_to_statics_u(const short* __restrict__ pcm, const short* __restrict__ s
         for (int us = 0; us < kUSub; ++us) {
         if (!__all_sync(0xffffffffu, ug == group && us == sub)) continue;
         const TmemExchange ex{(uint32_t)(ug * 32) << 16};
-        unsigned char* raw_g = smem_u + ug * (2 * kTRawBytes);
-        float* pbuf_g = reinterpret_cast<float*>(smem_u + kUOffPbuf + ug * (2 * kUPbufBytes));
-        float* ss_g = reinterpret_cast<float*>(smem_u + kUOffSs) + ug * (2 * kUSub * 32);
-        float* x_g = reinterpret_cast<float*>(smem_u + kUOffX) + ug * (2 * 2 * 32);
-        const uint32_t bar_raw = bar0 + 16 * ug, bar_empty = bar0 + 64 + 16 * ug;
-        // raw samples of a tile: ONE bulk copy (its frames overlap: (n - 1) * 160 + 400 samples) by lane 0 of sub-warp 3
-        auto fetch = [&](int it, int b) {
-            const int tile = (blockIdx.x + it * gridDim.x) * kUGroups + ug;
-            if (tile >= n_tiles || lane != 0) return;
-            const TileDesc* td = tiles + tile;
+        unsigned char* raw_g = smem_u + ug * (kURawBufs * kURawBytes);
+        float* pbuf_g = reinterpret_cast<float*>(smem_u + kUOffPbuf + ug * (kUPbufBufs * kUPbufBytes));
+        float* ss_g = reinterpret_cast<float*>(smem_u + kUOffSs) + ug * (kUPbufBufs * kUSub * 32);
+        float* x_g = reinterpret_cast<float*>(smem_u + kUOffX) + ug * (kUPbufBufs * 2 * 32);
+        const uint32_t bar_raw = bar0 + 16 * ug, bar_empty = bar0 + 64 + 16 * ug, bar_drain = bar0 + 128 + 8 * ug;
+        // raw samples: lane 0 of sub-warp 3 copies a tile as four chunks (frames 8 c .. 8 c + 7), kURawBufs tiles ahead; the
+        // descriptor it needs was prefetched into L1 at the top of the previous tile
+        auto desc_of = [&](int it) { return tiles + ((blockIdx.x + it * gridDim.x) * kUGroups + ug); };
+        auto prefetch_desc = [&](int it) {
+            if ((blockIdx.x + it * gridDim.x) * kUGroups + ug < n_tiles && lane == 0)
+                asm volatile("prefetch.global.L1 [%0];" :: "l"(desc_of(it)));
+        };
+        auto fetch = [&](int it, int rb) {
+            if ((blockIdx.x + it * gridDim.x) * kUGroups + ug >= n_tiles || lane != 0) return;
+            const TileDesc* td = desc_of(it);
             const long long off = td->pcm_off;
             const int2 ns = *reinterpret_cast<const int2*>(&td->n_frames);        // n_frames, src_sel
-            const uint32_t bytes = (uint32_t)((ns.x - 1) * 160 + 400) * 2u;
-            mbar_expect_tx(bar_raw + 8 * b, bytes);
-            bulk_g2s(smem_u32(raw_g + b * kTRawBytes), (ns.y ? scratch : pcm) + off, bytes, bar_raw + 8 * b);
+            mbar_expect_tx(bar_raw + 8 * rb, (uint32_t)((ns.x - 1) * 160 + 400 + ((ns.x - 1) >> 3) * 240) * 2u);
+            const short* src = (ns.y ? scratch : pcm) + off;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const int cnt = min(ns.x - 8 * c, 8);
+                if (cnt > 0) bulk_g2s(smem_u32(raw_g + rb * kURawBytes + c * (kUChunkVecs * 16)), src + c * (8 * 160),
+                                      (uint32_t)((cnt - 1) * 160 + 400) * 2u, bar_raw + 8 * rb);
+            }
         };
-        if (us == kUSub - 1) { fetch(0, 0); fetch(1, 1); }
+        if (us == kUSub - 1) { fetch(0, 0); if (kURawBufs == 2) fetch(1, 1); prefetch_desc(kURawBufs); }
+        const int lane_vec = (frame >> 3) * kUChunkVecs + (frame & 7) * kTFrameVecs;      // this lane's first vector in a raw buffer
 #pragma unroll 1
         for (int it = 0; it < n_iter; ++it) {
             const int t = (blockIdx.x + it * gridDim.x) * kUGroups + ug;
             if (t >= n_tiles) break;
-            const int b = it & 1;
-            const uint32_t par = (uint32_t)(it >> 1) & 1u;
-            mbar_wait_vote(bar_raw + 8 * b, par);
-            const uint4* raw4 = reinterpret_cast<const uint4*>(raw_g + b * kTRawBytes) + lane * kTFrameVecs;
+            const int rb = kURawBufs == 2 ? (it & 1) : 0, pb = kUPbufBufs == 2 ? (it & 1) : 0;
+            mbar_wait_vote(bar_raw + 8 * rb, (uint32_t)(kURawBufs == 2 ? it >> 1 : it) & 1u);
+            if (it > 0) {                                           // every warp of the group has loaded its last pair of tile it - 1
+                mbar_wait_vote(bar_drain, (uint32_t)(it - 1) & 1u);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            }
+            const uint4* raw4 = reinterpret_cast<const uint4*>(raw_g + rb * kURawBytes) + lane_vec;
             const float ss = k1t_stage_a(raw4, ex, us, us + 1);
             ex.wait_st();
             k1u_group_sync(ug);                                      // exchange complete, this buffer's samples consumed
-            if (us == kUSub - 1) fetch(it + 2, b);                  // refill it for the tile after the next one
-            if (it >= 2) mbar_wait_vote(bar_empty + 8 * b, par ^ 1u);   // the epilogue of tile it - 2 has drained pbuf[b]
-            ss_g[(b * kUSub + us) * 32 + lane] = ss;
-            float* pcol = pbuf_g + b * (kUPRows * kUPS) + lane;
+            if (us == kUSub - 1) { fetch(it + kURawBufs, rb); prefetch_desc(it + kURawBufs + 1); }
+            // the epilogue of the previous user of pbuf[pb] has drained it
+            if (it >= kUPbufBufs) mbar_wait_vote(bar_empty + 8 * pb, (uint32_t)((kUPbufBufs == 2 ? it >> 1 : it) - 1) & 1u);
+            ss_g[(pb * kUSub + us) * 32 + lane] = ss;
+            float* pcol = pbuf_g + pb * (kUPRows * kUPS) + lane - kUPBin0 * kUPS;      // row = bin - kUPBin0
 #pragma unroll 1
             for (int pp = 0; pp < 2; ++pp) {
                 float x0, x256;
-                k1t_pair<kUPS>(ex, 2 * us + pp, tw, pcol, x0, x256);
-                if (us == 0 && pp == 0) { x_g[(b * 2 + 0) * 32 + lane] = x0; x_g[(b * 2 + 1) * 32 + lane] = x256; }
+                // "exchange drained" is signalled as soon as this warp's last pair sits in registers (split-phase: the
+                // group does not meet again before the next tile's stage A stores)
+                k1t_pair<kUPS, kUPBin0, 127>(ex, 2 * us + pp, tw, pcol, x0, x256, [&] {
+                    if (pp == 1) {
+                        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                        if (lane == 0) mbar_arrive(bar_drain);
+                    }
+                });
+                if (us == 0 && pp == 0) { x_g[(pb * 2 + 0) * 32 + lane] = x0; x_g[(pb * 2 + 1) * 32 + lane] = x256; }
             }
-            ubar_arrive(5 + 2 * ug + b, 160);                       // power bins of this tile complete
-            k1u_group_sync(ug);                                      // exchange drained
+            ubar_arrive(5 + 2 * ug + pb, 160);                      // power bins of this tile complete
         }
         }}
     } else {
@@ -777,27 +819,27 @@ k_frames_to_statics_u(const short* __restrict__ pcm, const short* __restrict__ s
 #pragma unroll 1
         for (int ug = 0; ug < kUGroups; ++ug) {
         if (!__all_sync(0xffffffffu, ug == group)) continue;
-        const float* pbuf_g = reinterpret_cast<const float*>(smem_u + kUOffPbuf + ug * (2 * kUPbufBytes));
-        const float* ss_g = reinterpret_cast<const float*>(smem_u + kUOffSs) + ug * (2 * kUSub * 32);
-        const float* x_g = reinterpret_cast<const float*>(smem_u + kUOffX) + ug * (2 * 2 * 32);
+        const float* pbuf_g = reinterpret_cast<const float*>(smem_u + kUOffPbuf + ug * (kUPbufBufs * kUPbufBytes));
+        const float* ss_g = reinterpret_cast<const float*>(smem_u + kUOffSs) + ug * (kUPbufBufs * kUSub * 32);
+        const float* x_g = reinterpret_cast<const float*>(smem_u + kUOffX) + ug * (kUPbufBufs * 2 * 32);
         const uint32_t bar_empty = bar0 + 64 + 16 * ug;
 #pragma unroll 1
         for (int it = 0; it < n_iter; ++it) {
             const int t = (blockIdx.x + it * gridDim.x) * kUGroups + ug;
             if (t >= n_tiles) break;
-            const int b = it & 1;
+            const int pb = kUPbufBufs == 2 ? (it & 1) : 0;
             float* out_t = statics + tiles[t].stat_off;
-            ubar_sync(5 + 2 * ug + b, 160);
-            const float* ssb = ss_g + b * kUSub * 32 + lane;
+            ubar_sync(5 + 2 * ug + pb, 160);
+            const float* ssb = ss_g + pb * kUSub * 32 + lane;
             const float ss = (ssb[0] + ssb[32]) + (ssb[64] + ssb[96]);
-            const float energy = frame_energy(ss, x_g[(b * 2 + 0) * 32 + lane], x_g[(b * 2 + 1) * 32 + lane], P.pscale);
-            const float* pb = pbuf_g + b * (kUPRows * kUPS);
+            const float energy = frame_energy(ss, x_g[(pb * 2 + 0) * 32 + lane], x_g[(pb * 2 + 1) * 32 + lane], P.pscale);
+            const float* pbp = pbuf_g + pb * (kUPRows * kUPS) - kUPBin0 * kUPS;         // row = bin - kUPBin0
             // mel -> log -> DCT for this lane's frame (compile-time filterbank plan, weights in the constant bank)
-            if (EPI == 1) epi_tile_spec_e<PlanMfcc40, 13, true, true, kUPS>(pb, energy, out_t, P.epi_w, P.dc_elim != 0, lane);
-            else if (P.fbank_log) epi_tile_spec_e<PlanFbank80, 80, false, true, kUPS>(pb, energy, out_t, P.epi_w, false, lane);
-            else epi_tile_spec_e<PlanFbank80, 80, false, false, kUPS>(pb, energy, out_t, P.epi_w, false, lane);
+            if (EPI == 1) epi_tile_spec_e<PlanMfcc40, 13, true, true, kUPS>(pbp, energy, out_t, P.epi_w, P.dc_elim != 0, lane, frame);
+            else if (P.fbank_log) epi_tile_spec_e<PlanFbank80, 80, false, true, kUPS>(pbp, energy, out_t, P.epi_w, false, lane, frame);
+            else epi_tile_spec_e<PlanFbank80, 80, false, false, kUPS>(pbp, energy, out_t, P.epi_w, false, lane, frame);
             __syncwarp();
-            if (lane == 0) mbar_arrive(bar_empty + 8 * b);
+            if (lane == 0) mbar_arrive(bar_empty + 8 * pb);
         }
         }
     }
