@@ -75,7 +75,7 @@ struct fe_handle {
     Lane lane[3];
 
     bool k2_split = false;            // FE_K2_SPLIT=1: statistics and cube as two kernels (K2a + K2b), the round-1 form
-    int k1t = 0;                      // FE_K1T=2: K1U (16 + 4 warps, uniform datapath); FE_K1T=1: the lane = frame / tensor-memory kernel (fe_k1t.cuh) where it applies; measured
+    int k1t = 2;                      // 2 (default): K1U where it applies; FE_K1T=0: always K1; FE_K1T=1: the lane = frame / tensor-memory kernel (fe_k1t.cuh) where it applies; measured
                                       // slower than K1 (profiles/r02_k1t.md), kept selectable for A/B runs
     int profiling = 0;
     // profiled runs since fe_set_profiling(1): one event set per run (no sync inside the timed region)
@@ -219,25 +219,31 @@ int launch_k1(fe_handle* h, cudaStream_t st, const void* pcm, const void* scratc
     if (grid <= 0) return FE_OK;
     const bool geo_main = c.frame_len == 400 && c.hop == 160;
     if (!geo_main && !fe_geometry_supported(c.frame_len, c.hop)) return fail(h, FE_ERR_INVALID, "unsupported frame geometry");
-    if (geo_main && !in_f32 && c.window == nullptr && (h->epi_plan == 1 || h->epi_plan == 2) && h->k1t) {
-        // K1T / K1U: lane = frame, exchange in tensor memory (fe_k1t.cuh)
+    // int16 PCM, rectangular window, a specialised filterbank plan (everything the reference runs): K1U, lane = frame
+    // with the FFT exchange in tensor memory (fe_k1t.cuh, k_frames_to_statics_u).  FE_K1T=0 keeps K1 for A/B runs,
+    // FE_K1T=1 selects the first tensor-memory kernel (two warps per tile; plans 1 and 2 only).
+    if (geo_main && !in_f32 && c.window == nullptr && h->epi_plan >= 1 && h->epi_plan <= 4 && h->k1t != 0 &&
+        !(h->k1t == 1 && h->epi_plan > 2)) {
         K1TParams T;
         memset(T.epi_w, 0, sizeof(T.epi_w));
         memcpy(T.epi_w, h->epi_w.data(), sizeof(float) * (size_t)h->epi_w_n);
         T.pscale = dt.pscale; T.fbank_log = dt.fbank_log; T.dc_elim = dt.dc_elim;
+#define FE_LAUNCH_K1U(EPI)                                                                                               \
+        do {                                                                                                             \
+            FE_CUDA(h, cudaFuncSetAttribute(k_frames_to_statics_u<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUSmem)); \
+            k_frames_to_statics_u<EPI><<<gu, kUThreads, kUSmem, st>>>((const short*)pcm, (const short*)scratch, tiles, n_tiles, T, statics); \
+        } while (0)
         if (h->k1t == 2) {
             const int gu = (int)std::min<long long>((n_tiles + kUGroups - 1) / kUGroups, (long long)h->num_sms);
-            if (h->epi_plan == 1) {
-                FE_CUDA(h, cudaFuncSetAttribute(k_frames_to_statics_u<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUSmem));
-                k_frames_to_statics_u<1><<<gu, kUThreads, kUSmem, st>>>((const short*)pcm, (const short*)scratch, tiles, n_tiles, T, statics);
-            } else {
-                FE_CUDA(h, cudaFuncSetAttribute(k_frames_to_statics_u<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUSmem));
-                k_frames_to_statics_u<2><<<gu, kUThreads, kUSmem, st>>>((const short*)pcm, (const short*)scratch, tiles, n_tiles, T, statics);
-            }
+            if (h->epi_plan == 1) FE_LAUNCH_K1U(1);
+            else if (h->epi_plan == 2) FE_LAUNCH_K1U(2);
+            else if (h->epi_plan == 3) FE_LAUNCH_K1U(3);
+            else FE_LAUNCH_K1U(4);
             h->launches++;
             FE_CUDA(h, cudaGetLastError());
             return FE_OK;
         }
+#undef FE_LAUNCH_K1U
         const int gt = (int)std::min<long long>((n_tiles + kK1TGroups - 1) / kK1TGroups, (long long)h->num_sms);
         if (h->epi_plan == 1) {
             FE_CUDA(h, cudaFuncSetAttribute(k_frames_to_statics_t<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kK1TSmem));
@@ -508,7 +514,7 @@ int fe_create(int device, fe_handle** out) {
         else FE_CUDA(nullptr, cudaStreamCreateWithFlags(&h->lane[i].stream, cudaStreamNonBlocking));
         FE_CUDA(nullptr, cudaEventCreateWithFlags(&h->lane[i].done, cudaEventDisableTiming));
     }
-    h->k1t = getenv("FE_K1T") ? atoi(getenv("FE_K1T")) : 0;
+    h->k1t = getenv("FE_K1T") ? atoi(getenv("FE_K1T")) : 2;
     h->k2_split = getenv("FE_K2_SPLIT") != nullptr;
     {   // K1T's twiddles: universal constants, float64 on the host, rounded once (idempotent across handles)
         std::vector<float4> t256p(128), t512p(64);

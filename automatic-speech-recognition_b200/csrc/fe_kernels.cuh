@@ -835,9 +835,13 @@ k_frames_to_statics_u(const short* __restrict__ pcm, const short* __restrict__ s
             const float energy = frame_energy(ss, x_g[(pb * 2 + 0) * 32 + lane], x_g[(pb * 2 + 1) * 32 + lane], P.pscale);
             const float* pbp = pbuf_g + pb * (kUPRows * kUPS) - kUPBin0 * kUPS;         // row = bin - kUPBin0
             // mel -> log -> DCT for this lane's frame (compile-time filterbank plan, weights in the constant bank)
+            // (EPI: 1 = 40 filters -> 13 cepstra, 3 = 40 -> 39 cepstra, 2 = fbank-80, 4 = fbank-40; as in k_frames_to_statics)
             if (EPI == 1) epi_tile_spec_e<PlanMfcc40, 13, true, true, kUPS>(pbp, energy, out_t, P.epi_w, P.dc_elim != 0, lane, frame);
-            else if (P.fbank_log) epi_tile_spec_e<PlanFbank80, 80, false, true, kUPS>(pbp, energy, out_t, P.epi_w, false, lane, frame);
-            else epi_tile_spec_e<PlanFbank80, 80, false, false, kUPS>(pbp, energy, out_t, P.epi_w, false, lane, frame);
+            else if (EPI == 3) epi_tile_spec_e<PlanMfcc40, 39, true, true, kUPS>(pbp, energy, out_t, P.epi_w, P.dc_elim != 0, lane, frame);
+            else if (EPI == 2 && P.fbank_log) epi_tile_spec_e<PlanFbank80, 80, false, true, kUPS>(pbp, energy, out_t, P.epi_w, false, lane, frame);
+            else if (EPI == 2) epi_tile_spec_e<PlanFbank80, 80, false, false, kUPS>(pbp, energy, out_t, P.epi_w, false, lane, frame);
+            else if (P.fbank_log) epi_tile_spec_e<PlanMfcc40, 40, false, true, kUPS>(pbp, energy, out_t, P.epi_w, false, lane, frame);
+            else epi_tile_spec_e<PlanMfcc40, 40, false, false, kUPS>(pbp, energy, out_t, P.epi_w, false, lane, frame);
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_empty + 8 * pb);
         }

@@ -138,11 +138,14 @@ def test_maximum_length_matches_reference_comment(pkg, ref, args):
 @pytest.mark.parametrize("variant", ["1", "2"])
 def test_k1t_tensor_memory_kernel(pkg, ref, corpus1, args, monkeypatch, variant):
     """FE_K1T=1 / 2 select the lane = frame kernels whose FFT exchange lives in tensor memory (fe_k1t.cuh; 2 = K1U,
-    16 FFT + 4 epilogue warps): same features as the default kernel to FP32 round-off, same parity against the oracle,
-    for both specialised plans."""
+    16 FFT + 4 epilogue warps, the default where it applies), FE_K1T=0 the 8-lanes-per-frame kernel K1: same features to
+    FP32 round-off, same parity against the oracle, for the specialised plans."""
     fr = importlib.import_module(PKG + ".frontend")
-    for kw, a in ((dict(), args), (dict(feat_type="fbank", feat_dim=80), make_args(feat_type="fbank", feat_dim=80))):
-        monkeypatch.delenv("FE_K1T", raising=False)
+    cases = [(dict(), args), (dict(feat_type="fbank", feat_dim=80), make_args(feat_type="fbank", feat_dim=80))]
+    if variant == "2":
+        cases += [(dict(feat_dim=39), make_args(feat_dim=39)), (dict(feat_type="fbank", feat_dim=40), make_args(feat_type="fbank", feat_dim=40))]
+    for kw, a in cases:
+        monkeypatch.setenv("FE_K1T", "0")
         fe0 = fr.Frontend(fr.FrontendConfig(**kw))
         base = fe0.extract(corpus1[:12])
         fe0.close()
