@@ -547,7 +547,8 @@ def main():
     ach = frames * W["flop_k1"] / k1 / 1e12
     nominal = 148 * 128 * 2 * 1.965e9 / 1e12
     roofline = {
-        "kernel": "k_frames_to_statics", "bound": "fp32", "achieved": ach, "peak": fp32_peak, "unit": "TFLOP/s",
+        "kernel": "k_frames_to_statics_u" if os.environ.get("FE_K1T", "2") == "2" else "k_frames_to_statics",
+        "bound": "fp32", "achieved": ach, "peak": fp32_peak, "unit": "TFLOP/s",
         "frac": ach / fp32_peak, "traffic": traffic, "traffic_source": traffic_source,
         "peak_source": "measured live, best of four FMA probes (fe_measure_fp32_peaks): what the FP32 pipe sustains depends on the operand "
                        "source -- scalar FFMA with a warp-uniform operand reaches the nominal rate, three register operands do not "
