@@ -90,8 +90,14 @@ FE_HD float k1t_stage_a(const uint4* raw4, EX& ex, int q_begin = 0, int q_end = 
             for (int a = 0; a < 16; ++a) {
                 if (a < 13) {
                     const uint32_t u = c == 0 ? w[a].x : (c == 1 ? w[a].y : (c == 2 ? w[a].z : w[a].w));
-#if defined(__CUDA_ARCH__) && defined(FE_K1T_ASM_CVT)
-                    asm("{\n\t.reg .b16 lo, hi;\n\tmov.b32 {lo, hi}, %2;\n\tcvt.rn.f32.s16 %0, lo;\n\tcvt.rn.f32.s16 %1, hi;\n\t}" : "=f"(re[a]), "=f"(im[a]) : "r"(u));
+#if defined(__CUDA_ARCH__)
+                    // high half: shift + an OPAQUE convert.  Left to itself the compiler moves the first butterfly level of
+                    // the imaginary parts into integer arithmetic (26 IADD3 per column) and then converts both the inputs
+                    // (for the sum of squares) and the sums: 13 more instructions per column (13.52 -> 13.16 ms).  The low
+                    // half converts with one I2F.S16 (XU pipe); both halves through the XU are slower (14.09), both
+                    // through PRMT / I2FP as well (13.68) -- profiles/r02b_k1u.md.
+                    re[a] = (float)(short)(u & 0xffffu);
+                    asm("cvt.rn.f32.s32 %0, %1;" : "=f"(im[a]) : "r"((int)u >> 16));
 #else
                     re[a] = (float)(short)(u & 0xffffu);
                     im[a] = (float)((int)u >> 16);

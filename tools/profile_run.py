@@ -13,7 +13,7 @@ pad = (lens + 7) // 8 * 8
 off = np.concatenate(([0], np.cumsum(pad)))[:-1]
 g = torch.Generator(device="cuda"); g.manual_seed(1)
 d = (torch.randn(int(pad.sum()), device="cuda", generator=g) * 3000).to(torch.int16)
-cfg = A.FrontendConfig(feat_type=feat, feat_dim=13 if feat == "mfcc" else 80)
+cfg = A.FrontendConfig(feat_type="mfcc", feat_dim=39) if feat == "mfcc39" else A.FrontendConfig(feat_type=feat, feat_dim=13 if feat == "mfcc" else 80)
 fe = A.Frontend(cfg); fe.set_profiling(True)
 out = None
 for it in range(reps):
