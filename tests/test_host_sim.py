@@ -69,3 +69,54 @@ def test_k1t_lane_per_frame_dataflow(host_sim, ref, utts):
     z = np.zeros(3000, np.int16)
     want = ref.mfcc(ref.pcm_to_float(z), 16000, 0.025, 0.010, 13)
     assert np.abs(host_sim(z, kernel="k1t") - want).max() < 1e-5       # digital silence: exact eps path
+
+
+# ---- K1U (fe_kernels.cuh: k_frames_to_statics_u): index identities of the chunked raw layout, checked on the CPU ----
+K1U_CHUNK_VECS = 191        # kUChunkVecs
+K1U_FRAME_VECS = 20         # kTFrameVecs: a frame starts 160 samples = 20 sixteen-byte vectors after the previous one
+
+
+def k1u_frame_of_lane(lane):
+    return 8 * (lane & 3) + 2 * (lane >> 3) + ((lane >> 2) & 1)
+
+
+def test_k1u_lane_frame_permutation_and_bank_groups():
+    frames = [k1u_frame_of_lane(l) for l in range(32)]
+    assert sorted(frames) == list(range(32))                        # every frame of the tile has exactly one lane
+    for w in range(50):                                             # the 50 vectors of a frame (400 samples)
+        for quarter in range(4):                                    # a 16-byte shared load is served per quarter warp
+            groups = set()
+            for l in range(8 * quarter, 8 * quarter + 8):
+                f = frames[l]
+                vec = (f >> 3) * K1U_CHUNK_VECS + (f & 7) * K1U_FRAME_VECS + w
+                groups.add(vec % 8)                                 # 8 bank groups of 16 bytes
+            assert len(groups) == 8, (w, quarter)                   # conflict-free
+    # the contiguous layout this replaced (lane = frame, stride 20 vectors) hits two bank groups per quarter warp
+    assert len({(20 * l) % 8 for l in range(8)}) == 2
+
+
+def test_k1u_chunks_cover_their_frames_and_fit():
+    assert 7 * K1U_FRAME_VECS + 50 <= K1U_CHUNK_VECS               # a chunk = 8 frames = 190 vectors
+    for n_frames in range(1, 33):
+        total = 0
+        for c in range(4):
+            cnt = min(n_frames - 8 * c, 8)
+            if cnt > 0:
+                samples = (cnt - 1) * 160 + 400                    # what the kernel copies for chunk c
+                total += samples
+                assert samples * 2 % 16 == 0                        # bulk copies are multiples of 16 bytes
+                # last frame of the chunk ends inside the tile's samples
+                assert c * 8 * 160 + samples <= (n_frames - 1) * 160 + 400
+        # the closed form the kernel passes to mbarrier.expect_tx
+        assert total == (n_frames - 1) * 160 + 400 + ((n_frames - 1) >> 3) * 240
+
+
+def test_k1u_power_rows_cover_the_plans(pkg):
+    """The K1U power buffers only keep bins 5..127 (kUPBin0, kUPRows): every bin the four specialised plans read."""
+    import importlib, re, os
+    src = open(os.path.join(os.path.dirname(pkg.library_path()), "csrc", "fe_plans_gen.h")).read()
+    for name in ("PlanMfcc40", "PlanFbank80"):
+        body = src[src.index("struct " + name):]
+        b0 = [int(x) for x in re.search(r"B0\[\d+\] = \{([^}]*)\}", body).group(1).split(",")]
+        n = [int(x) for x in re.search(r" N\[\d+\] = \{([^}]*)\}", body).group(1).split(",")]
+        assert min(b0) >= 5 and max(b + k - 1 for b, k in zip(b0, n)) <= 127
