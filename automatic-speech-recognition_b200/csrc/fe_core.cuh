@@ -618,17 +618,34 @@ FE_HD void epi_tile_spec_e(const float* pbuf, float energy, float* out_t, const 
             s[n] = lo + hi; d[n] = lo - hi;
         });
         const float* dw = w + Plan::NNZ;
+        // four coefficients at a time, two accumulators each: eight independent FMA chains (a single warp runs this code;
+        // with two chains it issues one FMA every other cycle at best)
+        constexpr int CB = 4;
 #pragma unroll
-        for (int c = 0; c < D; ++c) {
-            float a0 = 0.f, a1 = 0.f;
+        for (int c0 = 0; c0 < D; c0 += CB) {
+            float a0[CB], a1[CB];
+#pragma unroll
+            for (int j = 0; j < CB; ++j) { a0[j] = 0.f; a1[j] = 0.f; }
 #pragma unroll
             for (int n = 0; n < NH; n += 2) {
-                a0 = fmaf(dw[c * NH + n], (c & 1) ? d[n] : s[n], a0);
-                a1 = fmaf(dw[c * NH + n + 1], (c & 1) ? d[n + 1] : s[n + 1], a1);
+#pragma unroll
+                for (int j = 0; j < CB; ++j) {
+                    const int c = c0 + j;
+                    if (c < D) {
+                        a0[j] = fmaf(dw[c * NH + n], (c & 1) ? d[n] : s[n], a0[j]);
+                        a1[j] = fmaf(dw[c * NH + n + 1], (c & 1) ? d[n + 1] : s[n + 1], a1[j]);
+                    }
+                }
             }
-            float v = a0 + a1;
-            if (c == 0 && dc_elim) v = fe_log(energy);
-            out_t[c * 32 + frame] = v;
+#pragma unroll
+            for (int j = 0; j < CB; ++j) {
+                const int c = c0 + j;
+                if (c < D) {
+                    float v = a0[j] + a1[j];
+                    if (c == 0 && dc_elim) v = fe_log(energy);
+                    out_t[c * 32 + frame] = v;
+                }
+            }
         }
     }
 }
