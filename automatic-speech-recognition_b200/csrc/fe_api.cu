@@ -344,13 +344,13 @@ int launch_k0(fe_handle* h, cudaStream_t st, const short* src, const UttDesc* ut
     if (counts[0] > 0) {
         K0Taps<10, kK0Taps> W;
         memcpy(W.w, h->sp_taps.data() + h->sp_tap_off[speed_with_ratio(h, 10, 9)], sizeof(W.w));
-        k_resample_fast<10, 9, kK0Taps><<<grid(counts[0]), kK0Outputs / 10, 0, st>>>(src, utts, atiles, counts[0], W, dst, use_dst_off);
+        k_resample_fast<10, 9, kK0Taps><<<grid(counts[0]), kK0Outputs / (10 * kK0Groups), 0, st>>>(src, utts, atiles, counts[0], W, dst, use_dst_off);
         h->launches++;
     }
     if (counts[1] > 0) {
         K0Taps<10, kK0Taps> W;
         memcpy(W.w, h->sp_taps.data() + h->sp_tap_off[speed_with_ratio(h, 10, 11)], sizeof(W.w));
-        k_resample_fast<10, 11, kK0Taps><<<grid(counts[1]), kK0Outputs / 10, 0, st>>>(src, utts, atiles + counts[0], counts[1], W, dst, use_dst_off);
+        k_resample_fast<10, 11, kK0Taps><<<grid(counts[1]), kK0Outputs / (10 * kK0Groups), 0, st>>>(src, utts, atiles + counts[0], counts[1], W, dst, use_dst_off);
         h->launches++;
     }
     if (counts[2] > 0) {

@@ -1399,7 +1399,8 @@ k_resample(const short* __restrict__ pcm, const UttDesc* __restrict__ utts,
 // threads of the CTA are at the same (phase, tap), so the tap is a CONSTANT-BANK operand of the FFMA (the polyphase
 // table travels in the kernel parameters: compile-time offset, no register, no load), and one shared-memory load
 // of an input sample feeds ~UP FFMAs (windows of the UP phases overlap almost completely): T + DOWN - 1 loads for
-// UP * T FFMAs = 0.11 loads per FMA.  Lane stride of the window reads is DOWN words (odd: bank-conflict free).
+// UP * T FFMAs = 0.11 loads per FMA.  A thread takes G = 2 consecutive groups: every tap then serves two FMAs, i.e. half
+// the uniform loads per FMA (313 per 2 560 instead of per 1 280), and the two windows share all but DOWN samples.
 // Same summation order per output as k_resample and the oracle (t ascending).
 // Staging: the tile's input span is fetched as 16-byte vectors (8 int16 samples, at most two vectors per thread), one
 // tile AHEAD of the arithmetic -- the vectors for tile i + 1 are in flight in registers while tile i is computed.
@@ -1413,7 +1414,7 @@ struct K0Stage {
 };
 
 template <int UP, int T>
-struct K0Taps { float w[UP * T]; };     // [phase][tap]
+struct __align__(16) K0Taps { float w[UP * T]; };     // [phase][tap]
 
 // float -> int16, round half to even, saturating: one F2I instead of rint + min + max + cast (same result; NaN -> 0)
 __device__ __forceinline__ short f2s16_rn_sat(float a) {
@@ -1422,19 +1423,25 @@ __device__ __forceinline__ short f2s16_rn_sat(float a) {
     return r;
 }
 
-template <int UP, int DOWN, int T>
-__global__ void __launch_bounds__(kK0Outputs / UP)
+#ifndef FE_K0_GROUPS
+#define FE_K0_GROUPS 3             // groups of UP outputs per thread: every tap (a uniform load) then serves three FMAs
+#endif
+constexpr int kK0Groups = FE_K0_GROUPS;
+
+template <int UP, int DOWN, int T, int G = kK0Groups>
+__global__ void __launch_bounds__(kK0Outputs / (UP * G))
 k_resample_fast(const short* __restrict__ pcm, const UttDesc* __restrict__ utts,
                 const int2* __restrict__ atiles, int n_atiles,
                 const __grid_constant__ K0Taps<UP, T> W, short* __restrict__ dst, int use_dst_off) {
-    constexpr int THREADS = kK0Outputs / UP;                                 // one group of UP outputs per thread
+    constexpr int THREADS = kK0Outputs / (UP * G);                           // G consecutive groups of UP outputs per thread
     constexpr int HW = T / 2;
     constexpr int TILE_IN = kK0Outputs * DOWN / UP;                           // input samples a tile advances by (tiles start at
     static_assert(TILE_IN * UP == kK0Outputs * DOWN, "tile starts are phase 0");   // multiples of kK0Outputs: 32-bit index math)
-    static_assert(kK0Outputs % 8 == 0 && THREADS * UP == kK0Outputs && (DOWN & 1) == 1, "tile geometry");
+    static_assert(kK0Outputs % 8 == 0 && THREADS * UP * G == kK0Outputs && (DOWN & 1) == 1, "tile geometry");
     constexpr int OFF_LAST = ((UP - 1) * DOWN) / UP;                          // window start of the last phase relative to phase 0
     constexpr int NX = OFF_LAST + T;                                          // input samples one group touches
-    constexpr int SPAN = (THREADS - 1) * DOWN + NX;                           // input samples a tile touches
+    constexpr int NXG = NX + (G - 1) * DOWN;                                  // ... and a thread's G consecutive groups
+    constexpr int SPAN = (THREADS * G - 1) * DOWN + NX;                       // input samples a tile touches
     constexpr int NV = (SPAN + 7 + 7) / 8;                                    // 16-byte vectors covering it from an aligned start
     constexpr int VPT = (NV + THREADS - 1) / THREADS;
     __shared__ __align__(16) float xs[VPT * THREADS * 8];
@@ -1497,21 +1504,45 @@ k_resample_fast(const short* __restrict__ pcm, const UttDesc* __restrict__ utts,
         }
         __syncthreads();
         fetch(tile + gridDim.x, sg, te_n, u_n);                              // next tile's samples fly during the arithmetic
-        const float* xw = xs + tid * DOWN + (first - a0);                    // window of phase 0 of this thread's group
-        float acc[UP];
+        const float* xw = xs + tid * (G * DOWN) + (first - a0);              // window of phase 0 of this thread's first group
+        float acc[G][UP];
 #pragma unroll
-        for (int p = 0; p < UP; ++p) acc[p] = 0.f;
+        for (int i = 0; i < G; ++i)
 #pragma unroll
-        for (int k = 0; k < NX; ++k) {
-            const float xv = xw[k];
+            for (int p = 0; p < UP; ++p) acc[i][p] = 0.f;
+        // A ROLLED loop over chunks of TC taps: the straight-line form of G = 2 (3 000 instructions, 48 KB) no longer fits
+        // the instruction cache and runs at half the speed.  The chunk counter is a uniform loop counter, so the taps still
+        // reach the FMAs as uniform-register operands (LDCU c[0x0][UR + imm] from the kernel parameters).
+#ifndef FE_K0_TC
+#define FE_K0_TC 16
+#endif
+        constexpr int TC = FE_K0_TC, NW = TC + OFF_LAST + (G - 1) * DOWN;     // taps per chunk, samples a chunk touches
+        static_assert(T % TC == 0, "taps per chunk");
+#pragma unroll 1
+        for (int c = 0; c < T / TC; ++c) {
+            float xv[NW];
 #pragma unroll
-            for (int p = 0; p < UP; ++p) {
-                const int t = k - (p * DOWN) / UP;                            // tap index of this sample in phase p's window
-                if (t >= 0 && t < T) acc[p] = fmaf(W.w[((p * DOWN) % UP) * T + t], xv, acc[p]);
+            for (int m = 0; m < NW; ++m) xv[m] = xw[c * TC + m];
+            const float* wc = W.w + c * TC;
+#pragma unroll
+            for (int t4 = 0; t4 < TC; t4 += 4) {
+#pragma unroll
+                for (int p = 0; p < UP; ++p) {
+                    // four consecutive taps of output p's phase: one 16-byte uniform load
+                    const float4 w4 = *reinterpret_cast<const float4*>(wc + ((p * DOWN) % UP) * T + t4);
+                    const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+#pragma unroll
+                        for (int i = 0; i < G; ++i)
+                            acc[i][p] = fmaf(wv[e], xv[t4 + e + (p * DOWN) / UP + i * DOWN], acc[i][p]);
+                }
             }
         }
 #pragma unroll
-        for (int p = 0; p < UP; ++p) ys[tid * UP + p] = f2s16_rn_sat(acc[p] * u.gain);     // gain 1 = exact identity
+        for (int i = 0; i < G; ++i)
+#pragma unroll
+            for (int p = 0; p < UP; ++p) ys[(tid * G + i) * UP + p] = f2s16_rn_sat(acc[i][p] * u.gain);     // gain 1 = exact identity
         __syncthreads();
         const int n8 = nout >> 3;                                            // y is 16-byte aligned (offsets % 8 == 0, tiles % 8 == 0)
         for (int i = tid; i < n8; i += THREADS) reinterpret_cast<int4*>(y)[i] = reinterpret_cast<const int4*>(ys)[i];

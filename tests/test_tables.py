@@ -42,8 +42,8 @@ def test_frontend_config_geometry(pkg):
 def test_k0_fast_path_index_math(pkg):
     """The resampler's fast kernel (k_resample_fast) replaces the per-output 64-bit `j*down / up`, `% up` of the generic
     kernel by tile-level constants: tiles start at multiples of 2880 outputs (phase 0, a whole number of input
-    samples), thread g owns the UP consecutive outputs j = UP g + p, phase (p*down) % up, whose windows start at
-    g*down + (p*down)//up + (first - a0) of the staged span.  Check every (tile, thread, phase) against the
+    samples), group g is the UP consecutive outputs j = UP g + p, phase (p*down) % up, whose windows start at
+    g*down + (p*down)//up + (first - a0) of the staged span (a thread owns kK0Groups = 3 consecutive groups).  Check every (tile, thread, phase) against the
     defining formula y[j] = sum_t taps[(j*down) % up][t] * x[floor(j*down/up) - (T/2 - 1) + t]."""
     K0_OUT, UP, T = 2880, 10, pkg.tables.RESAMPLE_TAPS
     assert T == 128                                                     # kK0Taps in fe_kernels.cuh
@@ -55,7 +55,8 @@ def test_k0_fast_path_index_math(pkg):
         nx = ((UP - 1) * down) // UP + T
         span = (threads - 1) * down + nx
         nv = (span + 14) // 8
-        assert nv <= 2 * threads                                        # at most two staging vectors per thread
+        assert threads % 3 == 0 and (threads // 3) % 32 == 0            # kK0Groups = 3 groups per thread, whole warps
+        assert nv <= 6 * (threads // 3)                                 # at most six staging vectors per thread
         for tile in (0, 1, 7, 12345):
             te_y = tile * K0_OUT
             first = (te_y // K0_OUT) * tile_in - (HW - 1)
