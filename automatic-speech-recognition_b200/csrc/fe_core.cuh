@@ -598,16 +598,57 @@ FE_HD float mel_spec(const float* pcol, const float* w) {
     return v;
 }
 
+// Four filters at a time with two accumulators each: eight independent FMA chains (the epilogue runs in ONE warp per
+// lane group; with the two chains of mel_spec it is eligible to issue less than half of the time).
+template <class Plan, int M0, int M1, int M2, int M3, bool LOG, int PS = kPStride>
+FE_HD void mel_spec4(const float* pcol, const float* w, float (&out)[4]) {
+    constexpr int n0 = Plan::N[M0], n1 = Plan::N[M1], n2 = Plan::N[M2], n3 = Plan::N[M3];
+    constexpr int n01 = n0 > n1 ? n0 : n1, n23 = n2 > n3 ? n2 : n3, nmax = n01 > n23 ? n01 : n23;
+    float a0[4] = {0.f, 0.f, 0.f, 0.f}, a1[4] = {0.f, 0.f, 0.f, 0.f};
+    static_for<0, nmax>([&](auto ii) {
+        constexpr int i = decltype(ii)::value;
+        static_for<0, 4>([&](auto jj) {
+            constexpr int j = decltype(jj)::value;
+            constexpr int m = j == 0 ? M0 : (j == 1 ? M1 : (j == 2 ? M2 : M3));
+            constexpr int b0 = Plan::B0[m], nn = Plan::N[m], off = Plan::OFF[m];
+            if constexpr (i < nn) {
+                if (i & 1) a1[j] = fmaf(w[off + i], pcol[(b0 + i) * PS], a1[j]);
+                else a0[j] = fmaf(w[off + i], pcol[(b0 + i) * PS], a0[j]);
+            }
+        });
+    });
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        float v = a0[j] + a1[j];
+        v = v == 0.f ? kEpsF64 : v;             // speechpy.functions.zero_handling
+        if (LOG) v = fe_log(v);
+        out[j] = v;
+    }
+}
+
 // PS: row stride of the power buffer in floats; `energy`: this lane's (zero-handled) frame energy
 // `lane` selects the column of the power buffer, `frame` the position inside the tile's [D][32] statics block
 template <class Plan, int D, bool MFCC, bool LOG, int PS = kPStride>
 FE_HD void epi_tile_spec_e(const float* pbuf, float energy, float* out_t, const float* w, bool dc_elim, int lane, int frame) {
     const float* pcol = pbuf + lane;
     if constexpr (!MFCC) {
-        static_for<0, Plan::NF>([&](auto mi) {
-            constexpr int M = decltype(mi)::value;
-            out_t[M * 32 + frame] = mel_spec<Plan, M, LOG, PS>(pcol, w);
-        });
+        // measured on K1U (60 audio-h): the four-filter form helps the 80-filter bank (6.19 -> 6.06 ms), not the 40-filter
+        // ones (fbank-40 5.88 -> 5.97, 13 cepstra 13.02 -> 13.24 on the bench shard): their epilogue warp is not the limit
+        if constexpr (Plan::NF >= 80) {
+            static_assert(Plan::NF % 4 == 0, "filters are processed four at a time");
+            static_for<0, Plan::NF / 4>([&](auto mi) {
+                constexpr int M = 4 * decltype(mi)::value;
+                float v[4];
+                mel_spec4<Plan, M, M + 1, M + 2, M + 3, LOG, PS>(pcol, w, v);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) out_t[(M + j) * 32 + frame] = v[j];
+            });
+        } else {
+            static_for<0, Plan::NF>([&](auto mi) {
+                constexpr int M = decltype(mi)::value;
+                out_t[M * 32 + frame] = mel_spec<Plan, M, LOG, PS>(pcol, w);
+            });
+        }
     } else {
         constexpr int NH = Plan::NF / 2;
         static_assert(Plan::NF % 2 == 0, "the specialised plans have an even number of filters");
