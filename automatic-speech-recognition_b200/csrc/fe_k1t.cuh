@@ -71,7 +71,8 @@ FE_HD constexpr int k1t_row_b(int p) { return p == 0 ? 8 : 16 - p; }
 // scalar results can be stored as the (row a, row b) pairs the layout wants (8 pairs x 2 planes x st2 per column).
 // Returns the lane's sum of squares over the columns it processed (Parseval frame energy, sample units).
 // ---------------------------------------------------------------------------
-template <class EX>
+// ENERGY = false skips the sum of squares (filterbank features do not use the frame energy) and returns 0.
+template <bool ENERGY = true, class EX>
 FE_HD float k1t_stage_a(const uint4* raw4, EX& ex, int q_begin = 0, int q_end = 4) {
     float ss0 = 0.f, ss1 = 0.f, ss2 = 0.f, ss3 = 0.f;
 #if defined(__CUDA_ARCH__)
@@ -106,10 +107,12 @@ FE_HD float k1t_stage_a(const uint4* raw4, EX& ex, int q_begin = 0, int q_end = 
                     re[a] = 0.f; im[a] = 0.f;
                 }
             }
+            if (ENERGY) {
 #pragma unroll
-            for (int a = 0; a < 13; ++a) {
-                if (a & 1) { ss1 = fmaf(re[a], re[a], ss1); ss3 = fmaf(im[a], im[a], ss3); }
-                else { ss0 = fmaf(re[a], re[a], ss0); ss2 = fmaf(im[a], im[a], ss2); }
+                for (int a = 0; a < 13; ++a) {
+                    if (a & 1) { ss1 = fmaf(re[a], re[a], ss1); ss3 = fmaf(im[a], im[a], ss3); }
+                    else { ss0 = fmaf(re[a], re[a], ss0); ss2 = fmaf(im[a], im[a], ss2); }
+                }
             }
             fft16<13>(re, im);
             const int j = 4 * q + c;

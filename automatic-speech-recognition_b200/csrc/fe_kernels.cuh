@@ -789,13 +789,13 @@ k_frames_to_statics_u(const short* __restrict__ pcm, const short* __restrict__ s
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             }
             const uint4* raw4 = reinterpret_cast<const uint4*>(raw_g + rb * kURawBytes) + lane_vec;
-            const float ss = k1t_stage_a(raw4, ex, us, us + 1);
+            const float ss = k1t_stage_a<(EPI == 1 || EPI == 3)>(raw4, ex, us, us + 1);      // frame energy: cepstra only (c0)
             ex.wait_st();
             k1u_group_sync(ug);                                      // exchange complete, this buffer's samples consumed
             if (us == kUSub - 1) { fetch(it + kURawBufs, rb); prefetch_desc(it + kURawBufs + 1); }
             // the epilogue of the previous user of pbuf[pb] has drained it
             if (it >= kUPbufBufs) mbar_wait_vote(bar_empty + 8 * pb, (uint32_t)((kUPbufBufs == 2 ? it >> 1 : it) - 1) & 1u);
-            ss_g[(pb * kUSub + us) * 32 + lane] = ss;
+            if (EPI == 1 || EPI == 3) ss_g[(pb * kUSub + us) * 32 + lane] = ss;
             float* pcol = pbuf_g + pb * (kUPRows * kUPS) + lane - kUPBin0 * kUPS;      // row = bin - kUPBin0
 #pragma unroll 1
             for (int pp = 0; pp < 2; ++pp) {
@@ -830,9 +830,12 @@ k_frames_to_statics_u(const short* __restrict__ pcm, const short* __restrict__ s
             const int pb = kUPbufBufs == 2 ? (it & 1) : 0;
             float* out_t = statics + tiles[t].stat_off;
             ubar_sync(5 + 2 * ug + pb, 160);
-            const float* ssb = ss_g + pb * kUSub * 32 + lane;
-            const float ss = (ssb[0] + ssb[32]) + (ssb[64] + ssb[96]);
-            const float energy = frame_energy(ss, x_g[(pb * 2 + 0) * 32 + lane], x_g[(pb * 2 + 1) * 32 + lane], P.pscale);
+            float energy = 1.f;
+            if (EPI == 1 || EPI == 3) {
+                const float* ssb = ss_g + pb * kUSub * 32 + lane;
+                const float ss = (ssb[0] + ssb[32]) + (ssb[64] + ssb[96]);
+                energy = frame_energy(ss, x_g[(pb * 2 + 0) * 32 + lane], x_g[(pb * 2 + 1) * 32 + lane], P.pscale);
+            }
             const float* pbp = pbuf_g + pb * (kUPRows * kUPS) - kUPBin0 * kUPS;         // row = bin - kUPBin0
             // mel -> log -> DCT for this lane's frame (compile-time filterbank plan, weights in the constant bank)
             // (EPI: 1 = 40 filters -> 13 cepstra, 3 = 40 -> 39 cepstra, 2 = fbank-80, 4 = fbank-40; as in k_frames_to_statics)

@@ -61,7 +61,7 @@ def parse():
     ap.add_argument("--hours-per-gpu", type=float, default=None, help="default: 125 (configs4), 30 (configs1 / configs2)")
     ap.add_argument("--config", default="configs4", choices=sorted(WORKLOADS),
                     help="BASELINE.json configs[] entry; the driver's default run is configs4 (the headline metric)")
-    ap.add_argument("--files-hours", type=float, default=6.0,
+    ap.add_argument("--files-hours", type=float, default=16.0,
                     help="audio-hours of FLAC files per rank for the e2e_files leg (process_audios on paths); 0 = skip")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--cpu-sample-hours", type=float, default=None, help="audio-hours the CPU baseline times")
