@@ -1265,7 +1265,8 @@ __device__ __forceinline__ void cube_tile(const float* __restrict__ x, const flo
         __syncwarp();
         if (SEG == ROWLEN && RS == ROWLEN) {
             const int total = nrow * ROWLEN, n4 = total >> 2;
-            for (int i = lane; i < n4; i += 32) reinterpret_cast<float4*>(dst)[i] = reinterpret_cast<const float4*>(stage)[i];
+            // streaming stores: the cube is never read again on the device, it should not push the statics out of the L2
+            for (int i = lane; i < n4; i += 32) __stcs(reinterpret_cast<float4*>(dst) + i, reinterpret_cast<const float4*>(stage)[i]);
             for (int i = (n4 << 2) + lane; i < total; i += 32) dst[i] = stage[i];
         } else if (SEG % 4 == 0 && ROWLEN % 4 == 0) {
             constexpr int Q = SEG / 4;
@@ -1298,6 +1299,8 @@ k_utt_cmvn_cube(const UttDesc* __restrict__ utts, int n_utts, const float* __res
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int chunk = warp / U::WPC, wsub = warp % U::WPC;
     const bool deltas = flags & 4;
+    unsigned long long pol_keep;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_keep));
     for (int ui = blockIdx.x; ui < n_utts; ui += gridDim.x) {
         const UttDesc u = utts[ui];
         const int L = u.n_frames;
@@ -1313,7 +1316,9 @@ k_utt_cmvn_cube(const UttDesc* __restrict__ utts, int n_utts, const float* __res
             const bool live = b * 32 + lane < L;
 #pragma unroll
             for (int c = 0; c < U::SCH; ++c) {
-                const float d = live ? xb[c * 32] - shift[c] : 0.f;
+                float xv;        // evict-last: keep the utterance's statics in the L2 until phase 2 has read them again
+                asm volatile("ld.global.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(xv) : "l"(xb + c * 32), "l"(pol_keep));
+                const float d = live ? xv - shift[c] : 0.f;
                 s[c] += d; q[c] = fmaf(d, d, q[c]);
             }
         }
