@@ -62,7 +62,7 @@ def parse():
     ap.add_argument("--config", default="configs4", choices=sorted(WORKLOADS),
                     help="BASELINE.json configs[] entry; the driver's default run is configs4 (the headline metric)")
     ap.add_argument("--files-hours", type=float, default=16.0,
-                    help="audio-hours of FLAC files per rank for the e2e_files leg (process_audios on paths); 0 = skip")
+                    help="audio-hours of FLAC files per rank for the e2e_files leg (process_audios on paths; half of it per rank at N > 1); 0 = skip")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--cpu-sample-hours", type=float, default=None, help="audio-hours the CPU baseline times")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -464,7 +464,8 @@ def main():
     if a.files_hours > 0 and a.config == "configs4":
         h_pcm_t = h_out_t = h_pcm = h_out = None        # release the pinned 21 GB before the file leg
         try:
-            e2e_files = files_leg(pkg, a.files_hours, rank, local, world, dist if world > 1 else None, torch)
+            # N > 1: half the set per rank (the ranks share the host's cores for generating and encoding the files)
+            e2e_files = files_leg(pkg, a.files_hours if world == 1 else a.files_hours / 2, rank, local, world, dist if world > 1 else None, torch)
         except Exception as ex:
             e2e_files = {"value": None, "unit": UNIT, "error": str(ex)[:200]}
 
