@@ -24,9 +24,12 @@
 // Shared memory only stages the raw samples (one bulk copy per tile, double-buffered) and the lane's 129 power bins
 // ([bin][lane]).
 //
-// Status: parity-green, SLOWER than K1 (20.6 vs 16.7 ms on the bench shard) -- TMEM holds one frame per lane for four
-// warps per SM, and scalar straight-line code of this size is bound by instruction fetch, not issue
-// (profiles/r02_k1t.md).  Selected with FE_K1T=1 only.
+// Two kernels are built from these phases (fe_kernels.cuh):
+//   * k_frames_to_statics_u (K1U, the default): 16 FFT warps + 4 epilogue warps per SM, four warps share a tile (one
+//     column quad / two row pairs each), every warp-uniform quantity in the uniform datapath, conflict-free chunked raw
+//     layout: 13.0 ms on the bench shard = 0.66 of nominal FP32 (K1: 16.7 ms) -- profiles/r02b_k1u.md;
+//   * k_frames_to_statics_t (K1T, FE_K1T=1): the first form, two warps per tile, 19.2 ms -- TMEM holds one frame per
+//     lane for four warps per SM, and two warps per scheduler cannot keep the issue port busy (profiles/r02_k1t.md).
 //
 // The per-lane phases are host/device functions over an exchange accessor, so tests/host_sim replays them on the CPU
 // (exchange = a float[512]) against the float64 oracle before anything runs on a GPU.
