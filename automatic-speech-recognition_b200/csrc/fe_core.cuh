@@ -659,6 +659,14 @@ FE_HD void epi_tile_spec_e(const float* pbuf, float energy, float* out_t, const 
             s[n] = lo + hi; d[n] = lo - hi;
         });
         const float* dw = w + Plan::NNZ;
+        // Second fold for the even coefficients: cos(pi (2n + 1) c / (2 NF)) is symmetric (c = 0 mod 4) or antisymmetric
+        // (c = 2 mod 4) under n -> NH - 1 - n, so they need NH / 2 products of s[n] +- s[NH - 1 - n] (the table row's first
+        // half) instead of NH.  Odd coefficients keep the NH products of d[n].
+        static_assert(NH % 2 == 0, "second fold");
+        constexpr int NQ = NH / 2;
+        float ss[NQ], sd[NQ];
+#pragma unroll
+        for (int n = 0; n < NQ; ++n) { ss[n] = s[n] + s[NH - 1 - n]; sd[n] = s[n] - s[NH - 1 - n]; }
         // four coefficients at a time, two accumulators each: eight independent FMA chains (a single warp runs this code;
         // with two chains it issues one FMA every other cycle at best)
         constexpr int CB = 4;
@@ -673,8 +681,13 @@ FE_HD void epi_tile_spec_e(const float* pbuf, float energy, float* out_t, const 
                 for (int j = 0; j < CB; ++j) {
                     const int c = c0 + j;
                     if (c < D) {
-                        a0[j] = fmaf(dw[c * NH + n], (c & 1) ? d[n] : s[n], a0[j]);
-                        a1[j] = fmaf(dw[c * NH + n + 1], (c & 1) ? d[n + 1] : s[n + 1], a1[j]);
+                        if (c & 1) {
+                            a0[j] = fmaf(dw[c * NH + n], d[n], a0[j]);
+                            a1[j] = fmaf(dw[c * NH + n + 1], d[n + 1], a1[j]);
+                        } else if (n < NQ) {
+                            a0[j] = fmaf(dw[c * NH + n], (c & 2) ? sd[n] : ss[n], a0[j]);
+                            a1[j] = fmaf(dw[c * NH + n + 1], (c & 2) ? sd[n + 1] : ss[n + 1], a1[j]);
+                        }
                     }
                 }
             }
