@@ -87,8 +87,8 @@ def _sweep(pkg, make, steps, **sw):
         feats, _ = pkg.process_pcm(pcm, args, **sw)
         worst, units, bad, total, rng_db = 0.0, 0.0, 0, 0, []
         for x, f in zip(pcm, feats):
-            x64 = x.astype(np.float64)
-            want = R.features_one(x64, **sw).astype(np.float64)
+            x64 = R.pcm_to_float(x) if x.dtype == np.int16 else x.astype(np.float64)
+            want = R.features_one(x if x.dtype == np.int16 else x64, **sw).astype(np.float64)
             err = np.abs(f.astype(np.float64) - want)
             u = np.minimum(err / pu.ABS_TOL, err / (pu.REL_TOL * np.abs(want) + 1e-300))
             worst, units = max(worst, float(err.max())), max(units, float(u.max()))
@@ -120,13 +120,18 @@ def test_fp32_error_vs_in_frame_dynamic_range(pkg, ref):
     a, fa = _sweep(pkg, lambda r: _tilted_noise(48000, r, rng), steps)
     b, fb = _sweep(pkg, lambda r: _tilted_noise(48000, r, rng), steps, window=np.hanning(400))
     c, fc = _sweep(pkg, tone, steps)
+    # (d) the same tone over a floor as int16 PCM: the path the reference's files take, i.e. the lane-per-frame kernel K1U
+    # (float32 PCM runs on K1); 16-bit quantisation puts its own floor 98 dB below full scale
+    tone16 = lambda r: np.clip(np.rint(tone(r).astype(np.float64) * 32768.0 / 0.35), -32768, 32767).astype(np.int16)
+    d, fd = _sweep(pkg, tone16, (20, 30, 40, 50, 60, 70, 80))
     pu.record("dynamic_range", {
         "tilted_noise_rectangular_window": {"sweep": a, "first_step_out_of_tolerance_db": fa},
         "tilted_noise_hann_window": {"sweep": b, "first_step_out_of_tolerance_db": fb},
         "tone_over_white_floor_rectangular_window": {"sweep": c, "first_step_out_of_tolerance_db": fc},
+        "tone_over_white_floor_int16_k1u": {"sweep": d, "first_step_out_of_tolerance_db": fd},
         "input": "float32 PCM, 6 x 3 s per step, MFCC-39 + CMVN; step = spectral tilt over 0-4 kHz (a, b) or floor below the tone (c)",
         "tolerance": {"abs": pu.ABS_TOL, "rel": pu.REL_TOL}})
-    for rows in (a, b, c):
+    for rows in (a, b, c, d):
         by = {r["step_db"]: r for r in rows}
         for s_ in (20, 30, 40):                                        # the range broadband material and speech occupy
             assert by[s_]["elements_out_of_tolerance"] == 0, by[s_]
