@@ -653,7 +653,7 @@ k_frames_to_statics_t(const short* __restrict__ pcm, const short* __restrict__ s
 //                 -> arrive "pbuf[b] full"
 //     epilogue:   wait "pbuf[b] full" -> energy, mel, log, DCT -> statics -> arrive "pbuf[b] empty"
 //
-// What ptxas needs for uniform-register operands (measured on small probes, _scratch notes in profiles/r02_k1u.md):
+// What ptxas needs for uniform-register operands (found with small probe kernels and cuobjdump; profiles/r02b_k1u.md):
 //   * a value derived from threadIdx is never uniform to it; loop counters with constant or kernel-parameter bounds
 //     are.  So the roles are entered through `for (ug) for (us) if (vote(ug == group && us == sub))`: inside, (ug, us)
 //     are uniform loop counters and the tile index, buffer addresses, tensor-memory addresses, barrier ids and twiddle
